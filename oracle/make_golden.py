@@ -1,0 +1,214 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (read-only at /root/reference).
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python oracle/make_golden.py
+The committed .npz files are what tests read; this script documents how they were produced.
+
+Noise tape: torch.randn / torch.rand / torch.normal are wrapped for the duration of a sampler run so that
+every standard-normal vector and accept-uniform the reference consumes is recorded in call order.
+torch.normal(loc, scale) is replaced by loc + scale * torch.randn(...) (bitwise identical on CPU for the
+same generator state), so the recorded z reproduces the reference's proposals.
+Fixture parameter vectors are the ones of the reference's own unit tests (cited below).
+"""
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(ROOT / "oracle" / "kanga_stub"))
+sys.path.insert(0, str(REF))
+
+from torch.distributions import Normal  # noqa: E402
+from torch.utils.data import DataLoader  # noqa: E402
+
+from eeyore.chains import ChainList  # noqa: E402
+from eeyore.constants import loss_functions  # noqa: E402
+from eeyore.datasets import XYDataset  # noqa: E402
+from eeyore.models.mlp import MLP, Hyperparameters  # noqa: E402
+from eeyore.samplers import HMC, MALA, MetropolisHastings  # noqa: E402
+import eeyore.stats as st  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+OUT.mkdir(parents=True, exist_ok=True)
+
+# fixture thetas of the reference's tests
+THETA_221 = [1.1, -2.9, -0.4, 0.8, 4.3, 9.2, 4.44, -3.4, 7.2]            # tests/test_binary_classif_mlp221_log_lik.py:36
+THETA_2321 = [1.1, -2.9, -0.4, 0.8, 4.3, 9.2, 4.44, -3.4, 7.2, 1.2, -2.3, 0.4, -5.4, -3.3, 2.8, 2.9, 7.7, -4.4, 2,
+              6]                                                        # tests/test_binary_classif_mlp2321_log_lik.py:19-22 (first 20)
+THETA_433 = [0.7735, 0.8161, 0.3910, 0.9622, 0.3748, 0.8711, 0.3315, 0.5473, 0.8820,
+             0.0294, 0.9686, 0.8313, 0.6693, 0.8791, 0.6271, 0.8636, 0.3814, 0.0319,
+             0.5148, 0.5086, 0.7428, 0.5464, 0.5278, 0.6127, 0.4499, 0.1538, 0.9291]   # tests/test_multiclass_classif_mlp433_log_lik.py:36-39
+THETA_4323 = [0.2213, 0.5852, 0.1458, 0.5139, -0.1946, 0.0489, -0.1281, -0.7307,
+              0.2176, 0.3274, -1.3060, 0.3253, -0.4248, 1.7403, 0.6219, 0.2652,
+              -0.5310, -0.0291, 1.0262, -0.4920, 0.4391, -0.2450, 2.3145, -0.0788,
+              1.1180, -1.2803, -0.4435, 0.5371, -0.2440, -0.3574, 0.4446, -0.3453]     # tests/test_multiclass_classif_mlp4323_log_lik.py:19-25
+
+ARCHS = {
+    "221": dict(dims=[2, 2, 1], loss="binary_classification", data="xor", theta=THETA_221),
+    "2321": dict(dims=[2, 3, 2, 1], loss="binary_classification", data="xor", theta=THETA_2321),
+    "433": dict(dims=[4, 3, 3], loss="multiclass_classification", data="iris", theta=THETA_433),
+    "4323": dict(dims=[4, 3, 2, 3], loss="multiclass_classification", data="iris", theta=THETA_4323),
+}
+
+
+def load_data(name, dtype):
+    if name == "xor":
+        return XYDataset.from_eeyore("xor", dtype=dtype)
+    return XYDataset.from_eeyore("iris", yndmin=1, yonehot=True, dtype=dtype)
+
+
+def make_model(arch, dtype, prior_scale=None, temperature=None):
+    a = ARCHS[arch]
+    nl = len(a["dims"]) - 1
+    last = torch.sigmoid if a["loss"] == "binary_classification" else None
+    hp = Hyperparameters(dims=a["dims"], bias=nl * [True], activations=(nl - 1) * [torch.sigmoid] + [last])
+    model = MLP(loss=loss_functions[a["loss"]], hparams=hp, dtype=dtype, temperature=temperature)
+    if prior_scale is not None:
+        P = model.num_params()
+        model.prior = Normal(torch.zeros(P, dtype=dtype), prior_scale * torch.ones(P, dtype=dtype))
+    return model
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+def model_goldens():
+    out = {}
+    for dname in ("xor", "iris"):
+        d = load_data(dname, torch.float64)
+        out[f"{dname}_x"], out[f"{dname}_y"] = npy(d.x), npy(d.y)
+    gen = torch.Generator().manual_seed(1234)
+    for arch, a in ARCHS.items():
+        for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+            data = load_data(a["data"], dtype)
+            for ps, pst in ((1.0, "p1"), (100.0, "p100"), (math.sqrt(3.0), "psqrt3")):
+                for temp, tt in ((None, ""), (0.7, "_T07")):
+                    model = make_model(arch, dtype, prior_scale=ps, temperature=temp)
+                    P = model.num_params()
+                    fixed = torch.tensor(a["theta"], dtype=dtype)
+                    rnd = (torch.randn(12, P, generator=gen, dtype=torch.float64) * 1.5).to(dtype)
+                    thetas = torch.cat([fixed[None], rnd])
+                    lts, grads, lls, lps = [], [], [], []
+                    for th in thetas:
+                        lt, g = model.upto_grad_log_target(th.clone().detach(), data.x, data.y)
+                        lts.append(lt.item()); grads.append(npy(g))
+                        lls.append(model.log_lik(data.x, data.y).item()); lps.append(model.log_prior().item())
+                    key = f"{arch}_{tag}_{pst}{tt}"
+                    out[key + "_theta"] = npy(thetas)
+                    out[key + "_lt"] = np.array(lts); out[key + "_grad"] = np.stack(grads)
+                    out[key + "_ll"] = np.array(lls); out[key + "_lp"] = np.array(lps)
+    # saturation semantics: output bias pushed until p == 1.0 exactly
+    for dtype, tag, b in ((torch.float32, "f32", 20.0), (torch.float64, "f64", 40.0)):
+        model = make_model("221", dtype, prior_scale=1.0)
+        data = load_data("xor", dtype)
+        th = torch.tensor(THETA_221, dtype=dtype); th[8] = b; th[6] = 0.0; th[7] = 0.0
+        lt, g = model.upto_grad_log_target(th.clone().detach(), data.x, data.y)
+        out[f"sat_{tag}_theta"] = npy(th); out[f"sat_{tag}_lt"] = np.array(lt.item()); out[f"sat_{tag}_grad"] = npy(g)
+    np.savez_compressed(OUT / "model_goldens.npz", **out)
+    print("model_goldens", len(out))
+
+
+# ---------------------------------------------------------------------------------------------------
+class Tape:
+    """Records z (standard normals) and u (uniforms) in the reference's call order."""
+
+    def __enter__(self):
+        self.z, self.u = [], []
+        self._randn, self._rand, self._normal = torch.randn, torch.rand, torch.normal
+
+        def randn(*a, **k):
+            v = self._randn(*a, **k); self.z.append(npy(v).copy()); return v
+
+        def rand(*a, **k):
+            v = self._rand(*a, **k); self.u.append(npy(v).copy()); return v
+
+        def normal(loc, scale, *a, **k):
+            assert not a and not k
+            z = self._randn(loc.shape, dtype=loc.dtype); self.z.append(npy(z).copy())
+            return loc + scale * z
+
+        torch.randn, torch.rand, torch.normal = randn, rand, normal
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.rand, torch.normal = self._randn, self._rand, self._normal
+
+
+def run_sampler(name, kind, arch, dtype, n_iters, n_burnin, prior_scale, seed, **kw):
+    torch.manual_seed(seed)
+    a = ARCHS[arch]
+    data = load_data(a["data"], dtype)
+    loader = DataLoader(data, batch_size=len(data))
+    model = make_model(arch, dtype, prior_scale=prior_scale)
+    theta0 = model.prior.sample()
+    keys = ["sample", "target_val", "accepted"] + ([] if kind == "mh" else ["grad_val"])
+    chain = ChainList(keys=keys)
+    with Tape() as tape:
+        if kind == "mala":
+            s = MALA(model, theta0=theta0, dataloader=loader, step=kw["step"], chain=chain)
+        elif kind == "hmc":
+            s = HMC(model, theta0=theta0, dataloader=loader, step=kw["step"], num_steps=kw["num_steps"], chain=chain)
+        else:
+            s = MetropolisHastings(model, theta0=theta0, dataloader=loader, symmetric=kw.get("symmetric", True),
+                                   chain=chain)
+            if "prop_scale" in kw:
+                s.kernel.set_density_params(theta0.clone().detach(),
+                                            scale=torch.full_like(theta0, kw["prop_scale"]))
+        s.run(num_epochs=n_iters, num_burnin_epochs=n_burnin)
+    z = np.stack(tape.z); u = np.concatenate(tape.u)
+    assert z.shape[0] == n_iters and u.shape[0] == n_iters, (z.shape, u.shape)
+    out = dict(theta0=npy(theta0), z=z, u=u, n_iters=n_iters, n_burnin=n_burnin, prior_scale=prior_scale,
+               samples=npy(chain.get_samples()), target_vals=npy(chain.get_target_vals()),
+               accepted=np.array(chain.vals["accepted"], dtype=np.uint8),
+               final_sample=npy(s.current["sample"]), final_target=npy(s.current["target_val"]))
+    if kind != "mh":
+        out["grad_vals"] = npy(chain.get_grad_vals())
+    for k, v in kw.items():
+        out[k] = v
+    if kw.get("ess"):
+        out["multi_ess"] = chain.multi_ess()
+    np.savez_compressed(OUT / f"{name}.npz", **out)
+    print(name, "acceptance", out["accepted"].mean())
+
+
+def stats_goldens():
+    out = {}
+    chains = []
+    for i in range(1, 5):
+        c = np.loadtxt(REF / "examples" / "stats" / f"chain0{i}.csv", delimiter=",", skiprows=0)
+        chains.append(c)
+    x = np.stack(chains)                              # [4,1000,3]
+    out["chains"] = x
+    covs, inses, esss = [], [], []
+    for i in range(4):
+        t = torch.from_numpy(x[i])
+        covs.append(npy(st.cov(t))); inses.append(npy(st.inse_mc_cov(t))); esss.append(st.multi_ess(t))
+    out["cov"] = np.stack(covs); out["inse"] = np.stack(inses); out["multi_ess"] = np.array(esss)
+    rhat, *_ = st.multi_rhat(torch.from_numpy(x))
+    out["multi_rhat"] = np.array(complex(rhat).real if not isinstance(rhat, float) else rhat)
+    np.savez_compressed(OUT / "stats_goldens.npz", **out)
+    print("stats multi_ess", esss, "rhat", out["multi_rhat"])
+
+
+if __name__ == "__main__":
+    model_goldens()
+    s3 = math.sqrt(3.0)
+    # BASELINE.json configs[0]: MLP 2-2-1 XOR, single MALA chain, 1100 iterations (110 burn-in), fp64
+    run_sampler("mala_xor221_f64", "mala", "221", torch.float64, 1100, 110, s3, 0, step=1.74, ess=True)
+    run_sampler("mala_iris433_f32", "mala", "433", torch.float32, 120, 20, s3, 1, step=0.003)
+    run_sampler("mala_iris433_f64", "mala", "433", torch.float64, 120, 20, s3, 1, step=0.003)
+    run_sampler("hmc_xor2321_f64", "hmc", "2321", torch.float64, 160, 20, s3, 2, step=0.3, num_steps=10)
+    run_sampler("hmc_xor221_f64", "hmc", "221", torch.float64, 160, 20, s3, 3, step=0.9, num_steps=7)
+    run_sampler("hmc_xor2321_f64_s09", "hmc", "2321", torch.float64, 160, 20, s3, 2, step=0.9, num_steps=10)
+    run_sampler("hmc_iris433_f64", "hmc", "433", torch.float64, 60, 10, s3, 4, step=0.04, num_steps=10)
+    run_sampler("hmc_iris433_f32", "hmc", "433", torch.float32, 40, 10, s3, 4, step=0.02, num_steps=10)
+    run_sampler("mh_xor221_f64", "mh", "221", torch.float64, 400, 50, s3, 5)
+    run_sampler("mh_xor2321_f64_nonsym", "mh", "2321", torch.float64, 300, 0, s3, 6, symmetric=False,
+                prop_scale=0.4)
+    stats_goldens()
