@@ -1,0 +1,147 @@
+"""ctypes binding of libeeyore_b200.so (C ABI in include/eeyore_b200.h) and the in-tree build recipe.
+
+There is no CPU fallback: every compute entry point raises RuntimeError when the shared library is missing or
+no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import torch
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB_PATH = PKG / "libeeyore_b200.so"
+BUILD_DIR = PKG / "_build"
+
+F32, F64 = 0, 1
+ACT_NONE, ACT_SIGMOID = 0, 1
+LOSS_BINARY, LOSS_MULTICLASS = 0, 1
+RNG_PHILOX, RNG_TAPE = 0, 1
+EINVAL, EUNSUPPORTED, ECUDA, ENUMERIC = -1, -2, -3, -4
+
+DTYPE_IDS = {torch.float32: F32, torch.float64: F64}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+class RunParams(C.Structure):
+    """struct eeyore_b200_run_params"""
+    _fields_ = [
+        ("n_chains", C.c_int64), ("n_iters", C.c_int64), ("n_burnin", C.c_int64), ("thin", C.c_int64),
+        ("step", C.c_double), ("num_steps", C.c_int32), ("symmetric", C.c_int32),
+        ("has_temperature", C.c_int32), ("rng_mode", C.c_int32), ("temperature", C.c_double),
+        ("seed", C.c_uint64), ("iter_offset", C.c_uint64), ("chain_offset", C.c_uint64),
+        ("z_tape", C.c_void_p), ("u_tape", C.c_void_p),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("n_rows", C.c_int64),
+        ("prior_loc", C.c_void_p), ("prior_scale", C.c_void_p),
+        ("theta", C.c_void_p), ("target", C.c_void_p), ("grad", C.c_void_p),
+        ("out_samples", C.c_void_p), ("ss_iter", C.c_int64), ("ss_chain", C.c_int64), ("ss_param", C.c_int64),
+        ("out_target", C.c_void_p), ("out_grad", C.c_void_p), ("out_accepted", C.c_void_p),
+        ("accept_count", C.c_void_p),
+        ("lanes_per_chain", C.c_int32), ("reserved", C.c_int32),
+        ("stream", C.c_void_p),
+    ]
+
+
+# symbol -> (restype, argtypes); must list every function declared in include/eeyore_b200.h
+_VP, _I, _I64, _U64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
+SIGNATURES = {
+    "eeyore_b200_last_error": (C.c_char_p, []),
+    "eeyore_b200_version": (C.c_char_p, []),
+    "eeyore_b200_mlp_create": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _I, _I, C.POINTER(_VP)]),
+    "eeyore_b200_mlp_destroy": (_I, [_VP]),
+    "eeyore_b200_mlp_num_params": (_I, [_VP]),
+    "eeyore_b200_log_target_grad": (_I, [_VP, _I64, _VP, _VP, _VP, _I64, _VP, _VP, _I, _D, _VP, _VP, _VP, _VP, _I, _VP]),
+    "eeyore_b200_forward": (_I, [_VP, _I64, _VP, _VP, _I64, _VP, _VP]),
+    "eeyore_b200_num_saved": (_I64, [_I64, _I64, _I64]),
+    "eeyore_b200_mh_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_mala_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_hmc_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_smmala_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_philox_draws": (_I, [_I, _I64, _I, _U64, _U64, _U64, _VP, _VP, _VP]),
+    "eeyore_b200_fma_peak": (_I, [_I, _I, C.POINTER(_D)]),
+}
+
+_lib = None
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def build(verbose=False, jobs=None):
+    """Compile every CUDA source for sm_100a and link libeeyore_b200.so in-tree (nvcc cross-compiles without a GPU)."""
+    BUILD_DIR.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "eeyore_b200.h"]
+    newest_header = max(h.stat().st_mtime for h in headers)
+    objs, todo = [], []
+    for src in sources():
+        obj = BUILD_DIR / (src.stem + ".o")
+        objs.append(obj)
+        if not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, newest_header):
+            todo.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as ex:
+            list(ex.map(compile_one, todo))
+    if todo or not LIB_PATH.exists():
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded shared library (raises RuntimeError if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(eeyore_b200 has no CPU fallback)")
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("eeyore_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = lib().eeyore_b200_last_error().decode()
+    if rc in (EINVAL, EUNSUPPORTED):
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

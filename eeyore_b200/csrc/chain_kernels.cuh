@@ -1,0 +1,354 @@
+// Chain-batched kernels: thread mapping, shared-memory staging (cp.async.bulk / TMA 1-D bulk copy), on-device
+// Philox or tape noise, fused sampler loops with sample write-out.  One launch runs all iterations of all chains:
+// an entire MCMC run (every HMC trajectory of it) executes without leaving the SM.
+//
+// Replaces the loop of eeyore/samplers/serial_sampler.py:35-52 around <Sampler>.draw, for C independent chains
+// (the semantics of SerialSampler.benchmark, serial_sampler.py:54-126), and the model evaluation
+// eeyore/models/log_target_model.py:20-23.
+#pragma once
+#include "samplers.cuh"
+#include "philox.cuh"
+#include "registry.h"
+
+namespace eb {
+
+constexpr int kBlock = 128;
+
+template <typename T> struct ChainArgs {
+  long n_chains, n_iters, n_burnin, thin;
+  T step;
+  int num_steps, symmetric, has_temperature, rng_mode;
+  T temperature;
+  RngKey key;
+  uint32_t iter0, chain0;
+  const T* z_tape;
+  const T* u_tape;
+  const T* x;
+  const T* y;
+  int n_rows;
+  const T* ploc;
+  const T* pscale;
+  T* theta;
+  T* target;
+  T* grad;
+  T* out_samples;
+  long ss_i, ss_c, ss_p;
+  T* out_target;
+  T* out_grad;
+  uint8_t* out_acc;
+  uint32_t* acc_count;
+  T* out_ll;   // eval kernel only
+  T* out_lp;   // eval kernel only
+  int use_bulk;
+};
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+// shared-memory layout (bytes), identical on host (size) and device (carve)
+template <typename T, class NET> struct SmemLayout {
+  size_t off_bar, off_x, off_y, off_ploc, off_pivar, off_misc, off_cur_th, off_cur_g, total;
+  __host__ __device__ SmemLayout(int n_rows, int chains_per_block, bool with_cur) {
+    size_t o = 0;
+    off_bar = o; o += 16;
+    off_x = o; o += align16(sizeof(T) * (size_t)n_rows * NET::D0);
+    off_y = o; o += align16((sizeof(T) > 4 ? sizeof(T) : 4) * (size_t)n_rows);
+    off_ploc = o; o += align16(sizeof(T) * NET::P);
+    off_pivar = o; o += align16(sizeof(T) * NET::P);
+    off_misc = o; o += 16;
+    off_cur_th = o; if (with_cur) o += align16(sizeof(T) * NET::P * (size_t)chains_per_block);
+    off_cur_g = o; if (with_cur) o += align16(sizeof(T) * NET::P * (size_t)chains_per_block);
+    total = o;
+  }
+};
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------------------------
+EB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+EB_D void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+EB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+EB_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+EB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Stages x, y (or class labels), prior into shared memory and returns the block's DataView.
+template <typename T, class NET>
+EB_D DataView<T> stage_data(unsigned char* smem, const SmemLayout<T, NET>& lay, const ChainArgs<T>& a) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
+  T* xs = reinterpret_cast<T*>(smem + lay.off_x);
+  T* ys = reinterpret_cast<T*>(smem + lay.off_y);
+  int* cs = reinterpret_cast<int*>(smem + lay.off_y);
+  T* ploc = reinterpret_cast<T*>(smem + lay.off_ploc);
+  T* pivar = reinterpret_cast<T*>(smem + lay.off_pivar);
+  T* misc = reinterpret_cast<T*>(smem + lay.off_misc);
+  const int tid = threadIdx.x;
+  const int N = a.n_rows;
+
+  const uint32_t x_bytes = (uint32_t)(sizeof(T) * (size_t)N * NET::D0);
+  const uint32_t y_bytes = (uint32_t)(sizeof(T) * (size_t)N);
+  uint32_t xb = 0, yb = 0;  // bytes moved by the bulk engine
+  if (a.use_bulk) {
+    if ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) xb = x_bytes & ~15u;
+    if (NET::LOSS == LOSS_BINARY && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) yb = y_bytes & ~15u;
+  }
+  if (xb + yb > 0) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, xb + yb);
+      if (xb) bulk_g2s(xs, a.x, xb, bar);
+      if (yb) bulk_g2s(ys, a.y, yb, bar);
+    }
+  }
+  // tails (and everything, when the bulk path is off or the source is unaligned)
+  for (int i = xb / sizeof(T) + tid; i < N * NET::D0; i += blockDim.x) xs[i] = a.x[i];
+  if constexpr (NET::LOSS == LOSS_BINARY) {
+    for (int i = yb / sizeof(T) + tid; i < N; i += blockDim.x) ys[i] = a.y[i];
+  } else {
+    // torch.argmax(y, 1) of the one-hot row (first maximal index), constants.py:17
+    for (int i = tid; i < N; i += blockDim.x) {
+      const T* row = a.y + (size_t)i * NET::DL;
+      int best = 0;
+      T bv = row[0];
+      for (int k = 1; k < NET::DL; ++k) if (row[k] > bv) { bv = row[k]; best = k; }
+      cs[i] = best;
+    }
+  }
+  for (int j = tid; j < NET::P; j += blockDim.x) {
+    const T s = a.pscale[j];
+    ploc[j] = a.ploc[j];
+    pivar[j] = T(1) / (s * s);
+  }
+  if (tid == 0) {
+    T c = T(0);
+    for (int j = 0; j < NET::P; ++j) c += -log_t<T>(a.pscale[j]) - T(kLogSqrt2Pi);
+    misc[0] = c;
+  }
+  if (xb + yb > 0) mbar_wait(bar, 0);
+  __syncthreads();
+  DataView<T> d;
+  d.x = xs; d.y = ys; d.cls = cs; d.n_rows = N; d.ploc = ploc; d.pivar = pivar; d.lp_const = misc[0];
+  d.temperature = a.temperature; d.has_temperature = a.has_temperature != 0;
+  return d;
+}
+
+// ---- log_target / gradient of C chains (one evaluation) ---------------------------------------------------------
+template <typename T, class NET, int G>
+__global__ void __launch_bounds__(kBlock) eval_kernel(const ChainArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int CPB = kBlock / G;
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, false);
+  const DataView<T> d = stage_data<T, NET>(smem, lay, a);
+  const int sub = threadIdx.x % G;
+  long chain = (long)blockIdx.x * CPB + threadIdx.x / G;
+  const bool live = chain < a.n_chains;
+  if (!live) chain = a.n_chains - 1;  // keep every lane in the shuffles
+  T th[NET::P], g[NET::P];
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) th[j] = a.theta[chain * NET::P + j];
+  T lt, ll, lp;
+  if (a.grad != nullptr) eval_target<T, NET, G, true>(d, sub, th, lt, g, &ll, &lp);
+  else { int dummy = 0; eval_target<T, NET, G, false>(d, sub, th, lt, dummy, &ll, &lp); }
+  if (live && sub == 0) {
+    if (a.target) a.target[chain] = lt;
+    if (a.out_ll) a.out_ll[chain] = ll;
+    if (a.out_lp) a.out_lp[chain] = lp;
+    if (a.grad) {
+#pragma unroll
+      for (int j = 0; j < NET::P; ++j) a.grad[chain * NET::P + j] = g[j];
+    }
+  }
+}
+
+// ---- MLP.forward for C chains: out [C, N, DL] ---------------------------------------------------------------------
+template <typename T, class NET>
+__global__ void __launch_bounds__(kBlock) forward_kernel(const ChainArgs<T> a, T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const long chain = (long)blockIdx.x * kBlock + threadIdx.x;
+  T* xs = reinterpret_cast<T*>(smem);
+  for (int i = threadIdx.x; i < a.n_rows * NET::D0; i += blockDim.x) xs[i] = a.x[i];
+  __syncthreads();
+  if (chain >= a.n_chains) return;
+  T th[NET::P];
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) th[j] = a.theta[chain * NET::P + j];
+  for (int i = 0; i < a.n_rows; ++i) {
+    T o[NET::DL];
+    forward_row<T, NET>(th, xs + i * NET::D0, o);
+#pragma unroll
+    for (int k = 0; k < NET::DL; ++k) out[(chain * a.n_rows + i) * NET::DL + k] = o[k];
+  }
+}
+
+// ---- fused sampler: all iterations of all chains in one launch --------------------------------------------------
+template <typename T, class NET, int G, int KIND>
+__global__ void __launch_bounds__(kBlock) sampler_kernel(const ChainArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int CPB = kBlock / G;
+  constexpr int P = NET::P;
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, true);
+  const DataView<T> d = stage_data<T, NET>(smem, lay, a);
+  const int sub = threadIdx.x % G;
+  const int cl = threadIdx.x / G;
+  long chain = (long)blockIdx.x * CPB + cl;
+  const bool live = chain < a.n_chains;
+  if (!live) chain = a.n_chains - 1;
+
+  Cur<T> cur;
+  cur.th = reinterpret_cast<T*>(smem + lay.off_cur_th) + cl;
+  cur.g = reinterpret_cast<T*>(smem + lay.off_cur_g) + cl;
+  cur.stride = CPB;
+  T lt_cur = a.target[chain];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    if (j % G == sub) {
+      cur.th[j * CPB] = a.theta[chain * P + j];
+      if (KIND != KIND_MH) cur.g[j * CPB] = a.grad[chain * P + j];
+    }
+  }
+  __syncwarp();
+
+  const T step = a.step;
+  const T half_step = T(0.5) * step;
+  const T sd = sqrt_t<T>(step);  // numpy sqrt(step) cast to dtype, mala.py:40 (correctly rounded in both)
+  const uint32_t gchain = a.chain0 + (uint32_t)chain;
+  uint32_t n_acc = 0;
+
+  for (long t = 0; t < a.n_iters; ++t) {
+    T z[P], thp[P], gp[P];
+    T u, ltp;
+    if (a.rng_mode == 0) {
+      philox_normals<T, P>(z, a.key, gchain, a.iter0 + (uint32_t)t);
+      u = philox_uniform<T>(a.key, gchain, a.iter0 + (uint32_t)t);
+    } else {
+      const T* zt = a.z_tape + ((size_t)t * a.n_chains + chain) * P;
+#pragma unroll
+      for (int j = 0; j < P; ++j) z[j] = zt[j];
+      u = a.u_tape[(size_t)t * a.n_chains + chain];
+    }
+    bool acc;
+    if constexpr (KIND == KIND_MH) {
+      acc = mh_draw<T, NET, G>(d, sub, step, a.symmetric != 0, cur, lt_cur, z, u, thp, ltp);
+    } else if constexpr (KIND == KIND_MALA) {
+      acc = mala_draw<T, NET, G>(d, sub, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
+    } else {
+      acc = hmc_draw<T, NET, G>(d, sub, step, half_step, a.num_steps, cur, lt_cur, z, u, thp, gp, ltp);
+    }
+    if (acc) {  // uniform within the chain group: every lane holds identical values
+      lt_cur = ltp;
+      ++n_acc;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (j % G == sub) {
+          cur.th[j * CPB] = thp[j];
+          if (KIND != KIND_MH) cur.g[j * CPB] = gp[j];
+        }
+      }
+    }
+    __syncwarp();
+    if (t >= a.n_burnin && (t - a.n_burnin) % a.thin == 0 && live) {  // serial_sampler.py:46
+      const long s = (t - a.n_burnin) / a.thin;
+      if (a.out_samples) {
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          if (j % G == sub) a.out_samples[s * a.ss_i + chain * a.ss_c + j * a.ss_p] = cur.th[j * CPB];
+      }
+      if (KIND != KIND_MH && a.out_grad) {
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          if (j % G == sub) a.out_grad[s * a.ss_i + chain * a.ss_c + j * a.ss_p] = cur.g[j * CPB];
+      }
+      if (sub == 0) {
+        if (a.out_target) a.out_target[s * a.n_chains + chain] = lt_cur;
+        if (a.out_acc) a.out_acc[s * a.n_chains + chain] = acc ? 1 : 0;
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (j % G == sub) {
+        a.theta[chain * P + j] = cur.th[j * CPB];
+        if (KIND != KIND_MH) a.grad[chain * P + j] = cur.g[j * CPB];
+      }
+    }
+    if (sub == 0) {
+      a.target[chain] = lt_cur;
+      if (a.acc_count) a.acc_count[chain] += n_acc;
+    }
+  }
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------------------
+template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
+  constexpr int CPB = kBlock / G;
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, true);
+  auto kern = sampler_kernel<T, NET, G, KIND>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+  if (e != cudaSuccess) return e;
+  const long blocks = (a.n_chains + CPB - 1) / CPB;
+  kern<<<(unsigned)blocks, kBlock, lay.total, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T, class NET, int G> cudaError_t launch_eval_g(const ChainArgs<T>& a, cudaStream_t st) {
+  constexpr int CPB = kBlock / G;
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, false);
+  auto kern = eval_kernel<T, NET, G>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+  if (e != cudaSuccess) return e;
+  const long blocks = (a.n_chains + CPB - 1) / CPB;
+  kern<<<(unsigned)blocks, kBlock, lay.total, st>>>(a);
+  return cudaGetLastError();
+}
+
+#define EB_DISPATCH_G(G_, CALL)                 \
+  switch (G_) {                                 \
+    case 1: { constexpr int G = 1; CALL; }      \
+    case 4: { constexpr int G = 4; CALL; }      \
+    case 8: { constexpr int G = 8; CALL; }      \
+    case 16: { constexpr int G = 16; CALL; }    \
+    case 32: { constexpr int G = 32; CALL; }    \
+    default: return cudaErrorInvalidValue;      \
+  }
+
+template <typename T, class NET> cudaError_t launch_sampler(int kind, int lanes, const ChainArgs<T>& a, cudaStream_t st) {
+  switch (kind) {
+    case KIND_MH: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_MH>(a, st)))
+    case KIND_MALA: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_MALA>(a, st)))
+    case KIND_HMC: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_HMC>(a, st)))
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename T, class NET> cudaError_t launch_eval(int lanes, const ChainArgs<T>& a, cudaStream_t st) {
+  EB_DISPATCH_G(lanes, return (launch_eval_g<T, NET, G>(a, st)))
+}
+
+template <typename T, class NET> cudaError_t launch_forward(const ChainArgs<T>& a, T* out, cudaStream_t st) {
+  const size_t sm = sizeof(T) * (size_t)a.n_rows * NET::D0;
+  auto kern = forward_kernel<T, NET>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  const long blocks = (a.n_chains + kBlock - 1) / kBlock;
+  kern<<<(unsigned)blocks, kBlock, sm, st>>>(a, out);
+  return cudaGetLastError();
+}
+
+}  // namespace eb

@@ -1,0 +1,209 @@
+// Compile-time MLP: log-likelihood, log-prior, log-target and gradient for one chain, weights in registers.
+//
+// Replaces (reference paths):
+//   eeyore/models/model.py:44-55            flat theta layout: per layer W row-major [out,in], then bias
+//   eeyore/models/mlp.py:45-50              forward pass (sigmoid hidden units; sigmoid or identity head)
+//   eeyore/stats/loss.py:1-11               naive binary cross-entropy on probabilities, reduction='sum'
+//   eeyore/constants/constants.py:15-18     binary / multiclass loss table
+//   eeyore/models/bayesian_model.py:30-56   log_lik, log_prior (vector Normal), log_target, temperature
+//   eeyore/models/log_target_model.py:15-23 gradient (torch.autograd there; closed-form back-prop here)
+//
+// Everything is __host__ __device__ so tests/hostsim can execute the very same per-chain code on the CPU
+// as a pre-flight check (the shipped library contains only the device instantiations).
+#pragma once
+#include "common.cuh"
+
+namespace eb {
+
+enum { LOSS_BINARY = 0, LOSS_MULTICLASS = 1 };
+
+// Network with 2 or 3 dense layers (D3 == 0 -> 2 layers), all biases on, sigmoid hidden units;
+// head: sigmoid (binary, D_last == 1) or identity (multiclass logits).
+template <int LOSS_, int D0_, int D1_, int D2_, int D3_ = 0> struct Net {
+  static constexpr int LOSS = LOSS_;
+  static constexpr int NL = D3_ > 0 ? 3 : 2;
+  static constexpr int D0 = D0_, D1 = D1_, D2 = D2_, D3 = D3_;
+  static constexpr int DL = NL == 3 ? D3_ : D2_;
+  static constexpr int OFF0 = 0;
+  static constexpr int OFF1 = (D0_ + 1) * D1_;
+  static constexpr int OFF2 = OFF1 + (D1_ + 1) * D2_;
+  static constexpr int P = OFF2 + (NL == 3 ? (D2_ + 1) * D3_ : 0);
+  static_assert(LOSS_ != LOSS_BINARY || DL == 1, "binary head has one output");
+};
+
+// Per-block view of the (shared-memory resident) data set and prior.
+template <typename T> struct DataView {
+  const T* x;       // [N, D0]
+  const T* y;       // [N] binary targets (LOSS_BINARY)
+  const int* cls;   // [N] class index = argmax of the one-hot row (LOSS_MULTICLASS), constants.py:17
+  int n_rows;
+  const T* ploc;    // [P] prior mean
+  const T* pivar;   // [P] 1 / scale^2
+  T lp_const;       // sum_j ( -log scale_j - log sqrt(2 pi) )
+  T temperature;
+  bool has_temperature;
+};
+
+template <typename T, int DIN, int DOUT, int OFF, bool SIG, class TH>
+EB_HD void dense_fwd(const TH& th, const T (&in)[DIN], T (&out)[DOUT]) {
+#pragma unroll
+  for (int o = 0; o < DOUT; ++o) {
+    T a = th[OFF + DIN * DOUT + o];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) a = fma_t<T>(th[OFF + o * DIN + i], in[i], a);
+    out[o] = SIG ? sigmoid_t<T>(a) : a;
+  }
+}
+
+// Accumulates dW += delta (x) in, db += delta; if PROP also back-propagates through the sigmoid that produced `in`
+// (autograd order: grad * (1 - out) * out).
+template <typename T, int DIN, int DOUT, int OFF, bool PROP, class TH, class GV>
+EB_HD void dense_bwd(const TH& th, const T (&in)[DIN], const T (&dout)[DOUT], GV& g, T (&din)[DIN]) {
+#pragma unroll
+  for (int o = 0; o < DOUT; ++o) {
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) g[OFF + o * DIN + i] = fma_t<T>(dout[o], in[i], g[OFF + o * DIN + i]);
+    g[OFF + DIN * DOUT + o] += dout[o];
+  }
+  if (PROP) {
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) {
+      T s = T(0);
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) s = fma_t<T>(dout[o], th[OFF + o * DIN + i], s);
+      din[i] = s * (T(1) - in[i]) * in[i];
+    }
+  }
+}
+
+// Head: returns this row's log-likelihood term and the seed d ll / d a_L.
+template <typename T, class NET> EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) {
+  if constexpr (NET::LOSS == LOSS_BINARY) {
+    const T p = sigmoid_t<T>(a[0]);
+    if (p_out) *p_out = p;
+    T term;
+    // loss.py:2 evaluates log(p)*y + log(1-p)*(1-y); for y in {0,1} one product is 0 * log(.), which is NaN
+    // exactly when that log is -inf -- reproduced without evaluating the second log.
+    if (y == T(1)) term = (p == T(1)) ? qnan<T>() : log_t<T>(p);
+    else if (y == T(0)) term = (p == T(0)) ? qnan<T>() : log_t<T>(T(1) - p);
+    else term = log_t<T>(p) * y + log_t<T>(T(1) - p) * (T(1) - y);
+    // autograd of the naive form gives (y/p - (1-y)/(1-p)) (1-p) p = y - p, and NaN when p hits 0 or 1
+    delta[0] = (p == T(0) || p == T(1)) ? qnan<T>() : (y - p);
+    return term;
+  } else {
+    constexpr int K = NET::DL;
+    T m = a[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) m = a[k] > m ? a[k] : m;
+    T e[K];
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { e[k] = exp_t<T>(a[k] - m); s += e[k]; }
+    const T inv = T(1) / s;
+    const T ls = log_t<T>(s);
+    T term = T(0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool hit = (k == cls);
+      if (hit) term = a[k] - m - ls;
+      delta[k] = (hit ? T(1) : T(0)) - e[k] * inv;
+    }
+    return term;
+  }
+}
+
+// One data row: forward, loss, (optionally) backward; accumulates into ll and g.
+template <typename T, class NET, bool GRAD, class TH, class GV>
+EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g) {
+  T h0[NET::D0];
+#pragma unroll
+  for (int i = 0; i < NET::D0; ++i) h0[i] = xr[i];
+  T h1[NET::D1];
+  dense_fwd<T, NET::D0, NET::D1, NET::OFF0, true>(th, h0, h1);
+  if constexpr (NET::NL == 2) {
+    T a[NET::D2], dl[NET::D2];
+    dense_fwd<T, NET::D1, NET::D2, NET::OFF1, false>(th, h1, a);
+    ll += head_loss<T, NET>(a, y, cls, dl, (T*)nullptr);
+    if constexpr (GRAD) {
+      T d1[NET::D1], d0[NET::D0];
+      dense_bwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, dl, g, d1);
+      dense_bwd<T, NET::D0, NET::D1, NET::OFF0, false>(th, h0, d1, g, d0);
+    }
+  } else {
+    T h2[NET::D2];
+    dense_fwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, h2);
+    T a[NET::DL], dl[NET::DL];
+    dense_fwd<T, NET::D2, NET::DL, NET::OFF2, false>(th, h2, a);
+    ll += head_loss<T, NET>(a, y, cls, dl, (T*)nullptr);
+    if constexpr (GRAD) {
+      T d2[NET::D2], d1[NET::D1], d0[NET::D0];
+      dense_bwd<T, NET::D2, NET::DL, NET::OFF2, true>(th, h2, dl, g, d2);
+      dense_bwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, d2, g, d1);
+      dense_bwd<T, NET::D0, NET::D1, NET::OFF0, false>(th, h0, d1, g, d0);
+    }
+  }
+}
+
+// Network output for one row (MLP.forward): probability (binary) or logits (multiclass).
+template <typename T, class NET, class TH> EB_HD void forward_row(const TH& th, const T* xr, T (&out)[NET::DL]) {
+  T h0[NET::D0];
+#pragma unroll
+  for (int i = 0; i < NET::D0; ++i) h0[i] = xr[i];
+  T h1[NET::D1];
+  dense_fwd<T, NET::D0, NET::D1, NET::OFF0, true>(th, h0, h1);
+  constexpr bool sig_head = NET::LOSS == LOSS_BINARY;
+  if constexpr (NET::NL == 2) {
+    dense_fwd<T, NET::D1, NET::D2, NET::OFF1, sig_head>(th, h1, out);
+  } else {
+    T h2[NET::D2];
+    dense_fwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, h2);
+    dense_fwd<T, NET::D2, NET::DL, NET::OFF2, sig_head>(th, h2, out);
+  }
+}
+
+// log_target (and gradient) of one chain.  The G lanes of a chain group split the data rows (lane `sub` takes rows
+// sub, sub+G, ...), then all-reduce; every lane returns the same lt / g.  bayesian_model.py:52-56.
+template <typename T, class NET, int G, bool GRAD, class TH, class GV>
+EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g, T* ll_out = nullptr,
+                       T* lp_out = nullptr) {
+  T ll = T(0);
+  if constexpr (GRAD) {
+#pragma unroll
+    for (int j = 0; j < NET::P; ++j) g[j] = T(0);
+  }
+  for (int i = sub; i < d.n_rows; i += G) {
+    T y = T(0);
+    int cls = 0;
+    if constexpr (NET::LOSS == LOSS_BINARY) y = d.y[i]; else cls = d.cls[i];
+    accumulate_row<T, NET, GRAD>(th, d.x + i * NET::D0, y, cls, ll, g);
+  }
+#if defined(__CUDA_ARCH__)
+  if constexpr (G > 1) {
+    ll = group_allreduce<G>(ll);
+    if constexpr (GRAD) {
+#pragma unroll
+      for (int j = 0; j < NET::P; ++j) g[j] = group_allreduce<G>(g[j]);
+    }
+  }
+#endif
+  // vector Normal prior: sum_j -(theta_j - loc_j)^2 / (2 scale_j^2) - log scale_j - log sqrt(2 pi); bayesian_model.py:46-50
+  T lp = d.lp_const;
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) {
+    const T dd = th[j] - d.ploc[j];
+    lp = fma_t<T>(-(dd * dd), T(0.5) * d.pivar[j], lp);
+    if constexpr (GRAD) g[j] = fma_t<T>(-dd, d.pivar[j], g[j]);
+  }
+  if (d.has_temperature) {  // both terms scaled, bayesian_model.py:33-34,48-49
+    ll *= d.temperature; lp *= d.temperature;
+    if constexpr (GRAD) {
+#pragma unroll
+      for (int j = 0; j < NET::P; ++j) g[j] *= d.temperature;
+    }
+  }
+  lt = ll + lp;
+  if (ll_out) *ll_out = ll;
+  if (lp_out) *lp_out = lp;
+}
+
+}  // namespace eb

@@ -1,0 +1,113 @@
+// Per-chain MH / MALA / HMC draws on top of mlp_static.cuh (host+device code; thread mapping lives in
+// chain_kernels.cuh).  Each function performs ONE reference `draw` for the full-batch case (num_batches == 1, cached
+// current target / gradient reused) and returns the accept decision; the caller commits the proposal.
+//
+// Replaces (reference paths):
+//   eeyore/samplers/metropolis_hastings.py:41-73   MetropolisHastings.draw
+//   eeyore/samplers/mala.py:35-82                  MALA.kernel_mean / draw
+//   eeyore/samplers/hmc.py:91-170                  HMC.hamiltonian / leapfrog / draw
+//   eeyore/kernels/normalized_kernel.py:14-19      Normal sample / summed log_prob
+#pragma once
+#include "mlp_static.cuh"
+
+namespace eb {
+
+// The chain's current state (sample and gradient) lives in shared memory, element j at [j * stride];
+// the current target value stays in a register.
+template <typename T> struct Cur {
+  T* th;
+  T* g;
+  int stride;
+};
+
+constexpr double kLogSqrt2Pi = 0.9189385332046727;  // log(sqrt(2 pi)), torch.distributions.Normal.log_prob
+
+// metropolis_hastings.py:41-73.  z: standard normals; prop_scale: kernel scale (default 1, :25-28).
+template <typename T, class NET, int G>
+EB_HD bool mh_draw(const DataView<T>& d, int sub, T prop_scale, bool symmetric, const Cur<T>& cur, T lt_cur,
+                   const T (&z)[NET::P], T u, T (&thp)[NET::P], T& ltp) {
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(prop_scale, z[j], cur.th[j * cur.stride]);  // kernel.sample()
+  int dummy = 0;
+  eval_target<T, NET, G, false>(d, sub, thp, ltp, dummy);
+  T log_rate = ltp - lt_cur;                                                                     // :49
+  if (!symmetric) {                                                                              // :51-54
+    const T inv2var = T(1) / (T(2) * prop_scale * prop_scale);
+    const T lnorm = log_t<T>(prop_scale) + T(kLogSqrt2Pi);
+    T lq_f = T(0), lq_b = T(0);
+#pragma unroll
+    for (int j = 0; j < NET::P; ++j) {
+      const T a = thp[j] - cur.th[j * cur.stride];
+      const T b = cur.th[j * cur.stride] - thp[j];
+      lq_f += -(a * a) * inv2var - lnorm;
+      lq_b += -(b * b) * inv2var - lnorm;
+    }
+    log_rate = log_rate - lq_f;
+    log_rate = log_rate + lq_b;
+  }
+  return log_t<T>(u) < log_rate;                                                                 // :56 (NaN -> reject)
+}
+
+// mala.py:46-82.  sd = dtype(sqrt(step)) (mala.py:40); half_step = 0.5 * step (mala.py:36).
+template <typename T, class NET, int G>
+EB_HD bool mala_draw(const DataView<T>& d, int sub, T half_step, T sd, const Cur<T>& cur, T lt_cur,
+                     const T (&z)[NET::P], T u, T (&thp)[NET::P], T (&gp)[NET::P], T& ltp) {
+  const T inv2var = T(1) / (T(2) * (sd * sd));
+  const T lnorm = log_t<T>(sd) + T(kLogSqrt2Pi);
+  T lq_f = T(0);
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) {
+    const T mean = fma_t<T>(half_step, cur.g[j * cur.stride], cur.th[j * cur.stride]);  // kernel_mean(current)
+    thp[j] = fma_t<T>(sd, z[j], mean);                                                    // :53
+    const T dd = thp[j] - mean;
+    lq_f += -(dd * dd) * inv2var - lnorm;                                                 // log q(theta' | theta), :60
+  }
+  eval_target<T, NET, G, true>(d, sub, thp, ltp, gp);                                     // :55-56
+  T lq_b = T(0);
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) {
+    const T mean_p = fma_t<T>(half_step, gp[j], thp[j]);                                  // :62
+    const T dd = cur.th[j * cur.stride] - mean_p;
+    lq_b += -(dd * dd) * inv2var - lnorm;                                                 // log q(theta | theta'), :64
+  }
+  T log_rate = ltp - lt_cur;                                                              // :58
+  log_rate = log_rate - lq_f;
+  log_rate = log_rate + lq_b;
+  return log_t<T>(u) < log_rate;                                                          // :66
+}
+
+// hmc.py:126-170 with leapfrog :100-124.  p holds the momentum draw p0 on entry (overwritten).
+// The first gradient of the trajectory is the cached current gradient (the reference recomputes it at the same
+// point with the same data, hmc.py:104, so the value is identical); num_steps further evaluations follow.
+template <typename T, class NET, int G>
+EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_steps, const Cur<T>& cur, T lt_cur,
+                    T (&p)[NET::P], T u, T (&thp)[NET::P], T (&gp)[NET::P], T& ltp) {
+  T kin = T(0);
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) kin = fma_t<T>(p[j], p[j], kin);
+  const T h_cur = -lt_cur + T(0.5) * kin;                                                 // :137
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) {
+    thp[j] = cur.th[j * cur.stride];
+    p[j] = fma_t<T>(half_eps, cur.g[j * cur.stride], p[j]);                               // :105
+  }
+  ltp = lt_cur;
+  for (int s = 0; s < num_steps; ++s) {
+#pragma unroll
+    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);                // :110, :117
+    eval_target<T, NET, G, true>(d, sub, thp, ltp, gp);                                   // :113, :118
+    const T w = (s == num_steps - 1) ? half_eps : eps;                                    // :114, :119
+#pragma unroll
+    for (int j = 0; j < NET::P; ++j) p[j] = fma_t<T>(w, gp[j], p[j]);
+  }
+  // momentum negation (:122) leaves the kinetic energy unchanged
+  T kin1 = T(0);
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) kin1 = fma_t<T>(p[j], p[j], kin1);
+  const T h_prop = -ltp + T(0.5) * kin1;                                                  // :141
+  T rate = exp_t<T>(h_cur - h_prop);
+  rate = (rate > T(1)) ? T(1) : rate;                                                     // torch.min keeps NaN, :143-146
+  return u < rate;                                                                        // :148 (linear space)
+}
+
+}  // namespace eb

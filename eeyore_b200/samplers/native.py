@@ -1,0 +1,211 @@
+"""Shared machinery of the device samplers: state buffers, RNG bookkeeping and the fused-launch call.
+
+One `eeyore_b200_*_run` call advances C chains by n iterations and writes the saved states straight into
+structure-of-arrays device buffers; `current`, `chain` and `counter` are then updated so that the objects look
+exactly as after the reference's python loop (eeyore/samplers/serial_sampler.py:35-52).
+"""
+import ctypes as C
+
+import torch
+
+from .. import _native as nv
+from ..chains import ChainList, DeviceChains
+from ..datasets import DataCounter
+from .single_chain_serial_sampler import SingleChainSerialSampler
+
+
+class NativeChainSampler(SingleChainSerialSampler):
+    _entry = None          # name of the C entry point
+    _uses_grad = True
+
+    def _init_native(self, model, theta0, dataloader, data0, counter, chain, seed, lanes_per_chain, thin):
+        super().__init__(counter or DataCounter.from_dataloader(dataloader))
+        self.model = model
+        self.dataloader = dataloader
+        self.thin = thin
+        self.lanes_per_chain = lanes_per_chain
+        self._user_chain = chain
+        self.chain = chain if chain is not None else ChainList(keys=self._default_chain_keys())
+        self.seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._iter_offset = 0
+        self._tape = None
+        self._data_dev = None
+        self._device_blocks = []
+        self.num_chains = 1
+        self.current = {key: None for key in self.keys}
+        if theta0 is not None:
+            self.set_current(theta0.clone().detach(), data=data0)
+
+    def _default_chain_keys(self):
+        return ["sample", "target_val", "accepted"]
+
+    # -- state ---------------------------------------------------------------------------------------------------
+    def _reset_chain(self):
+        if isinstance(self.chain, ChainList):
+            self.chain.reset(keys=list(self.chain.vals.keys()))
+        self._device_blocks = []
+
+    def _stage(self, x, y):
+        m = self.model
+        return m._to_dev(x), m._to_dev(y)
+
+    def set_current(self, theta, data=None):
+        """<Sampler>.set_current of the reference (e.g. mala.py:26-29): evaluate target (and gradient) at theta.
+        theta may be [P] (one chain, reference behaviour) or [C, P] (C independent chains)."""
+        x, y = data or next(iter(self.dataloader))
+        m = self.model
+        th = m._to_dev(theta)
+        self._batched = th.dim() == 2
+        th = th.reshape(-1, m.num_params()).clone()
+        self.num_chains = th.shape[0]
+        xd, yd = self._stage(x, y)
+        self._data_dev = (xd, yd)
+        lt, g = m._eval(th, xd, yd, want_grad=self._uses_grad)
+        self._theta, self._lt, self._grad = th, lt, g
+        self._acc_count = torch.zeros(self.num_chains, dtype=torch.int32, device=th.device)
+        self._last_accepted = None
+        self._publish_current()
+        return x, y
+
+    def _publish_current(self):
+        sq = (lambda t: t) if self._batched else (lambda t: t[0])
+        self.current["sample"] = sq(self._theta)
+        self.current["target_val"] = sq(self._lt)
+        if self._uses_grad and "grad_val" in self.current:
+            self.current["grad_val"] = sq(self._grad)
+        if self._last_accepted is not None:
+            self.current["accepted"] = self._last_accepted if self._batched else int(self._last_accepted[0].item())
+        m = self.model
+        m._theta = self._theta[0]  # the reference leaves the model parameters at the current state
+
+    def reset(self, theta, data=None, reset_counter=True, reset_chain=True):
+        super().reset(theta.clone().detach(), data=data, reset_counter=reset_counter, reset_chain=reset_chain)
+
+    # -- noise ---------------------------------------------------------------------------------------------------
+    def set_noise_tape(self, z, u):
+        """Parity mode: feed the reference's proposal noise.  z [T, P] or [T, C, P] standard normals, u [T] or [T, C]
+        uniforms, consumed in order by subsequent draw()/run() calls."""
+        m = self.model
+        z, u = m._to_dev(z), m._to_dev(u)
+        self._tape = [z.reshape(z.shape[0], -1, m.num_params()), u.reshape(u.shape[0], -1), 0]
+
+    # -- one fused launch ----------------------------------------------------------------------------------------
+    def _fill_params(self, p):
+        """Sampler-specific fields of eeyore_b200_run_params."""
+        raise NotImplementedError
+
+    def _launch(self, n_iters, n_burnin, xd, yd, want=("sample", "target_val", "accepted")):
+        nv.require_cuda()
+        m = self.model
+        c, pn = self.num_chains, m.num_params()
+        dev = self._theta.device
+        thin = max(1, int(self.thin))
+        n_saved = int(nv.lib().eeyore_b200_num_saved(n_iters, n_burnin, thin))
+        out = {}
+        if n_saved > 0:
+            if "sample" in want:
+                out["sample"] = torch.empty(n_saved, pn, c, dtype=m.dtype, device=dev)
+            if "grad_val" in want and self._uses_grad:
+                out["grad_val"] = torch.empty(n_saved, pn, c, dtype=m.dtype, device=dev)
+            if "target_val" in want:
+                out["target_val"] = torch.empty(n_saved, c, dtype=m.dtype, device=dev)
+            out["accepted"] = torch.empty(n_saved, c, dtype=torch.uint8, device=dev)
+        loc, scale = m.prior_on_device()
+        p = nv.RunParams()
+        p.n_chains, p.n_iters, p.n_burnin, p.thin = c, n_iters, n_burnin, thin
+        p.has_temperature = 0 if m.temperature is None else 1
+        p.temperature = 0.0 if m.temperature is None else float(m.temperature)
+        p.seed, p.iter_offset, p.chain_offset = self.seed, self._iter_offset, getattr(self, "chain_offset", 0)
+        keep = []
+        if self._tape is not None:
+            z, u, pos = self._tape
+            if pos + n_iters > z.shape[0]:
+                raise RuntimeError("noise tape exhausted")
+            zz, uu = z[pos:pos + n_iters].contiguous(), u[pos:pos + n_iters].contiguous()
+            keep += [zz, uu]
+            p.rng_mode, p.z_tape, p.u_tape = nv.RNG_TAPE, zz.data_ptr(), uu.data_ptr()
+            self._tape[2] = pos + n_iters
+        else:
+            p.rng_mode = nv.RNG_PHILOX
+        p.x, p.y, p.n_rows = xd.data_ptr(), yd.data_ptr(), xd.shape[0]
+        m._check_data(xd, yd)
+        p.prior_loc, p.prior_scale = loc.data_ptr(), scale.data_ptr()
+        p.theta, p.target = self._theta.data_ptr(), self._lt.data_ptr()
+        p.grad = self._grad.data_ptr() if self._uses_grad else None
+        if "sample" in out:
+            p.out_samples, p.ss_iter, p.ss_chain, p.ss_param = out["sample"].data_ptr(), pn * c, 1, c
+        elif "grad_val" in out:
+            p.ss_iter, p.ss_chain, p.ss_param = pn * c, 1, c
+        if "grad_val" in out:
+            p.out_grad = out["grad_val"].data_ptr()
+        if "target_val" in out:
+            p.out_target = out["target_val"].data_ptr()
+        if "accepted" in out:
+            p.out_accepted = out["accepted"].data_ptr()
+        p.accept_count = self._acc_count.data_ptr()
+        p.lanes_per_chain = int(self.lanes_per_chain or 0)
+        p.stream = torch.cuda.current_stream(dev).cuda_stream
+        self._fill_params(p)
+        with torch.cuda.device(dev):
+            nv.check(getattr(nv.lib(), self._entry)(m.handle(), C.byref(p)))
+        self._iter_offset += n_iters
+        return out
+
+    def _wanted_keys(self):
+        if isinstance(self.chain, ChainList):
+            return tuple(self.chain.vals.keys())
+        return ("sample", "target_val", "accepted")
+
+    def _store(self, out):
+        if not out:
+            return
+        if self._batched:
+            self._device_blocks.append(out)
+        else:
+            self.chain.extend_from_device(
+                samples=out["sample"][:, :, 0] if "sample" in out else None,
+                target_vals=out["target_val"][:, 0] if "target_val" in out else None,
+                grad_vals=out["grad_val"][:, :, 0] if "grad_val" in out else None,
+                accepted=out["accepted"][:, 0])
+
+    def get_chain(self):
+        """ChainList for one chain (reference behaviour); DeviceChains when the sampler runs C chains."""
+        if not getattr(self, "_batched", False):
+            return self.chain
+        if not self._device_blocks:
+            raise RuntimeError("no saved states yet")
+        cat = lambda k: (torch.cat([b[k] for b in self._device_blocks]) if k in self._device_blocks[0] else None)
+        return DeviceChains(cat("sample"), cat("target_val"), cat("grad_val"), cat("accepted"),
+                            accept_count=self._acc_count, n_iters=self._iter_offset)
+
+    def _run_fused(self, n_iters):
+        """Full-batch run: all remaining iterations in one launch (serial_sampler.py:35-52)."""
+        if n_iters <= 0:
+            return
+        xd, yd = self._data_dev
+        n_burnin = max(0, min(n_iters, self.counter.num_burnin_iters - self.counter.idx))
+        before = self._acc_count.clone()
+        out = self._launch(n_iters, n_burnin, xd, yd, want=self._wanted_keys())
+        self._store(out)
+        if "accepted" in out:
+            self._last_accepted = out["accepted"][-1].to(torch.int64)
+        self.counter.increment_idx(n_iters)
+        self._publish_current()
+
+    def draw(self, x, y, savestate=False):
+        """One iteration on the batch (x, y) -- the reference's per-iteration entry point."""
+        xd, yd = self._stage(x, y)
+        if self.counter.num_batches != 1:  # e.g. mala.py:49-51: re-evaluate the current state on this mini-batch
+            self._lt, self._grad = self.model._eval(self._theta, xd, yd, want_grad=self._uses_grad)
+        out = self._launch(1, 0, xd, yd, want=self._wanted_keys())
+        self._last_accepted = out["accepted"][-1].to(torch.int64)
+        if savestate:
+            self._store(out)
+        self._publish_current()
+
+    def acceptance_counts(self):
+        """Accepted proposals per chain over every iteration run so far (burn-in included)."""
+        return self._acc_count
+
+    def _spawn(self, theta0):
+        raise NotImplementedError

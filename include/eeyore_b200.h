@@ -1,0 +1,134 @@
+/*
+ * eeyore_b200 -- C ABI of the B200-native sampler inner loop.
+ *
+ * The reference (papamarkou/eeyore) is pure Python and has no FFI; the seam this library sits behind is the
+ * Python method surface listed in SURVEY.md section 8(b).  Each entry point below cites the reference method
+ * it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory unless its name ends in _host; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream) and is asynchronous;
+ *   - dtype: EEYORE_B200_F32 or EEYORE_B200_F64 -- theta, x, y, prior and outputs all use it
+ *     (the reference's model.dtype, eeyore/models/model.py:7);
+ *   - theta is the reference's flat parameter vector (eeyore/models/model.py:44-55): per layer the weight
+ *     matrix row-major [d_out, d_in] followed by the bias [d_out]; C chains are stored [C, P] row-major;
+ *   - x is [N, d_0] row-major; y is [N] (binary, values in {0,1}) or one-hot [N, K] (multiclass), as produced
+ *     by eeyore/datasets/xydataset.py:11-53;
+ *   - return value: 0 on success, a negative EEYORE_B200_E* code otherwise; eeyore_b200_last_error() gives
+ *     the message (thread-local).  The Python layer raises RuntimeError / ValueError from it, matching the
+ *     reference's error behaviour.
+ */
+#ifndef EEYORE_B200_H
+#define EEYORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EEYORE_B200_F32 0
+#define EEYORE_B200_F64 1
+
+#define EEYORE_B200_ACT_NONE 0    /* activations[l] is None          (eeyore/models/mlp.py:48) */
+#define EEYORE_B200_ACT_SIGMOID 1 /* activations[l] is torch.sigmoid (eeyore/models/mlp.py:48-49) */
+
+#define EEYORE_B200_LOSS_BINARY 0     /* loss_functions['binary_classification']     (eeyore/constants/constants.py:16) */
+#define EEYORE_B200_LOSS_MULTICLASS 1 /* loss_functions['multiclass_classification'] (eeyore/constants/constants.py:17) */
+
+#define EEYORE_B200_RNG_PHILOX 0 /* on-device Philox4x32-10 keyed by (seed, chain, iteration) */
+#define EEYORE_B200_RNG_TAPE 1   /* noise read from z_tape / u_tape (parity runs against the reference) */
+
+#define EEYORE_B200_OK 0
+#define EEYORE_B200_EINVAL (-1)      /* bad argument           -> ValueError   */
+#define EEYORE_B200_EUNSUPPORTED (-2)/* architecture not built -> ValueError   */
+#define EEYORE_B200_ECUDA (-3)       /* CUDA runtime failure   -> RuntimeError */
+#define EEYORE_B200_ENUMERIC (-4)    /* numerical failure      -> RuntimeError */
+
+typedef struct eeyore_b200_mlp *eeyore_b200_mlp_t;
+
+const char *eeyore_b200_last_error(void);
+const char *eeyore_b200_version(void);
+
+/* mlp.Hyperparameters + MLP.__init__ (eeyore/models/mlp.py:9-43): describe the network once.
+ * dims[n_layers+1]; bias[n_layers] (0/1); act_ids[n_layers]; loss_id; dtype. */
+int eeyore_b200_mlp_create(int n_layers, const int *dims, const int *bias, const int *act_ids, int loss_id,
+                           int dtype, eeyore_b200_mlp_t *out);
+int eeyore_b200_mlp_destroy(eeyore_b200_mlp_t h);
+/* Model.num_params (eeyore/models/model.py:34-36) */
+int eeyore_b200_mlp_num_params(eeyore_b200_mlp_t h);
+
+/* BayesianModel.log_target + LogTargetModel.upto_grad_log_target
+ * (eeyore/models/bayesian_model.py:52-56, eeyore/models/log_target_model.py:20-23), batched over C chains.
+ * out_grad may be NULL (log_target only).  out_loglik / out_logprior may be NULL
+ * (BayesianModel.log_lik / log_prior, bayesian_model.py:30-35,46-50).
+ * has_temperature = 0 reproduces temperature=None. */
+int eeyore_b200_log_target_grad(eeyore_b200_mlp_t h, int64_t n_chains, const void *theta, const void *x,
+                                const void *y, int64_t n_rows, const void *prior_loc, const void *prior_scale,
+                                int has_temperature, double temperature, void *out_target, void *out_grad,
+                                void *out_loglik, void *out_logprior, int lanes_per_chain, void *stream);
+
+/* MLP.forward (eeyore/models/mlp.py:45-50): out [C, N, d_L] (probabilities for a sigmoid head, logits otherwise) */
+int eeyore_b200_forward(eeyore_b200_mlp_t h, int64_t n_chains, const void *theta, const void *x, int64_t n_rows,
+                        void *out, void *stream);
+
+typedef struct eeyore_b200_run_params {
+  int64_t n_chains;        /* C independent chains (SerialSampler.benchmark semantics, serial_sampler.py:54-126) */
+  int64_t n_iters;         /* iterations run by this call (= num_epochs when num_batches == 1) */
+  int64_t n_burnin;        /* leading iterations whose state is not saved (serial_sampler.py:46) */
+  int64_t thin;            /* keep every thin-th post-burn-in state; 1 = reference behaviour */
+  double step;             /* MALA/SMMALA/HMC step (mala.py:12, hmc.py:11); MH: proposal scale (metropolis_hastings.py:27) */
+  int32_t num_steps;       /* HMC leapfrog steps (hmc.py:11) */
+  int32_t symmetric;       /* MH: 1 = symmetric proposal (metropolis_hastings.py:10) */
+  int32_t has_temperature; /* 0 = temperature None */
+  int32_t rng_mode;        /* EEYORE_B200_RNG_* */
+  double temperature;
+  uint64_t seed;           /* Philox key */
+  uint64_t iter_offset;    /* Philox counter word: global iteration index of the first iteration of this call */
+  uint64_t chain_offset;   /* global chain id of local chain 0 (chain sharding across GPUs) */
+  const void *z_tape;      /* [n_iters, C, P] standard normals (tape mode) */
+  const void *u_tape;      /* [n_iters, C] uniforms (tape mode) */
+  const void *x;           /* [N, d0] */
+  const void *y;           /* [N] or [N, K] */
+  int64_t n_rows;
+  const void *prior_loc;   /* [P] */
+  const void *prior_scale; /* [P] */
+  void *theta;             /* in/out current['sample']     [C, P] */
+  void *target;            /* in/out current['target_val'] [C]    */
+  void *grad;              /* in/out current['grad_val']   [C, P] (unused by MH) */
+  void *out_samples;       /* saved 'sample' states, element (s,c,j) at s*ss_iter + c*ss_chain + j*ss_param; may be NULL */
+  int64_t ss_iter, ss_chain, ss_param;
+  void *out_target;        /* [n_saved, C] saved 'target_val'; may be NULL */
+  void *out_grad;          /* saved 'grad_val', same strides as out_samples; may be NULL */
+  uint8_t *out_accepted;   /* [n_saved, C] saved 'accepted'; may be NULL */
+  uint32_t *accept_count;  /* [C], incremented by the number of accepted proposals over all n_iters; may be NULL */
+  int32_t lanes_per_chain; /* threads cooperating on one chain (1,2,4,...,32); 0 = auto */
+  int32_t reserved;
+  void *stream;
+} eeyore_b200_run_params;
+
+/* number of states a run with these (n_iters, n_burnin, thin) saves */
+int64_t eeyore_b200_num_saved(int64_t n_iters, int64_t n_burnin, int64_t thin);
+
+/* MetropolisHastings.draw x n_iters (eeyore/samplers/metropolis_hastings.py:41-73) */
+int eeyore_b200_mh_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+/* MALA.draw x n_iters (eeyore/samplers/mala.py:46-82) */
+int eeyore_b200_mala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+/* HMC.draw + HMC.leapfrog x n_iters (eeyore/samplers/hmc.py:100-170) */
+int eeyore_b200_hmc_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+/* SMMALA (absent from the reference snapshot; SURVEY.md A.7, builder-defined): Fisher metric, batched Cholesky */
+int eeyore_b200_smmala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+
+/* Philox draws exactly as the samplers consume them (tests / reproducibility):
+ * out_z [n_chains, P] normals and out_u [n_chains] uniform of iteration `iter`. */
+int eeyore_b200_philox_draws(int dtype, int64_t n_chains, int n_params, uint64_t seed, uint64_t iter,
+                             uint64_t chain_offset, void *out_z, void *out_u, void *stream);
+
+/* Measured FMA peak of the device (dependent-free FFMA/DFMA chains); roofline denominator for the chain kernels */
+int eeyore_b200_fma_peak(int dtype, int iters, double *out_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEYORE_B200_H */

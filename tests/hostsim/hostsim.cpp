@@ -1,0 +1,148 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into libeeyore_b200.so and never used by the product path.
+//
+// Compiles the per-chain __host__ __device__ code of eeyore_b200/csrc (mlp_static.cuh, samplers.cuh, philox.cuh)
+// for the CPU with g++ so that the CPU-only test-suite can execute exactly the arithmetic the CUDA kernels run
+// (one lane per chain) and compare it with the oracle and the golden vectors before any GPU time is spent.
+// The thread mapping, shared-memory staging and shuffles of chain_kernels.cuh are NOT exercised here; the
+// `-m gpu` tests cover those through the real C ABI.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../eeyore_b200/csrc/samplers.cuh"
+#include "../../eeyore_b200/csrc/philox.cuh"
+#include "../../include/eeyore_b200.h"
+
+using namespace eb;
+
+template <typename T, class NET>
+static DataView<T> make_view(const T* x, const T* y, int N, const T* loc, const T* scale, int has_t, double temp,
+                             std::vector<T>& ys, std::vector<int>& cls, std::vector<T>& pivar) {
+  ys.assign(N, T(0)); cls.assign(N, 0); pivar.resize(NET::P);
+  if (NET::LOSS == LOSS_BINARY) for (int i = 0; i < N; ++i) ys[i] = y[i];
+  else for (int i = 0; i < N; ++i) {
+    int best = 0; T bv = y[(size_t)i * NET::DL];
+    for (int k = 1; k < NET::DL; ++k) if (y[(size_t)i * NET::DL + k] > bv) { bv = y[(size_t)i * NET::DL + k]; best = k; }
+    cls[i] = best;
+  }
+  T c = T(0);
+  for (int j = 0; j < NET::P; ++j) { pivar[j] = T(1) / (scale[j] * scale[j]); c += -log_t<T>(scale[j]) - T(kLogSqrt2Pi); }
+  DataView<T> d;
+  d.x = x; d.y = ys.data(); d.cls = cls.data(); d.n_rows = N; d.ploc = loc; d.pivar = pivar.data(); d.lp_const = c;
+  d.temperature = (T)temp; d.has_temperature = has_t != 0;
+  return d;
+}
+
+template <typename T, class NET>
+static void eval_all(int64_t C, const T* theta, const T* x, const T* y, int N, const T* loc, const T* scale, int has_t,
+                     double temp, T* out_lt, T* out_g) {
+  std::vector<T> ys, pivar; std::vector<int> cls;
+  DataView<T> d = make_view<T, NET>(x, y, N, loc, scale, has_t, temp, ys, cls, pivar);
+  for (int64_t c = 0; c < C; ++c) {
+    T th[NET::P], g[NET::P], lt;
+    for (int j = 0; j < NET::P; ++j) th[j] = theta[c * NET::P + j];
+    if (out_g) { eval_target<T, NET, 1, true>(d, 0, th, lt, g); for (int j = 0; j < NET::P; ++j) out_g[c * NET::P + j] = g[j]; }
+    else { int dummy = 0; eval_target<T, NET, 1, false>(d, 0, th, lt, dummy); }
+    out_lt[c] = lt;
+  }
+}
+
+template <typename T, class NET> static void run_all(int kind, const eeyore_b200_run_params& p) {
+  constexpr int P = NET::P;
+  std::vector<T> ys, pivar; std::vector<int> cls;
+  DataView<T> d = make_view<T, NET>((const T*)p.x, (const T*)p.y, (int)p.n_rows, (const T*)p.prior_loc,
+                                    (const T*)p.prior_scale, p.has_temperature, p.temperature, ys, cls, pivar);
+  T* theta = (T*)p.theta; T* target = (T*)p.target; T* grad = (T*)p.grad;
+  const T step = (T)p.step, half_step = T(0.5) * step, sd = sqrt_t<T>(step);
+  RngKey key{(uint32_t)(p.seed & 0xffffffffu), (uint32_t)(p.seed >> 32)};
+  const int64_t thin = p.thin < 1 ? 1 : p.thin;
+  for (int64_t c = 0; c < p.n_chains; ++c) {
+    T cth[P], cg[P];
+    for (int j = 0; j < P; ++j) { cth[j] = theta[c * P + j]; cg[j] = grad ? grad[c * P + j] : T(0); }
+    Cur<T> cur{cth, cg, 1};
+    T lt_cur = target[c];
+    uint32_t nacc = 0;
+    const uint32_t gchain = (uint32_t)p.chain_offset + (uint32_t)c;
+    for (int64_t t = 0; t < p.n_iters; ++t) {
+      T z[P], thp[P], gp[P], u, ltp;
+      if (p.rng_mode == EEYORE_B200_RNG_PHILOX) {
+        philox_normals<T, P>(z, key, gchain, (uint32_t)p.iter_offset + (uint32_t)t);
+        u = philox_uniform<T>(key, gchain, (uint32_t)p.iter_offset + (uint32_t)t);
+      } else {
+        const T* zt = (const T*)p.z_tape + ((size_t)t * p.n_chains + c) * P;
+        for (int j = 0; j < P; ++j) z[j] = zt[j];
+        u = ((const T*)p.u_tape)[(size_t)t * p.n_chains + c];
+      }
+      bool acc;
+      if (kind == 0) acc = mh_draw<T, NET, 1>(d, 0, step, p.symmetric != 0, cur, lt_cur, z, u, thp, ltp);
+      else if (kind == 1) acc = mala_draw<T, NET, 1>(d, 0, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
+      else acc = hmc_draw<T, NET, 1>(d, 0, step, half_step, p.num_steps, cur, lt_cur, z, u, thp, gp, ltp);
+      if (acc) { lt_cur = ltp; ++nacc; for (int j = 0; j < P; ++j) { cth[j] = thp[j]; if (kind != 0) cg[j] = gp[j]; } }
+      if (t >= p.n_burnin && (t - p.n_burnin) % thin == 0) {
+        const int64_t s = (t - p.n_burnin) / thin;
+        if (p.out_samples) for (int j = 0; j < P; ++j) ((T*)p.out_samples)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cth[j];
+        if (p.out_grad && kind != 0) for (int j = 0; j < P; ++j) ((T*)p.out_grad)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cg[j];
+        if (p.out_target) ((T*)p.out_target)[s * p.n_chains + c] = lt_cur;
+        if (p.out_accepted) p.out_accepted[s * p.n_chains + c] = acc ? 1 : 0;
+      }
+    }
+    for (int j = 0; j < P; ++j) { theta[c * P + j] = cth[j]; if (grad && kind != 0) grad[c * P + j] = cg[j]; }
+    target[c] = lt_cur;
+    if (p.accept_count) p.accept_count[c] += nacc;
+  }
+}
+
+#define NETS(X) X(221, LOSS_BINARY, 2, 2, 1) X(2321, LOSS_BINARY, 2, 3, 2, 1) X(433, LOSS_MULTICLASS, 4, 3, 3) X(4323, LOSS_MULTICLASS, 4, 3, 2, 3)
+
+extern "C" {
+
+int hostsim_eval(int arch, int dtype, int64_t C, const void* theta, const void* x, const void* y, int64_t N,
+                 const void* loc, const void* scale, int has_t, double temp, void* out_lt, void* out_g) {
+#define X(NAME, ...)                                                                                                   \
+  if (arch == NAME) {                                                                                                  \
+    using NET = Net<__VA_ARGS__>;                                                                                      \
+    if (dtype == EEYORE_B200_F64) eval_all<double, NET>(C, (const double*)theta, (const double*)x, (const double*)y, (int)N, (const double*)loc, (const double*)scale, has_t, temp, (double*)out_lt, (double*)out_g); \
+    else eval_all<float, NET>(C, (const float*)theta, (const float*)x, (const float*)y, (int)N, (const float*)loc, (const float*)scale, has_t, temp, (float*)out_lt, (float*)out_g); \
+    return 0;                                                                                                          \
+  }
+  NETS(X)
+#undef X
+  return -1;
+}
+
+int hostsim_run(int kind, int arch, int dtype, const eeyore_b200_run_params* p) {
+#define X(NAME, ...)                                                  \
+  if (arch == NAME) {                                                 \
+    using NET = Net<__VA_ARGS__>;                                     \
+    if (dtype == EEYORE_B200_F64) run_all<double, NET>(kind, *p);     \
+    else run_all<float, NET>(kind, *p);                               \
+    return 0;                                                         \
+  }
+  NETS(X)
+#undef X
+  return -1;
+}
+
+int hostsim_philox(int dtype, int64_t C, int P, uint64_t seed, uint64_t iter, uint64_t chain0, void* z, void* u) {
+  RngKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
+  for (int64_t c = 0; c < C; ++c) {
+    uint32_t gc = (uint32_t)chain0 + (uint32_t)c;
+    if (dtype == EEYORE_B200_F64) {
+      for (int j = 0; j < (P + 1) / 2; ++j) {
+        U4 w = philox4x32_10(U4{(uint32_t)j, (uint32_t)iter, gc, 0u}, key.k0, key.k1);
+        double a, b; box_muller<double>(Uni<double>::from(w.x, w.y), Uni<double>::from(w.z, w.w), &a, &b);
+        ((double*)z)[c * P + 2 * j] = a; if (2 * j + 1 < P) ((double*)z)[c * P + 2 * j + 1] = b;
+      }
+      ((double*)u)[c] = philox_uniform<double>(key, gc, (uint32_t)iter);
+    } else {
+      for (int j = 0; j < (P + 3) / 4; ++j) {
+        U4 w = philox4x32_10(U4{(uint32_t)j, (uint32_t)iter, gc, 0u}, key.k0, key.k1);
+        float v[4]; box_muller<float>(Uni<float>::from(w.x), Uni<float>::from(w.y), &v[0], &v[1]);
+        box_muller<float>(Uni<float>::from(w.z), Uni<float>::from(w.w), &v[2], &v[3]);
+        for (int k = 0; k < 4; ++k) if (4 * j + k < P) ((float*)z)[c * P + 4 * j + k] = v[k];
+      }
+      ((float*)u)[c] = philox_uniform<float>(key, gc, (uint32_t)iter);
+    }
+  }
+  return 0;
+}
+}

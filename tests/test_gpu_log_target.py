@@ -1,0 +1,146 @@
+"""GPU parity: chain-batched log_target / gradient kernel vs the reference's golden vectors and the oracle.
+Tolerances are BASELINE.json's: 1e-10 relative at fp64, 1e-5 at fp32 (2e-5 on gradients for the fp32 goldens, whose
+own summation-order noise is ~1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gpu_helpers import dataset, make_model, npy, T_DTYPES
+from helpers import ARCHS, NP_DTYPES, PRIOR_SCALES, RTOL, data_of, load, rel_err, spec_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("arch", list(ARCHS))
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("pst", list(PRIOR_SCALES))
+@pytest.mark.parametrize("tt,temp", [("", None), ("_T07", 0.7)])
+def test_batched_eval_vs_reference_goldens(arch, tag, pst, tt, temp):
+    mg = load("model_goldens")
+    key = f"{arch}_{tag}_{pst}{tt}"
+    m = make_model(arch, tag, PRIOR_SCALES[pst], temp)
+    ds = dataset(arch, tag)
+    theta = torch.from_numpy(mg[key + "_theta"]).to(T_DTYPES[tag])
+    tol = RTOL[tag] if tag == "f64" else 2e-5
+    for lanes in (0, 1, 4, 8, 16, 32):
+        lt, g = m.upto_grad_log_target_batch(theta, ds.x, ds.y, lanes=lanes)
+        lt, g = npy(lt), npy(g)
+        assert np.allclose(lt, mg[key + "_lt"], rtol=tol, atol=0), (lanes, lt, mg[key + "_lt"])
+        for c in range(theta.shape[0]):
+            assert rel_err(g[c], mg[key + "_grad"][c]) < tol, (lanes, c)
+        lt_only = npy(m.log_target_batch(theta, ds.x, ds.y, lanes=lanes))
+        assert np.array_equal(lt_only, lt)
+
+
+@pytest.mark.parametrize("arch", list(ARCHS))
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_single_chain_api_matches_reference(arch, tag):
+    """The reference's per-call surface: log_target, grad_log_target, upto_grad_log_target, log_lik, log_prior, forward."""
+    mg = load("model_goldens")
+    key = f"{arch}_{tag}_p100"
+    m = make_model(arch, tag, 100.0)
+    ds = dataset(arch, tag)
+    tol = RTOL[tag] if tag == "f64" else 2e-5
+    theta = torch.from_numpy(mg[key + "_theta"][0]).to(T_DTYPES[tag])
+    lt = m.log_target(theta.clone().detach(), ds.x, ds.y)
+    assert lt.dim() == 0 and abs(lt.item() - mg[key + "_lt"][0]) <= tol * abs(mg[key + "_lt"][0])
+    g = m.grad_log_target(lt)
+    assert g.shape == (m.num_params(),) and rel_err(npy(g), mg[key + "_grad"][0]) < tol
+    lt2, g2 = m.upto_grad_log_target(theta.clone().detach(), ds.x, ds.y)
+    assert lt2.item() == lt.item() and torch.equal(g2, g)
+    assert abs(m.log_lik(ds.x, ds.y).item() - mg[key + "_ll"][0]) <= tol * abs(mg[key + "_ll"][0])
+    assert abs(m.log_prior().item() - mg[key + "_lp"][0]) <= tol * abs(mg[key + "_lp"][0])
+    assert torch.equal(m.get_params(), theta.to(m.device))
+    out = npy(m(ds.x))
+    x, y = data_of(arch, NP_DTYPES[tag], mg)
+    ref = oracle.forward(spec_of(arch), npy(theta)[None], x)[-1][0]
+    assert out.shape == ref.shape and rel_err(out, ref) < (1e-12 if tag == "f64" else 1e-5)
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_saturation_gives_nan_like_the_reference(tag):
+    mg = load("model_goldens")
+    m = make_model("221", tag, 1.0)
+    ds = dataset("221", tag)
+    th = torch.from_numpy(mg[f"sat_{tag}_theta"]).to(T_DTYPES[tag])
+    lt, g = m.upto_grad_log_target(th, ds.x, ds.y)
+    assert torch.isnan(lt) and torch.isnan(g).all()
+    assert np.isnan(mg[f"sat_{tag}_lt"])
+
+
+@pytest.mark.parametrize("arch,tag,n_rows", [("433", "f64", 150), ("2321", "f64", 200), ("2321", "f32", 203),
+                                              ("4323", "f32", 77), ("221", "f64", 1), ("433", "f64", 3)])
+def test_random_data_vs_oracle_ragged_rows(arch, tag, n_rows):
+    """Synthetic data of the BASELINE shapes (iris-shaped N=150, noisy-XOR-shaped N=200) and ragged row counts that do
+    not divide the lane count or the 16-byte bulk-copy granule."""
+    rng = np.random.default_rng(n_rows)
+    dt = NP_DTYPES[tag]
+    spec = spec_of(arch)
+    d0, k = spec.dims[0], spec.dims[-1]
+    x = rng.normal(size=(n_rows, d0)).astype(dt)
+    if k == 1:
+        y = rng.integers(0, 2, size=(n_rows, 1)).astype(dt)
+    else:
+        y = np.eye(k, dtype=dt)[rng.integers(0, k, size=n_rows)]
+    C = 133
+    theta = (rng.normal(size=(C, spec.num_params)) * 0.8).astype(dt)
+    loc = rng.normal(size=spec.num_params).astype(dt) * 0.1
+    scale = (0.5 + rng.uniform(size=spec.num_params)).astype(dt)
+    m = make_model(arch, tag)
+    m.prior = torch.distributions.Normal(torch.from_numpy(loc), torch.from_numpy(scale))
+    lt_ref, g_ref = oracle.log_target_grad(spec, theta.astype(np.float64), x.astype(np.float64), y,
+                                           loc.astype(np.float64), scale.astype(np.float64))
+    tol = RTOL[tag] if tag == "f64" else 1e-5
+    for lanes in (1, 4, 8, 16, 32):
+        lt, g = m.upto_grad_log_target_batch(torch.from_numpy(theta), torch.from_numpy(x), torch.from_numpy(y), lanes=lanes)
+        assert np.allclose(npy(lt), lt_ref, rtol=tol * 10, atol=0), lanes
+        for c in range(C):
+            assert rel_err(npy(g)[c], g_ref[c]) < tol * 10, (lanes, c)
+
+
+def test_unaligned_data_pointer_takes_the_plain_load_path():
+    m = make_model("2321", "f64")
+    ds = dataset("2321", "f64")
+    buf = torch.zeros(9, dtype=torch.float64, device="cuda")
+    x_un = buf[1:9].view(4, 2)          # 8-byte aligned only
+    x_un.copy_(ds.x)
+    theta = torch.randn(5, 20, dtype=torch.float64)
+    a, ga = m.upto_grad_log_target_batch(theta, ds.x, ds.y)
+    b, gb = m.upto_grad_log_target_batch(theta, x_un, ds.y)
+    assert torch.equal(a, b) and torch.equal(ga, gb)
+
+
+def test_errors():
+    m = make_model("221", "f64")
+    ds = dataset("221", "f64")
+    with pytest.raises(ValueError):
+        m.log_target(torch.zeros(9, dtype=torch.float64), ds.x[:, :1], ds.y)
+    with pytest.raises(ValueError):
+        m.set_params(torch.zeros(4, dtype=torch.float64))
+    from eeyore_b200.constants import loss_functions
+    from eeyore_b200.models.mlp import MLP, Hyperparameters
+    odd = MLP(loss=loss_functions["binary_classification"], hparams=Hyperparameters([3, 5, 1]))
+    with pytest.raises(ValueError, match="3-5-1"):
+        odd.log_target(torch.zeros(odd.num_params(), dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64),
+                       torch.zeros(2, 1, dtype=torch.float64))
+
+
+def test_full_size_chain_batch_properties():
+    """BASELINE config 4 size (524,288 chains, 2-3-2-1, XOR): size-independent properties -- log_target = log_lik +
+    log_prior, invariance to the lane mapping, and a random subset against the oracle."""
+    m = make_model("2321", "f64", 3 ** 0.5)
+    ds = dataset("2321", "f64")
+    C = 524288
+    g = torch.Generator(device="cuda").manual_seed(0)
+    theta = torch.randn(C, 20, dtype=torch.float64, device="cuda", generator=g) * 1.7
+    xd, yd = m._to_dev(ds.x), m._to_dev(ds.y)
+    lt, gr, ll, lp = m._eval(theta, xd, yd, want_grad=True, parts=True)
+    assert torch.equal(lt, ll + lp)
+    lt4, gr4 = m._eval(theta, xd, yd, want_grad=True, lanes=4)
+    assert torch.allclose(lt, lt4, rtol=1e-13, atol=0) and torch.allclose(gr, gr4, rtol=1e-11, atol=1e-13)
+    idx = torch.randint(0, C, (257,), generator=torch.Generator().manual_seed(1))
+    lt_ref, g_ref = oracle.log_target_grad(spec_of("2321"), npy(theta[idx.cuda()]), npy(ds.x), npy(ds.y),
+                                           np.zeros(20), np.full(20, 3 ** 0.5))
+    assert np.allclose(npy(lt[idx.cuda()]), lt_ref, rtol=1e-10, atol=0)
+    assert rel_err(npy(gr[idx.cuda()]), g_ref) < 1e-10

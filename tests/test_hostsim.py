@@ -1,0 +1,177 @@
+"""CPU pre-flight of the DEVICE code: tests/hostsim compiles the __host__ __device__ per-chain functions of
+eeyore_b200/csrc (mlp_static.cuh, samplers.cuh, philox.cuh) with g++ and this file checks them against the golden
+vectors of the reference and against the oracle.  It is not a product path (nothing in eeyore_b200 loads it)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from eeyore_b200._native import RunParams, F32, F64
+from helpers import ARCHS, NP_DTYPES, PRIOR_SCALES, RTOL, data_of, load, rel_err, spec_of
+
+
+@pytest.fixture(scope="module")
+def sim():
+    import __graft_entry__ as g
+    lib = C.CDLL(str(g.build_hostsim()))
+    lib.hostsim_eval.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 2 + \
+                                [C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    lib.hostsim_run.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(RunParams)]
+    lib.hostsim_philox.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def dt_id(tag):
+    return F64 if tag == "f64" else F32
+
+
+def sim_eval(sim, arch, tag, theta, x, y, loc, scale, temp=None, grad=True):
+    dt = NP_DTYPES[tag]
+    theta = np.ascontiguousarray(theta, dt)
+    x = np.ascontiguousarray(x, dt); y = np.ascontiguousarray(y, dt)
+    lt = np.empty(theta.shape[0], dt)
+    g = np.empty_like(theta) if grad else None
+    rc = sim.hostsim_eval(int(arch), dt_id(tag), theta.shape[0], P(theta), P(x), P(y), x.shape[0], P(loc), P(scale),
+                          0 if temp is None else 1, 0.0 if temp is None else temp, P(lt), P(g) if grad else None)
+    assert rc == 0
+    return lt, g
+
+
+@pytest.mark.parametrize("arch", list(ARCHS))
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("pst", ["p1", "psqrt3"])
+@pytest.mark.parametrize("tt,temp", [("", None), ("_T07", 0.7)])
+def test_device_eval_matches_reference_goldens(sim, arch, tag, pst, tt, temp):
+    mg = load("model_goldens")
+    dt = NP_DTYPES[tag]
+    x, y = data_of(arch, dt, mg)
+    key = f"{arch}_{tag}_{pst}{tt}"
+    theta = mg[key + "_theta"].astype(dt)
+    n = theta.shape[1]
+    loc, scale = np.zeros(n, dt), np.full(n, PRIOR_SCALES[pst], dt)
+    lt, g = sim_eval(sim, arch, tag, theta, x, y, loc, scale, temp)
+    tol = RTOL[tag] if tag == "f64" else 2e-5
+    assert np.allclose(lt, mg[key + "_lt"], rtol=tol, atol=0)
+    for c in range(theta.shape[0]):
+        assert rel_err(g[c], mg[key + "_grad"][c]) < tol
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_device_saturation_nan(sim, tag):
+    mg = load("model_goldens")
+    dt = NP_DTYPES[tag]
+    x, y = data_of("221", dt, mg)
+    th = mg[f"sat_{tag}_theta"].astype(dt)[None]
+    lt, g = sim_eval(sim, "221", tag, th, x, y, np.zeros(9, dt), np.ones(9, dt))
+    assert np.isnan(lt[0]) and np.isnan(g).all()
+
+
+def run_params(dt, theta, lt, g, x, y, loc, scale, z, u, n_burnin, step, L=1, symmetric=1, seed=0, tape=True):
+    C_, n = theta.shape
+    T = z.shape[0] if tape else int(u)
+    ns = T - n_burnin
+    out = dict(sample=np.zeros((ns, C_, n), dt), target=np.zeros((ns, C_), dt), grad=np.zeros((ns, C_, n), dt),
+               acc=np.zeros((ns, C_), np.uint8), count=np.zeros(C_, np.uint32))
+    p = RunParams()
+    p.n_chains, p.n_iters, p.n_burnin, p.thin = C_, T, n_burnin, 1
+    p.step, p.num_steps, p.symmetric = step, L, symmetric
+    p.rng_mode = 1 if tape else 0
+    p.seed = seed
+    if tape:
+        p.z_tape, p.u_tape = z.ctypes.data, u.ctypes.data
+    p.x, p.y, p.n_rows = x.ctypes.data, y.ctypes.data, x.shape[0]
+    p.prior_loc, p.prior_scale = loc.ctypes.data, scale.ctypes.data
+    p.theta, p.target = theta.ctypes.data, lt.ctypes.data
+    p.grad = g.ctypes.data if g is not None else None
+    p.out_samples, p.ss_iter, p.ss_chain, p.ss_param = out["sample"].ctypes.data, C_ * n, n, 1
+    p.out_target, p.out_grad, p.out_accepted = out["target"].ctypes.data, out["grad"].ctypes.data, out["acc"].ctypes.data
+    p.accept_count = out["count"].ctypes.data
+    return p, out
+
+
+KINDS = {"mh": 0, "mala": 1, "hmc": 2}
+
+
+@pytest.mark.parametrize("name,kind,kw", [
+    ("mala_xor221_f64", "mala", dict(step=1.74)),
+    ("mala_iris433_f64", "mala", dict(step=0.003)),
+    ("hmc_xor2321_f64", "hmc", dict(step=0.3, L=10)),
+    ("hmc_xor2321_f64_s09", "hmc", dict(step=0.9, L=10)),
+    ("hmc_xor221_f64", "hmc", dict(step=0.9, L=7)),
+    ("hmc_iris433_f64", "hmc", dict(step=0.04, L=10)),
+    ("mh_xor221_f64", "mh", dict(step=1.0)),
+    ("mh_xor2321_f64_nonsym", "mh", dict(step=0.4, symmetric=0)),
+])
+def test_device_samplers_reproduce_reference_runs(sim, name, kind, kw):
+    """Fed the reference's proposal noise, the device sampler code reproduces its accept decisions and states."""
+    gd = load(name)
+    dt = np.float64
+    arch = name.split("_")[1].replace("xor", "").replace("iris", "")
+    x, y = data_of(arch, dt)
+    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    n = gd["theta0"].shape[0]
+    loc, scale = np.zeros(n, dt), np.full(n, float(gd["prior_scale"]), dt)
+    theta = gd["theta0"].astype(dt)[None].copy()
+    lt, g = sim_eval(sim, arch, "f64", theta, x, y, loc, scale)
+    z = np.ascontiguousarray(gd["z"].astype(dt)[:, None, :]); u = np.ascontiguousarray(gd["u"].astype(dt)[:, None])
+    p, out = run_params(dt, theta, lt, g, x, y, loc, scale, z, u, int(gd["n_burnin"]), **kw)
+    assert sim.hostsim_run(KINDS[kind], int(arch), F64, C.byref(p)) == 0
+    assert np.array_equal(out["acc"][:, 0], gd["accepted"])
+    assert rel_err(out["sample"][:, 0], gd["samples"]) < 1e-10
+    assert rel_err(out["target"][:, 0], gd["target_vals"]) < 1e-10
+    if kind != "mh":
+        assert rel_err(out["grad"][:, 0], gd["grad_vals"]) < 1e-9
+    assert rel_err(theta[0], gd["final_sample"]) < 1e-10
+    total_acc = int(out["count"][0])
+    assert total_acc >= int(gd["accepted"].sum())
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_device_philox_matches_oracle_stream(sim, tag):
+    dt = NP_DTYPES[tag]
+    Cn, Pn, seed, it, c0 = 37, 27, 0x1234567890ABCDEF, 12345, 1000
+    z = np.empty((Cn, Pn), dt); u = np.empty(Cn, dt)
+    assert sim.hostsim_philox(dt_id(tag), Cn, Pn, seed, it, c0, P(z), P(u)) == 0
+    zr = oracle.chain_normals(seed, np.arange(c0, c0 + Cn), it, Pn, dt)
+    ur = oracle.chain_uniforms(seed, np.arange(c0, c0 + Cn), it, dt)
+    tol = 1e-12 if tag == "f64" else 2e-5
+    assert np.max(np.abs(z - zr)) < tol * 10
+    assert np.array_equal(u, ur)
+    assert 0 < u.min() and u.max() < 1
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vectors for philox4x32-10."""
+    r = oracle.philox4x32_10([np.uint32(0)] * 4, (0, 0))
+    assert [int(v) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = oracle.philox4x32_10([np.uint32(0xffffffff)] * 4, (0xffffffff, 0xffffffff))
+    assert [int(v) for v in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = oracle.philox4x32_10([np.uint32(0x243f6a88), np.uint32(0x85a308d3), np.uint32(0x13198a2e), np.uint32(0x03707344)],
+                             (0xa4093822, 0x299f31d0))
+    assert [int(v) for v in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_device_philox_hmc_matches_oracle_with_same_stream(sim):
+    """Philox mode end to end: device code draws its own noise; the oracle is fed the oracle-side replica of the stream."""
+    dt = np.float64
+    arch, n, Cn, T, L, step, seed = "2321", 20, 5, 12, 6, 0.4, 99
+    x, y = data_of(arch, dt)
+    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    loc, scale = np.zeros(n, dt), np.full(n, 3 ** 0.5, dt)
+    rng = np.random.default_rng(5)
+    theta0 = rng.normal(size=(Cn, n))
+    theta = theta0.copy()
+    lt, g = sim_eval(sim, arch, "f64", theta, x, y, loc, scale)
+    p, out = run_params(dt, theta, lt, g, x, y, loc, scale, None, T, 0, step, L=L, seed=seed, tape=False)
+    p.chain_offset, p.iter_offset = 7, 3
+    assert sim.hostsim_run(2, int(arch), F64, C.byref(p)) == 0
+    z = np.stack([oracle.chain_normals(seed, np.arange(7, 7 + Cn), 3 + t, n) for t in range(T)])
+    u = np.stack([oracle.chain_uniforms(seed, np.arange(7, 7 + Cn), 3 + t) for t in range(T)])
+    ref = oracle.hmc_run(spec_of(arch), x, y, loc, scale, theta0, z, u, step, L)
+    assert np.array_equal(out["acc"], ref["accepted"])
+    assert rel_err(out["sample"], ref["sample"]) < 1e-9
