@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the sampler hot path (BASELINE.json metric: log-target+gradient evaluations per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (default cfg4 = BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on):
+MLP 2-3-2-1 on XOR, HMC with 10 leapfrog steps, 524,288 independent fp64 chains PER GPU (chains are sharded across
+ranks with no data-path collective => weak scaling), on-device Philox noise, random-init chain states.
+One step = one fused sampler launch advancing every chain by ITERS HMC iterations.
+Evaluations are counted as chains x leapfrog steps (the metric's own definition); the reference executes one
+extra, redundant, gradient evaluation per iteration (eeyore/samplers/hmc.py:104) which is not counted on either arm.
+
+Prints ONE JSON line (rank 0).  `value` is measured with the chain state resident in HBM; `e2e` is measured through
+the public sampler API with HOST (pinned) buffers: per step the chain states are copied host->device, the sampler
+runs, and the final states / targets / accept counts are copied device->host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+S3 = 3.0 ** 0.5
+
+WORKLOADS = {
+    # BASELINE.json configs[3]
+    "cfg4": dict(name="cfg4: MLP 2-3-2-1 XOR, HMC L=10, 524288 chains/GPU, fp64", dims=[2, 3, 2, 1], data="xor",
+                 loss="binary_classification", chains=524288, step=0.3, num_steps=10, iters=50, thin=10,
+                 flops_per_eval=368, dtype="f64"),
+    # BASELINE.json configs[1]
+    "cfg2": dict(name="cfg2: MLP 4-3-3 iris-shaped N=150, HMC L=10, 4096 chains/GPU, fp64", dims=[4, 3, 3], data="iris",
+                 loss="multiclass_classification", chains=4096, step=0.02, num_steps=10, iters=20, thin=5,
+                 flops_per_eval=15408, dtype="f64"),
+}
+
+
+def synthetic_data(w):
+    """cfg4: the XOR truth table; cfg2: iris-shaped synthetic data (3 Gaussian classes, 50 rows each, seed 1)."""
+    if w["data"] == "xor":
+        x = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=np.float64)
+        y = np.array([[0], [1], [1], [0]], dtype=np.float64)
+        return x, y
+    rng = np.random.default_rng(1)
+    centres = rng.normal(size=(3, 4)) * 2.0
+    x = np.concatenate([centres[k] + 0.5 * rng.normal(size=(50, 4)) for k in range(3)])
+    y = np.eye(3)[np.repeat(np.arange(3), 50)]
+    return x, y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy restatement of the reference path), all host cores
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wname, chains, iters, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import oracle
+    from oracle.mlp import MLPSpec
+    w = WORKLOADS[wname]
+    spec = MLPSpec(w["dims"], loss=w["loss"])
+    x, y = synthetic_data(w)
+    p = spec.num_params
+    rng = np.random.default_rng(seed)
+    theta = rng.normal(size=(chains, p)) * (1.0 if w["data"] == "xor" else 0.3)
+    z, u = rng.normal(size=(iters, chains, p)), rng.uniform(size=(iters, chains))
+    t0 = time.perf_counter()
+    oracle.hmc_run(spec, x, y, np.zeros(p), np.full(p, S3), theta, z, u, w["step"], w["num_steps"])
+    return time.perf_counter() - t0
+
+
+class CpuPool:
+    """One worker process per host core, started once (outside any timed region)."""
+
+    def __init__(self, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs)
+        self.pool.map(_cpu_worker, [("cfg4", 8, 1, s) for s in range(procs)])   # import / warm every worker
+
+    def throughput(self, wname, chains_per_proc, iters):
+        """evals/s of the oracle port with every worker running chains_per_proc chains for `iters` HMC iterations."""
+        w = WORKLOADS[wname]
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker, [(wname, chains_per_proc, iters, s) for s in range(self.procs)], chunksize=1)
+        wall = time.perf_counter() - t0
+        return self.procs * chains_per_proc * iters * w["num_steps"] / wall, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_sizes(wname):
+    w = WORKLOADS[wname]
+    if wname == "cfg4":
+        return 4096, 3          # chains per process, iterations
+    return 128, 2
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    procs = host_cores()
+    cpp, iters = cpu_sample_sizes(args.workload)
+    pool = CpuPool(procs)
+    for _ in range(args.warmup):
+        pool.throughput(args.workload, max(cpp // 8, 16), 1)
+    t_steps, evals = [], 0
+    for _ in range(args.steps):
+        v, wall = pool.throughput(args.workload, cpp, iters)
+        t_steps.append(wall)
+        evals += procs * cpp * iters * w["num_steps"]
+    pool.close()
+    total = sum(t_steps)
+    value = evals / total
+    sample = (f"each step: {procs} processes (one per host core) x {cpp} chains x {iters} HMC iterations "
+              f"(L={w['num_steps']}) of the numpy oracle port (oracle/samplers.py), chain-batched")
+    print(json.dumps({
+        "impl": "reference", "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": w["name"], "evals_counted_per_iteration": w["num_steps"]},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from torch.distributions import Normal
+    from torch.utils.data import DataLoader
+
+    from eeyore_b200 import _native as nv
+    from eeyore_b200.constants import loss_functions
+    from eeyore_b200.datasets import XYDataset
+    from eeyore_b200.models.mlp import MLP, Hyperparameters
+    from eeyore_b200.samplers import HMC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOADS[args.workload]
+    dt = torch.float64 if w["dtype"] == "f64" else torch.float32
+    x, y = synthetic_data(w)
+    ds = XYDataset(torch.from_numpy(x).to(dt), torch.from_numpy(y).to(dt))
+    nl = len(w["dims"]) - 1
+    binary = w["loss"] == "binary_classification"
+    hp = Hyperparameters(w["dims"], nl * [True], (nl - 1) * [torch.sigmoid] + [torch.sigmoid if binary else None])
+    model = MLP(loss=loss_functions[w["loss"]], hparams=hp, dtype=dt, device=dev)
+    P = model.num_params()
+    model.prior = Normal(torch.zeros(P, dtype=dt), S3 * torch.ones(P, dtype=dt))
+    C = args.chains or w["chains"]
+    iters, L, thin = args.iters or w["iters"], w["num_steps"], w["thin"]
+    gen = torch.Generator().manual_seed(1000 + rank)
+    theta_host = (torch.randn(C, P, generator=gen, dtype=dt) * (1.0 if w["data"] == "xor" else 0.3)).pin_memory()
+    loader = DataLoader(ds, batch_size=len(ds))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- device-resident arm: state stays in HBM, one fused launch per step --------------------------------------
+    sampler = HMC(model, theta0=theta_host.to(dev), dataloader=loader, step=w["step"], num_steps=L, seed=12345, thin=thin)
+    sampler.chain_offset = rank * C          # global chain ids => results independent of the sharding
+
+    def step_resident():
+        sampler._device_blocks = []          # saved states of the previous step are dropped (buffer is recycled)
+        sampler.counter.reset()
+        sampler.run(num_epochs=iters, num_burnin_epochs=0)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev[0].record()
+        for k in range(args.steps):
+            step_resident()
+            ev[k + 1].record()
+        barrier()
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
+    evals_step = C * iters * L
+    value = world * evals_step * args.steps / t_res
+    acc_rate = sampler.get_chain().acceptance().mean().item()
+
+    # ---- end-to-end arm: host buffers in, host results out, through the public API --------------------------------
+    out_theta = torch.empty(C, P, dtype=dt).pin_memory()
+    out_lt = torch.empty(C, dtype=dt).pin_memory()
+    out_acc = torch.empty(C, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        s = HMC(model, theta0=theta_host, dataloader=loader, step=w["step"], num_steps=L, seed=999, thin=thin)
+        s.chain_offset = rank * C
+        s.run(num_epochs=iters, num_burnin_epochs=0)
+        out_theta.copy_(s.current["sample"], non_blocking=True)
+        out_lt.copy_(s.current["target_val"], non_blocking=True)
+        out_acc.copy_(s.acceptance_counts(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_lt[0].item()
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    e2e_value = world * evals_step * args.steps / t_e2e
+    h2d = (theta_host.numel() + x.size + y.size) * theta_host.element_size()
+    d2h = sum(t.numel() * t.element_size() for t in (out_theta, out_lt, out_acc))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (sampler_kernel<..., KIND_HMC>) -------------------------------------------
+    import ctypes
+    peak = ctypes.c_double()
+    nv.check(nv.lib().eeyore_b200_fma_peak(nv.DTYPE_IDS[dt], 2000, ctypes.byref(peak)))
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    flops_launch = w["flops_per_eval"] * evals_step
+    achieved = flops_launch / avg_launch_s / 1e12
+    esz = theta_host.element_size()
+    n_saved = (iters + thin - 1) // thin
+    hbm_bytes = C * (2 * (2 * P + 1) * esz + n_saved * (P * esz + esz + 1) + 4)
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
+    roofline = {"bound": "fp64_fma" if w["dtype"] == "f64" else "fp32_fma", "achieved": achieved, "peak": peak.value,
+                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
+                "peak_source": "measured live by eeyore_b200_fma_peak (dependent-free FMA chains, this device)",
+                "algorithmic_flops_per_eval": w["flops_per_eval"], "avg_launch_ms": avg_launch_s * 1e3,
+                "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / avg_launch_s / 1e9,
+                             "peak_gbs": hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"}}
+
+    # ---- CPU baseline: the oracle port on one core, bounded sample -------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpp, it = cpu_sample_sizes(args.workload)
+        cpp *= 16
+        t = _cpu_worker((args.workload, cpp, it, 0))
+        cpu = {"value": cpp * it * L / t, "unit": "evals/s", "cores": 1, "kind": "port",
+               "sample": f"{cpp} chains x {it} HMC iterations (L={L}) of the numpy oracle port, one process, {t:.1f} s"}
+
+    print(json.dumps({
+        "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": w["name"], "chains_per_gpu": C, "hmc_iterations_per_step": iters, "num_steps": L,
+                   "step_size": w["step"], "thin": thin, "evals_counted_per_iteration": L,
+                   "evals_reference_executes_per_iteration": L + 1, "rng": "philox4x32-10 on device",
+                   "acceptance_rate": acc_rate,
+                   "l2": "chain state + saved samples per launch (%.0f MB) exceed the 126 MB L2" % (hbm_bytes / 1e6)},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * t_e2e / args.steps},
+        "gpu_launches": args.steps,
+        "gpu_launches_e2e": 2 * args.steps,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
+    ap.add_argument("--iters", type=int, default=0, help="override HMC iterations per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,7 @@ class RunParams(C.Structure):
         ("x", C.c_void_p), ("y", C.c_void_p), ("n_rows", C.c_int64),
         ("prior_loc", C.c_void_p), ("prior_scale", C.c_void_p),
         ("theta", C.c_void_p), ("target", C.c_void_p), ("grad", C.c_void_p),
+        ("st_chain", C.c_int64), ("st_param", C.c_int64),
         ("out_samples", C.c_void_p), ("ss_iter", C.c_int64), ("ss_chain", C.c_int64), ("ss_param", C.c_int64),
         ("out_target", C.c_void_p), ("out_grad", C.c_void_p), ("out_accepted", C.c_void_p),
         ("accept_count", C.c_void_p),
@@ -76,8 +77,21 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
-def build(verbose=False, jobs=None):
-    """Compile every CUDA source for sm_100a and link libeeyore_b200.so in-tree (nvcc cross-compiles without a GPU)."""
+def build(verbose=False, jobs=None, extra_flags=(), out=None, build_dir=None):
+    """Compile every CUDA source for sm_100a and link libeeyore_b200.so in-tree (nvcc cross-compiles without a GPU).
+    extra_flags / out / build_dir build an experimental variant next to the default library (EEYORE_B200_LIB selects it)."""
+    global BUILD_DIR, LIB_PATH
+    saved = (BUILD_DIR, LIB_PATH)
+    if out is not None:
+        LIB_PATH = Path(out)
+        BUILD_DIR = Path(build_dir or (str(out) + ".build"))
+    try:
+        return _build(verbose, jobs, tuple(extra_flags))
+    finally:
+        BUILD_DIR, LIB_PATH = saved
+
+
+def _build(verbose, jobs, extra_flags):
     BUILD_DIR.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "eeyore_b200.h"]
     newest_header = max(h.stat().st_mtime for h in headers)
@@ -90,7 +104,7 @@ def build(verbose=False, jobs=None):
 
     def compile_one(job):
         src, obj = job
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = ["nvcc", *NVCC_FLAGS, *extra_flags, "-c", str(src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -113,11 +127,12 @@ def lib():
     """The loaded shared library (raises RuntimeError if it has not been built)."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        path = Path(os.environ.get("EEYORE_B200_LIB", LIB_PATH))
+        if not path.exists():
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(eeyore_b200 has no CPU fallback)")
-        l = C.CDLL(str(LIB_PATH))
+        l = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args

@@ -31,6 +31,7 @@ template <typename T> struct ChainArgs {
   T* theta;
   T* target;
   T* grad;
+  long st_c, st_p;  // state layout: element (c, j) at c*st_c + j*st_p
   T* out_samples;
   long ss_i, ss_c, ss_p;
   T* out_target;
@@ -46,8 +47,8 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(
 
 // shared-memory layout (bytes), identical on host (size) and device (carve)
 template <typename T, class NET> struct SmemLayout {
-  size_t off_bar, off_x, off_y, off_ploc, off_pivar, off_misc, off_cur_th, off_cur_g, total;
-  __host__ __device__ SmemLayout(int n_rows, int chains_per_block, bool with_cur) {
+  size_t off_bar, off_x, off_y, off_ploc, off_pivar, off_misc, off_mom, total;
+  __host__ __device__ SmemLayout(int n_rows, int chains_per_block, bool with_momentum) {
     size_t o = 0;
     off_bar = o; o += 16;
     off_x = o; o += align16(sizeof(T) * (size_t)n_rows * NET::D0);
@@ -55,11 +56,19 @@ template <typename T, class NET> struct SmemLayout {
     off_ploc = o; o += align16(sizeof(T) * NET::P);
     off_pivar = o; o += align16(sizeof(T) * NET::P);
     off_misc = o; o += 16;
-    off_cur_th = o; if (with_cur) o += align16(sizeof(T) * NET::P * (size_t)chains_per_block);
-    off_cur_g = o; if (with_cur) o += align16(sizeof(T) * NET::P * (size_t)chains_per_block);
+    off_mom = o; if (with_momentum) o += align16(sizeof(T) * NET::P * (size_t)chains_per_block);
     total = o;
   }
 };
+
+// Resident blocks per SM the sampler kernels are compiled for (register budget = 65536 / (kBlock * blocks)):
+// theta' and the gradient accumulators (2 P values) must stay in registers.
+#ifndef EB_MINB_F64_SMALL
+#define EB_MINB_F64_SMALL 3
+#endif
+template <typename T, class NET> constexpr int min_blocks() {
+  return sizeof(T) == 8 ? (NET::P <= 20 ? EB_MINB_F64_SMALL : (NET::P <= 32 ? 3 : 2)) : (NET::P <= 32 ? 4 : 3);
+}
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------------------------
 EB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -197,32 +206,29 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ChainArgs<T> a, T
 }
 
 // ---- fused sampler: all iterations of all chains in one launch --------------------------------------------------
+// Register-resident per lane: the proposal theta' and the gradient accumulators.  Shared memory: data set, prior and
+// (HMC) the momentum.  Global memory (coalesced in the chain-minor layout): the chain's current sample / gradient, read
+// once per iteration and written on accept.
 template <typename T, class NET, int G, int KIND>
-__global__ void __launch_bounds__(kBlock) sampler_kernel(const ChainArgs<T> a) {
+__global__ void __launch_bounds__(kBlock, min_blocks<T, NET>()) sampler_kernel(const ChainArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int CPB = kBlock / G;
   constexpr int P = NET::P;
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, true);
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC);
   const DataView<T> d = stage_data<T, NET>(smem, lay, a);
   const int sub = threadIdx.x % G;
   const int cl = threadIdx.x / G;
   long chain = (long)blockIdx.x * CPB + cl;
   const bool live = chain < a.n_chains;
+  // lanes of a padding group shadow the last chain (so that every lane takes part in the shuffles) but never write
   if (!live) chain = a.n_chains - 1;
 
   Cur<T> cur;
-  cur.th = reinterpret_cast<T*>(smem + lay.off_cur_th) + cl;
-  cur.g = reinterpret_cast<T*>(smem + lay.off_cur_g) + cl;
-  cur.stride = CPB;
+  cur.th = a.theta + chain * a.st_c;
+  cur.g = (KIND != KIND_MH) ? a.grad + chain * a.st_c : nullptr;
+  cur.stride = a.st_p;
+  T* mom = reinterpret_cast<T*>(smem + lay.off_mom) + cl;
   T lt_cur = a.target[chain];
-#pragma unroll
-  for (int j = 0; j < P; ++j) {
-    if (j % G == sub) {
-      cur.th[j * CPB] = a.theta[chain * P + j];
-      if (KIND != KIND_MH) cur.g[j * CPB] = a.grad[chain * P + j];
-    }
-  }
-  __syncwarp();
 
   const T step = a.step;
   const T half_step = T(0.5) * step;
@@ -248,31 +254,34 @@ __global__ void __launch_bounds__(kBlock) sampler_kernel(const ChainArgs<T> a) {
     } else if constexpr (KIND == KIND_MALA) {
       acc = mala_draw<T, NET, G>(d, sub, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
     } else {
-      acc = hmc_draw<T, NET, G>(d, sub, step, half_step, a.num_steps, cur, lt_cur, z, u, thp, gp, ltp);
+      acc = hmc_draw<T, NET, G>(d, sub, step, half_step, a.num_steps, cur, lt_cur, z, mom, CPB, u, thp, gp, ltp);
     }
     if (acc) {  // uniform within the chain group: every lane holds identical values
       lt_cur = ltp;
       ++n_acc;
+      if (live) {
 #pragma unroll
-      for (int j = 0; j < P; ++j) {
-        if (j % G == sub) {
-          cur.th[j * CPB] = thp[j];
-          if (KIND != KIND_MH) cur.g[j * CPB] = gp[j];
+        for (int j = 0; j < P; ++j) {
+          if (j % G == sub) {
+            cur.th[j * cur.stride] = thp[j];
+            if (KIND != KIND_MH) cur.g[j * cur.stride] = gp[j];
+          }
         }
       }
     }
-    __syncwarp();
+    group_sync<G>();
     if (t >= a.n_burnin && (t - a.n_burnin) % a.thin == 0 && live) {  // serial_sampler.py:46
       const long s = (t - a.n_burnin) / a.thin;
+      // the proposal registers hold the new state on accept; otherwise re-read the (unchanged) current state
       if (a.out_samples) {
 #pragma unroll
         for (int j = 0; j < P; ++j)
-          if (j % G == sub) a.out_samples[s * a.ss_i + chain * a.ss_c + j * a.ss_p] = cur.th[j * CPB];
+          if (j % G == sub) a.out_samples[s * a.ss_i + chain * a.ss_c + j * a.ss_p] = acc ? thp[j] : cur.th[j * cur.stride];
       }
       if (KIND != KIND_MH && a.out_grad) {
 #pragma unroll
         for (int j = 0; j < P; ++j)
-          if (j % G == sub) a.out_grad[s * a.ss_i + chain * a.ss_c + j * a.ss_p] = cur.g[j * CPB];
+          if (j % G == sub) a.out_grad[s * a.ss_i + chain * a.ss_c + j * a.ss_p] = acc ? gp[j] : cur.g[j * cur.stride];
       }
       if (sub == 0) {
         if (a.out_target) a.out_target[s * a.n_chains + chain] = lt_cur;
@@ -280,25 +289,16 @@ __global__ void __launch_bounds__(kBlock) sampler_kernel(const ChainArgs<T> a) {
       }
     }
   }
-  if (live) {
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-      if (j % G == sub) {
-        a.theta[chain * P + j] = cur.th[j * CPB];
-        if (KIND != KIND_MH) a.grad[chain * P + j] = cur.g[j * CPB];
-      }
-    }
-    if (sub == 0) {
-      a.target[chain] = lt_cur;
-      if (a.acc_count) a.acc_count[chain] += n_acc;
-    }
+  if (live && sub == 0) {
+    a.target[chain] = lt_cur;
+    if (a.acc_count) a.acc_count[chain] += n_acc;
   }
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------------------
 template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
   constexpr int CPB = kBlock / G;
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, true);
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC);
   auto kern = sampler_kernel<T, NET, G, KIND>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return e;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <limits>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define EB_HD __host__ __device__ __forceinline__
@@ -30,8 +31,88 @@ template <typename T> EB_HD T fma_t(T a, T b, T c);
 template <> EB_HD float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> EB_HD double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
-// sigmoid exactly as the reference evaluates it: 1 / (1 + exp(-g))  (torch.sigmoid, eeyore/models/mlp.py:48-49)
+// ---- fp64 fast paths ----------------------------------------------------------------------------------------------
+// The chain kernels are bound by the FP64 pipe, and most FP64 instructions of an evaluation are spent inside exp() and
+// the division of the sigmoid.  These versions keep ~1 ulp accuracy (parity tolerance is 1e-10) but
+//   * read polynomial coefficients from the constant bank (DFMA takes c[bank][ofs] operands directly; the CUDA math
+//     library materialises each 64-bit coefficient with two UMOVs per use, ~26% of all issued instructions),
+//   * have no slow-path branches (arguments are clamped instead),
+//   * refine MUFU.RCP64H with two Newton steps instead of the IEEE-exact division sequence.
+#define EB_EXP_COEFFS                                                                                              \
+  {0.50000000000000011, 0.16666666666666669, 0.04166666666662399, 0.0083333333333300511, 0.0013888888917281794,   \
+   0.00019841269863105968, 2.4801521190217729e-05, 2.7557268378684192e-06, 2.7620138719733994e-07,                \
+   2.5100424157005067e-08}
+#if defined(__CUDACC__)
+static __constant__ double kExpCDev[10] = EB_EXP_COEFFS;
+#endif
+static const double kExpCHost[10] = EB_EXP_COEFFS;
+
+EB_HD int dbl_lo(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(v);
+#else
+  uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)(b & 0xffffffffu);
+#endif
+}
+EB_HD double dbl_add_exponent(double v, int k) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+#else
+  uint64_t b; memcpy(&b, &v, 8); b += (uint64_t)((int64_t)k << 52); memcpy(&v, &b, 8); return v;
+#endif
+}
+
+// exp(a) for |a| <= 700 (callers clamp); degree-11 polynomial on [-ln2/2, ln2/2], < 1 ulp; NaN propagates.
+EB_HD double exp_core(double a) {
+#if defined(__CUDA_ARCH__)
+  const double* c = kExpCDev;
+#else
+  const double* c = kExpCHost;
+#endif
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+  const double t = fma(a, 1.4426950408889634, magic);
+  const double kf = t - magic;
+  const int k = dbl_lo(t);
+  double r = fma(kf, -6.93147180369123816490e-01, a);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = c[9];
+#pragma unroll
+  for (int i = 8; i >= 0; --i) p = fma(p, r, c[i]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return dbl_add_exponent(p, k);
+}
+
+// exp(a) for a <= 0 (softmax numerators): anything below e^-700 is far under one ulp of the sum it is added to.
+EB_HD double exp_nonpos(double a) { return exp_core(a < -700.0 ? -700.0 : a); }
+
+// 1/d for finite d >= 1: MUFU.RCP64H seed + two Newton steps.
+EB_HD double rcp_ge1(double d) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / d;
+#endif
+}
+
+template <typename T> EB_HD T exp_nonpos_t(T a) { return exp_t<T>(a); }
+template <> EB_HD double exp_nonpos_t<double>(double a) { return exp_nonpos(a); }
+
+// sigmoid as the reference evaluates it, 1 / (1 + exp(-g))  (torch.sigmoid, eeyore/models/mlp.py:48-49).
 template <typename T> EB_HD T sigmoid_t(T g) { return T(1) / (T(1) + exp_t<T>(-g)); }
+// fp64: exp(-g) is clamped to [e^-700, e^700]; below, 1 + e == 1 exactly as in the reference; above, the result is
+// ~1e-304 where the reference underflows towards 0 -- the head of the network restores the exact-zero case (head_loss).
+template <> EB_HD double sigmoid_t<double>(double g) {
+  double a = -g;
+  a = (fabs(a) > 700.0) ? copysign(700.0, a) : a;  // NaN compares false and propagates
+  return rcp_ge1(1.0 + exp_core(a));
+}
 
 // cos/sin(2 pi u)
 template <typename T> EB_HD void sincos2pi(T u, T* s, T* c);

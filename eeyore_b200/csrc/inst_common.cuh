@@ -16,7 +16,7 @@ template <typename T, class NET> cudaError_t eval_entry(const EvalCall& c) {
   return launch_eval<T, NET>(c.lanes, a, c.stream);
 }
 
-template <typename T> ChainArgs<T> chain_args_from(const eeyore_b200_run_params& p, int use_bulk) {
+template <typename T> ChainArgs<T> chain_args_from(const eeyore_b200_run_params& p, int use_bulk, long NetP) {
   ChainArgs<T> a{};
   a.n_chains = p.n_chains; a.n_iters = p.n_iters; a.n_burnin = p.n_burnin; a.thin = p.thin < 1 ? 1 : p.thin;
   a.step = (T)p.step; a.num_steps = p.num_steps; a.symmetric = p.symmetric;
@@ -28,6 +28,8 @@ template <typename T> ChainArgs<T> chain_args_from(const eeyore_b200_run_params&
   a.x = (const T*)p.x; a.y = (const T*)p.y; a.n_rows = (int)p.n_rows;
   a.ploc = (const T*)p.prior_loc; a.pscale = (const T*)p.prior_scale;
   a.theta = (T*)p.theta; a.target = (T*)p.target; a.grad = (T*)p.grad;
+  a.st_c = p.st_chain; a.st_p = p.st_param;
+  if (a.st_c == 0 && a.st_p == 0) { a.st_c = NetP; a.st_p = 1; }
   a.out_samples = (T*)p.out_samples; a.ss_i = p.ss_iter; a.ss_c = p.ss_chain; a.ss_p = p.ss_param;
   a.out_target = (T*)p.out_target; a.out_grad = (T*)p.out_grad; a.out_acc = p.out_accepted;
   a.acc_count = p.accept_count;
@@ -37,7 +39,7 @@ template <typename T> ChainArgs<T> chain_args_from(const eeyore_b200_run_params&
 
 template <typename T, class NET>
 cudaError_t sampler_entry(int kind, const eeyore_b200_run_params& p, int lanes, int use_bulk) {
-  return launch_sampler<T, NET>(kind, lanes, chain_args_from<T>(p, use_bulk), (cudaStream_t)p.stream);
+  return launch_sampler<T, NET>(kind, lanes, chain_args_from<T>(p, use_bulk, NET::P), (cudaStream_t)p.stream);
 }
 
 template <typename T, class NET>

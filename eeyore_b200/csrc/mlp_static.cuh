@@ -13,6 +13,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef EB_ROW_UNROLL
+#define EB_ROW_UNROLL 1
+#endif
+
 namespace eb {
 
 enum { LOSS_BINARY = 0, LOSS_MULTICLASS = 1 };
@@ -79,7 +83,9 @@ EB_HD void dense_bwd(const TH& th, const T (&in)[DIN], const T (&dout)[DOUT], GV
 // Head: returns this row's log-likelihood term and the seed d ll / d a_L.
 template <typename T, class NET> EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) {
   if constexpr (NET::LOSS == LOSS_BINARY) {
-    const T p = sigmoid_t<T>(a[0]);
+    T p = sigmoid_t<T>(a[0]);
+    // the reference's p is exactly 0 once exp(-a) overflows (a < -709.78 in fp64); the fp64 fast sigmoid clamps
+    if (sizeof(T) == 8 && a[0] < T(-709.782712893384)) p = T(0);
     if (p_out) *p_out = p;
     T term;
     // loss.py:2 evaluates log(p)*y + log(1-p)*(1-y); for y in {0,1} one product is 0 * log(.), which is NaN
@@ -98,7 +104,7 @@ template <typename T, class NET> EB_HD T head_loss(T (&a)[NET::DL], T y, int cls
     T e[K];
     T s = T(0);
 #pragma unroll
-    for (int k = 0; k < K; ++k) { e[k] = exp_t<T>(a[k] - m); s += e[k]; }
+    for (int k = 0; k < K; ++k) { e[k] = exp_nonpos_t<T>(a[k] - m); s += e[k]; }
     const T inv = T(1) / s;
     const T ls = log_t<T>(s);
     T term = T(0);
@@ -171,6 +177,8 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
 #pragma unroll
     for (int j = 0; j < NET::P; ++j) g[j] = T(0);
   }
+  constexpr int kRowUnroll = EB_ROW_UNROLL;
+#pragma unroll kRowUnroll
   for (int i = sub; i < d.n_rows; i += G) {
     T y = T(0);
     int cls = 0;

@@ -12,12 +12,12 @@
 
 namespace eb {
 
-// The chain's current state (sample and gradient) lives in shared memory, element j at [j * stride];
-// the current target value stays in a register.
+// The chain's current state (sample and gradient) lives in global memory (the run's in/out state arrays), element j at
+// [j * stride] (chain-minor layout => coalesced); the current target value stays in a register.
 template <typename T> struct Cur {
   T* th;
   T* g;
-  int stride;
+  long stride;
 };
 
 constexpr double kLogSqrt2Pi = 0.9189385332046727;  // log(sqrt(2 pi)), torch.distributions.Normal.log_prob
@@ -76,34 +76,46 @@ EB_HD bool mala_draw(const DataView<T>& d, int sub, T half_step, T sd, const Cur
   return log_t<T>(u) < log_rate;                                                          // :66
 }
 
-// hmc.py:126-170 with leapfrog :100-124.  p holds the momentum draw p0 on entry (overwritten).
-// The first gradient of the trajectory is the cached current gradient (the reference recomputes it at the same
-// point with the same data, hmc.py:104, so the value is identical); num_steps further evaluations follow.
+// hmc.py:126-170 with leapfrog :100-124.  z is the momentum draw p0.  The momentum lives in shared memory (element j at
+// p[j * ps], one copy per chain, lane `sub` owns entries j % G == sub) so that only theta' and the gradient accumulators
+// occupy registers during an evaluation.
+// The first gradient of the trajectory is the cached current gradient (the reference recomputes it at the same point
+// with the same data, hmc.py:104, so the value is identical); num_steps further evaluations follow.
+template <int G> EB_HD void group_sync() {
+#if defined(__CUDA_ARCH__)
+  if (G > 1) __syncwarp();
+#endif
+}
+
 template <typename T, class NET, int G>
 EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_steps, const Cur<T>& cur, T lt_cur,
-                    T (&p)[NET::P], T u, T (&thp)[NET::P], T (&gp)[NET::P], T& ltp) {
+                    const T (&z)[NET::P], T* p, int ps, T u, T (&thp)[NET::P], T (&gp)[NET::P], T& ltp) {
   T kin = T(0);
 #pragma unroll
-  for (int j = 0; j < NET::P; ++j) kin = fma_t<T>(p[j], p[j], kin);
+  for (int j = 0; j < NET::P; ++j) kin = fma_t<T>(z[j], z[j], kin);
   const T h_cur = -lt_cur + T(0.5) * kin;                                                 // :137
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) {
     thp[j] = cur.th[j * cur.stride];
-    p[j] = fma_t<T>(half_eps, cur.g[j * cur.stride], p[j]);                               // :105
+    if (j % G == sub) p[j * ps] = fma_t<T>(half_eps, cur.g[j * cur.stride], z[j]);        // :105
   }
+  group_sync<G>();
   ltp = lt_cur;
   for (int s = 0; s < num_steps; ++s) {
 #pragma unroll
-    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);                // :110, :117
+    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j * ps], thp[j]);           // :110, :117
+    group_sync<G>();
     eval_target<T, NET, G, true>(d, sub, thp, ltp, gp);                                   // :113, :118
     const T w = (s == num_steps - 1) ? half_eps : eps;                                    // :114, :119
 #pragma unroll
-    for (int j = 0; j < NET::P; ++j) p[j] = fma_t<T>(w, gp[j], p[j]);
+    for (int j = 0; j < NET::P; ++j)
+      if (j % G == sub) p[j * ps] = fma_t<T>(w, gp[j], p[j * ps]);
+    group_sync<G>();
   }
   // momentum negation (:122) leaves the kinetic energy unchanged
   T kin1 = T(0);
 #pragma unroll
-  for (int j = 0; j < NET::P; ++j) kin1 = fma_t<T>(p[j], p[j], kin1);
+  for (int j = 0; j < NET::P; ++j) kin1 = fma_t<T>(p[j * ps], p[j * ps], kin1);
   const T h_prop = -ltp + T(0.5) * kin1;                                                  // :141
   T rate = exp_t<T>(h_cur - h_prop);
   rate = (rate > T(1)) ? T(1) : rate;                                                     // torch.min keeps NaN, :143-146

@@ -34,7 +34,7 @@ class NativeChainSampler(SingleChainSerialSampler):
         self.num_chains = 1
         self.current = {key: None for key in self.keys}
         if theta0 is not None:
-            self.set_current(theta0.clone().detach(), data=data0)
+            self.set_current(theta0, data=data0)   # set_current makes its own device copy
 
     def _default_chain_keys(self):
         return ["sample", "target_val", "accepted"]
@@ -61,11 +61,20 @@ class NativeChainSampler(SingleChainSerialSampler):
         xd, yd = self._stage(x, y)
         self._data_dev = (xd, yd)
         lt, g = m._eval(th, xd, yd, want_grad=self._uses_grad)
-        self._theta, self._lt, self._grad = th, lt, g
+        self._set_state(th, lt, g)
         self._acc_count = torch.zeros(self.num_chains, dtype=torch.int32, device=th.device)
         self._last_accepted = None
         self._publish_current()
         return x, y
+
+    def _set_state(self, th, lt, g):
+        """Device state in the chain-minor layout ([P, C] storage; `_theta` / `_grad` are its [C, P] views) so that the
+        sampler kernels read and write it coalesced."""
+        self._theta_soa = th.t().contiguous()
+        self._grad_soa = g.t().contiguous() if g is not None else None
+        self._theta = self._theta_soa.t()
+        self._grad = self._grad_soa.t() if g is not None else None
+        self._lt = lt
 
     def _publish_current(self):
         sq = (lambda t: t) if self._batched else (lambda t: t[0])
@@ -76,7 +85,7 @@ class NativeChainSampler(SingleChainSerialSampler):
         if self._last_accepted is not None:
             self.current["accepted"] = self._last_accepted if self._batched else int(self._last_accepted[0].item())
         m = self.model
-        m._theta = self._theta[0]  # the reference leaves the model parameters at the current state
+        m._theta = self._theta[0].contiguous()  # the reference leaves the model parameters at the current state
 
     def reset(self, theta, data=None, reset_counter=True, reset_chain=True):
         super().reset(theta.clone().detach(), data=data, reset_counter=reset_counter, reset_chain=reset_chain)
@@ -130,8 +139,9 @@ class NativeChainSampler(SingleChainSerialSampler):
         p.x, p.y, p.n_rows = xd.data_ptr(), yd.data_ptr(), xd.shape[0]
         m._check_data(xd, yd)
         p.prior_loc, p.prior_scale = loc.data_ptr(), scale.data_ptr()
-        p.theta, p.target = self._theta.data_ptr(), self._lt.data_ptr()
-        p.grad = self._grad.data_ptr() if self._uses_grad else None
+        p.theta, p.target = self._theta_soa.data_ptr(), self._lt.data_ptr()
+        p.grad = self._grad_soa.data_ptr() if self._uses_grad else None
+        p.st_chain, p.st_param = 1, c
         if "sample" in out:
             p.out_samples, p.ss_iter, p.ss_chain, p.ss_param = out["sample"].data_ptr(), pn * c, 1, c
         elif "grad_val" in out:
@@ -196,7 +206,8 @@ class NativeChainSampler(SingleChainSerialSampler):
         """One iteration on the batch (x, y) -- the reference's per-iteration entry point."""
         xd, yd = self._stage(x, y)
         if self.counter.num_batches != 1:  # e.g. mala.py:49-51: re-evaluate the current state on this mini-batch
-            self._lt, self._grad = self.model._eval(self._theta, xd, yd, want_grad=self._uses_grad)
+            lt, g = self.model._eval(self._theta.contiguous(), xd, yd, want_grad=self._uses_grad)
+            self._set_state(self._theta.contiguous(), lt, g)
         out = self._launch(1, 0, xd, yd, want=self._wanted_keys())
         self._last_accepted = out["accepted"][-1].to(torch.int64)
         if savestate:

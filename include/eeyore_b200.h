@@ -94,9 +94,12 @@ typedef struct eeyore_b200_run_params {
   int64_t n_rows;
   const void *prior_loc;   /* [P] */
   const void *prior_scale; /* [P] */
-  void *theta;             /* in/out current['sample']     [C, P] */
+  void *theta;             /* in/out current['sample']     [C, P] (see st_chain / st_param) */
   void *target;            /* in/out current['target_val'] [C]    */
   void *grad;              /* in/out current['grad_val']   [C, P] (unused by MH) */
+  int64_t st_chain, st_param; /* layout of theta / grad: element (c, j) at c*st_chain + j*st_param; 0,0 = row-major
+                                 [C, P] (st_chain = P, st_param = 1).  The device-resident path uses the chain-minor
+                                 layout (st_chain = 1, st_param = C) so that warps read and write the state coalesced. */
   void *out_samples;       /* saved 'sample' states, element (s,c,j) at s*ss_iter + c*ss_chain + j*ss_param; may be NULL */
   int64_t ss_iter, ss_chain, ss_param;
   void *out_target;        /* [n_saved, C] saved 'target_val'; may be NULL */

@@ -55,10 +55,11 @@ template <typename T, class NET> static void run_all(int kind, const eeyore_b200
   const T step = (T)p.step, half_step = T(0.5) * step, sd = sqrt_t<T>(step);
   RngKey key{(uint32_t)(p.seed & 0xffffffffu), (uint32_t)(p.seed >> 32)};
   const int64_t thin = p.thin < 1 ? 1 : p.thin;
+  const int64_t sc = (p.st_chain == 0 && p.st_param == 0) ? P : p.st_chain;
+  const int64_t sp = (p.st_chain == 0 && p.st_param == 0) ? 1 : p.st_param;
   for (int64_t c = 0; c < p.n_chains; ++c) {
-    T cth[P], cg[P];
-    for (int j = 0; j < P; ++j) { cth[j] = theta[c * P + j]; cg[j] = grad ? grad[c * P + j] : T(0); }
-    Cur<T> cur{cth, cg, 1};
+    Cur<T> cur{theta + c * sc, grad ? grad + c * sc : nullptr, (long)sp};
+    T mom[P];
     T lt_cur = target[c];
     uint32_t nacc = 0;
     const uint32_t gchain = (uint32_t)p.chain_offset + (uint32_t)c;
@@ -75,17 +76,16 @@ template <typename T, class NET> static void run_all(int kind, const eeyore_b200
       bool acc;
       if (kind == 0) acc = mh_draw<T, NET, 1>(d, 0, step, p.symmetric != 0, cur, lt_cur, z, u, thp, ltp);
       else if (kind == 1) acc = mala_draw<T, NET, 1>(d, 0, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
-      else acc = hmc_draw<T, NET, 1>(d, 0, step, half_step, p.num_steps, cur, lt_cur, z, u, thp, gp, ltp);
-      if (acc) { lt_cur = ltp; ++nacc; for (int j = 0; j < P; ++j) { cth[j] = thp[j]; if (kind != 0) cg[j] = gp[j]; } }
+      else acc = hmc_draw<T, NET, 1>(d, 0, step, half_step, p.num_steps, cur, lt_cur, z, mom, 1, u, thp, gp, ltp);
+      if (acc) { lt_cur = ltp; ++nacc; for (int j = 0; j < P; ++j) { cur.th[j * sp] = thp[j]; if (kind != 0) cur.g[j * sp] = gp[j]; } }
       if (t >= p.n_burnin && (t - p.n_burnin) % thin == 0) {
         const int64_t s = (t - p.n_burnin) / thin;
-        if (p.out_samples) for (int j = 0; j < P; ++j) ((T*)p.out_samples)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cth[j];
-        if (p.out_grad && kind != 0) for (int j = 0; j < P; ++j) ((T*)p.out_grad)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cg[j];
+        if (p.out_samples) for (int j = 0; j < P; ++j) ((T*)p.out_samples)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cur.th[j * sp];
+        if (p.out_grad && kind != 0) for (int j = 0; j < P; ++j) ((T*)p.out_grad)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cur.g[j * sp];
         if (p.out_target) ((T*)p.out_target)[s * p.n_chains + c] = lt_cur;
         if (p.out_accepted) p.out_accepted[s * p.n_chains + c] = acc ? 1 : 0;
       }
     }
-    for (int j = 0; j < P; ++j) { theta[c * P + j] = cth[j]; if (grad && kind != 0) grad[c * P + j] = cg[j]; }
     target[c] = lt_cur;
     if (p.accept_count) p.accept_count[c] += nacc;
   }
