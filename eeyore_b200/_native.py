@@ -66,6 +66,7 @@ SIGNATURES = {
     "eeyore_b200_mala_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_hmc_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_smmala_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "eeyore_b200_philox_draws": (_I, [_I, _I64, _I, _U64, _U64, _U64, _VP, _VP, _VP]),
     "eeyore_b200_fma_peak": (_I, [_I, _I, C.POINTER(_D)]),
 }

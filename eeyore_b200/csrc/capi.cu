@@ -45,6 +45,9 @@ using namespace eb;
 
 extern "C" {
 
+// shared with the other translation units of the library (not part of the public header)
+int eeyore_b200_set_error_(int code, const char* msg) { return fail(code, msg); }
+
 const char* eeyore_b200_last_error(void) { return g_err.c_str(); }
 const char* eeyore_b200_version(void) { return "eeyore_b200 0.1 (sm_100a)"; }
 

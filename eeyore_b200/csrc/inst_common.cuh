@@ -1,6 +1,7 @@
 // Instantiation helper: builds the NetEntry of one architecture for fp32 and fp64.
 #pragma once
 #include "chain_kernels.cuh"
+#include "smmala.cuh"
 #include "registry.h"
 
 namespace eb {
@@ -50,6 +51,14 @@ cudaError_t forward_entry(int64_t n_chains, const void* theta, const void* x, in
   return launch_forward<T, NET>(a, (T*)out, st);
 }
 
+template <typename T, class NET> cudaError_t smmala_entry(const eeyore_b200_run_params& p, int use_bulk) {
+  if constexpr (NET::LOSS == LOSS_BINARY) {
+    return launch_smmala<T, NET>(chain_args_from<T>(p, use_bulk, NET::P), (cudaStream_t)p.stream);
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+
 template <typename T, class NET> NetEntry make_entry(int dtype) {
   NetEntry e{};
   e.n_layers = NET::NL;
@@ -58,7 +67,7 @@ template <typename T, class NET> NetEntry make_entry(int dtype) {
   e.eval = &eval_entry<T, NET>;
   e.sampler = &sampler_entry<T, NET>;
   e.forward = &forward_entry<T, NET>;
-  e.smmala = nullptr;
+  e.smmala = NET::LOSS == LOSS_BINARY ? &smmala_entry<T, NET> : nullptr;
   return e;
 }
 

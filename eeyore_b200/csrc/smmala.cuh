@@ -1,0 +1,363 @@
+// Simplified manifold MALA with the expected-Fisher metric, one WARP per chain.
+//
+// The reference snapshot contains no SMMALA: this kernel is builder-defined and follows
+// the reference's MALA structure (eeyore/samplers/mala.py:46-82) with a MultivariateNormalKernel(loc, scale_tril)
+// proposal (eeyore/kernels/multivariate_normal_kernel.py:11-19):
+//   G(theta) = T [ sum_i p_i (1 - p_i) J_i J_i^T + diag(1 / scale^2) ],  J_i = d a_L,i / d theta   (binary head)
+//   G = R R^T (Cholesky, R lower);  mean(theta) = theta + step/2 G^-1 grad;  theta' = mean + sqrt(step) R^-T z
+//   log q(b | a) = -(P/2) log(2 pi step) + sum_j log R_jj(a) - |R(a)^T (b - mean(a))|^2 / (2 step)
+//   accept <=> Cholesky of G(theta') succeeded and log u < lt' - lt - log q(theta'|theta) + log q(theta|theta')
+// Parity is checked against oracle/samplers.py:smmala_run (parity unpinned by the reference).
+//
+// Work split inside the warp, per batch of 32 data rows:
+//   phase A (lane = data row): forward pass, Jacobian row J_i, log-lik term, gradient += (y_i - p_i) J_i;
+//                              J_i and w_i = p_i (1 - p_i) go to shared memory;
+//   phase B (lane = 2x4 tile of the lower triangle of G): G_tile += w_r J_r[a] J_r[b] over the 32 staged rows.
+// Then a warp-level in-place Cholesky, two triangular solves (lane = vector element) and the accept test.
+#pragma once
+#include "chain_kernels.cuh"
+
+namespace eb {
+
+constexpr int kSmWarps = 4;  // chains (warps) per block
+
+template <class NET> struct SmGeom {
+  static constexpr int P = NET::P;
+  static constexpr int RP = (P + 1) / 2;       // row pairs
+  static constexpr int CQ = (P + 3) / 4;       // column quads
+  static constexpr int PSV = 4 * CQ + 1;       // staged row: J (zero padded) then w
+  static constexpr int LD = P + 1;             // leading dimension of the P x P matrices in shared memory
+  static constexpr int ntiles() {
+    int n = 0;
+    for (int rp = 0; rp < RP; ++rp) n += (2 * rp + 1) / 4 + 1 < CQ ? (2 * rp + 1) / 4 + 1 : CQ;
+    return n;
+  }
+  static_assert(P <= 32, "one lane per vector element");
+};
+
+template <typename T, class NET> struct SmWarpMem {
+  using Geo = SmGeom<NET>;
+  T v[32 * Geo::PSV];
+  T mat[2][NET::P * Geo::LD];   // metric / Cholesky factors: [cur], [proposal] (roles swap on accept)
+  T dinv[2][32];                // 1 / R_jj
+  T vec[32];                    // scratch vector (lane-indexed)
+};
+
+// d a_L / d theta for one row (binary head, linear last pre-activation): back-propagation with seed 1.
+template <typename T, class NET, class TH>
+EB_HD void jacobian_row(const TH& th, const T* xr, T (&J)[NET::P], T& a_out) {
+#pragma unroll
+  for (int j = 0; j < NET::P; ++j) J[j] = T(0);
+  T h0[NET::D0];
+#pragma unroll
+  for (int i = 0; i < NET::D0; ++i) h0[i] = xr[i];
+  T h1[NET::D1];
+  dense_fwd<T, NET::D0, NET::D1, NET::OFF0, true>(th, h0, h1);
+  T one[1] = {T(1)};
+  if constexpr (NET::NL == 2) {
+    T a[NET::D2];
+    dense_fwd<T, NET::D1, NET::D2, NET::OFF1, false>(th, h1, a);
+    a_out = a[0];
+    T d1[NET::D1], d0[NET::D0];
+    dense_bwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, one, J, d1);
+    dense_bwd<T, NET::D0, NET::D1, NET::OFF0, false>(th, h0, d1, J, d0);
+  } else {
+    T h2[NET::D2];
+    dense_fwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, h2);
+    T a[NET::DL];
+    dense_fwd<T, NET::D2, NET::DL, NET::OFF2, false>(th, h2, a);
+    a_out = a[0];
+    T d2[NET::D2], d1[NET::D1], d0[NET::D0];
+    dense_bwd<T, NET::D2, NET::DL, NET::OFF2, true>(th, h2, one, J, d2);
+    dense_bwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, d2, J, d1);
+    dense_bwd<T, NET::D0, NET::D1, NET::OFF0, false>(th, h0, d1, J, d0);
+  }
+}
+
+template <typename T> EB_D T warp_sum(T v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// In-place Cholesky of the lower triangle of m (P x P, leading dimension LD); dinv[j] = 1 / R_jj.
+// Returns false if a pivot is not positive / not finite (linalg/is_pos_def.py:5-9 semantics); logdet = sum log R_jj.
+template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, T& logdet) {
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  T ld = T(0);
+  for (int j = 0; j < P; ++j) {
+    T d = m[j * LD + j];
+    for (int k = 0; k < j; ++k) d = fma_t<T>(-m[j * LD + k], m[j * LD + k], d);
+    if (!(d > T(0)) || !(d < T(INFINITY))) { ok = false; break; }
+    const T l = sqrt_t<T>(d);
+    const T li = T(1) / l;
+    ld += log_t<T>(l);
+    __syncwarp();
+    const int i = j + 1 + lane;
+    if (i < P) {
+      T s = m[i * LD + j];
+      for (int k = 0; k < j; ++k) s = fma_t<T>(-m[i * LD + k], m[j * LD + k], s);
+      m[i * LD + j] = s * li;
+    }
+    if (lane == 0) { m[j * LD + j] = l; dinv[j] = li; }
+    __syncwarp();
+  }
+  __syncwarp();
+  logdet = ld;
+  return ok;
+}
+
+// R y = b (forward substitution); lane i holds b_i on entry and y_i on return (i < P).
+template <typename T, int P, int LD> EB_D T warp_solve_lower(const T* R, const T* dinv, T b) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int j = 0; j < P; ++j) {
+    const T yj = __shfl_sync(0xffffffffu, b, j) * dinv[j];
+    if (lane == j) b = yj;
+    else if (lane > j && lane < P) b = fma_t<T>(-R[lane * LD + j], yj, b);
+  }
+  return b;
+}
+
+// R^T x = y (backward substitution); lane i holds y_i on entry and x_i on return.
+template <typename T, int P, int LD> EB_D T warp_solve_upper_t(const T* R, const T* dinv, T y) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int j = P - 1; j >= 0; --j) {
+    const T xj = __shfl_sync(0xffffffffu, y, j) * dinv[j];
+    if (lane == j) y = xj;
+    else if (lane < j) y = fma_t<T>(-R[j * LD + lane], xj, y);
+  }
+  return y;
+}
+
+// |R^T d|^2 with lane i holding d_i.
+template <typename T, int P, int LD> EB_D T warp_rt_norm2(const T* R, T d, T* scratch) {
+  const int lane = threadIdx.x & 31;
+  if (lane < P) scratch[lane] = d;
+  __syncwarp();
+  T w = T(0);
+  if (lane < P)
+    for (int j = lane; j < P; ++j) w = fma_t<T>(R[j * LD + lane], scratch[j], w);
+  __syncwarp();
+  return warp_sum<T>(w * w);
+}
+
+// log_target, gradient (replicated in every lane) and the metric's Cholesky factor (shared memory) at theta.
+template <typename T, class NET>
+EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, NET>& sm, int buf, int tile_rp,
+                      int tile_cq, T& lt, T (&g)[NET::P], T& logdet) {
+  using Geo = SmGeom<NET>;
+  constexpr int P = NET::P, PSV = Geo::PSV, LD = Geo::LD;
+  const int lane = threadIdx.x & 31;
+  T ll = T(0);
+#pragma unroll
+  for (int j = 0; j < P; ++j) g[j] = T(0);
+  T acc[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = T(0);
+
+  for (int base = 0; base < d.n_rows; base += 32) {
+    const int i = base + lane;
+    T* vrow = sm.v + lane * PSV;
+    if (i < d.n_rows) {
+      T J[P], a;
+      jacobian_row<T, NET>(th, d.x + i * NET::D0, J, a);
+      T al[1] = {a}, dl[1], p;
+      ll += head_loss<T, NET>(al, d.y[i], 0, dl, &p);
+#pragma unroll
+      for (int j = 0; j < P; ++j) { g[j] = fma_t<T>(dl[0], J[j], g[j]); vrow[j] = J[j]; }
+#pragma unroll
+      for (int j = P; j < PSV - 1; ++j) vrow[j] = T(0);
+      vrow[PSV - 1] = p * (T(1) - p);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PSV; ++j) vrow[j] = T(0);
+    }
+    __syncwarp();
+    const int rows = min(32, d.n_rows - base);
+    if (tile_rp >= 0) {
+      for (int r = 0; r < rows; ++r) {
+        const T* vr = sm.v + r * PSV;
+        const T w = vr[PSV - 1];
+        const T a0 = w * vr[2 * tile_rp], a1 = w * vr[2 * tile_rp + 1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const T b = vr[4 * tile_cq + c];
+          acc[0][c] = fma_t<T>(a0, b, acc[0][c]);
+          acc[1][c] = fma_t<T>(a1, b, acc[1][c]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  ll = warp_sum<T>(ll);
+#pragma unroll
+  for (int j = 0; j < P; ++j) g[j] = warp_sum<T>(g[j]);
+  T lp = d.lp_const;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const T dd = th[j] - d.ploc[j];
+    lp = fma_t<T>(-(dd * dd), T(0.5) * d.pivar[j], lp);
+    g[j] = fma_t<T>(-dd, d.pivar[j], g[j]);
+  }
+  if (d.has_temperature) {
+    ll *= d.temperature; lp *= d.temperature;
+#pragma unroll
+    for (int j = 0; j < P; ++j) g[j] *= d.temperature;
+  }
+  lt = ll + lp;
+  // assemble the lower triangle of G in shared memory
+  T* G = sm.mat[buf];
+  if (tile_rp >= 0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int row = 2 * tile_rp + r, col = 4 * tile_cq + c;
+        if (row < P && col <= row) {
+          T val = acc[r][c];
+          if (row == col) val += d.pivar[row];
+          if (d.has_temperature) val *= d.temperature;
+          G[row * LD + col] = val;
+        }
+      }
+  }
+  __syncwarp();
+  return warp_chol_inplace<T, P, LD>(G, sm.dinv[buf], logdet);
+}
+
+template <typename T, class NET>
+__global__ void __launch_bounds__(kSmWarps * 32) smmala_kernel(const ChainArgs<T> a) {
+  using Geo = SmGeom<NET>;
+  constexpr int P = NET::P, LD = Geo::LD;
+  static_assert(Geo::ntiles() <= 32, "one 2x4 metric tile per lane");
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout<T, NET> lay(a.n_rows, kSmWarps, false);
+  const DataView<T> d = stage_data<T, NET>(smem, lay, a);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SmWarpMem<T, NET>& sm = reinterpret_cast<SmWarpMem<T, NET>*>(smem + align16(lay.total))[warp];
+  long chain = (long)blockIdx.x * kSmWarps + warp;
+  const bool live = chain < a.n_chains;
+  if (!live) chain = a.n_chains - 1;
+
+  // lane -> 2x4 tile of the lower triangle
+  int tile_rp = -1, tile_cq = -1;
+  {
+    int t = 0;
+    for (int rp = 0; rp < Geo::RP; ++rp) {
+      const int ncq = min((2 * rp + 1) / 4 + 1, Geo::CQ);
+      for (int cq = 0; cq < ncq; ++cq, ++t)
+        if (t == lane) { tile_rp = rp; tile_cq = cq; }
+    }
+  }
+
+  const T step = a.step, half_step = T(0.5) * step, sq_step = sqrt_t<T>(step);
+  const T qconst = T(-0.5) * T(P) * log_t<T>(T(6.283185307179586) * step);
+  const uint32_t gchain = a.chain0 + (uint32_t)chain;
+
+  // current state: lane j holds element j of the sample, its gradient and the proposal mean
+  T thc_l = T(0), gc_l = T(0), lt_c, logdet_c;
+  int cur = 0;
+  bool ok_c;
+  {
+    T th0[P], g0[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) th0[j] = a.theta[chain * a.st_c + j * a.st_p];
+    ok_c = smmala_eval<T, NET>(d, th0, sm, cur, tile_rp, tile_cq, lt_c, g0, logdet_c);
+#pragma unroll
+    for (int j = 0; j < P; ++j) if (lane == j) { gc_l = g0[j]; thc_l = th0[j]; }
+  }
+  T mean_c = thc_l + half_step * warp_solve_upper_t<T, P, LD>(sm.mat[cur], sm.dinv[cur],
+                                                            warp_solve_lower<T, P, LD>(sm.mat[cur], sm.dinv[cur], gc_l));
+  uint32_t n_acc = 0;
+
+  for (long t = 0; t < a.n_iters; ++t) {
+    // ---- noise: lane j owns z_j ------------------------------------------------------------------------------
+    T zl = T(0), u;
+    if (a.rng_mode == 0) {
+      constexpr int PER = sizeof(T) == 8 ? 2 : 4;
+      const int blk = lane / PER;
+      if (lane < P) {
+        U4 w = philox4x32_10(U4{(uint32_t)blk, a.iter0 + (uint32_t)t, gchain, 0u}, a.key.k0, a.key.k1);
+        T v[4];
+        if constexpr (sizeof(T) == 8) {
+          box_muller<T>(Uni<double>::from(w.x, w.y), Uni<double>::from(w.z, w.w), &v[0], &v[1]);
+          v[2] = v[3] = T(0);
+        } else {
+          box_muller<T>(Uni<float>::from(w.x), Uni<float>::from(w.y), &v[0], &v[1]);
+          box_muller<T>(Uni<float>::from(w.z), Uni<float>::from(w.w), &v[2], &v[3]);
+        }
+        const int k = lane % PER;
+        zl = k == 0 ? v[0] : (k == 1 ? v[1] : (k == 2 ? v[2] : v[3]));
+      }
+      u = philox_uniform<T>(a.key, gchain, a.iter0 + (uint32_t)t);
+    } else {
+      if (lane < P) zl = a.z_tape[((size_t)t * a.n_chains + chain) * P + lane];
+      u = a.u_tape[(size_t)t * a.n_chains + chain];
+    }
+    // ---- proposal theta' = mean_c + sqrt(step) R^-T z ---------------------------------------------------------
+    const T propl = mean_c + sq_step * warp_solve_upper_t<T, P, LD>(sm.mat[cur], sm.dinv[cur], zl);
+    const int nxt = cur ^ 1;
+    T lt_p, logdet_p, gpl = T(0);
+    bool ok_p;
+    {
+      T th_p[P], g_p[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) th_p[j] = __shfl_sync(0xffffffffu, propl, j);
+      ok_p = smmala_eval<T, NET>(d, th_p, sm, nxt, tile_rp, tile_cq, lt_p, g_p, logdet_p);
+#pragma unroll
+      for (int j = 0; j < P; ++j) if (lane == j) gpl = g_p[j];
+    }
+    bool acc = false;
+    T mean_p = T(0);
+    if (ok_p && ok_c) {
+      mean_p = propl + half_step * warp_solve_upper_t<T, P, LD>(sm.mat[nxt], sm.dinv[nxt],
+                                                              warp_solve_lower<T, P, LD>(sm.mat[nxt], sm.dinv[nxt], gpl));
+      const T q_f = qconst + logdet_c - warp_rt_norm2<T, P, LD>(sm.mat[cur], propl - mean_c, sm.vec) / (T(2) * step);
+      const T q_b = qconst + logdet_p - warp_rt_norm2<T, P, LD>(sm.mat[nxt], thc_l - mean_p, sm.vec) / (T(2) * step);
+      const T log_rate = lt_p - lt_c - q_f + q_b;
+      acc = log_t<T>(u) < log_rate;
+    }
+    if (acc) {
+      ++n_acc;
+      cur = nxt;
+      lt_c = lt_p; logdet_c = logdet_p; mean_c = mean_p; thc_l = propl; gc_l = gpl;
+    }
+    if (t >= a.n_burnin && (t - a.n_burnin) % a.thin == 0 && live && lane < P) {
+      const long s = (t - a.n_burnin) / a.thin;
+      if (a.out_samples) a.out_samples[s * a.ss_i + chain * a.ss_c + lane * a.ss_p] = thc_l;
+      if (a.out_grad) a.out_grad[s * a.ss_i + chain * a.ss_c + lane * a.ss_p] = gc_l;
+      if (lane == 0) {
+        if (a.out_target) a.out_target[s * a.n_chains + chain] = lt_c;
+        if (a.out_acc) a.out_acc[s * a.n_chains + chain] = acc ? 1 : 0;
+      }
+    }
+  }
+  if (live) {
+    if (lane < P) {
+      a.theta[chain * a.st_c + lane * a.st_p] = thc_l;
+      a.grad[chain * a.st_c + lane * a.st_p] = gc_l;
+    }
+    if (lane == 0) {
+      a.target[chain] = lt_c;
+      if (a.acc_count) a.acc_count[chain] += n_acc;
+    }
+  }
+}
+
+template <typename T, class NET> cudaError_t launch_smmala(const ChainArgs<T>& a, cudaStream_t st) {
+  const SmemLayout<T, NET> lay(a.n_rows, kSmWarps, false);
+  const size_t smem = align16(lay.total) + kSmWarps * sizeof(SmWarpMem<T, NET>);
+  auto kern = smmala_kernel<T, NET>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long blocks = (a.n_chains + kSmWarps - 1) / kSmWarps;
+  kern<<<(unsigned)blocks, kSmWarps * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace eb

@@ -1,0 +1,1 @@
+from .is_pos_def import is_pos_def

@@ -123,6 +123,20 @@ int eeyore_b200_hmc_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
 /* SMMALA (absent from the reference snapshot; SURVEY.md A.7, builder-defined): Fisher metric, batched Cholesky */
 int eeyore_b200_smmala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
 
+/* Chain diagnostics on the device, one CTA per chain (samples element (s, c, j) at s*ss_iter + c*ss_chain + j*ss_param;
+ * n_params <= 32).  Any output pointer may be NULL.
+ *   out_mean [C,P]     ChainList.mean                        (eeyore/chains/chain_list.py:69-71)
+ *   out_cov  [C,P,P]   stats.cov                             (eeyore/stats/cov.py:5-15)
+ *   out_inse [C,P,P]   stats.inse_mc_cov, adjust=False       (eeyore/stats/inse_mc_cov.py:9-83)
+ *   out_ess  [C]       stats.multi_ess                       (eeyore/stats/multi_ess.py:6-14)
+ *   out_status [C]     0 = ok, 1 = 'Not enough samples' (inse_mc_cov.py:44-45; the Python layer raises RuntimeError)
+ *   out_lags [C,2]     (first lag index with a positive-definite estimate, last accepted lag index)
+ *   out_acf  [C, max_lag+1, P]  autocorrelation function (builder-defined; absent from the reference) */
+int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int n_params, const void *samples,
+                            int64_t ss_iter, int64_t ss_chain, int64_t ss_param, void *out_mean, void *out_cov,
+                            void *out_inse, void *out_ess, int32_t *out_status, int32_t *out_lags, int max_lag,
+                            void *out_acf, void *stream);
+
 /* Philox draws exactly as the samplers consume them (tests / reproducibility):
  * out_z [n_chains, P] normals and out_u [n_chains] uniform of iteration `iter`. */
 int eeyore_b200_philox_draws(int dtype, int64_t n_chains, int n_params, uint64_t seed, uint64_t iter,

@@ -105,7 +105,7 @@ def test_product_does_not_import_oracle():
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
     for f in (ROOT / "eeyore_b200" / "csrc").glob("*.cu*"):
-        assert "oracle/" not in f.read_text() or f.name == "philox.cuh", f
+        assert "#include \"../../oracle" not in f.read_text() and "oracle.h" not in f.read_text(), f
 
 
 def test_data_counter():
