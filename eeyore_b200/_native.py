@@ -67,6 +67,12 @@ SIGNATURES = {
     "eeyore_b200_hmc_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_smmala_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
+    "eeyore_b200_dp_num_params": (_I, []),
+    "eeyore_b200_dp_loglik_grad": (_I, [_VP, _VP, _VP, _I64, _VP, _VP]),
+    "eeyore_b200_dp_finish": (_I, [_VP, _VP, _VP, _VP, _I, _D, _VP, _VP, _VP]),
+    "eeyore_b200_dp_hmc_begin": (_I, [_VP, _VP, _D, _U64, _U64, _VP, _VP, _VP, _VP, _VP]),
+    "eeyore_b200_dp_hmc_step": (_I, [_VP, _D, _I, _VP, _VP, _VP, _VP]),
+    "eeyore_b200_dp_hmc_accept": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U64, _U64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "eeyore_b200_philox_draws": (_I, [_I, _I64, _I, _U64, _U64, _U64, _VP, _VP, _VP]),
     "eeyore_b200_fma_peak": (_I, [_I, _I, C.POINTER(_D)]),
 }

@@ -126,10 +126,45 @@ class MLP(BayesianModel):
         if y.numel() != n * k:
             raise ValueError(f"y must hold {n}x{k} entries, got {tuple(y.shape)}")
 
+    def is_data_parallel(self):
+        """True for the wide architecture served by the data-parallel kernel (eeyore_b200/csrc/datapar.cu): one
+        parameter vector, rows spread over the SMs (and, with DataShardedHMC, over the GPUs)."""
+        return (list(self.hp.dims) == [16, 64, 64, 1] and self.dtype == torch.float32
+                and self.loss.loss_id == nv.LOSS_BINARY and all(self.hp.bias))
+
+    def _eval_data_parallel(self, theta, x, y, group=None):
+        """theta [C,P] -> (lt [C] float64->dtype, grad [C,P]); rows of (x, y) are this rank's shard."""
+        import ctypes as C
+        dev = theta.device
+        c, p = theta.shape
+        loc, scale = self.prior_on_device()
+        sums = torch.empty(p + 1, dtype=torch.float64, device=dev)
+        lt64 = torch.empty(1, dtype=torch.float64, device=dev)
+        lt = torch.empty(c, dtype=self.dtype, device=dev)
+        g = torch.empty(c, p, dtype=self.dtype, device=dev)
+        yv = y.reshape(-1)
+        with torch.cuda.device(dev):
+            st = nv.stream_ptr(dev)
+            for i in range(c):
+                nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(theta[i]), nv.ptr(x), nv.ptr(yv), x.shape[0],
+                                                             nv.ptr(sums), st))
+                if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                         and getattr(self, "data_sharded", False)):
+                    torch.distributed.all_reduce(sums, group=group)
+                nv.check(nv.lib().eeyore_b200_dp_finish(nv.ptr(sums), nv.ptr(theta[i]), nv.ptr(loc), nv.ptr(scale),
+                                                        0 if self.temperature is None else 1,
+                                                        0.0 if self.temperature is None else float(self.temperature),
+                                                        nv.ptr(lt64), nv.ptr(g[i]), st))
+                lt[i] = lt64[0]
+        return lt, g
+
     def _eval(self, theta, x, y, want_grad=True, parts=False, lanes=0):
         """theta [C,P], x [N,d0], y: device tensors of the model dtype.  Returns (lt [C], grad [C,P] | None[, ll, lp])."""
         nv.require_cuda()
         self._check_data(x, y)
+        if self.is_data_parallel() and not parts:
+            lt, g = self._eval_data_parallel(theta.contiguous(), x, y)
+            return lt, (g if want_grad else None)
         c = theta.shape[0]
         loc, scale = self.prior_on_device()
         dev = theta.device

@@ -1,3 +1,4 @@
+from .data_sharded_hmc import DataShardedHMC, shard_rows
 from .hmc import HMC
 from .mala import MALA
 from .metropolis_hastings import MetropolisHastings

@@ -137,6 +137,29 @@ int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int 
                             void *out_inse, void *out_ess, int32_t *out_status, int32_t *out_lags, int max_lag,
                             void *out_acf, void *stream);
 
+/* ---- data-parallel path (BASELINE config 5: MLP 16-64-64-1, fp32, rows sharded across GPUs) -----------------------
+ * One parameter vector, millions of rows.  Each rank evaluates its row shard; the caller all-reduces out_sums
+ * (P + 1 doubles) over the ranks (NCCL) and then calls dp_finish, which adds the prior once.
+ * Replaces eeyore/models/log_target_model.py:20-23 for large N; theta fp32 [P] in the reference layout. */
+int eeyore_b200_dp_num_params(void);
+/* out_sums[0] = sum_i loglik_i, out_sums[1 + j] = d/dtheta_j sum_i loglik_i over this rank's rows (fp64, deterministic) */
+int eeyore_b200_dp_loglik_grad(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
+                               void *stream);
+/* target (fp64 scalar) and gradient (fp32 [P]) from the all-reduced sums: adds the Normal log-prior
+ * (eeyore/models/bayesian_model.py:46-56) and applies the temperature */
+int eeyore_b200_dp_finish(const void *sums, const void *theta, const void *prior_loc, const void *prior_scale,
+                          int has_temperature, double temperature, void *out_target, void *out_grad, void *stream);
+/* HMC.draw pieces for a replicated chain state (eeyore/samplers/hmc.py:100-170): momentum draw + first half step;
+ * momentum / position update after each evaluation; accept test and commit.  z_tape / u_tape NULL = Philox. */
+int eeyore_b200_dp_hmc_begin(const void *theta_cur, const void *grad_cur, double step, uint64_t seed, uint64_t iter,
+                             const void *z_tape, void *momentum, void *theta_prop, void *kin0, void *stream);
+int eeyore_b200_dp_hmc_step(const void *grad_prop, double step, int last, void *momentum, void *theta_prop, void *kin1,
+                            void *stream);
+int eeyore_b200_dp_hmc_accept(void *theta_cur, void *grad_cur, void *target_cur, const void *theta_prop,
+                              const void *grad_prop, const void *target_prop, const void *kin0, const void *kin1,
+                              uint64_t seed, uint64_t iter, const void *u_tape, void *out_sample, void *out_target,
+                              uint8_t *out_accepted, uint32_t *accept_count, void *stream);
+
 /* Philox draws exactly as the samplers consume them (tests / reproducibility):
  * out_z [n_chains, P] normals and out_u [n_chains] uniform of iteration `iter`. */
 int eeyore_b200_philox_draws(int dtype, int64_t n_chains, int n_params, uint64_t seed, uint64_t iter,

@@ -196,8 +196,43 @@ def stats_goldens():
     print("stats multi_ess", esss, "rhat", out["multi_rhat"])
 
 
+def datapar_goldens():
+    """BASELINE config 5 architecture (16-64-64-1, fp32) on a 4,099-row synthetic binary data set (ragged on purpose:
+    not a multiple of the 128-row tile nor of 4): log_target and gradient from the unmodified reference."""
+    rng = np.random.default_rng(4)
+    n = 4099
+    x = rng.normal(size=(n, 16)).astype(np.float32)
+    teacher = rng.normal(size=16).astype(np.float32)
+    y = ((x @ teacher + 0.5 * rng.normal(size=n)) > 0).astype(np.float32)[:, None]
+    hp = Hyperparameters(dims=[16, 64, 64, 1], bias=3 * [True], activations=3 * [torch.sigmoid])
+    model = MLP(loss=loss_functions["binary_classification"], hparams=hp, dtype=torch.float32)
+    P = model.num_params()
+    model.prior = Normal(torch.zeros(P), math.sqrt(3.0) * torch.ones(P))
+    thetas = (rng.normal(size=(3, P)) * np.array([0.1, 0.3, 0.6])[:, None]).astype(np.float32)
+    lts, grads = [], []
+    for th in thetas:
+        lt, g = model.upto_grad_log_target(torch.from_numpy(th).clone(), torch.from_numpy(x), torch.from_numpy(y))
+        lts.append(lt.item()); grads.append(npy(g))
+    # fp64 run of the same reference code for an error yardstick
+    model64 = MLP(loss=loss_functions["binary_classification"], hparams=hp, dtype=torch.float64)
+    model64.prior = Normal(torch.zeros(P, dtype=torch.float64), math.sqrt(3.0) * torch.ones(P, dtype=torch.float64))
+    lts64, grads64 = [], []
+    for th in thetas:
+        lt, g = model64.upto_grad_log_target(torch.from_numpy(th).double(), torch.from_numpy(x).double(),
+                                             torch.from_numpy(y).double())
+        lts64.append(lt.item()); grads64.append(npy(g))
+    np.savez_compressed(OUT / "dp_goldens.npz", x=x, y=y, theta=thetas, lt=np.array(lts), grad=np.stack(grads),
+                        lt64=np.array(lts64), grad64=np.stack(grads64).astype(np.float32))
+    print("dp_goldens", lts, "fp32-vs-fp64 grad rel err",
+          [float(np.abs(grads[i] - grads64[i]).max() / np.abs(grads64[i]).max()) for i in range(3)])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dp":
+        datapar_goldens()
+        sys.exit(0)
     model_goldens()
+    datapar_goldens()
     s3 = math.sqrt(3.0)
     # BASELINE.json configs[0]: MLP 2-2-1 XOR, single MALA chain, 1100 iterations (110 burn-in), fp64
     run_sampler("mala_xor221_f64", "mala", "221", torch.float64, 1100, 110, s3, 0, step=1.74, ess=True)

@@ -1,0 +1,141 @@
+"""GPU parity: data-parallel evaluation kernel (MLP 16-64-64-1, fp32; BASELINE config 5) and the data-sharded HMC.
+Tolerance stated by BASELINE.json for fp32: 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+from torch.distributions import Normal
+
+import oracle
+from eeyore_b200 import _native as nv
+from eeyore_b200.constants import loss_functions
+from eeyore_b200.models.mlp import MLP, Hyperparameters
+from eeyore_b200.samplers import DataShardedHMC, shard_rows
+from gpu_helpers import npy
+from helpers import load, rel_err
+from oracle.mlp import MLPSpec, BINARY
+
+pytestmark = pytest.mark.gpu
+S3 = 3 ** 0.5
+SPEC = MLPSpec([16, 64, 64, 1], loss=BINARY)
+P = 5313
+
+
+def wide_model(prior_scale=S3, temperature=None):
+    hp = Hyperparameters([16, 64, 64, 1], 3 * [True], 3 * [torch.sigmoid])
+    m = MLP(loss=loss_functions["binary_classification"], hparams=hp, dtype=torch.float32, temperature=temperature)
+    m.prior = Normal(torch.zeros(P), prior_scale * torch.ones(P))
+    return m
+
+
+def synth(n, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, 16)).astype(np.float32)
+    t = rng.normal(size=16).astype(np.float32)
+    y = ((x @ t + 0.5 * rng.normal(size=n)) > 0).astype(np.float32)[:, None]
+    return x, y
+
+
+def test_reference_golden_16_64_64_1():
+    gd = load("dp_goldens")
+    m = wide_model()
+    assert m.num_params() == P == nv.lib().eeyore_b200_dp_num_params()
+    x, y = torch.from_numpy(gd["x"]), torch.from_numpy(gd["y"])
+    for i in range(3):
+        lt, g = m.upto_grad_log_target(torch.from_numpy(gd["theta"][i]), x, y)
+        assert abs(lt.item() - gd["lt"][i]) < 1e-5 * abs(gd["lt"][i])
+        assert rel_err(npy(g), gd["grad"][i]) < 1e-5
+        assert rel_err(npy(g), gd["grad64"][i]) < 2e-6           # closer to the fp64 run of the reference than fp32 is
+        assert abs(m.log_target(torch.from_numpy(gd["theta"][i]), x, y).item() - gd["lt"][i]) < 1e-5 * abs(gd["lt"][i])
+    lt, g = m.upto_grad_log_target_batch(torch.from_numpy(gd["theta"]), x, y)
+    assert np.allclose(npy(lt), gd["lt"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 127, 128, 129, 1000, 4099])
+def test_ragged_row_counts_vs_oracle(n):
+    x, y = synth(n, seed=n)
+    rng = np.random.default_rng(n + 1)
+    theta = (rng.normal(size=(2, P)) * 0.3).astype(np.float32)
+    m = wide_model(temperature=0.8 if n == 129 else None)
+    lt, g = m.upto_grad_log_target_batch(torch.from_numpy(theta), torch.from_numpy(x), torch.from_numpy(y))
+    lt_ref, g_ref = oracle.log_target_grad(SPEC, theta.astype(np.float64), x.astype(np.float64), y, np.zeros(P),
+                                           np.full(P, S3), 0.8 if n == 129 else None)
+    assert np.allclose(npy(lt), lt_ref, rtol=1e-5)
+    for c in range(2):
+        assert rel_err(npy(g)[c], g_ref[c]) < 1e-5
+
+
+def test_saturation_nan_semantics():
+    x, y = synth(300)
+    theta = np.zeros(P, np.float32)
+    theta[-1] = 40.0                                   # p == 1.0f for every row -> 0 * log(0) = NaN in the reference form
+    m = wide_model()
+    lt, g = m.upto_grad_log_target(torch.from_numpy(theta), torch.from_numpy(x), torch.from_numpy(y))
+    assert torch.isnan(lt) and torch.isnan(g).all()
+
+
+def dp_sums(theta, x, y):
+    sums = torch.empty(P + 1, dtype=torch.float64, device="cuda")
+    nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(x), nv.ptr(y), x.shape[0], nv.ptr(sums), None))
+    return sums
+
+
+def test_row_shards_add_up_and_are_deterministic():
+    n = 200_003
+    x, y = synth(n, seed=5)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda().reshape(-1)
+    theta = torch.from_numpy((np.random.default_rng(0).normal(size=P) * 0.2).astype(np.float32)).cuda()
+    full = dp_sums(theta, xd, yd)
+    assert torch.equal(full, dp_sums(theta, xd, yd))                      # fixed-order reduction: bitwise repeatable
+    for world in (2, 3, 8):
+        tot = torch.zeros_like(full)
+        covered = 0
+        for r in range(world):
+            lo, hi = shard_rows(n, world, r)
+            assert lo % 4 == 0
+            covered += hi - lo
+            if hi > lo:
+                tot += dp_sums(theta, xd[lo:hi], yd[lo:hi])
+        assert covered == n
+        assert rel_err(npy(tot[1:]), npy(full[1:])) < 1e-6 and abs(tot[0].item() - full[0].item()) < 1e-7 * abs(full[0].item())
+    ll_ref = oracle.log_lik(SPEC, npy(theta).astype(np.float64)[None], x.astype(np.float64), y)[0]
+    assert abs(full[0].item() - ll_ref) < 1e-5 * abs(ll_ref)
+
+
+def test_data_sharded_hmc_vs_oracle():
+    n, T, L, step = 2048, 4, 5, 0.002
+    x, y = synth(n, seed=9)
+    rng = np.random.default_rng(2)
+    theta0 = (rng.normal(size=P) * 0.2).astype(np.float32)
+    z = rng.normal(size=(T, P)).astype(np.float32)
+    u = rng.uniform(size=T).astype(np.float32)
+    m = wide_model()
+    s = DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), step=step, num_steps=L)
+    s.set_noise_tape(torch.from_numpy(z), torch.from_numpy(u))
+    samples, targets, accepted = s.run(num_epochs=T, num_burnin_epochs=1)
+    ref = oracle.hmc_run(SPEC, x.astype(np.float64), y, np.zeros(P), np.full(P, S3), theta0.astype(np.float64)[None],
+                         z.astype(np.float64)[:, None], u.astype(np.float64)[:, None], step, L, n_burnin=1)
+    assert 0 < ref["accepted"].sum()
+    assert np.array_equal(npy(accepted), ref["accepted"][:, 0])
+    assert rel_err(npy(samples), ref["sample"][:, 0]) < 1e-4
+    assert np.allclose(npy(targets), ref["target_val"][:, 0], rtol=1e-4)
+    assert s.n_evals == 1 + T * L and len(s.get_chain()) == T - 1
+    # Philox mode: reproducible, and the simulated two-shard exchange gives the same chain as one shard
+    a = DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), step=step, num_steps=L, seed=3)
+    sa, _, acc_a = a.run(num_epochs=3, num_burnin_epochs=0)
+    b = DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), step=step, num_steps=L, seed=3)
+    sb, _, acc_b = b.run(num_epochs=3, num_burnin_epochs=0)
+    assert torch.equal(sa, sb) and torch.equal(acc_a, acc_b)
+
+
+def test_full_tile_count_large_shard_linearity():
+    """1M rows (config 5's per-GPU shard at 8 GPUs): sums over the shard equal the sum of the sums over its halves."""
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, 16, device="cuda", generator=g)
+    y = (torch.rand(n, device="cuda", generator=g) < 0.5).float()
+    theta = torch.randn(P, device="cuda", generator=g) * 0.1
+    full = dp_sums(theta, x, y)
+    h = n // 2
+    parts = dp_sums(theta, x[:h], y[:h]) + dp_sums(theta, x[h:], y[h:])
+    assert rel_err(npy(parts), npy(full)) < 1e-9
+    assert torch.isfinite(full).all()
