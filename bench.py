@@ -37,6 +37,14 @@ WORKLOADS = {
     "cfg4": dict(name="cfg4: MLP 2-3-2-1 XOR, HMC L=10, 524288 chains/GPU, fp64", dims=[2, 3, 2, 1], data="xor",
                  loss="binary_classification", chains=524288, step=0.3, num_steps=10, iters=50, thin=10,
                  flops_per_eval=368, dtype="f64"),
+    # BASELINE.json configs[2] (SMMALA is builder-defined: absent from the reference snapshot)
+    "cfg3": dict(name="cfg3: MLP 2-3-2-1 noisy-XOR-shaped N=200, SMMALA (Fisher metric, in-warp Cholesky), 16384 chains/GPU, fp64",
+                 dims=[2, 3, 2, 1], data="noisy_xor", loss="binary_classification", chains=16384, step=0.7, num_steps=1,
+                 iters=20, thin=5, flops_per_eval=14480 + 160000 + 2667 + 800, dtype="f64", kind="smmala"),
+    # BASELINE.json configs[4]: one chain, data sharded over the ranks, NCCL all-reduce per evaluation (strong scaling)
+    "cfg5": dict(name="cfg5: MLP 16-64-64-1, 8388608 synthetic rows sharded over the GPUs, HMC L=10, fp32",
+                 dims=[16, 64, 64, 1], data="teacher", loss="binary_classification", chains=1, step=2e-4, num_steps=10,
+                 iters=2, thin=1, flops_per_eval=29056 * 8388608, rows=8388608, dtype="f32", kind="datapar"),
     # BASELINE.json configs[1]
     "cfg2": dict(name="cfg2: MLP 4-3-3 iris-shaped N=150, HMC L=10, 4096 chains/GPU, fp64", dims=[4, 3, 3], data="iris",
                  loss="multiclass_classification", chains=4096, step=0.02, num_steps=10, iters=20, thin=5,
@@ -49,6 +57,12 @@ def synthetic_data(w):
     if w["data"] == "xor":
         x = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=np.float64)
         y = np.array([[0], [1], [1], [0]], dtype=np.float64)
+        return x, y
+    if w["data"] == "noisy_xor":          # 50 points per XOR corner + N(0, 0.15^2), seed 3
+        rng = np.random.default_rng(3)
+        corners = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=np.float64)
+        x = np.concatenate([c + 0.15 * rng.normal(size=(50, 2)) for c in corners])
+        y = np.concatenate([np.full((50, 1), float(int(c[0]) ^ int(c[1]))) for c in corners])
         return x, y
     rng = np.random.default_rng(1)
     centres = rng.normal(size=(3, 4)) * 2.0
@@ -112,7 +126,10 @@ def _cpu_worker(args):
     theta = rng.normal(size=(chains, p)) * (1.0 if w["data"] == "xor" else 0.3)
     z, u = rng.normal(size=(iters, chains, p)), rng.uniform(size=(iters, chains))
     t0 = time.perf_counter()
-    oracle.hmc_run(spec, x, y, np.zeros(p), np.full(p, S3), theta, z, u, w["step"], w["num_steps"])
+    if w.get("kind") == "smmala":
+        oracle.smmala_run(spec, x, y, np.zeros(p), np.full(p, S3), theta * 0.5, z, u, w["step"])
+    else:
+        oracle.hmc_run(spec, x, y, np.zeros(p), np.full(p, S3), theta, z, u, w["step"], w["num_steps"])
     return time.perf_counter() - t0
 
 
@@ -149,6 +166,8 @@ def cpu_sample_sizes(wname):
     w = WORKLOADS[wname]
     if wname == "cfg4":
         return 4096, 3          # chains per process, iterations
+    if wname == "cfg3":
+        return 64, 2
     return 128, 2
 
 
@@ -166,7 +185,7 @@ def run_reference_arm(args):
     for _ in range(args.steps):
         v, wall = pool.throughput(args.workload, cpp, iters)
         t_steps.append(wall)
-        evals += procs * cpp * iters * w["num_steps"]
+        evals += procs * cpp * iters * (1 if w.get("kind") == "smmala" else w["num_steps"])
     pool.close()
     total = sum(t_steps)
     value = evals / total
@@ -221,7 +240,7 @@ def run_ours(args):
     C = args.chains or w["chains"]
     iters, L, thin = args.iters or w["iters"], w["num_steps"], w["thin"]
     gen = torch.Generator().manual_seed(1000 + rank)
-    theta_host = (torch.randn(C, P, generator=gen, dtype=dt) * (1.0 if w["data"] == "xor" else 0.3)).pin_memory()
+    theta_host = (torch.randn(C, P, generator=gen, dtype=dt) * {"xor": 1.0, "noisy_xor": 0.5}.get(w["data"], 0.3)).pin_memory()
     loader = DataLoader(ds, batch_size=len(ds))
 
     def barrier():
@@ -237,7 +256,15 @@ def run_ours(args):
         return t.item()
 
     # ---- device-resident arm: state stays in HBM, one fused launch per step --------------------------------------
-    sampler = HMC(model, theta0=theta_host.to(dev), dataloader=loader, step=w["step"], num_steps=L, seed=12345, thin=thin)
+    kind = w.get("kind", "hmc")
+
+    def make_sampler(theta0, seed):
+        if kind == "smmala":
+            from eeyore_b200.samplers import SMMALA
+            return SMMALA(model, theta0=theta0, dataloader=loader, step=w["step"], seed=seed, thin=thin)
+        return HMC(model, theta0=theta0, dataloader=loader, step=w["step"], num_steps=L, seed=seed, thin=thin)
+
+    sampler = make_sampler(theta_host.to(dev), 12345)
     sampler.chain_offset = rank * C          # global chain ids => results independent of the sharding
 
     def step_resident():
@@ -258,7 +285,7 @@ def run_ours(args):
         barrier()
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
-    evals_step = C * iters * L
+    evals_step = C * iters * (1 if kind == "smmala" else L)
     value = world * evals_step * args.steps / t_res
     acc_rate = sampler.get_chain().acceptance().mean().item()
 
@@ -268,7 +295,7 @@ def run_ours(args):
     out_acc = torch.empty(C, dtype=torch.int32).pin_memory()
 
     def step_e2e():
-        s = HMC(model, theta0=theta_host, dataloader=loader, step=w["step"], num_steps=L, seed=999, thin=thin)
+        s = make_sampler(theta_host, 999)
         s.chain_offset = rank * C
         s.run(num_epochs=iters, num_burnin_epochs=0)
         out_theta.copy_(s.current["sample"], non_blocking=True)
@@ -322,7 +349,7 @@ def run_ours(args):
         cpp, it = cpu_sample_sizes(args.workload)
         cpp *= 16
         t = _cpu_worker((args.workload, cpp, it, 0))
-        cpu = {"value": cpp * it * L / t, "unit": "evals/s", "cores": 1, "kind": "port",
+        cpu = {"value": cpp * it * (1 if kind == "smmala" else L) / t, "unit": "evals/s", "cores": 1, "kind": "port",
                "sample": f"{cpp} chains x {it} HMC iterations (L={L}) of the numpy oracle port, one process, {t:.1f} s"}
 
     print(json.dumps({
@@ -346,6 +373,128 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_datapar(args):
+    """BASELINE config 5: one replicated chain, rows sharded over the ranks (strong scaling), NCCL all-reduce of the
+    1 + P partial sums after every local evaluation.  One step = `iters` HMC iterations (L evaluations each, every
+    evaluation over ALL rows)."""
+    import torch
+    import torch.distributed as dist
+    from torch.distributions import Normal
+
+    from eeyore_b200.constants import loss_functions
+    from eeyore_b200.models.mlp import MLP, Hyperparameters
+    from eeyore_b200.samplers import DataShardedHMC, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    n_total = args.rows or w["rows"]
+    lo, hi = shard_rows(n_total, world, rank)
+    gen = torch.Generator(device=dev).manual_seed(4)           # same stream on every rank; each keeps its slice
+    teacher = torch.randn(16, device=dev, generator=gen)
+    x = torch.empty(hi - lo, 16, device=dev)
+    y = torch.empty(hi - lo, device=dev)
+    chunk = 1 << 20
+    for c0 in range(0, n_total, chunk):                         # generate the global data set chunk-wise, keep [lo, hi)
+        c1 = min(n_total, c0 + chunk)
+        xc = torch.randn(c1 - c0, 16, device=dev, generator=gen)
+        yc = ((xc @ teacher + 0.5 * torch.randn(c1 - c0, device=dev, generator=gen)) > 0).float()
+        a, b = max(lo, c0), min(hi, c1)
+        if b > a:
+            x[a - lo:b - lo], y[a - lo:b - lo] = xc[a - c0:b - c0], yc[a - c0:b - c0]
+    hp = Hyperparameters(w["dims"], 3 * [True], 3 * [torch.sigmoid])
+    model = MLP(loss=loss_functions[w["loss"]], hparams=hp, dtype=torch.float32, device=dev)
+    P = model.num_params()
+    model.prior = Normal(torch.zeros(P), S3 * torch.ones(P))
+    iters, L = args.iters or w["iters"], w["num_steps"]
+    theta_host = (torch.randn(P, generator=torch.Generator().manual_seed(5)) * 0.1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    sampler = DataShardedHMC(model, theta_host.to(dev), x, y, step=w["step"], num_steps=L, seed=7)
+    for _ in range(args.warmup):
+        sampler.run(num_epochs=iters, num_burnin_epochs=0)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev[0].record()
+        for k in range(args.steps):
+            sampler.run(num_epochs=iters, num_burnin_epochs=0)
+            ev[k + 1].record()
+        barrier()
+    t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
+    evals_step = iters * L
+    value = evals_step * args.steps / t_res
+    acc = sampler.acceptance_count() / max(1, sampler._iter)
+
+    out_theta = torch.empty(iters, P).pin_memory()
+
+    def step_e2e():
+        s = DataShardedHMC(model, theta_host, x, y, step=w["step"], num_steps=L, seed=11)   # chain state from the host
+        samples, targets, accepted = s.run(num_epochs=iters, num_burnin_epochs=0)
+        out_theta.copy_(samples, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    if rank == 0:
+        import ctypes
+        from eeyore_b200 import _native as nv
+        peak = ctypes.c_double()
+        nv.check(nv.lib().eeyore_b200_fma_peak(nv.F32, 4000, ctypes.byref(peak)))
+        # dominant kernel: dp_eval_kernel, one launch per evaluation over this rank's shard
+        flops_launch = 29056.0 * (hi - lo)
+        launch_s = t_res / (args.steps * evals_step)            # upper bound: includes the small kernels + all-reduce
+        achieved = flops_launch / launch_s / 1e12
+        print(json.dumps({
+            "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "rows_total": n_total, "rows_per_gpu": hi - lo,
+                       "hmc_iterations_per_step": iters, "num_steps": L, "evals_counted_per_iteration": L,
+                       "exchange": "all-reduce of 1+P fp64 partial sums per evaluation (NCCL)" if world > 1 else "none (1 GPU)",
+                       "acceptance_rate": acc, "l2": "x shard (%.0f MB) exceeds the 126 MB L2" % ((hi - lo) * 68 / 1e6),
+                       "data_resident": "x, y shards stay in HBM across steps; e2e copies the chain state in and the samples out"},
+            "e2e": {"value": evals_step * args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": P * 4,
+                    "d2h_bytes_per_step": iters * P * 4, "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": args.steps * iters * (2 + 4 * L),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                         "frac": achieved / peak.value, "traffic": None,
+                         "peak_source": "measured live by eeyore_b200_fma_peak (this device)",
+                         "algorithmic_flops_per_row": 29056,
+                         "note": "per-evaluation time includes the reduce/finish/leapfrog kernels and the all-reduce",
+                         "hbm_view": {"algorithmic_bytes_per_launch": (hi - lo) * 68,
+                                      "achieved_gbs": (hi - lo) * 68 / launch_s / 1e9}},
+            "cpu_baseline": None,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,10 +504,13 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--iters", type=int, default=0, help="override HMC iterations per step")
+    ap.add_argument("--rows", type=int, default=0, help="cfg5: override the total number of data rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif WORKLOADS[args.workload].get("kind") == "datapar":
+        run_datapar(args)
     else:
         run_ours(args)
 
