@@ -44,10 +44,20 @@ class DataShardedHMC:
         self._iter = 0
         self._tape = None
         self.n_evals = 0
-        self._theta_c = model._to_dev(theta0).reshape(-1).clone()
+        self._theta_c = torch.empty(p, **f32)
         self._grad_c = torch.empty(p, **f32)
-        self._evaluate(self._theta_c, self._lt_c, self._grad_c)
         self.current = {"sample": self._theta_c, "target_val": self._lt_c[0], "grad_val": self._grad_c, "accepted": None}
+        self.reset(theta0)
+
+    def reset(self, theta, data=None, reset_counter=True, reset_chain=True):
+        """SingleChainSerialSampler.reset (single_chain_serial_sampler.py:33-38): restart the chain at theta (host or
+        device tensor) re-using every device buffer; re-evaluates target and gradient there."""
+        self._theta_c.copy_(torch.as_tensor(theta).reshape(-1), non_blocking=True)
+        if reset_chain:
+            self.chain.reset(keys=list(self.chain.vals.keys()))
+        if reset_counter:
+            self._acc_count.zero_()
+        self._evaluate(self._theta_c, self._lt_c, self._grad_c)
 
     def _all_reduce(self, t):
         if torch.distributed.is_available() and torch.distributed.is_initialized() and \
