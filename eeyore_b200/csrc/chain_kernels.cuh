@@ -9,6 +9,7 @@
 #include "samplers.cuh"
 #include "philox.cuh"
 #include "registry.h"
+#include <type_traits>
 
 namespace eb {
 
@@ -47,8 +48,8 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(
 
 // shared-memory layout (bytes), identical on host (size) and device (carve)
 template <typename T, class NET> struct SmemLayout {
-  size_t off_bar, off_x, off_y, off_ploc, off_pivar, off_misc, off_mom, total;
-  __host__ __device__ SmemLayout(int n_rows, int chains_per_block, bool with_momentum) {
+  size_t off_bar, off_x, off_y, off_ploc, off_pivar, off_misc, off_mom, off_grad, total;
+  __host__ __device__ SmemLayout(int n_rows, int chains_per_block, bool with_momentum, bool with_grad = false) {
     size_t o = 0;
     off_bar = o; o += 16;
     off_x = o; o += align16(sizeof(T) * (size_t)n_rows * NET::D0);
@@ -57,17 +58,32 @@ template <typename T, class NET> struct SmemLayout {
     off_pivar = o; o += align16(sizeof(T) * NET::P);
     off_misc = o; o += 16;
     off_mom = o; if (with_momentum) o += align16(sizeof(T) * NET::P * (size_t)chains_per_block);
+    off_grad = o; if (with_grad) o += align16(sizeof(T) * NET::P * (size_t)kBlock);
     total = o;
   }
 };
 
 // Resident blocks per SM the sampler kernels are compiled for (register budget = 65536 / (kBlock * blocks)):
 // theta' and the gradient accumulators (2 P values) must stay in registers.
-#ifndef EB_MINB_F64_SMALL
-#define EB_MINB_F64_SMALL 3
+// fp64 gradient accumulators of the gradient-based samplers live in shared memory (one column per thread) when the
+// parameter vector is large enough that theta' + accumulators would not fit a 128-register budget.
+template <typename T, class NET, int KIND> constexpr bool grad_in_smem() {
+  // measured on B200 (config 4): 128 registers + shared-memory accumulators = 9.3e9 evals/s, 168 registers with
+  // register accumulators = 10.4e9 evals/s  -> kept off by default
+#ifdef EB_GRAD_IN_SMEM
+  return sizeof(T) == 8 && NET::P >= 16 && KIND != KIND_MH;
+#else
+  return false;
 #endif
-template <typename T, class NET> constexpr int min_blocks() {
-  return sizeof(T) == 8 ? (NET::P <= 20 ? EB_MINB_F64_SMALL : (NET::P <= 32 ? 3 : 2)) : (NET::P <= 32 ? 4 : 3);
+}
+#ifndef EB_MINB_F64_LARGE
+#define EB_MINB_F64_LARGE 2
+#endif
+// Resident CTAs per SM the sampler kernels are compiled for (register budget = 65536 / (kBlock * blocks)).
+template <typename T, class NET, int KIND> constexpr int min_blocks() {
+  if (sizeof(T) == 4) return NET::P <= 32 ? 4 : 3;
+  if (grad_in_smem<T, NET, KIND>()) return NET::P <= 20 ? 4 : 3;
+  return NET::P <= 20 ? 3 : (NET::P <= 32 ? EB_MINB_F64_LARGE : 2);
 }
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------------------------
@@ -108,6 +124,7 @@ EB_D DataView<T> stage_data(unsigned char* smem, const SmemLayout<T, NET>& lay, 
   T* misc = reinterpret_cast<T*>(smem + lay.off_misc);
   const int tid = threadIdx.x;
   const int N = a.n_rows;
+  if constexpr (sizeof(T) == 8) exp_table_init();  // visible after the __syncthreads() below
 
   const uint32_t x_bytes = (uint32_t)(sizeof(T) * (size_t)N * NET::D0);
   const uint32_t y_bytes = (uint32_t)(sizeof(T) * (size_t)N);
@@ -191,6 +208,7 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ChainArgs<T> a, T
   extern __shared__ __align__(16) unsigned char smem[];
   const long chain = (long)blockIdx.x * kBlock + threadIdx.x;
   T* xs = reinterpret_cast<T*>(smem);
+  if constexpr (sizeof(T) == 8) exp_table_init();
   for (int i = threadIdx.x; i < a.n_rows * NET::D0; i += blockDim.x) xs[i] = a.x[i];
   __syncthreads();
   if (chain >= a.n_chains) return;
@@ -210,11 +228,12 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ChainArgs<T> a, T
 // (HMC) the momentum.  Global memory (coalesced in the chain-minor layout): the chain's current sample / gradient, read
 // once per iteration and written on accept.
 template <typename T, class NET, int G, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<T, NET>()) sampler_kernel(const ChainArgs<T> a) {
+__global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_kernel(const ChainArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int CPB = kBlock / G;
   constexpr int P = NET::P;
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC);
+  constexpr bool GSM = grad_in_smem<T, NET, KIND>();
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, GSM);
   const DataView<T> d = stage_data<T, NET>(smem, lay, a);
   const int sub = threadIdx.x % G;
   const int cl = threadIdx.x / G;
@@ -237,7 +256,9 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET>()) sampler_kernel(c
   uint32_t n_acc = 0;
 
   for (long t = 0; t < a.n_iters; ++t) {
-    T z[P], thp[P], gp[P];
+    T z[P], thp[P];
+    typename std::conditional<GSM, StridedVec<T>, RegVec<T, P>>::type gp;
+    if constexpr (GSM) { gp.base = reinterpret_cast<T*>(smem + lay.off_grad) + threadIdx.x; gp.stride = kBlock; }
     T u, ltp;
     if (a.rng_mode == 0) {
       philox_normals<T, P>(z, a.key, gchain, a.iter0 + (uint32_t)t);
@@ -298,7 +319,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET>()) sampler_kernel(c
 // ---- launchers ----------------------------------------------------------------------------------------------------
 template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
   constexpr int CPB = kBlock / G;
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC);
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, grad_in_smem<T, NET, KIND>());
   auto kern = sampler_kernel<T, NET, G, KIND>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return e;

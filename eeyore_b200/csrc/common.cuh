@@ -34,19 +34,11 @@ template <> EB_HD double fma_t<double>(double a, double b, double c) { return fm
 // ---- fp64 fast paths ----------------------------------------------------------------------------------------------
 // The chain kernels are bound by the FP64 pipe, and most FP64 instructions of an evaluation are spent inside exp() and
 // the division of the sigmoid.  These versions keep ~1 ulp accuracy (parity tolerance is 1e-10) but
-//   * read polynomial coefficients from the constant bank (DFMA takes c[bank][ofs] operands directly; the CUDA math
-//     library materialises each 64-bit coefficient with two UMOVs per use, ~26% of all issued instructions),
+//   * use a 64-entry 2^(j/64) table in shared memory + a degree-5 polynomial (the CUDA math library evaluates a
+//     degree-11 polynomial and materialises each 64-bit coefficient with two UMOVs per use, ~26% of all issued
+//     instructions in the first version of the kernels),
 //   * have no slow-path branches (arguments are clamped instead),
-//   * refine MUFU.RCP64H with two Newton steps instead of the IEEE-exact division sequence.
-#define EB_EXP_COEFFS                                                                                              \
-  {0.50000000000000011, 0.16666666666666669, 0.04166666666662399, 0.0083333333333300511, 0.0013888888917281794,   \
-   0.00019841269863105968, 2.4801521190217729e-05, 2.7557268378684192e-06, 2.7620138719733994e-07,                \
-   2.5100424157005067e-08}
-#if defined(__CUDACC__)
-static __constant__ double kExpCDev[10] = EB_EXP_COEFFS;
-#endif
-static const double kExpCHost[10] = EB_EXP_COEFFS;
-
+//   * refine MUFU.RCP64H with one cubic step instead of the IEEE-exact division sequence.
 EB_HD int dbl_lo(double v) {
 #if defined(__CUDA_ARCH__)
   return __double2loint(v);
@@ -62,39 +54,59 @@ EB_HD double dbl_add_exponent(double v, int k) {
 #endif
 }
 
-// exp(a) for |a| <= 700 (callers clamp); degree-11 polynomial on [-ln2/2, ln2/2], < 1 ulp; NaN propagates.
-EB_HD double exp_core(double a) {
-#if defined(__CUDA_ARCH__)
-  const double* c = kExpCDev;
-#else
-  const double* c = kExpCHost;
+// Table of 2^(j/64).  Device: a per-CTA shared-memory copy filled by exp_table_init() in the kernel prologue (the lookup
+// index differs per lane, which the constant bank would serialise); host (tests/hostsim): the plain array.
+static const double kExp2TabHost[64] = {
+#include "exp_table.inc"
+};
+#if defined(__CUDACC__)
+static __constant__ double kExp2TabDev[64] = {
+#include "exp_table.inc"
+};
+EB_D double* exp_table_smem() {
+  __shared__ double tab[64];
+  return tab;
+}
+// every thread of the CTA calls this once before the first fp64 sigmoid / softmax; followed by a __syncthreads()
+EB_D void exp_table_init() {
+  double* t = exp_table_smem();
+  for (int j = threadIdx.x; j < 64; j += blockDim.x) t[j] = kExp2TabDev[j];
+}
 #endif
+
+// exp(a) for |a| <= 700 (callers clamp): a = (64 k + j) ln2/64 + r, |r| <= ln2/128; exp(a) = 2^k * 2^(j/64) * P5(r).
+// 10 FP64-pipe instructions (the degree-11 single-polynomial version needed 15); ~1.5 ulp; NaN propagates.
+EB_HD double exp_core(double a) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
-  const double t = fma(a, 1.4426950408889634, magic);
-  const double kf = t - magic;
-  const int k = dbl_lo(t);
-  double r = fma(kf, -6.93147180369123816490e-01, a);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  double p = c[9];
-#pragma unroll
-  for (int i = 8; i >= 0; --i) p = fma(p, r, c[i]);
+  const double t = fma(a, 92.332482616893657, magic);            // 64 / ln 2
+  const double nf = t - magic;
+  const int n = dbl_lo(t);
+  double r = fma(nf, -1.08304246932675596e-02, a);                 // ln2_hi / 64 (32 significant bits: nf * hi is exact)
+  r = fma(nf, -2.98158582698529328e-12, r);                        // ln2_lo / 64
+#if defined(__CUDA_ARCH__)
+  const double tj = exp_table_smem()[n & 63];
+#else
+  const double tj = kExp2TabHost[n & 63];
+#endif
+  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return dbl_add_exponent(p, k);
+  return dbl_add_exponent(tj * p, n >> 6);
 }
 
 // exp(a) for a <= 0 (softmax numerators): anything below e^-700 is far under one ulp of the sum it is added to.
 EB_HD double exp_nonpos(double a) { return exp_core(a < -700.0 ? -700.0 : a); }
 
-// 1/d for finite d >= 1: MUFU.RCP64H seed + two Newton steps.
+// 1/d for finite d >= 1: MUFU.RCP64H seed + one cubic (Halley-type) refinement, 3 DFMA.
 EB_HD double rcp_ge1(double d) {
 #if defined(__CUDA_ARCH__)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+  // one third-order step: r <- r (1 + e + e^2), e = 1 - d r; seed error < 2^-20 -> < 2^-60
+  const double e = fma(-d, r, 1.0);
+  r = fma(r, fma(e, e, e), r);
   return r;
 #else
   return 1.0 / d;
