@@ -76,6 +76,9 @@ template <typename T, class NET, int KIND> constexpr bool grad_in_smem() {
   return false;
 #endif
 }
+#ifndef EB_MINB_F64_SMALL
+#define EB_MINB_F64_SMALL 3
+#endif
 #ifndef EB_MINB_F64_LARGE
 #define EB_MINB_F64_LARGE 2
 #endif
@@ -83,7 +86,7 @@ template <typename T, class NET, int KIND> constexpr bool grad_in_smem() {
 template <typename T, class NET, int KIND> constexpr int min_blocks() {
   if (sizeof(T) == 4) return NET::P <= 32 ? 4 : 3;
   if (grad_in_smem<T, NET, KIND>()) return NET::P <= 20 ? 4 : 3;
-  return NET::P <= 20 ? 3 : (NET::P <= 32 ? EB_MINB_F64_LARGE : 2);
+  return NET::P <= 20 ? EB_MINB_F64_SMALL : (NET::P <= 32 ? EB_MINB_F64_LARGE : 2);
 }
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------------------------
@@ -233,7 +236,11 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
   constexpr int CPB = kBlock / G;
   constexpr int P = NET::P;
   constexpr bool GSM = grad_in_smem<T, NET, KIND>();
+#ifdef EB_THETA_IN_SMEM
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, true);
+#else
   const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, GSM);
+#endif
   const DataView<T> d = stage_data<T, NET>(smem, lay, a);
   const int sub = threadIdx.x % G;
   const int cl = threadIdx.x / G;
@@ -256,7 +263,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
   uint32_t n_acc = 0;
 
   for (long t = 0; t < a.n_iters; ++t) {
-    T z[P], thp[P];
+    T z[P];
+#ifdef EB_THETA_IN_SMEM
+    constexpr bool TSM = sizeof(T) == 8 && KIND == KIND_HMC;
+#else
+    constexpr bool TSM = false;
+#endif
+    typename std::conditional<TSM, StridedVec<T>, RegVec<T, P>>::type thp;
+    if constexpr (TSM) { thp.base = reinterpret_cast<T*>(smem + lay.off_grad) + threadIdx.x; thp.stride = kBlock; }
     typename std::conditional<GSM, StridedVec<T>, RegVec<T, P>>::type gp;
     if constexpr (GSM) { gp.base = reinterpret_cast<T*>(smem + lay.off_grad) + threadIdx.x; gp.stride = kBlock; }
     T u, ltp;
@@ -319,7 +333,11 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
 // ---- launchers ----------------------------------------------------------------------------------------------------
 template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
   constexpr int CPB = kBlock / G;
+#ifdef EB_THETA_IN_SMEM
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, true);
+#else
   const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, grad_in_smem<T, NET, KIND>());
+#endif
   auto kern = sampler_kernel<T, NET, G, KIND>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return e;

@@ -46,8 +46,12 @@ template <> struct Uni<float> {
   static EB_HD float from(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f; }  // 2^-24
 };
 
+// log of a uniform in (0, 1): a positive normal number in both precisions
+template <typename T> EB_HD T log_unit_t(T u) { return log_t<T>(u); }
+template <> EB_HD double log_unit_t<double>(double u) { return log_pos_normal(u); }
+
 template <typename T> EB_HD void box_muller(T u1, T u2, T* z0, T* z1) {
-  T r = sqrt_t<T>(T(-2) * log_t<T>(u1));
+  T r = sqrt_t<T>(T(-2) * log_unit_t<T>(u1));
   T s, c;
   sincos2pi<T>(u2, &s, &c);
   *z0 = r * c; *z1 = r * s;

@@ -36,9 +36,9 @@ template <typename T> struct StridedVec {
 };
 
 // metropolis_hastings.py:41-73.  z: standard normals; prop_scale: kernel scale (default 1, :25-28).
-template <typename T, class NET, int G>
+template <typename T, class NET, int G, class TV>
 EB_HD bool mh_draw(const DataView<T>& d, int sub, T prop_scale, bool symmetric, const Cur<T>& cur, T lt_cur,
-                   const T (&z)[NET::P], T u, T (&thp)[NET::P], T& ltp) {
+                   const T (&z)[NET::P], T u, TV& thp, T& ltp) {
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(prop_scale, z[j], cur.th[j * cur.stride]);  // kernel.sample()
   int dummy = 0;
@@ -62,9 +62,9 @@ EB_HD bool mh_draw(const DataView<T>& d, int sub, T prop_scale, bool symmetric, 
 }
 
 // mala.py:46-82.  sd = dtype(sqrt(step)) (mala.py:40); half_step = 0.5 * step (mala.py:36).
-template <typename T, class NET, int G, class GV>
+template <typename T, class NET, int G, class GV, class TV>
 EB_HD bool mala_draw(const DataView<T>& d, int sub, T half_step, T sd, const Cur<T>& cur, T lt_cur,
-                     const T (&z)[NET::P], T u, T (&thp)[NET::P], GV& gp, T& ltp) {
+                     const T (&z)[NET::P], T u, TV& thp, GV& gp, T& ltp) {
   const T inv2var = T(1) / (T(2) * (sd * sd));
   const T lnorm = log_t<T>(sd) + T(kLogSqrt2Pi);
   T lq_f = T(0);
@@ -100,9 +100,9 @@ template <int G> EB_HD void group_sync() {
 #endif
 }
 
-template <typename T, class NET, int G, class GV>
+template <typename T, class NET, int G, class GV, class TV>
 EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_steps, const Cur<T>& cur, T lt_cur,
-                    const T (&z)[NET::P], T* p, int ps, T u, T (&thp)[NET::P], GV& gp, T& ltp) {
+                    const T (&z)[NET::P], T* p, int ps, T u, TV& thp, GV& gp, T& ltp) {
   T kin = T(0);
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) kin = fma_t<T>(z[j], z[j], kin);
