@@ -75,41 +75,66 @@ def synthetic_data(w):
 # clocks sampling (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason poller for the timed region (rank 0 only), through NVML in-process (the data source of
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`).  Spawning nvidia-smi itself next to a
+    launch-heavy timed region is avoided on purpose: its start-up / teardown (NVML init and shutdown) was measured to
+    stall kernel submission for hundreds of milliseconds on these boxes.  NVML is initialised once, before the warm-up;
+    only samples taken between mark_begin() and mark_end() are summarised."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index, enabled=True):
-        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
+        self.index, self.rows, self.enabled, self.h = index, [], enabled, None
+        self.t0, self.t1, self._stop = 0.0, float("inf"), False
 
-    def __enter__(self):
-        if not self.enabled:      # only rank 0 polls: concurrent nvidia-smi queries perturb launch-heavy timed regions
+    def start(self):
+        if not self.enabled:
             return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.h = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        while not self._stop:
+            try:
+                sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                why = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), sm, why))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
-    def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-            self.t.join(timeout=2)
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self._stop = True
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        rows = [r for r in self.rows if self.t0 <= r[0] <= self.t1]
+        if not rows:
+            rows = self.rows[-3:]
+        sm = [r[1] for r in rows]
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        reasons = sorted(n for n, b in self.REASONS.items() if mask & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "samples": len(sm), "source": "NVML (nvmlDeviceGetClockInfo / CurrentClocksThrottleReasons), 50 ms period"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -274,17 +299,20 @@ def run_ours(args):
         sampler.counter.reset()
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
 
+    clocks = ClockSampler(local, enabled=(rank == 0)).start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local, enabled=(rank == 0)) as clocks:
-        barrier()
-        ev[0].record()
-        for k in range(args.steps):
-            step_resident()
-            ev[k + 1].record()
-        barrier()
+    barrier()
+    clocks.mark_begin()
+    ev[0].record()
+    for k in range(args.steps):
+        step_resident()
+        ev[k + 1].record()
+    barrier()
+    clocks.mark_end()
+    clocks.stop()
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
     evals_step = C * iters * (1 if kind == "smmala" else L)
@@ -429,17 +457,20 @@ def run_datapar(args):
         return t.item()
 
     sampler = DataShardedHMC(model, theta_host.to(dev), x, y, step=w["step"], num_steps=L, seed=7)
+    clocks = ClockSampler(local, enabled=(rank == 0)).start()
     for _ in range(args.warmup):
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local, enabled=(rank == 0)) as clocks:
-        barrier()
-        ev[0].record()
-        for k in range(args.steps):
-            sampler.run(num_epochs=iters, num_burnin_epochs=0)
-            ev[k + 1].record()
-        barrier()
+    barrier()
+    clocks.mark_begin()
+    ev[0].record()
+    for k in range(args.steps):
+        sampler.run(num_epochs=iters, num_burnin_epochs=0)
+        ev[k + 1].record()
+    barrier()
+    clocks.mark_end()
+    clocks.stop()
     t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
     evals_step = iters * L
     value = evals_step * args.steps / t_res

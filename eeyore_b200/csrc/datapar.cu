@@ -20,6 +20,13 @@
 #include "philox.cuh"
 #include "../../include/eeyore_b200.h"
 
+#ifndef DP_UNROLL_KMAJOR
+#define DP_UNROLL_KMAJOR 16
+#endif
+#ifndef DP_UNROLL_KMINOR
+#define DP_UNROLL_KMINOR 8
+#endif
+
 namespace eb {
 
 constexpr int DP_D0 = 16, DP_H = 64;
@@ -81,7 +88,8 @@ __device__ __forceinline__ float dp_sigmoid(float z) { return __frcp_rn(1.0f + _
 template <int TM, int TN, int K>
 __device__ __forceinline__ void gemm_kmajor(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb,
                                             int row0, int col0, float (&acc)[TM][TN]) {
-#pragma unroll 4
+  constexpr int kUnroll = DP_UNROLL_KMAJOR;
+#pragma unroll kUnroll
   for (int k = 0; k < K; ++k) {
     float a[TM], b[TN];
 #pragma unroll
@@ -99,7 +107,8 @@ __device__ __forceinline__ void gemm_kmajor(const float* __restrict__ At, int ld
 template <int TM, int TN, int VS>
 __device__ __forceinline__ void gemm_kminor(const float* __restrict__ U, const float* __restrict__ V, int u0, int v0,
                                             float (&acc)[TM][TN]) {
-#pragma unroll 2
+  constexpr int kUnroll = DP_UNROLL_KMINOR;
+#pragma unroll kUnroll
   for (int r = 0; r < DP_R; r += 4) {
     float4 a[TM], b[TN];
 #pragma unroll
