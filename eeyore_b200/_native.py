@@ -47,6 +47,9 @@ class RunParams(C.Structure):
         ("out_target", C.c_void_p), ("out_grad", C.c_void_p), ("out_accepted", C.c_void_p),
         ("accept_count", C.c_void_p),
         ("lanes_per_chain", C.c_int32), ("reserved", C.c_int32),
+        ("tuner_l", C.c_double), ("tuner_d", C.c_double), ("tuner_m", C.c_double), ("tuner_logeub", C.c_double),
+        ("tuner_has_eub", C.c_int32), ("tuner_pad", C.c_int32), ("tuner_iter0", C.c_int64), ("tuner_burnin", C.c_int64),
+        ("tuner_state", C.c_void_p),
         ("stream", C.c_void_p),
     ]
 

@@ -121,10 +121,14 @@ static int run_common(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p, int 
   if (kind != KIND_MH && !p->grad) return fail(EEYORE_B200_EINVAL, "grad state required");
   if (p->rng_mode == EEYORE_B200_RNG_TAPE && (!p->z_tape || !p->u_tape))
     return fail(EEYORE_B200_EINVAL, "tape mode needs z_tape and u_tape");
-  if (kind == KIND_HMC && p->num_steps < 1) return fail(EEYORE_B200_EINVAL, "num_steps must be >= 1");
+  if (kind == KIND_HMC && !p->tuner_state && p->num_steps < 1) return fail(EEYORE_B200_EINVAL, "num_steps must be >= 1");
   if (!(p->step > 0)) return fail(EEYORE_B200_EINVAL, "step must be positive");
   if (p->n_iters == 0) return EEYORE_B200_OK;
   const int lanes = choose_lanes(p->n_chains, p->n_rows, p->lanes_per_chain);
+  if (kind == KIND_HMC && p->tuner_state != nullptr) {
+    if (!(p->tuner_l > 0)) return fail(EEYORE_B200_EINVAL, "tuner_l must be positive");
+    kind = KIND_HMC_TUNED;
+  }
   cudaError_t e = h->net->sampler(kind, *p, lanes, use_bulk());
   if (e != cudaSuccess) return cuda_fail(e, name);
   return EEYORE_B200_OK;

@@ -39,6 +39,9 @@ template <typename T> struct ChainArgs {
   T* out_grad;
   uint8_t* out_acc;
   uint32_t* acc_count;
+  DaTuner tuner;       // HMC only; tuner_state == nullptr disables
+  long tuner_iter0, tuner_burnin;
+  double* tuner_state;
   T* out_ll;   // eval kernel only
   T* out_lp;   // eval kernel only
   int use_bulk;
@@ -235,11 +238,12 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int CPB = kBlock / G;
   constexpr int P = NET::P;
+  constexpr bool IS_HMC = KIND == KIND_HMC || KIND == KIND_HMC_TUNED;
   constexpr bool GSM = grad_in_smem<T, NET, KIND>();
 #ifdef EB_THETA_IN_SMEM
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, true);
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, IS_HMC, true);
 #else
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, GSM);
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, IS_HMC, GSM);
 #endif
   const DataView<T> d = stage_data<T, NET>(smem, lay, a);
   const int sub = threadIdx.x % G;
@@ -256,16 +260,28 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
   T* mom = reinterpret_cast<T*>(smem + lay.off_mom) + cl;
   T lt_cur = a.target[chain];
 
-  const T step = a.step;
-  const T half_step = T(0.5) * step;
+  T step = a.step;
+  T half_step = T(0.5) * step;
   const T sd = sqrt_t<T>(step);  // numpy sqrt(step) cast to dtype, mala.py:40 (correctly rounded in both)
   const uint32_t gchain = a.chain0 + (uint32_t)chain;
   uint32_t n_acc = 0;
+  // per-chain dual-averaging tuner (HMC): every lane of the chain group carries the same state
+  constexpr bool tuned = KIND == KIND_HMC_TUNED;
+  double tn_barh = 0.0, tn_logbare = 0.0, tn_step = 0.0;
+  int num_steps = a.num_steps;
+  if (tuned) {
+    tn_barh = a.tuner_state[chain];
+    tn_logbare = a.tuner_state[a.n_chains + chain];
+    tn_step = a.tuner_state[2 * a.n_chains + chain];
+    num_steps = live ? (int)a.tuner_state[3 * a.n_chains + chain] : 1;   // padding groups do the minimum of work
+    step = (T)tn_step;
+    half_step = (T)(0.5 * tn_step);
+  }
 
   for (long t = 0; t < a.n_iters; ++t) {
     T z[P];
 #ifdef EB_THETA_IN_SMEM
-    constexpr bool TSM = sizeof(T) == 8 && KIND == KIND_HMC;
+    constexpr bool TSM = sizeof(T) == 8 && IS_HMC;
 #else
     constexpr bool TSM = false;
 #endif
@@ -289,7 +305,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
     } else if constexpr (KIND == KIND_MALA) {
       acc = mala_draw<T, NET, G>(d, sub, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
     } else {
-      acc = hmc_draw<T, NET, G>(d, sub, step, half_step, a.num_steps, cur, lt_cur, z, mom, CPB, u, thp, gp, ltp);
+      T rate;
+      acc = hmc_draw<T, NET, G>(d, sub, step, half_step, num_steps, cur, lt_cur, z, mom, CPB, u, thp, gp, ltp, &rate);
+      if (tuned && live && t < a.tuner_burnin) {                                          // hmc.py:158-163
+        da_tune(a.tuner, (double)rate, a.tuner_iter0 + t + 1, t != a.tuner_burnin - 1, tn_barh, tn_logbare, tn_step,
+                num_steps);
+        step = (T)tn_step;
+        half_step = (T)(0.5 * tn_step);
+      }
     }
     if (acc) {  // uniform within the chain group: every lane holds identical values
       lt_cur = ltp;
@@ -327,6 +350,12 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
   if (live && sub == 0) {
     a.target[chain] = lt_cur;
     if (a.acc_count) a.acc_count[chain] += n_acc;
+    if (tuned) {
+      a.tuner_state[chain] = tn_barh;
+      a.tuner_state[a.n_chains + chain] = tn_logbare;
+      a.tuner_state[2 * a.n_chains + chain] = tn_step;
+      a.tuner_state[3 * a.n_chains + chain] = (double)num_steps;
+    }
   }
 }
 
@@ -334,9 +363,9 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
 template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
   constexpr int CPB = kBlock / G;
 #ifdef EB_THETA_IN_SMEM
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, true);
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC || KIND == KIND_HMC_TUNED, true);
 #else
-  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC, grad_in_smem<T, NET, KIND>());
+  const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC || KIND == KIND_HMC_TUNED, grad_in_smem<T, NET, KIND>());
 #endif
   auto kern = sampler_kernel<T, NET, G, KIND>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
@@ -372,6 +401,7 @@ template <typename T, class NET> cudaError_t launch_sampler(int kind, int lanes,
     case KIND_MH: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_MH>(a, st)))
     case KIND_MALA: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_MALA>(a, st)))
     case KIND_HMC: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_HMC>(a, st)))
+    case KIND_HMC_TUNED: EB_DISPATCH_G(lanes, return (launch_sampler_g<T, NET, G, KIND_HMC_TUNED>(a, st)))
   }
   return cudaErrorInvalidValue;
 }

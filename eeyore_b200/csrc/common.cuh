@@ -251,9 +251,16 @@ template <> EB_HD void sincos2pi<double>(double u, double* s, double* c) {
 #if defined(__CUDACC__)
 // xor-butterfly all-reduce over the G lanes of a chain group (G a power of two <= 32).
 // fp add is commutative, so every lane ends with the bitwise-identical sum.
+// Lane mask of the G-lane chain group the calling lane belongs to.  Groups of one warp may diverge from each other
+// (per-chain leapfrog counts under the dual-averaging tuner), so every intra-group primitive names only its own lanes.
+template <int G> EB_D unsigned group_mask() {
+  if (G >= 32) return 0xffffffffu;
+  return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+}
 template <int G, typename T> EB_D T group_allreduce(T v) {
+  const unsigned mask = group_mask<G>();
 #pragma unroll
-  for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(mask, v, m);
   return v;
 }
 #endif

@@ -6,7 +6,7 @@
 
 namespace eb {
 
-enum { KIND_MH = 0, KIND_MALA = 1, KIND_HMC = 2 };
+enum { KIND_MH = 0, KIND_MALA = 1, KIND_HMC = 2, KIND_HMC_TUNED = 3 };  // TUNED: HMC + per-chain dual averaging
 
 struct EvalCall {
   int64_t n_chains;

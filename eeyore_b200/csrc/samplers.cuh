@@ -96,13 +96,13 @@ EB_HD bool mala_draw(const DataView<T>& d, int sub, T half_step, T sd, const Cur
 // with the same data, hmc.py:104, so the value is identical); num_steps further evaluations follow.
 template <int G> EB_HD void group_sync() {
 #if defined(__CUDA_ARCH__)
-  if (G > 1) __syncwarp();
+  if (G > 1) __syncwarp(group_mask<G>());
 #endif
 }
 
 template <typename T, class NET, int G, class GV, class TV>
 EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_steps, const Cur<T>& cur, T lt_cur,
-                    const T (&z)[NET::P], T* p, int ps, T u, TV& thp, GV& gp, T& ltp) {
+                    const T (&z)[NET::P], T* p, int ps, T u, TV& thp, GV& gp, T& ltp, T* rate_out = nullptr) {
   T kin = T(0);
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) kin = fma_t<T>(z[j], z[j], kin);
@@ -132,7 +132,29 @@ EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_st
   const T h_prop = -ltp + T(0.5) * kin1;                                                  // :141
   T rate = exp_t<T>(h_cur - h_prop);
   rate = (rate > T(1)) ? T(1) : rate;                                                     // torch.min keeps NaN, :143-146
+  if (rate_out) *rate_out = rate;
   return u < rate;                                                                        // :148 (linear space)
+}
+
+// HMCDATuner.tune (eeyore/tuners/hmcda_tuner.py:44-59) for one chain, in fp64 like the reference's python floats.
+// g = 0.05, t0 = 10, k = 0.75 (:26-30).  `it` = counter.idx + 1.  A NaN rate (diverged trajectory) counts as 0 -- the
+// reference would poison its tuner state with NaN for the rest of the run.
+struct DaTuner {
+  double l, d, m, logeub;
+  int has_eub;
+};
+EB_HD void da_tune(const DaTuner& tn, double rate, long it, bool return_e, double& barh, double& logbare, double& step,
+                   int& num_steps) {
+  if (!(rate == rate)) rate = 0.0;
+  const double d_w = 1.0 / ((double)it + 10.0);
+  const double e_w = 1.0 / pow((double)it, 0.75);
+  barh = (1.0 - d_w) * barh + d_w * (tn.d - rate);
+  double loge = tn.m - sqrt((double)it) * barh / 0.05;
+  if (tn.has_eub) loge = loge < tn.logeub ? loge : tn.logeub;
+  logbare = e_w * loge + (1.0 - e_w) * logbare;
+  step = exp(return_e ? loge : logbare);
+  const double q = rint(tn.l / step);                                                     // round half to even, :41-42
+  num_steps = q >= 1.0 ? (q < 100000.0 ? (int)q : 100000) : 1;
 }
 
 }  // namespace eb

@@ -1,0 +1,2 @@
+from .hmcda_tuner import HMCDATuner
+from .tuner import Tuner

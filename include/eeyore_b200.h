@@ -108,6 +108,18 @@ typedef struct eeyore_b200_run_params {
   uint32_t *accept_count;  /* [C], incremented by the number of accepted proposals over all n_iters; may be NULL */
   int32_t lanes_per_chain; /* threads cooperating on one chain (1,2,4,...,32); 0 = auto */
   int32_t reserved;
+  /* HMC dual-averaging step-size tuner: HMCDATuner.tune hooked into HMC.draw during burn-in
+   * (eeyore/tuners/hmcda_tuner.py:8-59, eeyore/samplers/hmc.py:158-163).  tuner_state == NULL disables it.
+   * One independent tuner per chain; python-float (fp64) arithmetic as in the reference. */
+  double tuner_l;          /* target trajectory length: num_steps = max(1, round(l / step)) */
+  double tuner_d;          /* target acceptance rate (0.65) */
+  double tuner_m;          /* log(10 * e0), HMCDATuner.set_m */
+  double tuner_logeub;     /* log of the step upper bound (used when tuner_has_eub) */
+  int32_t tuner_has_eub;
+  int32_t tuner_pad;
+  int64_t tuner_iter0;     /* counter.idx at the first iteration of this call */
+  int64_t tuner_burnin;    /* leading iterations of this call that still tune (num_burnin_iters - counter.idx, >= 0) */
+  double *tuner_state;     /* in/out [4, C]: barh, logbare, step, num_steps */
   void *stream;
 } eeyore_b200_run_params;
 

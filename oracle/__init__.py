@@ -22,6 +22,6 @@ Every function cites the reference file:line it follows (paths relative to
 """
 
 from .mlp import MLPSpec, log_lik, log_prior, log_target, log_target_grad, forward  # noqa: F401
-from .samplers import mh_run, mala_run, hmc_run, smmala_run, fisher_metric  # noqa: F401
+from .samplers import mh_run, mala_run, hmc_run, smmala_run, fisher_metric, DATuner  # noqa: F401
 from .stats import cov, inse_mc_cov, multi_ess, acf, is_pos_def  # noqa: F401
 from .philox import philox4x32_10, chain_uniforms, chain_normals  # noqa: F401

@@ -30,6 +30,7 @@ from eeyore.constants import loss_functions  # noqa: E402
 from eeyore.datasets import XYDataset  # noqa: E402
 from eeyore.models.mlp import MLP, Hyperparameters  # noqa: E402
 from eeyore.samplers import HMC, MALA, MetropolisHastings  # noqa: E402
+from eeyore.tuners import HMCDATuner  # noqa: E402
 import eeyore.stats as st  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
@@ -153,7 +154,9 @@ def run_sampler(name, kind, arch, dtype, n_iters, n_burnin, prior_scale, seed, *
         if kind == "mala":
             s = MALA(model, theta0=theta0, dataloader=loader, step=kw["step"], chain=chain)
         elif kind == "hmc":
-            s = HMC(model, theta0=theta0, dataloader=loader, step=kw["step"], num_steps=kw["num_steps"], chain=chain)
+            tuner = HMCDATuner(l=kw["tuner_l"], e0=kw["step"], eub=kw.get("tuner_eub")) if "tuner_l" in kw else None
+            s = HMC(model, theta0=theta0, dataloader=loader, step=kw["step"], num_steps=kw.get("num_steps", 1), tuner=tuner,
+                    chain=chain)
         else:
             s = MetropolisHastings(model, theta0=theta0, dataloader=loader, symmetric=kw.get("symmetric", True),
                                    chain=chain)
@@ -173,6 +176,8 @@ def run_sampler(name, kind, arch, dtype, n_iters, n_burnin, prior_scale, seed, *
         out[k] = v
     if kw.get("ess"):
         out["multi_ess"] = chain.multi_ess()
+    if "tuner_l" in kw:
+        out["final_step"], out["final_num_steps"] = s.step, s.num_steps
     np.savez_compressed(OUT / f"{name}.npz", **out)
     print(name, "acceptance", out["accepted"].mean())
 
@@ -231,6 +236,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dp":
         datapar_goldens()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tuner":
+        s3 = math.sqrt(3.0)
+        run_sampler("hmcda_xor2321_f64", "hmc", "2321", torch.float64, 90, 50, s3, 7, step=0.05, tuner_l=0.6)
+        run_sampler("hmcda_iris433_f64", "hmc", "433", torch.float64, 70, 40, s3, 8, step=0.01, tuner_l=0.15, tuner_eub=0.05)
+        sys.exit(0)
     model_goldens()
     datapar_goldens()
     s3 = math.sqrt(3.0)
@@ -243,6 +253,8 @@ if __name__ == "__main__":
     run_sampler("hmc_xor2321_f64_s09", "hmc", "2321", torch.float64, 160, 20, s3, 2, step=0.9, num_steps=10)
     run_sampler("hmc_iris433_f64", "hmc", "433", torch.float64, 60, 10, s3, 4, step=0.04, num_steps=10)
     run_sampler("hmc_iris433_f32", "hmc", "433", torch.float32, 40, 10, s3, 4, step=0.02, num_steps=10)
+    run_sampler("hmcda_xor2321_f64", "hmc", "2321", torch.float64, 90, 50, s3, 7, step=0.05, tuner_l=0.6)
+    run_sampler("hmcda_iris433_f64", "hmc", "433", torch.float64, 70, 40, s3, 8, step=0.01, tuner_l=0.15, tuner_eub=0.05)
     run_sampler("mh_xor221_f64", "mh", "221", torch.float64, 400, 50, s3, 5)
     run_sampler("mh_xor2321_f64_nonsym", "mh", "2321", torch.float64, 300, 0, s3, 6, symmetric=False,
                 prop_scale=0.4)

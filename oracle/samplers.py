@@ -114,13 +114,46 @@ def leapfrog(spec: MLPSpec, x, y, loc, scale, theta, p0, step, num_steps, temper
     return pos, -mom, lt, g
 
 
+class DATuner:
+    """Dual-averaging step-size tuner, one independent state per chain; restatement of
+    eeyore/tuners/hmcda_tuner.py:8-59 (python float64 arithmetic) for a given initial step e0."""
+
+    def __init__(self, l, e0, n_chains, d=0.65, eub=None):
+        self.l, self.d = float(l), float(d)
+        self.m = math.log(10 * e0)                                   # set_m, :32-33
+        self.logeub = None if eub is None else math.log(eub)
+        self.barh = np.zeros(n_chains)
+        self.logbare = np.zeros(n_chains)
+        self.g, self.t0, self.k = 0.05, 10, 0.75
+        self.step = np.full(n_chains, float(e0))
+        self.num_steps = self.steps_for(self.step)
+
+    def steps_for(self, e):
+        return np.maximum(1, np.rint(self.l / e)).astype(np.int64)   # max(1, round(l / e)), :41-42 (round half to even)
+
+    def tune(self, rate, idx, return_e=True):                        # :44-59
+        it = idx + 1
+        d_w = 1 / (it + self.t0)
+        e_w = 1 / (it ** self.k)
+        self.barh = (1 - d_w) * self.barh + d_w * (self.d - rate)
+        loge = self.m - math.sqrt(it) * self.barh / self.g
+        if self.logeub is not None:
+            loge = np.minimum(loge, self.logeub)
+        self.logbare = e_w * loge + (1 - e_w) * self.logbare
+        self.step = np.exp(loge) if return_e else np.exp(self.logbare)
+        self.num_steps = self.steps_for(self.step)
+
+
 def hmc_run(spec: MLPSpec, x, y, loc, scale, theta0, z, u, step, num_steps, n_burnin=0,
-            temperature=None, thin=1):
-    """hmc.py:126-170.  z[t] is the momentum draw p0 of iteration t."""
+            temperature=None, thin=1, tuner=None):
+    """hmc.py:126-170.  z[t] is the momentum draw p0 of iteration t.  With a DATuner the step size and the number of
+    leapfrog steps of every chain are adapted during burn-in (hmc.py:158-163)."""
     theta = np.array(np.atleast_2d(theta0), copy=True)
     dt = theta.dtype
     lt, g = log_target_grad(spec, theta, x, y, loc, scale, temperature)
     store = {}
+    if tuner is not None:
+        return _hmc_run_tuned(spec, x, y, loc, scale, theta, lt, g, z, u, n_burnin, temperature, thin, tuner)
     for t in range(z.shape[0]):
         p0 = z[t].astype(dt)
         h_cur = -lt + dt.type(0.5) * (p0 ** 2).sum(axis=1)                       # :137, :91-98
@@ -136,6 +169,35 @@ def hmc_run(spec: MLPSpec, x, y, loc, scale, theta0, z, u, step, num_steps, n_bu
         _collect(store, t, n_burnin, thin, sample=theta, target_val=lt, grad_val=g,
                  accepted=acc.astype(np.uint8))
     return _finish(store, dict(sample=theta, target_val=lt, grad_val=g))
+
+
+def _hmc_run_tuned(spec, x, y, loc, scale, theta, lt, g, z, u, n_burnin, temperature, thin, tuner):
+    """Per-chain step sizes: chains are advanced one by one (the leapfrog length differs between chains)."""
+    dt = theta.dtype
+    C = theta.shape[0]
+    store = {}
+    for t in range(z.shape[0]):
+        acc = np.zeros(C, dtype=bool)
+        rate = np.zeros(C)
+        for c in range(C):
+            p0 = z[t, c:c + 1].astype(dt)
+            h_cur = -lt[c:c + 1] + dt.type(0.5) * (p0 ** 2).sum(axis=1)
+            prop, p1, lt_p, g_p = leapfrog(spec, x, y, loc, scale, theta[c:c + 1], p0, float(tuner.step[c]),
+                                           int(tuner.num_steps[c]), temperature)
+            with np.errstate(invalid="ignore", over="ignore"):
+                h_prop = -lt_p + dt.type(0.5) * (p1 ** 2).sum(axis=1)
+                r = np.exp(h_cur - h_prop)
+                r = np.where(np.isnan(r), r, np.minimum(r, dt.type(1)))
+                a = u[t, c].astype(dt) < r[0]
+            rate[c] = r[0]
+            if a:
+                theta[c], g[c], lt[c] = prop[0], g_p[0], lt_p[0]
+            acc[c] = a
+        if t < n_burnin:                                                          # hmc.py:158-163
+            tuner.tune(rate, t, return_e=(t != n_burnin - 1))
+        _collect(store, t, n_burnin, thin, sample=theta, target_val=lt, grad_val=g, accepted=acc.astype(np.uint8))
+    return _finish(store, dict(sample=theta, target_val=lt, grad_val=g, step=tuner.step.copy(),
+                               num_steps=tuner.num_steps.copy()))
 
 
 # --------------------------------------------------------------------------------------

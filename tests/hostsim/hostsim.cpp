@@ -63,6 +63,16 @@ template <typename T, class NET> static void run_all(int kind, const eeyore_b200
     T lt_cur = target[c];
     uint32_t nacc = 0;
     const uint32_t gchain = (uint32_t)p.chain_offset + (uint32_t)c;
+    const bool tuned = kind == 2 && p.tuner_state != nullptr;
+    DaTuner tn{p.tuner_l, p.tuner_d, p.tuner_m, p.tuner_logeub, p.tuner_has_eub};
+    double tn_barh = 0, tn_logbare = 0, tn_step = 0;
+    int num_steps = p.num_steps;
+    T cstep = step, chalf = half_step;
+    if (tuned) {
+      tn_barh = p.tuner_state[c]; tn_logbare = p.tuner_state[p.n_chains + c]; tn_step = p.tuner_state[2 * p.n_chains + c];
+      num_steps = (int)p.tuner_state[3 * p.n_chains + c];
+      cstep = (T)tn_step; chalf = (T)(0.5 * tn_step);
+    }
     for (int64_t t = 0; t < p.n_iters; ++t) {
       T z[P], thp[P], gp[P], u, ltp;
       if (p.rng_mode == EEYORE_B200_RNG_PHILOX) {
@@ -76,7 +86,14 @@ template <typename T, class NET> static void run_all(int kind, const eeyore_b200
       bool acc;
       if (kind == 0) acc = mh_draw<T, NET, 1>(d, 0, step, p.symmetric != 0, cur, lt_cur, z, u, thp, ltp);
       else if (kind == 1) acc = mala_draw<T, NET, 1>(d, 0, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
-      else acc = hmc_draw<T, NET, 1>(d, 0, step, half_step, p.num_steps, cur, lt_cur, z, mom, 1, u, thp, gp, ltp);
+      else {
+        T rate;
+        acc = hmc_draw<T, NET, 1>(d, 0, cstep, chalf, num_steps, cur, lt_cur, z, mom, 1, u, thp, gp, ltp, &rate);
+        if (tuned && t < p.tuner_burnin) {
+          da_tune(tn, (double)rate, p.tuner_iter0 + t + 1, t != p.tuner_burnin - 1, tn_barh, tn_logbare, tn_step, num_steps);
+          cstep = (T)tn_step; chalf = (T)(0.5 * tn_step);
+        }
+      }
       if (acc) { lt_cur = ltp; ++nacc; for (int j = 0; j < P; ++j) { cur.th[j * sp] = thp[j]; if (kind != 0) cur.g[j * sp] = gp[j]; } }
       if (t >= p.n_burnin && (t - p.n_burnin) % thin == 0) {
         const int64_t s = (t - p.n_burnin) / thin;
@@ -88,6 +105,10 @@ template <typename T, class NET> static void run_all(int kind, const eeyore_b200
     }
     target[c] = lt_cur;
     if (p.accept_count) p.accept_count[c] += nacc;
+    if (tuned) {
+      p.tuner_state[c] = tn_barh; p.tuner_state[p.n_chains + c] = tn_logbare; p.tuner_state[2 * p.n_chains + c] = tn_step;
+      p.tuner_state[3 * p.n_chains + c] = (double)num_steps;
+    }
   }
 }
 

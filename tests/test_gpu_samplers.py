@@ -230,3 +230,55 @@ def test_full_size_hmc_config4_properties():
     ref = oracle.hmc_run(spec_of("2321"), x, y, np.zeros(20), np.full(20, 3 ** 0.5), npy(theta0[idx]), z, u, step, L)
     assert np.array_equal(npy(got.accepted_soa[:, idx]), ref["accepted"])
     assert rel_err(npy(got.get_samples()[idx].permute(1, 0, 2)), ref["sample"]) < 1e-9
+
+
+@pytest.mark.parametrize("name,arch,l,e0,eub", [("hmcda_xor2321_f64", "2321", 0.6, 0.05, None),
+                                                 ("hmcda_iris433_f64", "433", 0.15, 0.01, 0.05)])
+def test_hmc_with_hmcda_tuner_reference_trajectories(name, arch, l, e0, eub):
+    """HMC + HMCDATuner (hmc.py:17-28,158-163; tuners/hmcda_tuner.py:8-59), adaptation on device."""
+    from eeyore_b200.tuners import HMCDATuner
+    gd = load(name)
+    m = make_model(arch, "f64", float(gd["prior_scale"]))
+    ds = dataset(arch, "f64")
+    s = HMC(m, theta0=torch.from_numpy(gd["theta0"]), dataloader=loader(ds), tuner=HMCDATuner(l=l, e0=e0, eub=eub),
+            chain=ChainList(keys=["sample", "target_val", "accepted", "grad_val"]))
+    assert s.step == e0 and s.num_steps == max(1, round(l / e0))
+    s.set_noise_tape(torch.from_numpy(gd["z"]), torch.from_numpy(gd["u"]))
+    s.run(num_epochs=int(gd["n_iters"]), num_burnin_epochs=int(gd["n_burnin"]))
+    ch = s.get_chain()
+    assert np.array_equal(np.array(ch.vals["accepted"], dtype=np.uint8), gd["accepted"])
+    assert rel_err(npy(ch.get_samples()), gd["samples"]) < 1e-9
+    assert abs(s.step - float(gd["final_step"])) < 1e-11 * float(gd["final_step"])
+    assert s.num_steps == int(gd["final_num_steps"])
+
+
+def test_hmcda_tuner_many_chains_vs_oracle_and_split_runs():
+    from eeyore_b200.tuners import HMCDATuner
+    arch, P, C, T, nb, l, e0 = "2321", 20, 21, 40, 25, 0.5, 0.08
+    rng = np.random.default_rng(4)
+    theta0 = rng.normal(size=(C, P))
+    z, u = rng.normal(size=(T, C, P)), rng.uniform(size=(T, C))
+    s3 = 3 ** 0.5
+    x, y = data_of(arch, np.float64)
+    ref = oracle.hmc_run(spec_of(arch), x, y, np.zeros(P), np.full(P, s3), theta0, z, u, e0, 1, n_burnin=nb,
+                         tuner=oracle.DATuner(l=l, e0=e0, n_chains=C))
+    m = make_model(arch, "f64", s3)
+    ds = dataset(arch, "f64")
+    for lanes in (1, 4):
+        s = HMC(m, theta0=torch.from_numpy(theta0), dataloader=loader(ds), tuner=HMCDATuner(l=l, e0=e0), lanes_per_chain=lanes)
+        s.set_noise_tape(torch.from_numpy(z), torch.from_numpy(u))
+        s.run(num_epochs=T, num_burnin_epochs=nb)
+        got = s.get_chain()
+        assert np.array_equal(npy(got.accepted_soa), ref["accepted"])
+        assert rel_err(npy(got.get_samples().permute(1, 0, 2)), ref["sample"]) < 1e-8
+        assert np.allclose(npy(s.step), ref["final"]["step"], rtol=1e-10)
+        assert np.array_equal(npy(s.num_steps), ref["final"]["num_steps"])
+    assert len(np.unique(ref["final"]["num_steps"])) > 1 or len(np.unique(np.round(ref["final"]["step"], 6))) > 1
+    # Philox mode: burn-in split over two run() calls == one call (tuner iteration index and burn-in window carry over)
+    a = HMC(m, theta0=torch.from_numpy(theta0), dataloader=loader(ds), tuner=HMCDATuner(l=l, e0=e0), seed=9)
+    a.run(num_epochs=T, num_burnin_epochs=nb)
+    b = HMC(m, theta0=torch.from_numpy(theta0), dataloader=loader(ds), tuner=HMCDATuner(l=l, e0=e0), seed=9)
+    b.run(num_epochs=10, num_burnin_epochs=nb)      # 10 tuning iterations ...
+    b.run(num_epochs=T, num_burnin_epochs=nb)       # ... then the remaining 30 (15 still tuning)
+    assert torch.equal(a.get_chain().samples_soa, b.get_chain().samples_soa)
+    assert torch.equal(a.step, b.step)

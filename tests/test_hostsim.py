@@ -175,3 +175,31 @@ def test_device_philox_hmc_matches_oracle_with_same_stream(sim):
     ref = oracle.hmc_run(spec_of(arch), x, y, loc, scale, theta0, z, u, step, L)
     assert np.array_equal(out["acc"], ref["accepted"])
     assert rel_err(out["sample"], ref["sample"]) < 1e-9
+
+
+@pytest.mark.parametrize("name,arch,l,e0,eub", [("hmcda_xor2321_f64", "2321", 0.6, 0.05, None),
+                                                 ("hmcda_iris433_f64", "433", 0.15, 0.01, 0.05)])
+def test_device_hmc_dual_averaging_tuner_reproduces_reference(sim, name, arch, l, e0, eub):
+    """HMC + HMCDATuner of the reference (hmc.py:158-163, tuners/hmcda_tuner.py): the device recurrence reproduces the
+    adapted step sizes, trajectory lengths and therefore the accept decisions of the reference run."""
+    import math
+    gd = load(name)
+    dt = np.float64
+    x, y = data_of(arch, dt)
+    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    n = gd["theta0"].shape[0]
+    loc, scale = np.zeros(n, dt), np.full(n, float(gd["prior_scale"]), dt)
+    theta = gd["theta0"].astype(dt)[None].copy()
+    lt, g = sim_eval(sim, arch, "f64", theta, x, y, loc, scale)
+    z = np.ascontiguousarray(gd["z"].astype(dt)[:, None, :]); u = np.ascontiguousarray(gd["u"].astype(dt)[:, None])
+    nb = int(gd["n_burnin"])
+    p, out = run_params(dt, theta, lt, g, x, y, loc, scale, z, u, nb, e0, L=max(1, round(l / e0)))
+    state = np.array([[0.0], [0.0], [e0], [float(max(1, round(l / e0)))]])
+    p.tuner_l, p.tuner_d, p.tuner_m = l, 0.65, math.log(10 * e0)
+    p.tuner_has_eub, p.tuner_logeub = (0, 0.0) if eub is None else (1, math.log(eub))
+    p.tuner_iter0, p.tuner_burnin, p.tuner_state = 0, nb, state.ctypes.data
+    assert sim.hostsim_run(2, int(arch), F64, C.byref(p)) == 0
+    assert np.array_equal(out["acc"][:, 0], gd["accepted"])
+    assert rel_err(out["sample"][:, 0], gd["samples"]) < 1e-9
+    assert abs(state[2, 0] - float(gd["final_step"])) < 1e-11 * float(gd["final_step"])
+    assert int(state[3, 0]) == int(gd["final_num_steps"])

@@ -143,3 +143,12 @@ def test_inse_not_enough_samples():
     x = np.array([[0.0, 1.0], [1.0, 0.0], [0.5, 0.5]])
     with pytest.raises(RuntimeError, match="Not enough samples"):
         oracle.inse_mc_cov(x)
+
+
+@pytest.mark.parametrize("name,l,e0,eub", [("hmcda_xor2321_f64", 0.6, 0.05, None), ("hmcda_iris433_f64", 0.15, 0.01, 0.05)])
+def test_hmc_with_dual_averaging_tuner(name, l, e0, eub):
+    """HMC + HMCDATuner (eeyore/tuners/hmcda_tuner.py, hmc.py:158-163): step size and trajectory length adapt in burn-in."""
+    tuner = oracle.DATuner(l=l, e0=e0, n_chains=1, eub=eub)
+    out, gd = _check_run(name, oracle.hmc_run, step=e0, num_steps=1, tuner=tuner)
+    assert abs(out["final"]["step"][0] - float(gd["final_step"])) < 1e-12 * float(gd["final_step"])
+    assert int(out["final"]["num_steps"][0]) == int(gd["final_num_steps"])
