@@ -365,8 +365,12 @@ def run_ours(args):
     hbm_bytes = C * (2 * (2 * P + 1) * esz + n_saved * (P * esz + esz + 1) + 4)
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
+    traffic = None
+    tfile = ROOT / "profiles" / "r01_traffic_cfg4.json"
+    if args.workload == "cfg4" and not args.chains and not args.iters and tfile.exists():
+        traffic = json.loads(tfile.read_text())["dram_bytes_total"]   # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
     roofline = {"bound": "fp64_fma" if w["dtype"] == "f64" else "fp32_fma", "achieved": achieved, "peak": peak.value,
-                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
                 "peak_source": "measured live by eeyore_b200_fma_peak (dependent-free FMA chains, this device)",
                 "algorithmic_flops_per_eval": w["flops_per_eval"], "avg_launch_ms": avg_launch_s * 1e3,
                 "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / avg_launch_s / 1e9,
