@@ -62,6 +62,7 @@ SIGNATURES = {
     "eeyore_b200_mlp_create": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _I, _I, C.POINTER(_VP)]),
     "eeyore_b200_mlp_destroy": (_I, [_VP]),
     "eeyore_b200_mlp_num_params": (_I, [_VP]),
+    "eeyore_b200_mlp_is_specialised": (_I, [_VP]),
     "eeyore_b200_log_target_grad": (_I, [_VP, _I64, _VP, _VP, _VP, _I64, _VP, _VP, _I, _D, _VP, _VP, _VP, _VP, _I, _VP]),
     "eeyore_b200_forward": (_I, [_VP, _I64, _VP, _VP, _I64, _VP, _VP]),
     "eeyore_b200_num_saved": (_I64, [_I64, _I64, _I64]),

@@ -5,6 +5,7 @@
 #include <string>
 #include "registry.h"
 #include "philox.cuh"
+#include "generic.cuh"
 
 namespace eb {
 extern const NetEntry kNet_221_f32, kNet_221_f64, kNet_2321_f32, kNet_2321_f64, kNet_433_f32, kNet_433_f64,
@@ -37,11 +38,36 @@ static int choose_lanes(int64_t n_chains, int64_t n_rows, int requested) {
 }
 }  // namespace eb
 
+namespace eb {
+// runtime-shape fallback (generic.cu)
+cudaError_t generic_eval(const GenNet& net, int dtype, const EvalCall& c, void* out_fwd);
+cudaError_t generic_sampler(const GenNet& net, int dtype, int kind, const eeyore_b200_run_params& p);
+}  // namespace eb
+
 struct eeyore_b200_mlp {
-  const eb::NetEntry* net;
+  const eb::NetEntry* net;   // compile-time specialisation, or nullptr -> runtime-shape path
+  eb::GenNet gen;
+  int dtype, n_params;
 };
 
 using namespace eb;
+
+// forward pass of the runtime-shape path: the staging code reads a prior, so a unit prior is provided
+static cudaError_t generic_forward_(eeyore_b200_mlp_t h, EvalCall c, void* out) {
+  const size_t bytes = (size_t)h->gen.P * (h->dtype == EEYORE_B200_F64 ? 8 : 4);
+  void* ones = nullptr;
+  cudaError_t e = cudaMallocAsync(&ones, bytes, c.stream);
+  if (e != cudaSuccess) return e;
+  // any finite positive scale works: 0x3c.. patterns are avoided by filling with 1.0 through a tiny kernel-free trick:
+  // cudaMemsetAsync cannot write 1.0, so fill on the host side
+  std::string host(bytes, 0);
+  if (h->dtype == EEYORE_B200_F64) { double* p = (double*)host.data(); for (int j = 0; j < h->gen.P; ++j) p[j] = 1.0; }
+  else { float* p = (float*)host.data(); for (int j = 0; j < h->gen.P; ++j) p[j] = 1.0f; }
+  e = cudaMemcpyAsync(ones, host.data(), bytes, cudaMemcpyHostToDevice, c.stream);
+  if (e == cudaSuccess) { cudaStreamSynchronize(c.stream); c.ploc = ones; c.pscale = ones; c.y = c.x; e = generic_eval(h->gen, h->dtype, c, out); }
+  cudaFreeAsync(ones, c.stream);
+  return e;
+}
 
 extern "C" {
 
@@ -58,31 +84,39 @@ int eeyore_b200_mlp_create(int n_layers, const int* dims, const int* bias, const
   if (dtype != EEYORE_B200_F32 && dtype != EEYORE_B200_F64) return fail(EEYORE_B200_EINVAL, "dtype must be f32 or f64");
   if (loss_id != EEYORE_B200_LOSS_BINARY && loss_id != EEYORE_B200_LOSS_MULTICLASS)
     return fail(EEYORE_B200_EINVAL, "unknown loss id");
-  for (int l = 0; l < n_layers; ++l) {
-    if (!bias[l]) return fail(EEYORE_B200_EUNSUPPORTED, "layers without bias are not built into this library");
-    const int want = (l < n_layers - 1) ? EEYORE_B200_ACT_SIGMOID
-                                        : (loss_id == EEYORE_B200_LOSS_BINARY ? EEYORE_B200_ACT_SIGMOID : EEYORE_B200_ACT_NONE);
-    if (act_ids[l] != want)
-      return fail(EEYORE_B200_EUNSUPPORTED,
-                  "supported activations: sigmoid hidden units; sigmoid head (binary) or None head (multiclass)");
-  }
-  for (const NetEntry* e : kNets) {
-    if (e->n_layers != n_layers || e->loss != loss_id || e->dtype != dtype) continue;
-    bool same = true;
-    for (int l = 0; l <= n_layers; ++l) same = same && (e->dims[l] == dims[l]);
-    if (same) {
-      *out = new eeyore_b200_mlp{e};
-      return EEYORE_B200_OK;
+  if (n_layers > kGenMaxLayers) return fail(EEYORE_B200_EUNSUPPORTED, "at most 8 dense layers");
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims[l] < 1) return fail(EEYORE_B200_EINVAL, "layer widths must be positive");
+  for (int l = 0; l < n_layers; ++l)
+    if (act_ids[l] != EEYORE_B200_ACT_NONE && act_ids[l] != EEYORE_B200_ACT_SIGMOID)
+      return fail(EEYORE_B200_EUNSUPPORTED, "supported activations: torch.sigmoid and None");
+  // the binary loss is evaluated on probabilities (sigmoid head, one output); the multiclass loss on logits (None head)
+  if (loss_id == EEYORE_B200_LOSS_BINARY && (act_ids[n_layers - 1] != EEYORE_B200_ACT_SIGMOID || dims[n_layers] != 1))
+    return fail(EEYORE_B200_EUNSUPPORTED, "binary_classification needs a single sigmoid output unit");
+  if (loss_id == EEYORE_B200_LOSS_MULTICLASS && act_ids[n_layers - 1] != EEYORE_B200_ACT_NONE)
+    return fail(EEYORE_B200_EUNSUPPORTED, "multiclass_classification needs a None (logit) head");
+  bool standard = true;   // all biases on, sigmoid hidden units: eligible for a compile-time specialisation
+  for (int l = 0; l < n_layers; ++l) standard = standard && bias[l] && (l == n_layers - 1 || act_ids[l] == EEYORE_B200_ACT_SIGMOID);
+  auto* h = new eeyore_b200_mlp{};
+  h->net = nullptr; h->dtype = dtype;
+  h->gen = make_gen_net(n_layers, dims, bias, act_ids, loss_id);
+  h->n_params = h->gen.P;
+  if (standard && n_layers <= 3 && !getenv("EEYORE_B200_FORCE_GENERIC")) {
+    for (const NetEntry* e : kNets) {
+      if (e->n_layers != n_layers || e->loss != loss_id || e->dtype != dtype) continue;
+      bool same = true;
+      for (int l = 0; l <= n_layers; ++l) same = same && (e->dims[l] == dims[l]);
+      if (same) { h->net = e; break; }
     }
   }
-  std::string d;
-  for (int l = 0; l <= n_layers; ++l) d += (l ? "-" : "") + std::to_string(dims[l]);
-  return fail(EEYORE_B200_EUNSUPPORTED, "architecture " + d + " is not among the compiled specialisations "
-              "(add an EB_INSTANTIATE_NET line under eeyore_b200/csrc and rebuild)");
+  *out = h;
+  return EEYORE_B200_OK;
 }
 
 int eeyore_b200_mlp_destroy(eeyore_b200_mlp_t h) { delete h; return EEYORE_B200_OK; }
-int eeyore_b200_mlp_num_params(eeyore_b200_mlp_t h) { return h ? h->net->n_params : EEYORE_B200_EINVAL; }
+int eeyore_b200_mlp_num_params(eeyore_b200_mlp_t h) { return h ? h->n_params : EEYORE_B200_EINVAL; }
+/* 1 if the handle is served by a compile-time specialisation, 0 for the runtime-shape kernels */
+int eeyore_b200_mlp_is_specialised(eeyore_b200_mlp_t h) { return h && h->net ? 1 : 0; }
 
 int eeyore_b200_log_target_grad(eeyore_b200_mlp_t h, int64_t n_chains, const void* theta, const void* x, const void* y,
                                 int64_t n_rows, const void* prior_loc, const void* prior_scale, int has_temperature,
@@ -93,7 +127,8 @@ int eeyore_b200_log_target_grad(eeyore_b200_mlp_t h, int64_t n_chains, const voi
   EvalCall c{n_chains, theta, x, y, n_rows, prior_loc, prior_scale, has_temperature, temperature,
              out_target, out_grad, out_loglik, out_logprior,
              choose_lanes(n_chains, n_rows, lanes_per_chain), use_bulk(), (cudaStream_t)stream};
-  cudaError_t e = h->net->eval(c);
+  cudaError_t e = h->net ? h->net->eval(c) : generic_eval(h->gen, h->dtype, c, nullptr);
+  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, "network too large for the runtime-shape kernels (per-thread vectors exceed shared memory)");
   if (e != cudaSuccess) return cuda_fail(e, "log_target_grad");
   return EEYORE_B200_OK;
 }
@@ -102,7 +137,14 @@ int eeyore_b200_forward(eeyore_b200_mlp_t h, int64_t n_chains, const void* theta
                         void* out, void* stream) {
   if (!h || !theta || !x || !out) return fail(EEYORE_B200_EINVAL, "null argument");
   if (n_chains < 1 || n_rows < 1) return fail(EEYORE_B200_EINVAL, "n_chains and n_rows must be positive");
-  cudaError_t e = h->net->forward(n_chains, theta, x, n_rows, out, (cudaStream_t)stream);
+  cudaError_t e;
+  if (h->net) {
+    e = h->net->forward(n_chains, theta, x, n_rows, out, (cudaStream_t)stream);
+  } else {
+    EvalCall c{n_chains, theta, x, x /*unused*/, n_rows, nullptr, nullptr, 0, 0.0, nullptr, nullptr, nullptr, nullptr, 1, 0,
+               (cudaStream_t)stream};
+    e = generic_forward_(h, c, out);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "forward");
   return EEYORE_B200_OK;
 }
@@ -129,7 +171,14 @@ static int run_common(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p, int 
     if (!(p->tuner_l > 0)) return fail(EEYORE_B200_EINVAL, "tuner_l must be positive");
     kind = KIND_HMC_TUNED;
   }
-  cudaError_t e = h->net->sampler(kind, *p, lanes, use_bulk());
+  cudaError_t e;
+  if (h->net) {
+    e = h->net->sampler(kind, *p, lanes, use_bulk());
+  } else {
+    if (kind == KIND_HMC_TUNED) return fail(EEYORE_B200_EUNSUPPORTED, "HMCDATuner needs a compiled network specialisation");
+    e = generic_sampler(h->gen, h->dtype, kind, *p);
+    if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, "network too large for the runtime-shape kernels");
+  }
   if (e != cudaSuccess) return cuda_fail(e, name);
   return EEYORE_B200_OK;
 }
@@ -140,7 +189,8 @@ int eeyore_b200_hmc_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p) { 
 
 int eeyore_b200_smmala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p) {
   if (!h || !p) return fail(EEYORE_B200_EINVAL, "null argument");
-  if (!h->net->smmala) return fail(EEYORE_B200_EUNSUPPORTED, "SMMALA is built for binary-classification networks only");
+  if (!h->net || !h->net->smmala)
+    return fail(EEYORE_B200_EUNSUPPORTED, "SMMALA is built for the compiled binary-classification networks only");
   if (p->n_chains < 1 || p->n_rows < 1 || p->n_iters < 0) return fail(EEYORE_B200_EINVAL, "bad sizes");
   if (!p->theta || !p->target || !p->grad || !p->x || !p->y || !p->prior_loc || !p->prior_scale)
     return fail(EEYORE_B200_EINVAL, "null state / data pointer");

@@ -58,6 +58,9 @@ int eeyore_b200_mlp_create(int n_layers, const int *dims, const int *bias, const
 int eeyore_b200_mlp_destroy(eeyore_b200_mlp_t h);
 /* Model.num_params (eeyore/models/model.py:34-36) */
 int eeyore_b200_mlp_num_params(eeyore_b200_mlp_t h);
+/* 1 if the network is served by a compile-time specialisation (2-2-1, 2-3-2-1, 4-3-3, 4-3-2-3 with all biases and
+ * sigmoid hidden units), 0 if by the runtime-shape kernels (any dims <= 8 layers, bias flags, sigmoid / None) */
+int eeyore_b200_mlp_is_specialised(eeyore_b200_mlp_t h);
 
 /* BayesianModel.log_target + LogTargetModel.upto_grad_log_target
  * (eeyore/models/bayesian_model.py:52-56, eeyore/models/log_target_model.py:20-23), batched over C chains.

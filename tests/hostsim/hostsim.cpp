@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../eeyore_b200/csrc/samplers.cuh"
 #include "../../eeyore_b200/csrc/philox.cuh"
+#include "../../eeyore_b200/csrc/generic.cuh"
 #include "../../include/eeyore_b200.h"
 
 using namespace eb;
@@ -164,6 +165,104 @@ int hostsim_philox(int dtype, int64_t C, int P, uint64_t seed, uint64_t iter, ui
       ((float*)u)[c] = philox_uniform<float>(key, gc, (uint32_t)iter);
     }
   }
+  return 0;
+}
+}
+
+// ---- runtime-shape path (generic.cuh) on the CPU: per-thread vectors are plain arrays (stride 1) ---------------------
+template <typename T>
+static DataView<T> gen_view(const GenNet& n, const T* x, const T* y, int N, const T* loc, const T* scale, int has_t, double temp,
+                            std::vector<T>& ys, std::vector<int>& cls, std::vector<T>& pivar) {
+  const int dl = n.dims[n.nl];
+  ys.assign(N, T(0)); cls.assign(N, 0); pivar.resize(n.P);
+  if (n.loss == LOSS_BINARY) for (int i = 0; i < N; ++i) ys[i] = y[i];
+  else for (int i = 0; i < N; ++i) {
+    int best = 0; T bv = y[(size_t)i * dl];
+    for (int k = 1; k < dl; ++k) if (y[(size_t)i * dl + k] > bv) { bv = y[(size_t)i * dl + k]; best = k; }
+    cls[i] = best;
+  }
+  T c = T(0);
+  for (int j = 0; j < n.P; ++j) { pivar[j] = T(1) / (scale[j] * scale[j]); c += -log_t<T>(scale[j]) - T(kLogSqrt2Pi); }
+  DataView<T> d;
+  d.x = x; d.y = ys.data(); d.cls = cls.data(); d.n_rows = N; d.ploc = loc; d.pivar = pivar.data(); d.lp_const = c;
+  d.temperature = (T)temp; d.has_temperature = has_t != 0;
+  return d;
+}
+
+template <typename T>
+static void gen_eval_all(const GenNet& n, int64_t C, const T* theta, const T* x, const T* y, int N, const T* loc, const T* scale,
+                         int has_t, double temp, T* out_lt, T* out_g) {
+  std::vector<T> ys, pivar; std::vector<int> cls;
+  DataView<T> d = gen_view<T>(n, x, y, N, loc, scale, has_t, temp, ys, cls, pivar);
+  std::vector<T> hbuf(n.H), da(n.maxd), db(n.maxd), th(n.P), g(n.P);
+  GenWork<T> w{StridedVec<T>{hbuf.data(), 1}, StridedVec<T>{da.data(), 1}, StridedVec<T>{db.data(), 1}};
+  for (int64_t c = 0; c < C; ++c) {
+    for (int j = 0; j < n.P; ++j) th[j] = theta[c * n.P + j];
+    StridedVec<T> thv{th.data(), 1}, gv{g.data(), 1};
+    T lt;
+    if (out_g) { gen_eval_target<T, true>(n, d, thv, w, lt, gv); for (int j = 0; j < n.P; ++j) out_g[c * n.P + j] = g[j]; }
+    else { int dummy = 0; gen_eval_target<T, false>(n, d, thv, w, lt, dummy); }
+    out_lt[c] = lt;
+  }
+}
+
+template <typename T> static void gen_run_all(const GenNet& n, int kind, const eeyore_b200_run_params& p) {
+  const int P = n.P;
+  std::vector<T> ys, pivar; std::vector<int> cls;
+  DataView<T> d = gen_view<T>(n, (const T*)p.x, (const T*)p.y, (int)p.n_rows, (const T*)p.prior_loc, (const T*)p.prior_scale,
+                              p.has_temperature, p.temperature, ys, cls, pivar);
+  T* theta = (T*)p.theta; T* target = (T*)p.target; T* grad = (T*)p.grad;
+  const T step = (T)p.step, half_step = T(0.5) * step, sd = sqrt_t<T>(step);
+  RngKey key{(uint32_t)(p.seed & 0xffffffffu), (uint32_t)(p.seed >> 32)};
+  const int64_t thin = p.thin < 1 ? 1 : p.thin;
+  std::vector<T> hbuf(n.H), da(n.maxd), db(n.maxd), zb(P), thb(P), gb(P);
+  GenWork<T> w{StridedVec<T>{hbuf.data(), 1}, StridedVec<T>{da.data(), 1}, StridedVec<T>{db.data(), 1}};
+  StridedVec<T> z{zb.data(), 1}, thp{thb.data(), 1}, gp{gb.data(), 1};
+  for (int64_t c = 0; c < p.n_chains; ++c) {
+    Cur<T> cur{theta + c * P, grad ? grad + c * P : nullptr, 1};
+    T lt_cur = target[c];
+    uint32_t nacc = 0;
+    const uint32_t gchain = (uint32_t)p.chain_offset + (uint32_t)c;
+    for (int64_t t = 0; t < p.n_iters; ++t) {
+      T u, ltp;
+      if (p.rng_mode == EEYORE_B200_RNG_PHILOX) {
+        gen_philox_normals<T>(z, P, key, gchain, (uint32_t)p.iter_offset + (uint32_t)t);
+        u = philox_uniform<T>(key, gchain, (uint32_t)p.iter_offset + (uint32_t)t);
+      } else {
+        const T* zt = (const T*)p.z_tape + ((size_t)t * p.n_chains + c) * P;
+        for (int j = 0; j < P; ++j) z[j] = zt[j];
+        u = ((const T*)p.u_tape)[(size_t)t * p.n_chains + c];
+      }
+      bool acc;
+      if (kind == 0) acc = gen_mh_draw<T>(n, d, w, step, p.symmetric != 0, cur, lt_cur, z, u, thp, ltp);
+      else if (kind == 1) acc = gen_mala_draw<T>(n, d, w, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
+      else acc = gen_hmc_draw<T>(n, d, w, step, half_step, p.num_steps, cur, lt_cur, z, u, thp, gp, ltp);
+      if (acc) { lt_cur = ltp; ++nacc; for (int j = 0; j < P; ++j) { cur.th[j] = thp[j]; if (kind != 0) cur.g[j] = gp[j]; } }
+      if (t >= p.n_burnin && (t - p.n_burnin) % thin == 0) {
+        const int64_t s = (t - p.n_burnin) / thin;
+        if (p.out_samples) for (int j = 0; j < P; ++j) ((T*)p.out_samples)[s * p.ss_iter + c * p.ss_chain + j * p.ss_param] = cur.th[j];
+        if (p.out_target) ((T*)p.out_target)[s * p.n_chains + c] = lt_cur;
+        if (p.out_accepted) p.out_accepted[s * p.n_chains + c] = acc ? 1 : 0;
+      }
+    }
+    target[c] = lt_cur;
+    if (p.accept_count) p.accept_count[c] += nacc;
+  }
+}
+
+extern "C" {
+int hostsim_gen_eval(int nl, const int* dims, const int* bias, const int* act, int loss, int dtype, int64_t C, const void* theta,
+                     const void* x, const void* y, int64_t N, const void* loc, const void* scale, int has_t, double temp,
+                     void* out_lt, void* out_g) {
+  GenNet n = make_gen_net(nl, dims, bias, act, loss);
+  if (dtype == EEYORE_B200_F64) gen_eval_all<double>(n, C, (const double*)theta, (const double*)x, (const double*)y, (int)N, (const double*)loc, (const double*)scale, has_t, temp, (double*)out_lt, (double*)out_g);
+  else gen_eval_all<float>(n, C, (const float*)theta, (const float*)x, (const float*)y, (int)N, (const float*)loc, (const float*)scale, has_t, temp, (float*)out_lt, (float*)out_g);
+  return n.P;
+}
+int hostsim_gen_run(int kind, int nl, const int* dims, const int* bias, const int* act, int loss, int dtype,
+                    const eeyore_b200_run_params* p) {
+  GenNet n = make_gen_net(nl, dims, bias, act, loss);
+  if (dtype == EEYORE_B200_F64) gen_run_all<double>(n, kind, *p); else gen_run_all<float>(n, kind, *p);
   return 0;
 }
 }

@@ -120,10 +120,13 @@ def test_errors():
         m.set_params(torch.zeros(4, dtype=torch.float64))
     from eeyore_b200.constants import loss_functions
     from eeyore_b200.models.mlp import MLP, Hyperparameters
-    odd = MLP(loss=loss_functions["binary_classification"], hparams=Hyperparameters([3, 5, 1]))
-    with pytest.raises(ValueError, match="3-5-1"):
-        odd.log_target(torch.zeros(odd.num_params(), dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64),
+    bad = MLP(loss=loss_functions["binary_classification"], hparams=Hyperparameters([3, 5, 1], activations=[torch.sigmoid, None]))
+    with pytest.raises(ValueError, match="sigmoid output"):
+        bad.log_target(torch.zeros(bad.num_params(), dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64),
                        torch.zeros(2, 1, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        MLP(loss=loss_functions["binary_classification"], hparams=Hyperparameters([3, 5, 1], activations=[torch.tanh, torch.sigmoid])
+            ).log_target(torch.zeros(26, dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64), torch.zeros(2, 1, dtype=torch.float64))
 
 
 def test_full_size_chain_batch_properties():
@@ -170,3 +173,77 @@ def test_fp64_fast_sigmoid_accuracy():
     fin = np.isfinite(lt_ref)
     assert np.allclose(npy(lt)[fin], lt_ref[fin], rtol=1e-12, atol=0)
     assert np.array_equal(np.isnan(npy(lt)), np.isnan(lt_ref))
+
+
+GEN_CASES = [
+    ([3, 5, 1], [True, True], [torch.sigmoid, torch.sigmoid], "binary_classification"),
+    ([4, 3, 3], [True, False], [torch.sigmoid, None], "multiclass_classification"),
+    ([4, 6, 5, 4, 3], [True, False, True, True], [torch.sigmoid, None, torch.sigmoid, None], "multiclass_classification"),
+    ([2, 4, 1], [False, False], [None, torch.sigmoid], "binary_classification"),
+    ([5, 7, 3, 2, 4, 1], [True] * 5, [torch.sigmoid] * 5, "binary_classification"),
+    ([10, 16, 16, 1], [True] * 3, [torch.sigmoid] * 3, "binary_classification"),
+]
+
+
+@pytest.mark.parametrize("dims,bias,acts,loss", GEN_CASES)
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_runtime_shape_networks_vs_oracle(dims, bias, acts, loss, tag):
+    """mlp.Hyperparameters in full generality (dims, per-layer bias flags, sigmoid / None activations; mlp.py:9-19,37-50)
+    through the runtime-shape kernels, incl. samplers."""
+    from eeyore_b200.constants import loss_functions
+    from eeyore_b200.models.mlp import MLP, Hyperparameters
+    from eeyore_b200.samplers import HMC, MALA, MetropolisHastings
+    from eeyore_b200.datasets import XYDataset
+    from gpu_helpers import loader
+    from oracle.mlp import MLPSpec
+    dt, tdt = NP_DTYPES[tag], T_DTYPES[tag]
+    spec = MLPSpec(dims, loss=loss, bias=bias, activations=["sigmoid" if a is not None else None for a in acts])
+    rng = np.random.default_rng(sum(dims))
+    n = 37
+    x = rng.normal(size=(n, dims[0])).astype(dt)
+    k = dims[-1]
+    y = (rng.integers(0, 2, size=(n, 1)).astype(dt) if k == 1 else np.eye(k, dtype=dt)[rng.integers(0, k, size=n)])
+    m = MLP(loss=loss_functions[loss], hparams=Hyperparameters(dims, bias, acts), dtype=tdt)
+    P = m.num_params()
+    assert P == spec.num_params
+    loc = (rng.normal(size=P) * 0.1).astype(dt); scale = (0.5 + rng.uniform(size=P)).astype(dt)
+    m.prior = torch.distributions.Normal(torch.from_numpy(loc), torch.from_numpy(scale))
+    C = 70
+    theta = (rng.normal(size=(C, P)) * 0.5).astype(dt)
+    lt, g = m.upto_grad_log_target_batch(torch.from_numpy(theta), torch.from_numpy(x), torch.from_numpy(y))
+    lt_ref, g_ref = oracle.log_target_grad(spec, theta.astype(np.float64), x.astype(np.float64), y, loc.astype(np.float64),
+                                           scale.astype(np.float64))
+    tol = 1e-10 if tag == "f64" else 2e-5
+    assert np.allclose(npy(lt), lt_ref, rtol=tol, atol=0)
+    for c in range(C):
+        assert rel_err(npy(g)[c], g_ref[c]) < tol
+    out = npy(m.forward_batch(torch.from_numpy(theta[:3]), torch.from_numpy(x)))
+    ref_out = oracle.forward(spec, theta[:3].astype(np.float64), x.astype(np.float64))[-1]
+    assert rel_err(out, ref_out) < (1e-12 if tag == "f64" else 1e-5)
+    if tag == "f32":
+        return
+    T, nb = 8, 2
+    z, u = rng.normal(size=(T, C, P)), rng.uniform(size=(T, C))
+    ds = XYDataset(torch.from_numpy(x), torch.from_numpy(y))
+    for cls, kw, ref_fn in ((MetropolisHastings, dict(scale=0.05), lambda: oracle.mh_run(spec, x, y, loc, scale, theta, z, u, n_burnin=nb, prop_scale=0.05)),
+                            (MALA, dict(step=0.01), lambda: oracle.mala_run(spec, x, y, loc, scale, theta, z, u, 0.01, n_burnin=nb)),
+                            (HMC, dict(step=0.03, num_steps=3), lambda: oracle.hmc_run(spec, x, y, loc, scale, theta, z, u, 0.03, 3, n_burnin=nb))):
+        s = cls(m, theta0=torch.from_numpy(theta), dataloader=loader(ds), **kw)
+        s.set_noise_tape(torch.from_numpy(z), torch.from_numpy(u))
+        s.run(num_epochs=T, num_burnin_epochs=nb)
+        got, ref = s.get_chain(), ref_fn()
+        assert np.array_equal(npy(got.accepted_soa), ref["accepted"]), cls.__name__
+        assert rel_err(npy(got.get_samples().permute(1, 0, 2)), ref["sample"]) < 1e-10
+
+
+def test_runtime_shape_path_agrees_with_the_specialisation(monkeypatch):
+    m = make_model("2321", "f64", 1.7)
+    ds = dataset("2321", "f64")
+    th = torch.randn(50, 20, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    a, ga = m.upto_grad_log_target_batch(th, ds.x, ds.y)
+    monkeypatch.setenv("EEYORE_B200_FORCE_GENERIC", "1")
+    m2 = make_model("2321", "f64", 1.7)
+    b, gb = m2.upto_grad_log_target_batch(th, ds.x, ds.y)
+    from eeyore_b200 import _native as nv
+    assert nv.lib().eeyore_b200_mlp_is_specialised(m.handle()) == 1 and nv.lib().eeyore_b200_mlp_is_specialised(m2.handle()) == 0
+    assert torch.allclose(a, b, rtol=1e-13, atol=0) and torch.allclose(ga, gb, rtol=1e-11, atol=1e-13)

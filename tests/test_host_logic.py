@@ -54,10 +54,18 @@ def test_mlp_create_errors_without_gpu():
     dims = (C.c_int * 3)(2, 2, 1); bias = (C.c_int * 2)(1, 1); acts = (C.c_int * 2)(1, 1)
     assert lib.eeyore_b200_mlp_create(2, dims, bias, acts, 0, 1, C.byref(h)) == 0
     assert lib.eeyore_b200_mlp_num_params(h) == 9
+    assert lib.eeyore_b200_mlp_is_specialised(h) == 1
     lib.eeyore_b200_mlp_destroy(h)
+    # any other small network is served by the runtime-shape kernels
     dims = (C.c_int * 3)(7, 5, 1)
-    rc = lib.eeyore_b200_mlp_create(2, dims, bias, acts, 0, 1, C.byref(h))
-    assert rc == nv.EUNSUPPORTED and b"7-5-1" in lib.eeyore_b200_last_error()
+    bias0 = (C.c_int * 2)(0, 1)
+    assert lib.eeyore_b200_mlp_create(2, dims, bias0, acts, 0, 1, C.byref(h)) == 0
+    assert lib.eeyore_b200_mlp_num_params(h) == 7 * 5 + 6 and lib.eeyore_b200_mlp_is_specialised(h) == 0
+    lib.eeyore_b200_mlp_destroy(h)
+    # binary loss on a None head is not a probability: unsupported
+    acts_bad = (C.c_int * 2)(1, 0)
+    rc = lib.eeyore_b200_mlp_create(2, dims, bias, acts_bad, 0, 1, C.byref(h))
+    assert rc == nv.EUNSUPPORTED and b"sigmoid output" in lib.eeyore_b200_last_error()
     with pytest.raises(ValueError):
         nv.check(rc)
 

@@ -203,3 +203,87 @@ def test_device_hmc_dual_averaging_tuner_reproduces_reference(sim, name, arch, l
     assert rel_err(out["sample"][:, 0], gd["samples"]) < 1e-9
     assert abs(state[2, 0] - float(gd["final_step"])) < 1e-11 * float(gd["final_step"])
     assert int(state[3, 0]) == int(gd["final_num_steps"])
+
+
+GEN_CASES = [
+    # dims, bias, activations (None = identity), loss
+    ([3, 5, 1], [True, True], ["sigmoid", "sigmoid"], "binary_classification"),
+    ([2, 3, 2, 1], [True, True, True], ["sigmoid", "sigmoid", "sigmoid"], "binary_classification"),
+    ([4, 3, 3], [True, False], ["sigmoid", None], "multiclass_classification"),
+    ([4, 6, 5, 4, 3], [True, False, True, True], ["sigmoid", None, "sigmoid", None], "multiclass_classification"),
+    ([2, 4, 1], [False, False], [None, "sigmoid"], "binary_classification"),
+    ([5, 7, 3, 2, 4, 1], [True] * 5, ["sigmoid"] * 5, "binary_classification"),
+]
+
+
+def gen_problem(dims, loss, n_rows, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n_rows, dims[0]))
+    k = dims[-1]
+    y = rng.integers(0, 2, size=(n_rows, 1)).astype(np.float64) if k == 1 else np.eye(k)[rng.integers(0, k, size=n_rows)]
+    return x, y
+
+
+@pytest.mark.parametrize("dims,bias,acts,loss", GEN_CASES)
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_runtime_shape_eval_matches_oracle(sim, dims, bias, acts, loss, tag):
+    """Arbitrary dims / bias flags / activations (mlp.Hyperparameters, eeyore/models/mlp.py:9-19) through the runtime-shape
+    device code."""
+    from oracle.mlp import MLPSpec
+    sim.hostsim_gen_eval.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                     C.c_int64] + [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 2 + [C.c_int, C.c_double,
+                                                                                                      C.c_void_p, C.c_void_p]
+    dt = NP_DTYPES[tag]
+    spec = MLPSpec(dims, loss=loss, bias=bias, activations=acts)
+    x, y = gen_problem(dims, loss, 23, sum(dims))
+    rng = np.random.default_rng(1)
+    theta = (rng.normal(size=(9, spec.num_params)) * 0.7).astype(dt)
+    loc = (rng.normal(size=spec.num_params) * 0.1).astype(dt)
+    scale = (0.5 + rng.uniform(size=spec.num_params)).astype(dt)
+    nl = len(dims) - 1
+    lt = np.empty(9, dt); g = np.empty_like(theta)
+    xs, ys = np.ascontiguousarray(x, dt), np.ascontiguousarray(y, dt)
+    P_ = sim.hostsim_gen_eval(nl, (C.c_int * (nl + 1))(*dims), (C.c_int * nl)(*[int(b) for b in bias]),
+                              (C.c_int * nl)(*[1 if a else 0 for a in acts]), 0 if loss == "binary_classification" else 1,
+                              dt_id(tag), 9, P(theta), P(xs), P(ys), 23, P(loc), P(scale), 1, 0.9, P(lt), P(g))
+    assert P_ == spec.num_params
+    lt_ref, g_ref = oracle.log_target_grad(spec, theta.astype(np.float64), x, y, loc.astype(np.float64),
+                                           scale.astype(np.float64), 0.9)
+    tol = 1e-11 if tag == "f64" else 2e-5
+    assert np.allclose(lt, lt_ref, rtol=tol, atol=0)
+    for c in range(9):
+        assert rel_err(g[c], g_ref[c]) < tol
+
+
+@pytest.mark.parametrize("kind", ["mh", "mala", "hmc"])
+def test_runtime_shape_samplers_match_oracle(sim, kind):
+    from oracle.mlp import MLPSpec
+    sim.hostsim_gen_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                    C.POINTER(RunParams)]
+    dims, bias, acts, loss = GEN_CASES[3]
+    spec = MLPSpec(dims, loss=loss, bias=bias, activations=acts)
+    dt = np.float64
+    x, y = gen_problem(dims, loss, 17, 3)
+    n, Cn, T = spec.num_params, 4, 9
+    rng = np.random.default_rng(2)
+    theta0 = rng.normal(size=(Cn, n)) * 0.4
+    z, u = rng.normal(size=(T, Cn, n)), rng.uniform(size=(T, Cn))
+    loc, scale = np.zeros(n), np.full(n, 1.3)
+    kw = dict(mh=dict(step=0.05), mala=dict(step=0.03), hmc=dict(step=0.06, L=4))[kind]
+    if kind == "mh":
+        ref = oracle.mh_run(spec, x, y, loc, scale, theta0, z, u, n_burnin=2, prop_scale=0.05)
+    elif kind == "mala":
+        ref = oracle.mala_run(spec, x, y, loc, scale, theta0, z, u, 0.03, n_burnin=2)
+    else:
+        ref = oracle.hmc_run(spec, x, y, loc, scale, theta0, z, u, 0.06, 4, n_burnin=2)
+    theta = theta0.copy()
+    lt_, g_ = oracle.log_target_grad(spec, theta, x, y, loc, scale)
+    lt, g = np.ascontiguousarray(lt_), np.ascontiguousarray(g_)
+    xs, ys = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    p, out = run_params(dt, theta, lt, g, xs, ys, loc, scale, np.ascontiguousarray(z), np.ascontiguousarray(u), 2, **kw)
+    nl = len(dims) - 1
+    assert sim.hostsim_gen_run(KINDS[kind], nl, (C.c_int * (nl + 1))(*dims), (C.c_int * nl)(*[int(b) for b in bias]),
+                               (C.c_int * nl)(*[1 if a else 0 for a in acts]), 1, F64, C.byref(p)) == 0
+    assert ref["accepted"].mean() > 0
+    assert np.array_equal(out["acc"], ref["accepted"])
+    assert rel_err(out["sample"], ref["sample"]) < 1e-10
