@@ -73,3 +73,39 @@ class ChainLists:
 
     def multi_ess_summary(self, g=lambda x: sum(x) / len(x), mc_cov_mat=None, method="inse", adjust=False):
         return g(self.multi_ess(mc_cov_mat=mc_cov_mat, method=method, adjust=adjust))
+
+    def mc_se(self, mc_cov_mat=None, method="inse", adjust=False):
+        """chain_lists.py:64-71: per-chain Monte Carlo standard errors, [C, P]."""
+        cov_ = self.mc_cov(method=method, adjust=adjust) if mc_cov_mat is None else torch.stack(list(mc_cov_mat))
+        return torch.diagonal(cov_, dim1=1, dim2=2).sqrt()
+
+    def mc_se_summary(self, g=lambda x: torch.mean(x, dim=0), mc_cov_mat=None, method="inse", adjust=False):
+        return g(self.mc_se(mc_cov_mat=mc_cov_mat, method=method, adjust=adjust))
+
+    def mc_cov_summary(self, g=lambda m: torch.mean(m, dim=0), method="inse", adjust=False):
+        return g(self.mc_cov(method=method, adjust=adjust))
+
+    def multi_rhat(self, mc_cov_mat=None, method="inse", adjust=False):
+        """chain_lists.py:122-123."""
+        from .. import stats as st
+        return st.multi_rhat(self.get_samples(), mc_cov_mat=mc_cov_mat, method=method, adjust=adjust)
+
+    def summary(self, keys=("multi_ess", "multi_rhat"), g_mean_summary=lambda x: torch.mean(x, dim=0),
+                g_mc_se_summary=lambda x: torch.mean(x, dim=0), g_acceptance_summary=lambda x: sum(x) / len(x),
+                g_multi_ess_summary=lambda x: sum(x) / len(x), mc_cov_mat=None, method="inse", adjust=False):
+        """chain_lists.py:125-155."""
+        out = {}
+        if mc_cov_mat is None and any(k in keys for k in ("mc_se", "multi_rhat")):
+            mc_cov_mat = self.mc_cov(method=method, adjust=adjust)
+        for key in keys:
+            if key == "mean":
+                out[key] = self.mean_summary(g=g_mean_summary)
+            elif key == "mc_se":
+                out[key] = self.mc_se_summary(g=g_mc_se_summary, mc_cov_mat=mc_cov_mat)
+            elif key == "acceptance":
+                out[key] = self.acceptance_summary(g=g_acceptance_summary)
+            elif key == "multi_ess":
+                out[key] = self.multi_ess_summary(g=g_multi_ess_summary, method=method, adjust=adjust)
+            elif key == "multi_rhat":
+                out[key] = self.multi_rhat(mc_cov_mat=mc_cov_mat, method=method, adjust=adjust)[0]
+        return out

@@ -72,6 +72,11 @@ class DeviceChains:
         from .. import stats as st
         return st.multi_ess_soa(self.samples_soa)
 
+    def multi_rhat(self):
+        """Across-chain multivariate R-hat (eeyore/stats/multi_rhat.py) of the saved samples."""
+        from .. import stats as st
+        return st.multi_rhat(self.get_samples())
+
     def acf(self, max_lag):
         from .. import stats as st
         return st.acf_soa(self.samples_soa, max_lag)

@@ -80,7 +80,7 @@ const char* eeyore_b200_version(void) { return "eeyore_b200 0.1 (sm_100a)"; }
 int eeyore_b200_mlp_create(int n_layers, const int* dims, const int* bias, const int* act_ids, int loss_id, int dtype,
                            eeyore_b200_mlp_t* out) {
   if (!dims || !bias || !act_ids || !out) return fail(EEYORE_B200_EINVAL, "null argument");
-  if (n_layers < 2) return fail(EEYORE_B200_EINVAL, "an MLP needs at least 3 dims (eeyore/models/mlp.py:15-16)");
+  if (n_layers < 1) return fail(EEYORE_B200_EINVAL, "at least one dense layer is needed");  // 1 = LogisticRegression
   if (dtype != EEYORE_B200_F32 && dtype != EEYORE_B200_F64) return fail(EEYORE_B200_EINVAL, "dtype must be f32 or f64");
   if (loss_id != EEYORE_B200_LOSS_BINARY && loss_id != EEYORE_B200_LOSS_MULTICLASS)
     return fail(EEYORE_B200_EINVAL, "unknown loss id");

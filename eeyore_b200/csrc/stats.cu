@@ -226,9 +226,12 @@ template <typename T> __global__ void __launch_bounds__(kStatThreads) chain_stat
       T* dst = phase2 ? Sig1 : Sig;
       for (int e = tid; e < P * P; e += blockDim.x) {
         const int r = e / P, q = e % P, et = q * P + r;
-        const T g0 = A0[e] * inv_n, g0t = A0[et] * inv_n, g1 = A1[e] * inv_n, g1t = A1[et] * inv_n;
-        const T gam = ((g0 + g1) + (g0t + g1t)) / T(2);                // :32-33 (exactly symmetric)
-        if (m == 0) dst[e] = -g0 + T(2) * gam;                         // :35-36
+        // Gam = sym(gam0 + gam1), :32-33.  Written with pure additions before the scaling so that FMA contraction
+        // cannot round element (r, q) and (q, r) differently: the reference's is_pos_def demands EXACT symmetry.
+        const T se = A0[e] + A1[e], st = A0[et] + A1[et];
+        const T gam = (se + st) * (T(0.5) * inv_n);
+        const T g0 = A0[e] * inv_n;
+        if (m == 0) dst[e] = T(2) * gam - g0;                          // :35-36 (A0 is exactly symmetric at lag 0)
         else dst[e] = Sig[e] + T(2) * gam;                             // :37-38, :62
       }
       __syncthreads();

@@ -148,3 +148,67 @@ def acf(x, max_lag):
 def acf_soa(samples_soa, max_lag):
     """[n, P, C] -> [C, max_lag+1, P]."""
     return chain_stats(samples_soa, layout="npc", want=(), max_lag=max_lag)["acf"]
+
+
+def cor_from_cov(x):
+    """eeyore/stats/cor_from_cov.py."""
+    sd = x.diag().sqrt()
+    return x / sd[:, None] / sd[None, :]
+
+
+def cor(x, rowvar=False):
+    """eeyore/stats/cor.py."""
+    return cor_from_cov(cov(x, rowvar=rowvar))
+
+
+def mc_cor(x, method="inse", adjust=False, rowvar=False):
+    """eeyore/stats/mc_cor.py."""
+    return cor_from_cov(mc_cov(x, method=method, adjust=adjust, rowvar=rowvar))
+
+
+def _is_pd(m):
+    return bool(torch.equal(m, m.t()) and torch.linalg.cholesky_ex(m).info.item() == 0)
+
+
+def nearest_pd(a):
+    """Higham's nearest positive-definite matrix; mirror of eeyore/linalg/nearest_pd.py:9-42 (the reference's fallback
+    loop calls the removed torch.eig; torch.linalg.eigvalsh is used here)."""
+    b = (a + a.t()) / 2
+    _, s, vh = torch.linalg.svd(b)
+    h = vh.t() @ torch.diag(s) @ vh
+    a3 = (b + h) / 2
+    a3 = (a3 + a3.t()) / 2
+    spacing = torch.finfo(a.dtype).eps * torch.linalg.norm(a).item()
+    eye, k = torch.eye(a.shape[0], dtype=a.dtype, device=a.device), 1
+    while not _is_pd(a3) and k < 100:
+        mineig = torch.linalg.eigvalsh(a3).min().item()
+        a3 = a3 + eye * (-mineig * k ** 2 + spacing)
+        k += 1
+    return a3
+
+
+def multi_rhat(x, mc_cov_mat=None, method="inse", adjust=False):
+    """Multivariate potential scale reduction factor; mirror of eeyore/stats/multi_rhat.py:10-40 for x [C, n, P].
+    The per-chain INSE covariances and chain means come from one device launch (chain_stats); what is left is P x P
+    algebra.  Returns (rhat, imag part, W, B, is_w_pd, is_b_pd) like the reference."""
+    c, n, p = x.shape
+    if mc_cov_mat is None:
+        key = {"inse": "inse", "iid": "cov"}[method]
+        if adjust:
+            raise NotImplementedError("adjust=True is not available")
+        out = chain_stats(x, want=("mean", key))
+        w, means = out[key].mean(0), out["mean"]
+    else:
+        w = torch.stack(list(mc_cov_mat)).to(x.device if x.is_cuda else _device_of(x)).mean(0)
+        means = chain_stats(x, want=("mean",))["mean"]
+    is_w_pd = _is_pd(w)
+    if not is_w_pd:
+        w = nearest_pd(w)
+    b = chain_stats(means[None], want=("cov",))["cov"][0]          # cov(x.mean(1)), multi_rhat.py:28
+    is_b_pd = _is_pd(b)
+    if not is_b_pd:
+        b = nearest_pd(b)
+    eig = torch.linalg.eigvals(torch.linalg.inv(w) @ b)
+    i = eig.real.argmax().item()
+    rhat = ((n - 1) / n) + ((c + 1) / c) * eig.real[i].item()
+    return rhat, eig.imag[i].item(), w, b, is_w_pd, is_b_pd

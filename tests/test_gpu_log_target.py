@@ -247,3 +247,41 @@ def test_runtime_shape_path_agrees_with_the_specialisation(monkeypatch):
     from eeyore_b200 import _native as nv
     assert nv.lib().eeyore_b200_mlp_is_specialised(m.handle()) == 1 and nv.lib().eeyore_b200_mlp_is_specialised(m2.handle()) == 0
     assert torch.allclose(a, b, rtol=1e-13, atol=0) and torch.allclose(ga, gb, rtol=1e-11, atol=1e-13)
+
+
+def test_posterior_predictive_and_logistic_regression():
+    """BayesianModel.predictive_posterior(_from_dataset) (bayesian_model.py:58-67,
+    integrators/mcintegrator.py:16-63) as one batched launch, and LogisticRegression (models/logistic_regression.py)."""
+    from eeyore_b200.constants import loss_functions
+    from eeyore_b200.models import LogisticRegression
+    from eeyore_b200.models.logistic_regression import Hyperparameters as LRH
+    from oracle.mlp import MLPSpec
+    m = make_model("433", "f64", 1.0)
+    ds = dataset("433", "f64")
+    rng = np.random.default_rng(0)
+    S = 50
+    th = rng.normal(size=(S, 27)) * 0.3
+    th[7, 3] = np.nan                                                   # a NaN sample is dropped, mcintegrator.py:24-25
+    val, dropped = m.predictive_posterior(torch.from_numpy(th), ds.x[:5], ds.y[:5])
+    ll = oracle.log_lik(spec_of("433"), th, npy(ds.x[:5]), npy(ds.y[:5]))
+    assert dropped == 1 and abs(val.item() - np.nanmean(np.exp(ll))) < 1e-12 * np.nanmean(np.exp(ll))
+    integ, idx, nd = m.predictive_posterior_from_dataset(list(torch.from_numpy(th)), ds, 12, shuffle=False)
+    for k in range(12):
+        llk = oracle.log_lik(spec_of("433"), th, npy(ds.x[k:k + 1]), npy(ds.y[k:k + 1]))
+        assert abs(integ[k].item() - np.nanmean(np.exp(llk))) < 1e-11 * np.nanmean(np.exp(llk))
+    assert idx.tolist() == list(range(12)) and nd.tolist() == [1] * 12
+    # logistic regression = one dense layer with a sigmoid head
+    lr = LogisticRegression(loss=loss_functions["binary_classification"], hparams=LRH(input_size=6, output_size=1))
+    assert lr.num_params() == 7
+    x = rng.normal(size=(40, 6)); y = (rng.uniform(size=(40, 1)) < 0.5).astype(np.float64)
+    thl = rng.normal(size=(9, 7))
+    lt, g = lr.upto_grad_log_target_batch(torch.from_numpy(thl), torch.from_numpy(x), torch.from_numpy(y))
+    spec = MLPSpec([6, 1], loss="binary_classification", bias=[True], activations=["sigmoid"]) if False else None
+    # closed form: ll = sum y log s + (1-y) log(1-s), s = sigmoid(x w + b); prior N(0, 1)
+    w_, b_ = thl[:, :6], thl[:, 6]
+    s = 1 / (1 + np.exp(-(x @ w_.T + b_)))                              # [40, 9]
+    ll_ref = (np.log(s) * y + np.log(1 - s) * (1 - y)).sum(0)
+    lp_ref = (-0.5 * thl ** 2 - 0.5 * np.log(2 * np.pi)).sum(1)
+    assert np.allclose(npy(lt), ll_ref + lp_ref, rtol=1e-11)
+    g_ref = np.concatenate([((y - s).T @ x), (y - s).sum(0)[:, None]], axis=1) - thl
+    assert rel_err(npy(g), g_ref) < 1e-11

@@ -114,3 +114,24 @@ def test_device_chains_diagnostics_after_sampling():
     else:
         with pytest.raises(RuntimeError, match="Not enough samples"):
             chains.multi_ess()
+
+
+def test_multi_rhat_reference_golden():
+    """multi_rhat (eeyore/stats/multi_rhat.py:10-40) on the reference's four example chains."""
+    gd = load("stats_goldens")
+    x = torch.from_numpy(gd["chains"])
+    rhat, imag, w, b, w_pd, b_pd = st.multi_rhat(x)
+    assert abs(rhat - float(gd["multi_rhat"])) < 1e-9 and abs(rhat - 1.0134832973360262) < 1e-9
+    assert imag == 0 and w_pd and b_pd
+    lists = ChainLists(vals={"sample": [list(x[i].unbind(0)) for i in range(4)], "accepted": [[1] * 1000] * 4})
+    assert abs(lists.multi_rhat()[0] - rhat) < 1e-12
+    summ = lists.summary(keys=["mean", "mc_se", "acceptance", "multi_ess", "multi_rhat"])
+    assert abs(summ["multi_rhat"] - rhat) < 1e-12 and summ["acceptance"] == 1
+    assert abs(summ["multi_ess"] - gd["multi_ess"].mean()) < 1e-6
+    assert np.allclose(npy(summ["mc_se"]), np.sqrt(np.stack([np.diag(gd["inse"][i]) for i in range(4)])).mean(0), rtol=1e-9)
+    c = npy(st.cor(x[0]))
+    assert np.allclose(np.diag(c), 1.0) and np.allclose(c, np.corrcoef(gd["chains"][0].T), rtol=1e-10)
+    assert np.allclose(np.diag(npy(st.mc_cor(x[0]))), 1.0)
+    m = torch.tensor([[1.0, 2.0], [2.0, 1.0]], dtype=torch.float64)
+    from eeyore_b200.stats.stats import _is_pd
+    assert _is_pd(st.nearest_pd(m))
