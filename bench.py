@@ -289,7 +289,8 @@ def run_ours(args):
         if kind == "smmala":
             from eeyore_b200.samplers import SMMALA
             return SMMALA(model, theta0=theta0, dataloader=loader, step=w["step"], seed=seed, thin=thin)
-        return HMC(model, theta0=theta0, dataloader=loader, step=w["step"], num_steps=L, seed=seed, thin=thin)
+        return HMC(model, theta0=theta0, dataloader=loader, step=w["step"], num_steps=L, seed=seed, thin=thin,
+                   lanes_per_chain=args.lanes)
 
     sampler = make_sampler(theta_host.to(dev), 12345)
     sampler.chain_offset = rank * C          # global chain ids => results independent of the sharding
@@ -544,6 +545,7 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--iters", type=int, default=0, help="override HMC iterations per step")
     ap.add_argument("--rows", type=int, default=0, help="cfg5: override the total number of data rows")
+    ap.add_argument("--lanes", type=int, default=0, help="threads cooperating on one chain (0 = library heuristic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

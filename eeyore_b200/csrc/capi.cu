@@ -26,7 +26,9 @@ static int use_bulk() {
 // lanes per chain: enough threads to fill the 148 SMs, never more lanes than data rows
 static int choose_lanes(int64_t n_chains, int64_t n_rows, int requested) {
   if (requested > 0) return requested;
-  const int64_t want = 148LL * 4 * 128;
+  // measured on B200 (config 2: 4096 chains, N = 150, P = 27, fp64): 8 lanes/chain 2.7e8 evals/s, 4 lanes 2.1e8,
+  // 16 lanes 2.0e8, 32 lanes 1.4e8 -- the replicated per-lane work (prior, leapfrog, all-reduce) outweighs occupancy
+  const int64_t want = 148LL * 192;
   const int cands[] = {1, 4, 8, 16, 32};
   int g = 1;
   for (int c : cands) {
