@@ -462,7 +462,7 @@ def run_datapar(args):
         return t.item()
 
     sampler = DataShardedHMC(model, theta_host.to(dev), x, y, step=w["step"], num_steps=L, seed=7)
-    clocks = ClockSampler(local, enabled=(rank == 0)).start()
+    clocks = ClockSampler(local, enabled=(rank == 0 and not os.environ.get("EEYORE_BENCH_NO_CLOCKS"))).start()
     for _ in range(args.warmup):
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
     barrier()
@@ -477,6 +477,7 @@ def run_datapar(args):
     clocks.mark_end()
     clocks.stop()
     t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
+    per_step_ms = [round(ev[k].elapsed_time(ev[k + 1]), 2) for k in range(args.steps)]
     evals_step = iters * L
     value = evals_step * args.steps / t_res
     acc = sampler.acceptance_count() / max(1, sampler._iter)
@@ -516,7 +517,8 @@ def run_datapar(args):
             "config": {"workload": w["name"], "rows_total": n_total, "rows_per_gpu": hi - lo,
                        "hmc_iterations_per_step": iters, "num_steps": L, "evals_counted_per_iteration": L,
                        "exchange": "all-reduce of 1+P fp64 partial sums per evaluation (NCCL)" if world > 1 else "none (1 GPU)",
-                       "acceptance_rate": acc, "l2": "x shard (%.0f MB) exceeds the 126 MB L2" % ((hi - lo) * 68 / 1e6),
+                       "acceptance_rate": acc, "per_step_ms": per_step_ms,
+                       "l2": "x shard (%.0f MB) exceeds the 126 MB L2" % ((hi - lo) * 68 / 1e6),
                        "data_resident": "x, y shards stay in HBM across steps; e2e copies the chain state in and the samples out"},
             "e2e": {"value": evals_step * args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": P * 4,
                     "d2h_bytes_per_step": iters * P * 4, "ms_per_step": 1e3 * t_e2e / args.steps},

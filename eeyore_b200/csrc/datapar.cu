@@ -516,8 +516,15 @@ static int dp_cuda(cudaError_t e, const char* where) {
 
 int eeyore_b200_dp_num_params(void) { return DP_P; }
 
+int64_t eeyore_b200_dp_workspace_bytes(void) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int64_t)sizeof(double) * sms * (DP_P + 1);
+}
+
 int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
-                               void* stream) {
+                               void* workspace, void* stream) {
   if (!theta || !x || !y || !out_sums || n_rows < 1) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: bad argument");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: x and y must be 16-byte aligned (TMA bulk copy)");
@@ -527,16 +534,23 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long n_tiles = (n_rows + DP_R - 1) / DP_R;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  double* partials = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&partials, sizeof(double) * (size_t)grid * (DP_P + 1), st);
-  if (e != cudaSuccess) return dp_cuda(e, "dp_loglik_grad(alloc)");
-  e = cudaFuncSetAttribute(dp_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DpSmem));
-  if (e != cudaSuccess) return dp_cuda(e, "dp_loglik_grad(attr)");
+  double* partials = (double*)workspace;     // caller-owned [SMs, P + 1] doubles, or NULL: stream-ordered temporary
+  cudaError_t e;
+  if (!workspace) {
+    e = cudaMallocAsync((void**)&partials, sizeof(double) * (size_t)grid * (DP_P + 1), st);
+    if (e != cudaSuccess) return dp_cuda(e, "dp_loglik_grad(alloc)");
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(dp_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DpSmem));
+    if (e != cudaSuccess) return dp_cuda(e, "dp_loglik_grad(attr)");
+    attr_set = true;
+  }
   dp_eval_kernel<<<grid, DP_THREADS, sizeof(DpSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
                                                            (long)n_rows, partials);
   dp_reduce_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
   e = cudaGetLastError();
-  cudaFreeAsync(partials, st);
+  if (!workspace) cudaFreeAsync(partials, st);
   return dp_cuda(e, "dp_loglik_grad");
 }
 

@@ -147,7 +147,7 @@ class MLP(BayesianModel):
             st = nv.stream_ptr(dev)
             for i in range(c):
                 nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(theta[i]), nv.ptr(x), nv.ptr(yv), x.shape[0],
-                                                             nv.ptr(sums), st))
+                                                             nv.ptr(sums), None, st))
                 if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                          and getattr(self, "data_sharded", False)):
                     torch.distributed.all_reduce(sums, group=group)

@@ -38,6 +38,7 @@ class DataShardedHMC:
         dev, p = self.x.device, model.num_params()
         f32, f64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.float64, device=dev)
         self._sums = torch.empty(p + 1, **f64)
+        self._work = torch.empty(int(nv.lib().eeyore_b200_dp_workspace_bytes()) // 8, **f64)   # per-CTA partial sums
         self._theta_p, self._grad_p, self._mom = (torch.empty(p, **f32) for _ in range(3))
         self._lt_c, self._lt_p, self._kin0, self._kin1 = (torch.empty(1, **f64) for _ in range(4))
         self._acc_count = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -69,7 +70,7 @@ class DataShardedHMC:
         loc, scale = m.prior_on_device()
         st = nv.stream_ptr(self.x.device)
         nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0],
-                                                nv.ptr(self._sums), st))
+                                                nv.ptr(self._sums), nv.ptr(self._work), st))
         self._reduce(self._sums)                 # the one exchange step of the path: 1 + P doubles
         nv.check(lib.eeyore_b200_dp_finish(nv.ptr(self._sums), nv.ptr(theta), nv.ptr(loc), nv.ptr(scale),
                                            0 if m.temperature is None else 1,

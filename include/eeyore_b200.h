@@ -159,7 +159,9 @@ int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int 
 int eeyore_b200_dp_num_params(void);
 /* out_sums[0] = sum_i loglik_i, out_sums[1 + j] = d/dtheta_j sum_i loglik_i over this rank's rows (fp64, deterministic) */
 int eeyore_b200_dp_loglik_grad(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
-                               void *stream);
+                               void *workspace, void *stream);
+/* size of the optional caller-owned workspace of dp_loglik_grad (per-CTA partial sums); NULL workspace = temporary */
+int64_t eeyore_b200_dp_workspace_bytes(void);
 /* target (fp64 scalar) and gradient (fp32 [P]) from the all-reduced sums: adds the Normal log-prior
  * (eeyore/models/bayesian_model.py:46-56) and applies the temperature */
 int eeyore_b200_dp_finish(const void *sums, const void *theta, const void *prior_loc, const void *prior_scale,

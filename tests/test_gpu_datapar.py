@@ -75,7 +75,7 @@ def test_saturation_nan_semantics():
 
 def dp_sums(theta, x, y):
     sums = torch.empty(P + 1, dtype=torch.float64, device="cuda")
-    nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(x), nv.ptr(y), x.shape[0], nv.ptr(sums), None))
+    nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(x), nv.ptr(y), x.shape[0], nv.ptr(sums), None, None))
     return sums
 
 

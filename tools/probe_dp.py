@@ -43,7 +43,7 @@ timed("fresh sampler + run(2) + sync", fresh_sync)
 timed("ctor only", lambda: DataShardedHMC(m, th, x, y, step=2e-5, num_steps=10, seed=7))
 import eeyore_b200._native as nv
 sums = torch.empty(P+1, dtype=torch.float64, device=dev); thd = th.to(dev)
-timed("dp_loglik_grad only x20", lambda: [nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(thd), nv.ptr(x), nv.ptr(y), x.shape[0], nv.ptr(sums), nv.stream_ptr(dev))) for _ in range(20)])
+timed("dp_loglik_grad only x20", lambda: [nv.check(nv.lib().eeyore_b200_dp_loglik_grad(nv.ptr(thd), nv.ptr(x), nv.ptr(y), x.shape[0], nv.ptr(sums), None, nv.stream_ptr(dev))) for _ in range(20)])
 if world > 1:
     timed("allreduce only x20", lambda: [dist.all_reduce(sums) for _ in range(20)])
     dist.destroy_process_group()
