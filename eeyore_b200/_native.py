@@ -73,6 +73,7 @@ SIGNATURES = {
     "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "eeyore_b200_dp_num_params": (_I, []),
     "eeyore_b200_dp_loglik_grad": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    "eeyore_b200_dp_loglik_grad_ffma": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     "eeyore_b200_dp_workspace_bytes": (_I64, []),
     "eeyore_b200_dp_finish": (_I, [_VP, _VP, _VP, _VP, _I, _D, _VP, _VP, _VP]),
     "eeyore_b200_dp_hmc_begin": (_I, [_VP, _VP, _D, _U64, _U64, _VP, _VP, _VP, _VP, _VP]),

@@ -18,6 +18,7 @@
 #include <string>
 #include "common.cuh"
 #include "philox.cuh"
+#include "datapar.cuh"
 #include "../../include/eeyore_b200.h"
 
 #ifndef DP_UNROLL_KMAJOR
@@ -29,16 +30,7 @@
 
 namespace eb {
 
-constexpr int DP_D0 = 16, DP_H = 64;
-constexpr int DP_R = 128;            // rows per tile
 constexpr int DP_RS = DP_R + 4;      // row stride of feature-major buffers (floats); RS % 32 == 4
-constexpr int DP_THREADS = 256;
-constexpr int DP_OFF_B0 = DP_H * DP_D0;                 // 1024
-constexpr int DP_OFF_W1 = (DP_D0 + 1) * DP_H;           // 1088
-constexpr int DP_OFF_B1 = DP_OFF_W1 + DP_H * DP_H;      // 5184
-constexpr int DP_OFF_W2 = DP_OFF_B1 + DP_H;             // 5248
-constexpr int DP_OFF_B2 = DP_OFF_W2 + DP_H;             // 5312
-constexpr int DP_P = DP_OFF_B2 + 1;                     // 5313
 constexpr double kLogSqrt2PiD = 0.9189385332046727;     // log(sqrt(2 pi))
 
 struct DpSmem {
@@ -523,9 +515,9 @@ int64_t eeyore_b200_dp_workspace_bytes(void) {
   return (int64_t)sizeof(double) * sms * (DP_P + 1);
 }
 
-int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
+int eeyore_b200_dp_loglik_grad_ffma(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
                                void* workspace, void* stream) {
-  if (!theta || !x || !y || !out_sums || n_rows < 1) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: bad argument");
+  if (!theta || !x || !y || !out_sums || n_rows < 1) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad_ffma: bad argument");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: x and y must be 16-byte aligned (TMA bulk copy)");
   cudaStream_t st = (cudaStream_t)stream;

@@ -1,0 +1,516 @@
+// Tensor-core (tcgen05 + TMEM) version of the data-parallel log-likelihood + gradient kernel of BASELINE config 5
+// (MLP 16-64-64-1, fp32, millions of rows, one parameter vector).  Same contract and same output as
+// dp_eval_kernel in datapar.cu, which it replaces on the product path:
+//   eeyore/models/mlp.py:45-50 (forward), eeyore/stats/loss.py:1-11 (naive BCE on probabilities),
+//   eeyore/models/bayesian_model.py:30-35 (log_lik), eeyore/models/log_target_model.py:15-23 (gradient).
+//
+// Why tensor cores here and nowhere else: the two hidden layers are dense 64-wide contractions over 128-row tiles
+// (29,056 FLOP per row); the chain-batched kernels have no such contraction.
+//
+// fp32 parity on bf16 tensor cores: every operand x is split exactly into three bf16 pieces x = x1 + x2 + x3
+// (8 + 8 + 8 significant bits) and every product A B is evaluated as the six leading piece products
+//   A1 B1 + A1 B2 + A2 B1 + A1 B3 + A3 B1 + A2 B2        (dropped terms <= 2^-24 relative)
+// accumulated in fp32 in TMEM.  The B pieces are laid out side by side along N, so one product costs three MMAs
+// (A1 x [B1 B2 B3], A2 x [B1 B2], A3 x [B1]) into three 64-column accumulator groups that the epilogue adds up.
+//
+// Per 128-row tile (persistent CTAs, one per SM, 256 threads; thread = (row, half of the 64 features)):
+//   P0  x tile (TMA bulk copy) -> bf16 pieces in shared memory                      MMA1  Z1 = X W0^T
+//   P1  H1 = sigmoid(Z1 + b0) -> pieces (smem) + fp32 copy parked in TMEM           MMA2  Z2 = H1 W1^T
+//   P2  H2, head, log-lik, delta3, dW2 (warp butterfly), Delta2 -> pieces           MMA3  D1 = Delta2 W1
+//                                                                                    MMA4  [db1 dW1] = Delta2^T [1 H1]
+//   P3  Delta1 = D1 H1 (1 - H1) -> pieces (over Delta2)                             MMA5  [db0 dW0] = Delta1^T [1 X]
+//   P4  weight-gradient accumulators TMEM -> fp64 registers (per tile, so fp32 accumulation never spans > 128 rows)
+// One shared-memory copy of each activation serves both orientations: the SWIZZLE_NONE core-matrix layout of tc05.cuh
+// is a K-major operand for the forward / back-propagation GEMMs and an MN-major operand for the weight-gradient GEMMs.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string>
+#include "datapar.cuh"
+#include "tc05.cuh"
+#include "../../include/eeyore_b200.h"
+
+namespace eb {
+
+using namespace tc;
+
+constexpr uint32_t TC_CS = 2048;                 // chunk stride of [128 x C] activation buffers (128 rows * 16 B)
+constexpr uint32_t TC_ACT = 8 * TC_CS;           // one bf16 piece of a [128 x 64] activation: 16 KB
+constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] x tile: 4 KB
+constexpr uint32_t TC_WCS = 192 * 16;            // chunk stride of the piece-stacked weight buffers ([192 x K])
+// TMEM columns (fp32)
+constexpr uint32_t TM_Z1 = 0;                    // Z1 (3 groups of 64), later D1
+constexpr uint32_t TM_Z2 = 192;                  // Z2 (3 groups of 64), later [ones(8) | dW1 (3 x 64)] on lanes 16q..16q+15
+constexpr uint32_t TM_H1 = 392;                  // H1 in fp32 (P1 -> P3)
+constexpr uint32_t TM_W0 = 456;                  // [ones(8) | dW0 (3 x 16)]
+
+struct TcSmem {
+  alignas(1024) uint16_t ones_h[1024];           // 2 KB of bf16 1.0: the N-chunk in front of the H1 pieces
+  alignas(16) uint16_t h1[3 * TC_ACT / 2];       // H1 pieces
+  alignas(16) uint16_t ones_x[1024];             // the N-chunk in front of the x pieces
+  alignas(16) uint16_t xp[3 * TC_XP / 2];        // x pieces
+  alignas(16) uint16_t dl[3 * TC_ACT / 2];       // Delta2, then Delta1 pieces
+  alignas(16) uint16_t w0s[2 * TC_WCS / 2];      // rows 64 p + o, cols j      (B of MMA1)
+  alignas(16) uint16_t w1a[8 * TC_WCS / 2];      // rows 64 p + o, cols i      (B of MMA2)
+  alignas(16) uint16_t w1b[8 * TC_WCS / 2];      // rows 64 p + i, cols o      (B of MMA3)
+  alignas(16) float xs[DP_R * DP_D0];            // raw x tile, TMA destination
+  alignas(16) float ys[DP_R];
+  alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
+  alignas(16) float exch[2][DP_R];
+  alignas(8) unsigned long long bar[6];          // 0: x tile, 1..5: MMA groups
+  float b2;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ float tc_sigmoid(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+
+// d = {hi half: b, lo half: a} as bf16 (round to nearest even)
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// 8 consecutive fp32 values -> three 16-byte rows of bf16 pieces (exact: v = p1 + p2 + p3 + O(2^-25 v))
+__device__ __forceinline__ void split3(const float* v, uint4& p1, uint4& p2, uint4& p3) {
+  uint32_t a[4], b[4], c[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x0 = v[2 * j], x1 = v[2 * j + 1];
+    const uint32_t h = pack_bf16x2(x0, x1);
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+    const uint32_t m = pack_bf16x2(r0, r1);
+    const float s0 = r0 - __uint_as_float(m << 16), s1 = r1 - __uint_as_float(m & 0xffff0000u);
+    a[j] = h;
+    b[j] = m;
+    c[j] = pack_bf16x2(s0, s1);
+  }
+  p1 = make_uint4(a[0], a[1], a[2], a[3]);
+  p2 = make_uint4(b[0], b[1], b[2], b[3]);
+  p3 = make_uint4(c[0], c[1], c[2], c[3]);
+}
+// scalar version for the weight staging
+__device__ __forceinline__ void split3_scalar(float x, uint16_t& p1, uint16_t& p2, uint16_t& p3) {
+  const uint32_t h = pack_bf16x2(x, 0.f);
+  const float r = x - __uint_as_float(h << 16);
+  const uint32_t m = pack_bf16x2(r, 0.f);
+  const float s = r - __uint_as_float(m << 16);
+  p1 = (uint16_t)h;
+  p2 = (uint16_t)m;
+  p3 = (uint16_t)pack_bf16x2(s, 0.f);
+}
+
+// 32 features of one row, starting at chunk `chunk0` (8 features per chunk) -> the three piece buffers
+__device__ __forceinline__ void store_pieces32(unsigned char* base, uint32_t piece_bytes, int chunk0, int r, const float* v) {
+  unsigned char* p = base + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)chunk0 * TC_CS;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 p1, p2, p3;
+    split3(v + 8 * c, p1, p2, p3);
+    *reinterpret_cast<uint4*>(p + c * TC_CS) = p1;
+    *reinterpret_cast<uint4*>(p + c * TC_CS + piece_bytes) = p2;
+    *reinterpret_cast<uint4*>(p + c * TC_CS + 2 * piece_bytes) = p3;
+  }
+}
+
+// v[j] = sum of the three accumulator groups (64 columns apart) at columns col0 + j, j < 32
+__device__ __forceinline__ void load_sum3(uint32_t taddr, float* v) {
+  uint32_t a[32], b[32], c[32];
+  tmem_ld32(taddr, a);
+  tmem_ld32(taddr + 64, b);
+  tmem_ld32(taddr + 128, c);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(c[j]) + __uint_as_float(b[j])) + __uint_as_float(a[j]);
+}
+
+// reduce-scatter over the 32 lanes: on return t[0] of lane l = sum over lanes of their t[l]
+template <int W>
+__device__ __forceinline__ void butterfly_step(float* t, int lane) {
+  const bool up = (lane & W) != 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float send = up ? t[i] : t[i + W];
+    const float keep = up ? t[i + W] : t[i];
+    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+  }
+}
+
+// one A piece per MMA against the first (3 - a) B pieces; D groups are 64 (or N_PIECE) columns wide
+//   a_desc[a]: descriptors of the three A pieces;  b_desc: descriptor of [B1 B2 B3] (pieces adjacent along N)
+template <int M, int N_LEAD, int N_PIECE, int A_MN, int B_MN>
+__device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_desc, uint64_t b_desc, uint32_t a_step,
+                                            uint32_t b_step, int k_steps) {
+  constexpr uint32_t id0 = idesc_bf16(M, N_LEAD + 3 * N_PIECE, A_MN, B_MN);
+  constexpr uint32_t id1 = idesc_bf16(M, N_LEAD + 2 * N_PIECE, A_MN, B_MN);
+  constexpr uint32_t id2 = idesc_bf16(M, N_LEAD + 1 * N_PIECE, A_MN, B_MN);
+  for (int k = 0; k < k_steps; ++k) {
+    const uint64_t bd = desc_advance(b_desc, k * b_step);
+    mma_bf16(d_tmem, desc_advance(a_desc[0], k * a_step), bd, id0, k > 0);
+    mma_bf16(d_tmem, desc_advance(a_desc[1], k * a_step), bd, id1, 1u);
+    mma_bf16(d_tmem, desc_advance(a_desc[2], k * a_step), bd, id2, 1u);
+  }
+}
+
+// partials: [gridDim.x][DP_P + 1] doubles: [0] = log-likelihood, [1 + j] = d loglik / d theta_j
+__global__ void __launch_bounds__(DP_THREADS, 1)
+dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, const float* __restrict__ y, long n_rows,
+                  double* __restrict__ partials) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;   // TMEM lane quadrant; which half of the 64 features
+  const int r = 32 * q + lane;              // this thread's row of the tile (= TMEM lane)
+  const long n_tiles = (n_rows + DP_R - 1) / DP_R;
+
+  // ---- one-time staging: weights as bf16 pieces, constants, barriers, TMEM ------------------------------------------
+  for (int e = tid; e < DP_H * DP_D0; e += DP_THREADS) {  // W0[o][j]
+    const int o = e / DP_D0, j = e % DP_D0;
+    uint16_t p[3];
+    split3_scalar(theta[e], p[0], p[1], p[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS)) = p[k];
+  }
+  for (int e = tid; e < DP_H * DP_H; e += DP_THREADS) {   // W1[o][i]
+    const int o = e / DP_H, i = e % DP_H;
+    uint16_t p[3];
+    split3_scalar(theta[DP_OFF_W1 + e], p[0], p[1], p[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1a) + cm_off(64 * k + o, i, TC_WCS)) = p[k];
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * k + i, o, TC_WCS)) = p[k];
+    }
+  }
+  for (int e = tid; e < 1024; e += DP_THREADS) {
+    s.ones_h[e] = 0x3F80;
+    s.ones_x[e] = 0x3F80;
+  }
+  if (tid < DP_H) {
+    s.b0[tid] = theta[DP_OFF_B0 + tid];
+    s.b1[tid] = theta[DP_OFF_B1 + tid];
+    s.w2[tid] = theta[DP_OFF_W2 + tid];
+  }
+  if (tid == 0) {
+    s.b2 = theta[DP_OFF_B2];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) mbar_init(&s.bar[b], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = s.tmem_base;
+  const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
+
+  // descriptors (built once; K steps advance the start address)
+  uint64_t dXa[3], dH1a[3], dDLa[3], dDLm[3];
+  {
+    const uint32_t ax = smem_u32(s.xp), ah = smem_u32(s.h1), ad = smem_u32(s.dl);
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      dXa[p] = smem_desc(ax + p * TC_XP, TC_CS, 128);      // K-major A (M = row, K = input feature)
+      dH1a[p] = smem_desc(ah + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = hidden unit)
+      dDLa[p] = smem_desc(ad + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = output unit)
+      dDLm[p] = smem_desc(ad + p * TC_ACT, 128, TC_CS);    // MN-major A (M = unit, K = row)
+    }
+  }
+  const uint64_t dW0 = smem_desc(smem_u32(s.w0s), TC_WCS, 128);      // K-major B (N = 64 p + o, K = j)
+  const uint64_t dW1a = smem_desc(smem_u32(s.w1a), TC_WCS, 128);     // K-major B (N = 64 p + o, K = i)
+  const uint64_t dW1b = smem_desc(smem_u32(s.w1b), TC_WCS, 128);     // K-major B (N = 64 p + i, K = o)
+  const uint64_t dH1m = smem_desc(smem_u32(s.ones_h), 128, TC_CS);   // MN-major B (N = [1 x8 | H1 pieces], K = row)
+  const uint64_t dXm = smem_desc(smem_u32(s.ones_x), 128, TC_CS);    // MN-major B (N = [1 x8 | x pieces], K = row)
+
+  // persistent FP64 accumulators: lanes 0..15 of every warp own unit o = 16 q + lane (M = 64 accumulator layout)
+  double g1[32], g0[8];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) g1[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g0[i] = 0.0;
+  double gb1 = 0.0, gb0 = 0.0, gw2 = 0.0, gb2 = 0.0, ll = 0.0;
+
+  auto issue_x = [&](long tile) {
+    const long r0 = tile * DP_R;
+    const int rows = (int)min((long)DP_R, n_rows - r0);
+    const uint32_t xb = (uint32_t)rows * DP_D0 * 4, yb = (uint32_t)(rows & ~3) * 4;
+    mbar_expect_tx(&s.bar[0], xb + yb);
+    bulk_g2s(s.xs, x + r0 * DP_D0, xb, &s.bar[0]);
+    if (yb) bulk_g2s(s.ys, y + r0, yb, &s.bar[0]);
+  };
+
+  long tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_x(tile);
+  uint32_t par = 0;
+  for (; tile < n_tiles; tile += gridDim.x, par ^= 1u) {
+    const long row0 = tile * DP_R;
+    const int rows = (int)min((long)DP_R, n_rows - row0);
+    // ---- P0: x tile -> bf16 pieces; y into a register -----------------------------------------------------------------
+    mbar_wait(&s.bar[0], par);
+    float yv = 0.f;
+    {
+      float v[8];
+      if (r < rows) {
+        const float4 a = *reinterpret_cast<const float4*>(&s.xs[r * DP_D0 + 8 * hf]);
+        const float4 b = *reinterpret_cast<const float4*>(&s.xs[r * DP_D0 + 8 * hf + 4]);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        yv = (r < (rows & ~3)) ? s.ys[r] : y[row0 + r];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      uint4 p1, p2, p3;
+      split3(v, p1, p2, p3);
+      unsigned char* dst = reinterpret_cast<unsigned char*>(s.xp) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + hf * TC_CS;
+      *reinterpret_cast<uint4*>(dst) = p1;
+      *reinterpret_cast<uint4*>(dst + TC_XP) = p2;
+      *reinterpret_cast<uint4*>(dst + 2 * TC_XP) = p3;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z1, dXa, dW0, 0, 0, 1);          // MMA1: Z1 = X W0^T
+        mma_commit(&s.bar[1]);
+        const long next = tile + gridDim.x;                                   // the raw tile has been consumed
+        if (next < n_tiles) issue_x(next);
+      }
+      __syncwarp();
+    }
+    // ---- P1: H1 = sigmoid(Z1 + b0) ------------------------------------------------------------------------------------
+    mbar_wait(&s.bar[1], par);
+    fence_after_sync();
+    {
+      float v[32];
+      load_sum3(tm_lane + TM_Z1 + 32 * hf, v);
+      uint32_t hbits[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = tc_sigmoid(v[j] + s.b0[32 * hf + j]);
+        hbits[j] = __float_as_uint(v[j]);
+      }
+      tmem_st32(tm_lane + TM_H1 + 32 * hf, hbits);
+      store_pieces32(reinterpret_cast<unsigned char*>(s.h1), TC_ACT, 4 * hf, r, v);
+      tmem_st_wait();
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z2, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA2: Z2 = H1 W1^T
+        mma_commit(&s.bar[2]);
+      }
+      __syncwarp();
+    }
+    // ---- P2: H2, head, log-likelihood, delta3, dW2, Delta2 -------------------------------------------------------------
+    mbar_wait(&s.bar[2], par);
+    fence_after_sync();
+    {
+      float h[32];
+      load_sum3(tm_lane + TM_Z2 + 32 * hf, h);
+      float apart = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        h[j] = tc_sigmoid(h[j] + s.b1[32 * hf + j]);
+        apart = fmaf(h[j], s.w2[32 * hf + j], apart);
+      }
+      s.exch[hf][r] = apart;
+      fence_before_sync();
+      __syncthreads();
+      const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
+      float d = 0.f;
+      if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
+        const float p = 1.0f / (1.0f + expf(-a));
+        float term;
+        if (yv == 1.0f) term = (p == 1.0f) ? NAN : logf(p);
+        else if (yv == 0.0f) term = (p == 0.0f) ? NAN : logf(1.0f - p);
+        else term = logf(p) * yv + logf(1.0f - p) * (1.0f - yv);
+        d = (p == 0.0f || p == 1.0f) ? NAN : (yv - p);
+        if (hf == 0) {
+          ll += (double)term;
+          gb2 += (double)d;
+        }
+      }
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        t[j] = d * h[j];                                                   // dW2 terms
+        h[j] = d * s.w2[32 * hf + j] * (1.f - h[j]) * h[j];                // Delta2
+      }
+      store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, h);
+      butterfly_step<16>(t, lane);
+      butterfly_step<8>(t, lane);
+      butterfly_step<4>(t, lane);
+      butterfly_step<2>(t, lane);
+      butterfly_step<1>(t, lane);
+      gw2 += (double)t[0];                                                 // unit 32 hf + lane, rows of quadrant q
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z1, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA3: D1 = Delta2 W1
+        mma_commit(&s.bar[3]);
+        mma_product<64, 8, 64, 1, 1>(tm + TM_Z2, dDLm, dH1m, 256, 256, 8);                 // MMA4: Delta2^T [1 H1]
+        mma_commit(&s.bar[4]);
+      }
+      __syncwarp();
+    }
+    // ---- P3: Delta1 = D1 H1 (1 - H1), written over Delta2 once MMA4 has read it ----------------------------------------
+    mbar_wait(&s.bar[3], par);
+    fence_after_sync();
+    {
+      float v[32];
+      load_sum3(tm_lane + TM_Z1 + 32 * hf, v);
+      uint32_t hbits[32];
+      tmem_ld32(tm_lane + TM_H1 + 32 * hf, hbits);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float h1 = __uint_as_float(hbits[j]);
+        v[j] = v[j] * (1.f - h1) * h1;
+      }
+      mbar_wait(&s.bar[4], par);
+      store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, v);
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        mma_product<64, 8, 16, 1, 1>(tm + TM_W0, dDLm, dXm, 256, 256, 8);                  // MMA5: Delta1^T [1 X]
+        mma_commit(&s.bar[5]);
+      }
+      __syncwarp();
+    }
+    // ---- P4: fold this tile's weight-gradient sums into the FP64 accumulators ------------------------------------------
+    fence_after_sync();   // MMA4 is complete (bar[4] observed above)
+    {
+      float v[32];
+      load_sum3(tm_lane + TM_Z2 + 8 + 32 * hf, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g1[i] += (double)v[i];
+      uint32_t o4[4];
+      tmem_ld4(tm_lane + TM_Z2, o4);
+      tmem_ld_wait();
+      gb1 += (double)__uint_as_float(o4[0]);
+    }
+    mbar_wait(&s.bar[5], par);
+    fence_after_sync();
+    {
+      uint32_t a[8], b[8], c[8], o4[4];
+      tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, a);
+      tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, b);
+      tmem_ld8(tm_lane + TM_W0 + 8 + 32 + 8 * hf, c);
+      tmem_ld4(tm_lane + TM_W0, o4);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g0[i] += (double)((__uint_as_float(c[i]) + __uint_as_float(b[i])) + __uint_as_float(a[i]));
+      gb0 += (double)__uint_as_float(o4[0]);
+    }
+    // the next tile's P0 ends with fence_before_sync + __syncthreads before any MMA overwrites these TMEM columns
+  }
+
+  // ---- write this CTA's partial sums ---------------------------------------------------------------------------------
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+  double* out = partials + (size_t)blockIdx.x * (DP_P + 1);
+  if (lane < 16) {
+    const int o = 16 * q + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[1 + DP_OFF_W1 + o * DP_H + 32 * hf + i] = g1[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[1 + o * DP_D0 + 8 * hf + j] = g0[j];
+    if (hf == 0) {
+      out[1 + DP_OFF_B1 + o] = gb1;
+      out[1 + DP_OFF_B0 + o] = gb0;
+    }
+  }
+  // dW2: unit 32 hf + lane, partial over the rows of quadrant q; log-likelihood and db2: fixed-order block sums
+  double* red = reinterpret_cast<double*>(s.dl);   // the activation buffers are free now
+  red[tid] = gw2;
+  red[DP_THREADS + tid] = ll;
+  red[2 * DP_THREADS + tid] = gb2;
+  __syncthreads();
+  if (tid < DP_H) {
+    const int h2 = tid >> 5, l2 = tid & 31;
+    double t = 0.0;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) t += red[(4 * h2 + qq) * 32 + l2];
+    out[1 + DP_OFF_W2 + tid] = t;
+  }
+  if (tid == 64) {
+    double t = 0.0;
+    for (int i = 0; i < DP_R; ++i) t += red[DP_THREADS + i];      // hf == 0 threads are tid 0..127
+    out[0] = t;
+  }
+  if (tid == 96) {
+    double t = 0.0;
+    for (int i = 0; i < DP_R; ++i) t += red[2 * DP_THREADS + i];
+    out[1 + DP_OFF_B2] = t;
+  }
+}
+
+// out[e] = sum over CTAs of partials[cta][e], fixed order
+__global__ void dp_reduce_tc_kernel(const double* __restrict__ partials, int n_parts, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > DP_P) return;
+  double t = 0.0;
+  for (int c = 0; c < n_parts; ++c) t += partials[(size_t)c * (DP_P + 1) + e];
+  out[e] = t;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+int eeyore_b200_set_error_(int code, const char* msg);
+
+int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
+                               void* workspace, void* stream) {
+  if (!theta || !x || !y || !out_sums || n_rows < 1) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: bad argument");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: x and y must be 16-byte aligned (TMA bulk copy)");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto fail = [](cudaError_t e, const char* where) {
+    std::string m = std::string(where) + ": " + cudaGetErrorString(e);
+    return eeyore_b200_set_error_(EEYORE_B200_ECUDA, m.c_str());
+  };
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long n_tiles = (n_rows + DP_R - 1) / DP_R;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  double* partials = (double*)workspace;     // caller-owned [SMs, P + 1] doubles, or NULL: stream-ordered temporary
+  cudaError_t e;
+  if (!workspace) {
+    e = cudaMallocAsync((void**)&partials, sizeof(double) * (size_t)grid * (DP_P + 1), st);
+    if (e != cudaSuccess) return fail(e, "dp_loglik_grad(alloc)");
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(dp_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+    if (e != cudaSuccess) return fail(e, "dp_loglik_grad(attr)");
+    attr_set = true;
+  }
+  dp_eval_tc_kernel<<<grid, DP_THREADS, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
+                                                              (long)n_rows, partials);
+  dp_reduce_tc_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
+  e = cudaGetLastError();
+  if (!workspace) cudaFreeAsync(partials, st);
+  if (e != cudaSuccess) return fail(e, "dp_loglik_grad");
+  return EEYORE_B200_OK;
+}
+
+}  // extern "C"

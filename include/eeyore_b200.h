@@ -160,6 +160,10 @@ int eeyore_b200_dp_num_params(void);
 /* out_sums[0] = sum_i loglik_i, out_sums[1 + j] = d/dtheta_j sum_i loglik_i over this rank's rows (fp64, deterministic) */
 int eeyore_b200_dp_loglik_grad(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
                                void *workspace, void *stream);
+/* the same sums from the FP32 CUDA-core formulation (no tensor cores): kept as an independent cross-check of the
+ * tcgen05 kernel and as the A/B line of bench.py; not used by the product path */
+int eeyore_b200_dp_loglik_grad_ffma(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
+                                    void *workspace, void *stream);
 /* size of the optional caller-owned workspace of dp_loglik_grad (per-CTA partial sums); NULL workspace = temporary */
 int64_t eeyore_b200_dp_workspace_bytes(void);
 /* target (fp64 scalar) and gradient (fp32 [P]) from the all-reduced sums: adds the Normal log-prior
