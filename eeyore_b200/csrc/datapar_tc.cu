@@ -63,7 +63,27 @@ struct TcSmem {
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
 
-__device__ __forceinline__ float tc_sigmoid(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+#ifdef DP_TC_PROFILE
+__device__ unsigned long long dp_tc_prof[16];
+#define TC_STAMP(i)                                                        \
+  do {                                                                     \
+    if (blockIdx.x == 0 && tid == 32) {                                    \
+      const long long now_ = clock64();                                    \
+      dp_tc_prof[i] += (unsigned long long)(now_ - last_);                 \
+      last_ = now_;                                                        \
+    }                                                                      \
+  } while (0)
+#else
+#define TC_STAMP(i)
+#endif
+
+// 1 / (1 + 2^(-z log2 e)): two MUFU ops (ex2, rcp; both within 2 ulp) and no slow path -- exp overflow gives exactly 0
+__device__ __forceinline__ float tc_sigmoid(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // d = {hi half: b, lo half: a} as bf16 (round to nearest even)
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -243,11 +263,15 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   long tile = blockIdx.x;
   if (tid == 0 && tile < n_tiles) issue_x(tile);
   uint32_t par = 0;
+#ifdef DP_TC_PROFILE
+  long long last_ = clock64();
+#endif
   for (; tile < n_tiles; tile += gridDim.x, par ^= 1u) {
     const long row0 = tile * DP_R;
     const int rows = (int)min((long)DP_R, n_rows - row0);
     // ---- P0: x tile -> bf16 pieces; y into a register -----------------------------------------------------------------
     mbar_wait(&s.bar[0], par);
+    TC_STAMP(0);
     float yv = 0.f;
     {
       float v[8];
@@ -280,8 +304,10 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       }
       __syncwarp();
     }
+    TC_STAMP(1);
     // ---- P1: H1 = sigmoid(Z1 + b0) ------------------------------------------------------------------------------------
     mbar_wait(&s.bar[1], par);
+    TC_STAMP(2);
     fence_after_sync();
     {
       float v[32];
@@ -307,8 +333,10 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       }
       __syncwarp();
     }
+    TC_STAMP(3);
     // ---- P2: H2, head, log-likelihood, delta3, dW2, Delta2 -------------------------------------------------------------
     mbar_wait(&s.bar[2], par);
+    TC_STAMP(4);
     fence_after_sync();
     {
       float h[32];
@@ -363,8 +391,10 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       }
       __syncwarp();
     }
+    TC_STAMP(5);
     // ---- P3: Delta1 = D1 H1 (1 - H1), written over Delta2 once MMA4 has read it ----------------------------------------
     mbar_wait(&s.bar[3], par);
+    TC_STAMP(6);
     fence_after_sync();
     {
       float v[32];
@@ -377,7 +407,9 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         const float h1 = __uint_as_float(hbits[j]);
         v[j] = v[j] * (1.f - h1) * h1;
       }
+      TC_STAMP(7);
       mbar_wait(&s.bar[4], par);
+      TC_STAMP(8);
       store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, v);
     }
     fence_async_smem();
@@ -391,6 +423,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       }
       __syncwarp();
     }
+    TC_STAMP(9);
     // ---- P4: fold this tile's weight-gradient sums into the FP64 accumulators ------------------------------------------
     fence_after_sync();   // MMA4 is complete (bar[4] observed above)
     {
@@ -403,7 +436,9 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       tmem_ld_wait();
       gb1 += (double)__uint_as_float(o4[0]);
     }
+    TC_STAMP(10);
     mbar_wait(&s.bar[5], par);
+    TC_STAMP(11);
     fence_after_sync();
     {
       uint32_t a[8], b[8], c[8], o4[4];
@@ -416,6 +451,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       for (int i = 0; i < 8; ++i) g0[i] += (double)((__uint_as_float(c[i]) + __uint_as_float(b[i])) + __uint_as_float(a[i]));
       gb0 += (double)__uint_as_float(o4[0]);
     }
+    TC_STAMP(12);
     // the next tile's P0 ends with fence_before_sync + __syncthreads before any MMA overwrites these TMEM columns
   }
 
@@ -512,5 +548,16 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
   if (e != cudaSuccess) return fail(e, "dp_loglik_grad");
   return EEYORE_B200_OK;
 }
+
+#ifdef DP_TC_PROFILE
+/* debug builds only: cycles spent per phase by one warp of CTA 0, accumulated since the last call */
+int eeyore_b200_dp_tc_profile(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, dp_tc_prof, sizeof(unsigned long long) * 16);
+  unsigned long long zero[16] = {0};
+  cudaMemcpyToSymbol(dp_tc_prof, zero, sizeof(zero));
+  return 0;
+}
+#endif
 
 }  // extern "C"

@@ -1,0 +1,40 @@
+"""Phase-level cycle profile of the tcgen05 data-parallel kernel (needs a -DDP_TC_PROFILE build):
+   python tools/prof_dp_tc.py   (builds eeyore_b200/libeeyore_b200_prof.so if missing; run on the GPU box)"""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+LIB = ROOT / "eeyore_b200" / "libeeyore_b200_prof.so"
+if "build" in sys.argv:
+    from eeyore_b200 import _native as nv
+    nv.build(extra_flags=["-DDP_TC_PROFILE"], out=LIB)
+    sys.exit(0)
+os.environ["EEYORE_B200_LIB"] = str(LIB)
+import torch  # noqa: E402
+from eeyore_b200 import _native as nv  # noqa: E402
+
+P = 5313
+NAMES = ["wait x", "P0 split+sync", "wait MMA1", "P1 + sync", "wait MMA2", "P2 + sync", "wait MMA3", "P3 compute", "wait MMA4",
+         "P3 store + sync", "P4 dW1 flush", "wait MMA5", "P4 dW0 flush"]
+lib = nv.lib()
+n = 1 << 21
+g = torch.Generator(device="cuda").manual_seed(0)
+x = torch.randn(n, 16, device="cuda", generator=g)
+y = (torch.rand(n, device="cuda", generator=g) < 0.5).float()
+theta = torch.randn(P, device="cuda", generator=g) * 0.1
+out = torch.empty(P + 1, dtype=torch.float64, device="cuda")
+ws = torch.empty(lib.eeyore_b200_dp_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
+buf = (C.c_ulonglong * 16)()
+prof = lib.eeyore_b200_dp_tc_profile
+prof.argtypes = [C.POINTER(C.c_ulonglong)]
+for it in range(3):
+    nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(x), nv.ptr(y), n, nv.ptr(out), nv.ptr(ws), None))
+    prof(buf)
+tiles = (n // 128 + 147) // 148
+tot = sum(buf[:13])
+print(f"CTA 0: {tiles} tiles, {tot / tiles:.0f} cycles per tile")
+for i, nm in enumerate(NAMES):
+    print(f"  {nm:18s} {buf[i] / tiles:8.0f}  {100 * buf[i] / tot:5.1f}%")
