@@ -160,6 +160,39 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def _cpu_worker_dp(args):
+    """cfg5 on the CPU: one log-target + gradient evaluation of the numpy oracle port over a slice of `rows` synthetic rows
+    (the rows are independent, so the host cores shard them exactly as the GPUs do)."""
+    rows, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import oracle
+    from oracle.mlp import MLPSpec
+    w = WORKLOADS["cfg5"]
+    spec = MLPSpec(w["dims"], loss=w["loss"])
+    p = spec.num_params
+    rng = np.random.default_rng(seed)
+    theta = rng.normal(size=(1, p)) * 0.1
+    t_total, chunk = 0.0, 65536
+    for c0 in range(0, rows, chunk):
+        n = min(chunk, rows - c0)
+        x = rng.normal(size=(n, 16))
+        y = (rng.uniform(size=(n, 1)) < 0.5).astype(np.float64)
+        t0 = time.perf_counter()
+        oracle.log_target_grad(spec, theta, x, y, np.zeros(p), np.full(p, S3))
+        t_total += time.perf_counter() - t0
+    return t_total
+
+
+def cpu_datapar_throughput(pool, procs, sample_rows, n_total):
+    """Full-data-set evaluations per second of the oracle port: `sample_rows` rows split over the host cores, scaled to
+    n_total rows (the cost is linear in the row count)."""
+    per = max(1, sample_rows // procs)
+    t0 = time.perf_counter()
+    pool.pool.map(_cpu_worker_dp, [(per, s) for s in range(procs)], chunksize=1)
+    wall = time.perf_counter() - t0
+    return (per * procs / n_total) / wall, wall
+
+
 class CpuPool:
     """One worker process per host core, started once (outside any timed region)."""
 
@@ -204,6 +237,30 @@ def run_reference_arm(args):
         return
     w = WORKLOADS[args.workload]
     procs = host_cores()
+    if w.get("kind") == "datapar":
+        n_total = args.rows or w["rows"]
+        sample_rows = 1 << 20
+        pool = CpuPool(procs)
+        for _ in range(args.warmup):
+            cpu_datapar_throughput(pool, procs, 1 << 16, n_total)
+        walls, vals = [], []
+        for _ in range(args.steps):
+            v, wall = cpu_datapar_throughput(pool, procs, sample_rows, n_total)
+            vals.append(v)
+            walls.append(wall)
+        pool.close()
+        value = len(vals) / sum(1.0 / v for v in vals)
+        sample = (f"each step: one evaluation over {sample_rows} of the {n_total} rows, split over {procs} processes (one per host "
+                  f"core) of the numpy oracle port (oracle/mlp.py); evaluations/s scaled linearly to {n_total} rows")
+        print(json.dumps({
+            "impl": "reference", "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "rows_total": n_total, "evals_counted_per_iteration": w["num_steps"]},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
     cpp, iters = cpu_sample_sizes(args.workload)
     pool = CpuPool(procs)
     for _ in range(args.warmup):
@@ -501,15 +558,53 @@ def run_datapar(args):
     e1.record()
     barrier()
     t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    # ---- the dominant kernel alone (dp_eval_tc_kernel + its 21-CTA reduction), CUDA events on the launching stream -------
+    import ctypes
+    from eeyore_b200 import _native as nv
+    lib = nv.lib()
+    sums = torch.empty(P + 1, dtype=torch.float64, device=dev)
+    ws = torch.empty(lib.eeyore_b200_dp_workspace_bytes() // 8, dtype=torch.float64, device=dev)
+    th_dev = theta_host.to(dev)
+
+    def time_kernel(fn, reps=20):
+        for _ in range(3):
+            nv.check(fn(nv.ptr(th_dev), nv.ptr(x), nv.ptr(y), hi - lo, nv.ptr(sums), nv.ptr(ws), nv.stream_ptr(dev)))
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            nv.check(fn(nv.ptr(th_dev), nv.ptr(x), nv.ptr(y), hi - lo, nv.ptr(sums), nv.ptr(ws), nv.stream_ptr(dev)))
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+
+    barrier()
+    kernel_ms = max_over_ranks(time_kernel(lib.eeyore_b200_dp_loglik_grad))
+    ffma_ms = max_over_ranks(time_kernel(lib.eeyore_b200_dp_loglik_grad_ffma, reps=5))
     if rank == 0:
-        import ctypes
-        from eeyore_b200 import _native as nv
-        peak = ctypes.c_double()
-        nv.check(nv.lib().eeyore_b200_fma_peak(nv.F32, 4000, ctypes.byref(peak)))
-        # dominant kernel: dp_eval_kernel, one launch per evaluation over this rank's shard
+        peak32 = ctypes.c_double()
+        nv.check(lib.eeyore_b200_fma_peak(nv.F32, 4000, ctypes.byref(peak32)))
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+            tensor_peak, peak_src = float(peaks["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst; the kernel is timed alone)"
+        except Exception:
+            tensor_peak, peak_src = 1590.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
         flops_launch = 29056.0 * (hi - lo)
-        launch_s = t_res / (args.steps * evals_step)            # upper bound: includes the small kernels + all-reduce
-        achieved = flops_launch / launch_s / 1e12
+        achieved = flops_launch / (kernel_ms * 1e-3) / 1e12
+        # bf16 MMA work actually issued per 128-row tile: six piece products per GEMM; the M = 64 weight-gradient MMAs run
+        # at the cost of M = 128; ones columns for the bias sums
+        tiles = (hi - lo + 127) // 128
+        mma_flops_tile = 2 * 128 * 16 * (192 + 128 + 64) + 2 * (2 * 128 * 64 * (192 + 128 + 64)) \
+            + 2 * 128 * 128 * (200 + 136 + 72) + 2 * 128 * 128 * (56 + 40 + 24)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            procs = host_cores()
+            pool = CpuPool(procs)
+            cpu_datapar_throughput(pool, procs, 1 << 16, n_total)
+            v, wall = cpu_datapar_throughput(pool, procs, 1 << 20, n_total)
+            pool.close()
+            cpu = {"value": v, "unit": "evals/s", "cores": procs, "kind": "port",
+                   "sample": f"one evaluation over {1 << 20} of the {n_total} rows split over {procs} processes of the numpy oracle "
+                             f"port, {wall:.1f} s, scaled linearly to {n_total} rows"}
         print(json.dumps({
             "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
@@ -524,14 +619,20 @@ def run_datapar(args):
                     "d2h_bytes_per_step": iters * P * 4, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": args.steps * iters * (2 + 4 * L),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                         "frac": achieved / peak.value, "traffic": None,
-                         "peak_source": "measured live by eeyore_b200_fma_peak (this device)",
-                         "algorithmic_flops_per_row": 29056,
-                         "note": "per-evaluation time includes the reduce/finish/leapfrog kernels and the all-reduce",
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "dp_eval_tc_kernel (tcgen05 bf16 MMA, fp32 accumulate in TMEM)",
+                         "avg_launch_ms": kernel_ms, "algorithmic_flops_per_row": 29056,
+                         "bf16_mma_tflops_issued": tiles * mma_flops_tile / (kernel_ms * 1e-3) / 1e12,
+                         "note": "fp32 parity costs six bf16 piece products per GEMM: the tensor pipe executes %.1fx the "
+                                 "algorithmic FLOPs" % (mma_flops_tile / (29056.0 * 128)),
+                         "fp32_fma_view": {"peak": peak32.value, "frac": achieved / peak32.value,
+                                           "peak_source": "measured live by eeyore_b200_fma_peak (this device)",
+                                           "ffma_kernel_ms": ffma_ms, "speedup_over_ffma_kernel": ffma_ms / kernel_ms},
+                         "share_of_step": kernel_ms * evals_step / (1e3 * t_res / args.steps),
                          "hbm_view": {"algorithmic_bytes_per_launch": (hi - lo) * 68,
-                                      "achieved_gbs": (hi - lo) * 68 / launch_s / 1e9}},
-            "cpu_baseline": None,
+                                      "achieved_gbs": (hi - lo) * 68 / (kernel_ms * 1e-3) / 1e9}},
+            "cpu_baseline": cpu,
         }))
     if world > 1:
         dist.destroy_process_group()

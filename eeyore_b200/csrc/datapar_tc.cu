@@ -14,12 +14,12 @@
 // (A1 x [B1 B2 B3], A2 x [B1 B2], A3 x [B1]) into three 64-column accumulator groups that the epilogue adds up.
 //
 // Per 128-row tile (persistent CTAs, one per SM, 256 threads; thread = (row, half of the 64 features)):
-//   P0  x tile (TMA bulk copy) -> bf16 pieces in shared memory                      MMA1  Z1 = X W0^T
+//   P0  x tile (coalesced loads, prefetched one tile ahead) -> bf16 pieces in smem  MMA1  Z1 = X W0^T
 //   P1  H1 = sigmoid(Z1 + b0) -> pieces (smem) + fp32 copy parked in TMEM           MMA2  Z2 = H1 W1^T
 //   P2  H2, head, log-lik, delta3, dW2 (warp butterfly), Delta2 -> pieces           MMA3  D1 = Delta2 W1
 //                                                                                    MMA4  [db1 dW1] = Delta2^T [1 H1]
-//   P3  Delta1 = D1 H1 (1 - H1) -> pieces (over Delta2)                             MMA5  [db0 dW0] = Delta1^T [1 X]
-//   P4  weight-gradient accumulators TMEM -> fp64 registers (per tile, so fp32 accumulation never spans > 128 rows)
+//   P3  Delta1 = D1 H1 (1 - H1) -> pieces (second buffer: MMA4 may still be reading)  MMA5  [db0 dW0] = Delta1^T [1 X]
+//   P4  every TC_FLUSH tiles: weight-gradient accumulators TMEM -> fp64 registers (fp32 accumulation spans <= 512 rows)
 // One shared-memory copy of each activation serves both orientations: the SWIZZLE_NONE core-matrix layout of tc05.cuh
 // is a K-major operand for the forward / back-propagation GEMMs and an MN-major operand for the weight-gradient GEMMs.
 #include <cuda_runtime.h>
@@ -39,25 +39,25 @@ constexpr uint32_t TC_ACT = 8 * TC_CS;           // one bf16 piece of a [128 x 6
 constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] x tile: 4 KB
 constexpr uint32_t TC_WCS = 192 * 16;            // chunk stride of the piece-stacked weight buffers ([192 x K])
 // TMEM columns (fp32)
-constexpr uint32_t TM_Z1 = 0;                    // Z1 (3 groups of 64), later D1
-constexpr uint32_t TM_Z2 = 192;                  // Z2 (3 groups of 64), later [ones(8) | dW1 (3 x 64)] on lanes 16q..16q+15
+constexpr uint32_t TM_Z = 0;                     // Z1, then Z2, then D1 (3 groups of 64): one region, the phases are sequential
+constexpr uint32_t TM_W1 = 192;                  // [ones(8) | dW1 (3 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
 constexpr uint32_t TM_H1 = 392;                  // H1 in fp32 (P1 -> P3)
 constexpr uint32_t TM_W0 = 456;                  // [ones(8) | dW0 (3 x 16)]
+constexpr int TC_FLUSH = 4;                      // tiles between two folds of the TMEM weight-gradient sums into FP64
 
 struct TcSmem {
   alignas(1024) uint16_t ones_h[1024];           // 2 KB of bf16 1.0: the N-chunk in front of the H1 pieces
   alignas(16) uint16_t h1[3 * TC_ACT / 2];       // H1 pieces
   alignas(16) uint16_t ones_x[1024];             // the N-chunk in front of the x pieces
   alignas(16) uint16_t xp[3 * TC_XP / 2];        // x pieces
-  alignas(16) uint16_t dl[3 * TC_ACT / 2];       // Delta2, then Delta1 pieces
+  alignas(16) uint16_t dl[3 * TC_ACT / 2];       // Delta2 pieces
+  alignas(16) uint16_t dl1[3 * TC_ACT / 2];      // Delta1 pieces
   alignas(16) uint16_t w0s[2 * TC_WCS / 2];      // rows 64 p + o, cols j      (B of MMA1)
   alignas(16) uint16_t w1a[8 * TC_WCS / 2];      // rows 64 p + o, cols i      (B of MMA2)
   alignas(16) uint16_t w1b[8 * TC_WCS / 2];      // rows 64 p + i, cols o      (B of MMA3)
-  alignas(16) float xs[DP_R * DP_D0];            // raw x tile, TMA destination
-  alignas(16) float ys[DP_R];
   alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
   alignas(16) float exch[2][DP_R];
-  alignas(8) unsigned long long bar[6];          // 0: x tile, 1..5: MMA groups
+  alignas(8) unsigned long long bar[6];          // 1..5: MMA groups
   float b2;
   uint32_t tmem_base;
 };
@@ -160,13 +160,13 @@ __device__ __forceinline__ void butterfly_step(float* t, int lane) {
 //   a_desc[a]: descriptors of the three A pieces;  b_desc: descriptor of [B1 B2 B3] (pieces adjacent along N)
 template <int M, int N_LEAD, int N_PIECE, int A_MN, int B_MN>
 __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_desc, uint64_t b_desc, uint32_t a_step,
-                                            uint32_t b_step, int k_steps) {
+                                            uint32_t b_step, int k_steps, uint32_t accumulate = 0u) {
   constexpr uint32_t id0 = idesc_bf16(M, N_LEAD + 3 * N_PIECE, A_MN, B_MN);
   constexpr uint32_t id1 = idesc_bf16(M, N_LEAD + 2 * N_PIECE, A_MN, B_MN);
   constexpr uint32_t id2 = idesc_bf16(M, N_LEAD + 1 * N_PIECE, A_MN, B_MN);
   for (int k = 0; k < k_steps; ++k) {
     const uint64_t bd = desc_advance(b_desc, k * b_step);
-    mma_bf16(d_tmem, desc_advance(a_desc[0], k * a_step), bd, id0, k > 0);
+    mma_bf16(d_tmem, desc_advance(a_desc[0], k * a_step), bd, id0, (k > 0) ? 1u : accumulate);
     mma_bf16(d_tmem, desc_advance(a_desc[1], k * a_step), bd, id1, 1u);
     mma_bf16(d_tmem, desc_advance(a_desc[2], k * a_step), bd, id2, 1u);
   }
@@ -226,15 +226,16 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
 
   // descriptors (built once; K steps advance the start address)
-  uint64_t dXa[3], dH1a[3], dDLa[3], dDLm[3];
+  uint64_t dXa[3], dH1a[3], dDLa[3], dDLm[3], dDL1m[3];
   {
-    const uint32_t ax = smem_u32(s.xp), ah = smem_u32(s.h1), ad = smem_u32(s.dl);
+    const uint32_t ax = smem_u32(s.xp), ah = smem_u32(s.h1), ad = smem_u32(s.dl), ad1 = smem_u32(s.dl1);
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
       dXa[p] = smem_desc(ax + p * TC_XP, TC_CS, 128);      // K-major A (M = row, K = input feature)
       dH1a[p] = smem_desc(ah + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = hidden unit)
       dDLa[p] = smem_desc(ad + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = output unit)
       dDLm[p] = smem_desc(ad + p * TC_ACT, 128, TC_CS);    // MN-major A (M = unit, K = row)
+      dDL1m[p] = smem_desc(ad1 + p * TC_ACT, 128, TC_CS);
     }
   }
   const uint64_t dW0 = smem_desc(smem_u32(s.w0s), TC_WCS, 128);      // K-major B (N = 64 p + o, K = j)
@@ -251,39 +252,38 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   for (int i = 0; i < 8; ++i) g0[i] = 0.0;
   double gb1 = 0.0, gb0 = 0.0, gw2 = 0.0, gb2 = 0.0, ll = 0.0;
 
-  auto issue_x = [&](long tile) {
-    const long r0 = tile * DP_R;
-    const int rows = (int)min((long)DP_R, n_rows - r0);
-    const uint32_t xb = (uint32_t)rows * DP_D0 * 4, yb = (uint32_t)(rows & ~3) * 4;
-    mbar_expect_tx(&s.bar[0], xb + yb);
-    bulk_g2s(s.xs, x + r0 * DP_D0, xb, &s.bar[0]);
-    if (yb) bulk_g2s(s.ys, y + r0, yb, &s.bar[0]);
+  // this thread's 8 features of its row and the row's label, loaded one tile ahead (rows are 64 B: two 16-byte loads)
+  float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+  float ynext = 0.f;
+  auto prefetch_x = [&](long tile) {
+    const long gr = tile * DP_R + r;
+    xa = xb = make_float4(0.f, 0.f, 0.f, 0.f);
+    ynext = 0.f;
+    if (tile < n_tiles && gr < n_rows) {
+      const float4* src = reinterpret_cast<const float4*>(x + gr * DP_D0 + 8 * hf);
+      xa = __ldg(src);
+      xb = __ldg(src + 1);
+      ynext = __ldg(y + gr);
+    }
   };
 
   long tile = blockIdx.x;
-  if (tid == 0 && tile < n_tiles) issue_x(tile);
+  prefetch_x(tile);
   uint32_t par = 0;
+  int it = 0;
 #ifdef DP_TC_PROFILE
   long long last_ = clock64();
 #endif
-  for (; tile < n_tiles; tile += gridDim.x, par ^= 1u) {
+  for (; tile < n_tiles; tile += gridDim.x, par ^= 1u, ++it) {
     const long row0 = tile * DP_R;
     const int rows = (int)min((long)DP_R, n_rows - row0);
-    // ---- P0: x tile -> bf16 pieces; y into a register -----------------------------------------------------------------
-    mbar_wait(&s.bar[0], par);
+    const bool fold = ((it + 1) % TC_FLUSH == 0) || (tile + gridDim.x >= n_tiles);
+    const uint32_t keep = (it % TC_FLUSH != 0) ? 1u : 0u;   // weight-gradient sums continue from the previous tile
+    // ---- P0: x tile -> bf16 pieces (rows beyond the data are zero) ---------------------------------------------------------
     TC_STAMP(0);
-    float yv = 0.f;
+    const float yv = ynext;
     {
-      float v[8];
-      if (r < rows) {
-        const float4 a = *reinterpret_cast<const float4*>(&s.xs[r * DP_D0 + 8 * hf]);
-        const float4 b = *reinterpret_cast<const float4*>(&s.xs[r * DP_D0 + 8 * hf + 4]);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        yv = (r < (rows & ~3)) ? s.ys[r] : y[row0 + r];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      }
+      const float v[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
       uint4 p1, p2, p3;
       split3(v, p1, p2, p3);
       unsigned char* dst = reinterpret_cast<unsigned char*>(s.xp) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + hf * TC_CS;
@@ -297,13 +297,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z1, dXa, dW0, 0, 0, 1);          // MMA1: Z1 = X W0^T
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);          // MMA1: Z1 = X W0^T
         mma_commit(&s.bar[1]);
-        const long next = tile + gridDim.x;                                   // the raw tile has been consumed
-        if (next < n_tiles) issue_x(next);
       }
       __syncwarp();
     }
+    prefetch_x(tile + gridDim.x);
     TC_STAMP(1);
     // ---- P1: H1 = sigmoid(Z1 + b0) ------------------------------------------------------------------------------------
     mbar_wait(&s.bar[1], par);
@@ -311,7 +310,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     fence_after_sync();
     {
       float v[32];
-      load_sum3(tm_lane + TM_Z1 + 32 * hf, v);
+      load_sum3(tm_lane + TM_Z + 32 * hf, v);
       uint32_t hbits[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -328,7 +327,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z2, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA2: Z2 = H1 W1^T
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA2: Z2 = H1 W1^T
         mma_commit(&s.bar[2]);
       }
       __syncwarp();
@@ -338,9 +337,10 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     mbar_wait(&s.bar[2], par);
     TC_STAMP(4);
     fence_after_sync();
+    float t[32], p_head = 0.5f, d_head = 0.f;
     {
       float h[32];
-      load_sum3(tm_lane + TM_Z2 + 32 * hf, h);
+      load_sum3(tm_lane + TM_Z + 32 * hf, h);
       float apart = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -348,35 +348,20 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         apart = fmaf(h[j], s.w2[32 * hf + j], apart);
       }
       s.exch[hf][r] = apart;
-      fence_before_sync();
-      __syncthreads();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share rows 32 q .. 32 q + 31
       const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
       float d = 0.f;
       if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
-        const float p = 1.0f / (1.0f + expf(-a));
-        float term;
-        if (yv == 1.0f) term = (p == 1.0f) ? NAN : logf(p);
-        else if (yv == 0.0f) term = (p == 0.0f) ? NAN : logf(1.0f - p);
-        else term = logf(p) * yv + logf(1.0f - p) * (1.0f - yv);
-        d = (p == 0.0f || p == 1.0f) ? NAN : (yv - p);
-        if (hf == 0) {
-          ll += (double)term;
-          gb2 += (double)d;
-        }
+        p_head = 1.0f / (1.0f + expf(-a));
+        d = (p_head == 0.0f || p_head == 1.0f) ? NAN : (yv - p_head);
       }
-      float t[32];
+      d_head = d;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         t[j] = d * h[j];                                                   // dW2 terms
         h[j] = d * s.w2[32 * hf + j] * (1.f - h[j]) * h[j];                // Delta2
       }
       store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, h);
-      butterfly_step<16>(t, lane);
-      butterfly_step<8>(t, lane);
-      butterfly_step<4>(t, lane);
-      butterfly_step<2>(t, lane);
-      butterfly_step<1>(t, lane);
-      gw2 += (double)t[0];                                                 // unit 32 hf + lane, rows of quadrant q
     }
     fence_async_smem();
     fence_before_sync();
@@ -384,21 +369,36 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z1, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA3: D1 = Delta2 W1
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA3: D1 = Delta2 W1
         mma_commit(&s.bar[3]);
-        mma_product<64, 8, 64, 1, 1>(tm + TM_Z2, dDLm, dH1m, 256, 256, 8);                 // MMA4: Delta2^T [1 H1]
+        mma_product<64, 8, 64, 1, 1>(tm + TM_W1, dDLm, dH1m, 256, 256, 8, keep);           // MMA4: Delta2^T [1 H1]
         mma_commit(&s.bar[4]);
       }
       __syncwarp();
     }
+    // in the shadow of MMA3: the log-likelihood term and the column sums for dW2
+    if (hf == 0 && r < rows) {
+      float term;
+      if (yv == 1.0f) term = (p_head == 1.0f) ? NAN : logf(p_head);
+      else if (yv == 0.0f) term = (p_head == 0.0f) ? NAN : logf(1.0f - p_head);
+      else term = logf(p_head) * yv + logf(1.0f - p_head) * (1.0f - yv);
+      ll += (double)term;
+      gb2 += (double)d_head;
+    }
+    butterfly_step<16>(t, lane);
+    butterfly_step<8>(t, lane);
+    butterfly_step<4>(t, lane);
+    butterfly_step<2>(t, lane);
+    butterfly_step<1>(t, lane);
+    gw2 += (double)t[0];                                                   // unit 32 hf + lane, rows of quadrant q
     TC_STAMP(5);
-    // ---- P3: Delta1 = D1 H1 (1 - H1), written over Delta2 once MMA4 has read it ----------------------------------------
+    // ---- P3: Delta1 = D1 H1 (1 - H1) ------------------------------------------------------------------------------------
     mbar_wait(&s.bar[3], par);
     TC_STAMP(6);
     fence_after_sync();
     {
       float v[32];
-      load_sum3(tm_lane + TM_Z1 + 32 * hf, v);
+      load_sum3(tm_lane + TM_Z + 32 * hf, v);
       uint32_t hbits[32];
       tmem_ld32(tm_lane + TM_H1 + 32 * hf, hbits);
       tmem_ld_wait();
@@ -408,9 +408,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         v[j] = v[j] * (1.f - h1) * h1;
       }
       TC_STAMP(7);
-      mbar_wait(&s.bar[4], par);
-      TC_STAMP(8);
-      store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, v);
+      store_pieces32(reinterpret_cast<unsigned char*>(s.dl1), TC_ACT, 4 * hf, r, v);
     }
     fence_async_smem();
     fence_before_sync();
@@ -418,29 +416,31 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<64, 8, 16, 1, 1>(tm + TM_W0, dDLm, dXm, 256, 256, 8);                  // MMA5: Delta1^T [1 X]
+        mma_product<64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);           // MMA5: Delta1^T [1 X]
         mma_commit(&s.bar[5]);
       }
       __syncwarp();
     }
     TC_STAMP(9);
-    // ---- P4: fold this tile's weight-gradient sums into the FP64 accumulators ------------------------------------------
-    fence_after_sync();   // MMA4 is complete (bar[4] observed above)
-    {
+    // ---- P4: every TC_FLUSH tiles fold the weight-gradient sums into the FP64 accumulators -----------------------------------
+    mbar_wait(&s.bar[4], par);
+    TC_STAMP(8);
+    fence_after_sync();
+    if (fold) {
       float v[32];
-      load_sum3(tm_lane + TM_Z2 + 8 + 32 * hf, v);
+      load_sum3(tm_lane + TM_W1 + 8 + 32 * hf, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) g1[i] += (double)v[i];
       uint32_t o4[4];
-      tmem_ld4(tm_lane + TM_Z2, o4);
+      tmem_ld4(tm_lane + TM_W1, o4);
       tmem_ld_wait();
       gb1 += (double)__uint_as_float(o4[0]);
     }
     TC_STAMP(10);
-    mbar_wait(&s.bar[5], par);
+    mbar_wait(&s.bar[5], par);   // also: MMA5 has finished reading the x pieces and Delta1
     TC_STAMP(11);
     fence_after_sync();
-    {
+    if (fold) {
       uint32_t a[8], b[8], c[8], o4[4];
       tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, a);
       tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, b);

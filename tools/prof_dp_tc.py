@@ -17,8 +17,8 @@ import torch  # noqa: E402
 from eeyore_b200 import _native as nv  # noqa: E402
 
 P = 5313
-NAMES = ["wait x", "P0 split+sync", "wait MMA1", "P1 + sync", "wait MMA2", "P2 + sync", "wait MMA3", "P3 compute", "wait MMA4",
-         "P3 store + sync", "P4 dW1 flush", "wait MMA5", "P4 dW0 flush"]
+NAMES = ["loop top", "P0 split+sync", "wait MMA1", "P1 + sync", "wait MMA2", "P2 + sync", "wait MMA3", "P3 compute", "wait MMA4",
+         "P3 store + sync", "P4 dW1 fold", "wait MMA5", "P4 dW0 fold"]
 lib = nv.lib()
 n = 1 << 21
 g = torch.Generator(device="cuda").manual_seed(0)
