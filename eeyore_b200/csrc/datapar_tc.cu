@@ -19,6 +19,7 @@
 //   P2  H2, head, log-lik, delta3, dW2 (warp butterfly), Delta2 -> pieces           MMA3  D1 = Delta2 W1
 //                                                                                    MMA4  [db1 dW1] = Delta2^T [1 H1]
 //   P3  Delta1 = D1 H1 (1 - H1) -> pieces (second buffer: MMA4 may still be reading)  MMA5  [db0 dW0] = Delta1^T [1 X]
+// (A ninth, issue-only warp was measured slower: three warps on one scheduler cap the kernel at 168 registers -> spills.)
 //   P4  every TC_FLUSH tiles: weight-gradient accumulators TMEM -> fp64 registers (fp32 accumulation spans <= 512 rows)
 // One shared-memory copy of each activation serves both orientations: the SWIZZLE_NONE core-matrix layout of tc05.cuh
 // is a K-major operand for the forward / back-propagation GEMMs and an MN-major operand for the weight-gradient GEMMs.
@@ -43,7 +44,8 @@ constexpr uint32_t TM_Z = 0;                     // Z1, then Z2, then D1 (3 grou
 constexpr uint32_t TM_W1 = 192;                  // [ones(8) | dW1 (3 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
 constexpr uint32_t TM_H1 = 392;                  // H1 in fp32 (P1 -> P3)
 constexpr uint32_t TM_W0 = 456;                  // [ones(8) | dW0 (3 x 16)]
-constexpr int TC_FLUSH = 4;                      // tiles between two folds of the TMEM weight-gradient sums into FP64
+constexpr int TC_FLUSH = 4;
+constexpr int TC_THREADS = DP_THREADS;           // 8 warps: every one an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
 
 struct TcSmem {
   alignas(1024) uint16_t ones_h[1024];           // 2 KB of bf16 1.0: the N-chunk in front of the H1 pieces
@@ -64,7 +66,7 @@ struct TcSmem {
 static_assert(sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
 
 #ifdef DP_TC_PROFILE
-__device__ unsigned long long dp_tc_prof[16];
+__device__ unsigned long long dp_tc_prof[24];
 #define TC_STAMP(i)                                                        \
   do {                                                                     \
     if (blockIdx.x == 0 && tid == 32) {                                    \
@@ -144,6 +146,17 @@ __device__ __forceinline__ void load_sum3(uint32_t taddr, float* v) {
   for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(c[j]) + __uint_as_float(b[j])) + __uint_as_float(a[j]);
 }
 
+// hi + lo += x, error-free (Knuth two-sum): a pair of fp32 registers carries ~46 significant bits.  The tile loop uses
+// these instead of FP64 adds: ncu showed every isolated DADD of the loop stalling for hundreds of cycles on the FP64 pipe
+// (stall_math_pipe_throttle), 8 % of the kernel for a handful of instructions per tile.
+__device__ __forceinline__ void acc2(float& hi, float& lo, float x) {
+  const float s = hi + x;
+  const float bb = s - hi;
+  const float e = (hi - (s - bb)) + (x - bb);
+  hi = s;
+  lo += e;
+}
+
 // reduce-scatter over the 32 lanes: on return t[0] of lane l = sum over lanes of their t[l]
 template <int W>
 __device__ __forceinline__ void butterfly_step(float* t, int lane) {
@@ -173,7 +186,7 @@ __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_d
 }
 
 // partials: [gridDim.x][DP_P + 1] doubles: [0] = log-likelihood, [1 + j] = d loglik / d theta_j
-__global__ void __launch_bounds__(DP_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, const float* __restrict__ y, long n_rows,
                   double* __restrict__ partials) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
@@ -182,9 +195,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   const int q = warp & 3, hf = warp >> 2;   // TMEM lane quadrant; which half of the 64 features
   const int r = 32 * q + lane;              // this thread's row of the tile (= TMEM lane)
   const long n_tiles = (n_rows + DP_R - 1) / DP_R;
+#ifdef DP_TC_PROFILE
+  long long last_ = clock64();
+#endif
 
   // ---- one-time staging: weights as bf16 pieces, constants, barriers, TMEM ------------------------------------------
-  for (int e = tid; e < DP_H * DP_D0; e += DP_THREADS) {  // W0[o][j]
+  for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) {  // W0[o][j]
     const int o = e / DP_D0, j = e % DP_D0;
     uint16_t p[3];
     split3_scalar(theta[e], p[0], p[1], p[2]);
@@ -192,7 +208,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     for (int k = 0; k < 3; ++k)
       *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS)) = p[k];
   }
-  for (int e = tid; e < DP_H * DP_H; e += DP_THREADS) {   // W1[o][i]
+  for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) {   // W1[o][i]
     const int o = e / DP_H, i = e % DP_H;
     uint16_t p[3];
     split3_scalar(theta[DP_OFF_W1 + e], p[0], p[1], p[2]);
@@ -202,7 +218,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * k + i, o, TC_WCS)) = p[k];
     }
   }
-  for (int e = tid; e < 1024; e += DP_THREADS) {
+  for (int e = tid; e < 1024; e += TC_THREADS) {
     s.ones_h[e] = 0x3F80;
     s.ones_x[e] = 0x3F80;
   }
@@ -245,12 +261,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   const uint64_t dXm = smem_desc(smem_u32(s.ones_x), 128, TC_CS);    // MN-major B (N = [1 x8 | x pieces], K = row)
 
   // persistent FP64 accumulators: lanes 0..15 of every warp own unit o = 16 q + lane (M = 64 accumulator layout)
-  double g1[32], g0[8];
+  float g1[32], g1e[32], g0[8], g0e[8];   // (sum, error term) pairs, see acc2
 #pragma unroll
-  for (int i = 0; i < 32; ++i) g1[i] = 0.0;
+  for (int i = 0; i < 32; ++i) g1[i] = g1e[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) g0[i] = 0.0;
-  double gb1 = 0.0, gb0 = 0.0, gw2 = 0.0, gb2 = 0.0, ll = 0.0;
+  for (int i = 0; i < 8; ++i) g0[i] = g0e[i] = 0.f;
+  float gb1 = 0.f, gb1e = 0.f, gb0 = 0.f, gb0e = 0.f, gw2 = 0.f, gw2e = 0.f, gb2 = 0.f, gb2e = 0.f, ll = 0.f, lle = 0.f;
 
   // this thread's 8 features of its row and the row's label, loaded one tile ahead (rows are 64 B: two 16-byte loads)
   float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
@@ -271,9 +287,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   prefetch_x(tile);
   uint32_t par = 0;
   int it = 0;
-#ifdef DP_TC_PROFILE
-  long long last_ = clock64();
-#endif
+  TC_STAMP(20);
   for (; tile < n_tiles; tile += gridDim.x, par ^= 1u, ++it) {
     const long row0 = tile * DP_R;
     const int rows = (int)min((long)DP_R, n_rows - row0);
@@ -297,7 +311,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);          // MMA1: Z1 = X W0^T
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);                        // MMA1: Z1 = X W0^T
         mma_commit(&s.bar[1]);
       }
       __syncwarp();
@@ -327,7 +341,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA2: Z2 = H1 W1^T
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS, 4);     // MMA2: Z2 = H1 W1^T
         mma_commit(&s.bar[2]);
       }
       __syncwarp();
@@ -347,8 +361,10 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         h[j] = tc_sigmoid(h[j] + s.b1[32 * hf + j]);
         apart = fmaf(h[j], s.w2[32 * hf + j], apart);
       }
+      TC_STAMP(13);
       s.exch[hf][r] = apart;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share rows 32 q .. 32 q + 31
+      TC_STAMP(14);
       const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
       float d = 0.f;
       if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
@@ -356,6 +372,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         d = (p_head == 0.0f || p_head == 1.0f) ? NAN : (yv - p_head);
       }
       d_head = d;
+      TC_STAMP(15);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         t[j] = d * h[j];                                                   // dW2 terms
@@ -363,34 +380,39 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       }
       store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, h);
     }
+    TC_STAMP(16);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS, 4);   // MMA3: D1 = Delta2 W1
+        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS, 4);     // MMA3: D1 = Delta2 W1
         mma_commit(&s.bar[3]);
-        mma_product<64, 8, 64, 1, 1>(tm + TM_W1, dDLm, dH1m, 256, 256, 8, keep);           // MMA4: Delta2^T [1 H1]
+        mma_product<64, 8, 64, 1, 1>(tm + TM_W1, dDLm, dH1m, 256, 256, 8, keep);             // MMA4: Delta2^T [1 H1]
         mma_commit(&s.bar[4]);
       }
       __syncwarp();
     }
+    TC_STAMP(17);
+    TC_STAMP(18);
     // in the shadow of MMA3: the log-likelihood term and the column sums for dW2
-    if (hf == 0 && r < rows) {
-      float term;
-      if (yv == 1.0f) term = (p_head == 1.0f) ? NAN : logf(p_head);
-      else if (yv == 0.0f) term = (p_head == 0.0f) ? NAN : logf(1.0f - p_head);
-      else term = logf(p_head) * yv + logf(1.0f - p_head) * (1.0f - yv);
-      ll += (double)term;
-      gb2 += (double)d_head;
+    if (hf == 0) {   // one branch-free log per row for hard labels; soft labels take the general form
+      const float qv = (yv == 1.0f) ? p_head : 1.0f - p_head;
+      float term = (yv == 1.0f && p_head == 1.0f) || (yv == 0.0f && p_head == 0.0f) ? NAN : logf(qv);
+      if (yv != 0.0f && yv != 1.0f) term = logf(p_head) * yv + logf(1.0f - p_head) * (1.0f - yv);
+      if (r < rows) {
+        acc2(ll, lle, term);
+        acc2(gb2, gb2e, d_head);
+      }
     }
+    TC_STAMP(19);
     butterfly_step<16>(t, lane);
     butterfly_step<8>(t, lane);
     butterfly_step<4>(t, lane);
     butterfly_step<2>(t, lane);
     butterfly_step<1>(t, lane);
-    gw2 += (double)t[0];                                                   // unit 32 hf + lane, rows of quadrant q
+    acc2(gw2, gw2e, t[0]);                                                 // unit 32 hf + lane, rows of quadrant q
     TC_STAMP(5);
     // ---- P3: Delta1 = D1 H1 (1 - H1) ------------------------------------------------------------------------------------
     mbar_wait(&s.bar[3], par);
@@ -416,7 +438,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);           // MMA5: Delta1^T [1 X]
+        mma_product<64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);             // MMA5: Delta1^T [1 X]
         mma_commit(&s.bar[5]);
       }
       __syncwarp();
@@ -430,11 +452,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       float v[32];
       load_sum3(tm_lane + TM_W1 + 8 + 32 * hf, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g1[i] += (double)v[i];
+      for (int i = 0; i < 32; ++i) acc2(g1[i], g1e[i], v[i]);
       uint32_t o4[4];
       tmem_ld4(tm_lane + TM_W1, o4);
       tmem_ld_wait();
-      gb1 += (double)__uint_as_float(o4[0]);
+      acc2(gb1, gb1e, __uint_as_float(o4[0]));
     }
     TC_STAMP(10);
     mbar_wait(&s.bar[5], par);   // also: MMA5 has finished reading the x pieces and Delta1
@@ -448,8 +470,8 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       tmem_ld4(tm_lane + TM_W0, o4);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g0[i] += (double)((__uint_as_float(c[i]) + __uint_as_float(b[i])) + __uint_as_float(a[i]));
-      gb0 += (double)__uint_as_float(o4[0]);
+      for (int i = 0; i < 8; ++i) acc2(g0[i], g0e[i], (__uint_as_float(c[i]) + __uint_as_float(b[i])) + __uint_as_float(a[i]));
+      acc2(gb0, gb0e, __uint_as_float(o4[0]));
     }
     TC_STAMP(12);
     // the next tile's P0 ends with fence_before_sync + __syncthreads before any MMA overwrites these TMEM columns
@@ -463,19 +485,19 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   if (lane < 16) {
     const int o = 16 * q + lane;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) out[1 + DP_OFF_W1 + o * DP_H + 32 * hf + i] = g1[i];
+    for (int i = 0; i < 32; ++i) out[1 + DP_OFF_W1 + o * DP_H + 32 * hf + i] = (double)g1[i] + (double)g1e[i];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[1 + o * DP_D0 + 8 * hf + j] = g0[j];
+    for (int j = 0; j < 8; ++j) out[1 + o * DP_D0 + 8 * hf + j] = (double)g0[j] + (double)g0e[j];
     if (hf == 0) {
-      out[1 + DP_OFF_B1 + o] = gb1;
-      out[1 + DP_OFF_B0 + o] = gb0;
+      out[1 + DP_OFF_B1 + o] = (double)gb1 + (double)gb1e;
+      out[1 + DP_OFF_B0 + o] = (double)gb0 + (double)gb0e;
     }
   }
   // dW2: unit 32 hf + lane, partial over the rows of quadrant q; log-likelihood and db2: fixed-order block sums
   double* red = reinterpret_cast<double*>(s.dl);   // the activation buffers are free now
-  red[tid] = gw2;
-  red[DP_THREADS + tid] = ll;
-  red[2 * DP_THREADS + tid] = gb2;
+  red[tid] = (double)gw2 + (double)gw2e;
+  red[DP_THREADS + tid] = (double)ll + (double)lle;
+  red[2 * DP_THREADS + tid] = (double)gb2 + (double)gb2e;
   __syncthreads();
   if (tid < DP_H) {
     const int h2 = tid >> 5, l2 = tid & 31;
@@ -494,6 +516,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     for (int i = 0; i < DP_R; ++i) t += red[2 * DP_THREADS + i];
     out[1 + DP_OFF_B2] = t;
   }
+  TC_STAMP(21);
 }
 
 // out[e] = sum over CTAs of partials[cta][e], fixed order
@@ -540,7 +563,7 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
     if (e != cudaSuccess) return fail(e, "dp_loglik_grad(attr)");
     attr_set = true;
   }
-  dp_eval_tc_kernel<<<grid, DP_THREADS, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
+  dp_eval_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
                                                               (long)n_rows, partials);
   dp_reduce_tc_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
   e = cudaGetLastError();
@@ -551,10 +574,10 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
 
 #ifdef DP_TC_PROFILE
 /* debug builds only: cycles spent per phase by one warp of CTA 0, accumulated since the last call */
-int eeyore_b200_dp_tc_profile(unsigned long long* out16) {
+int eeyore_b200_dp_tc_profile(unsigned long long* out24) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out16, dp_tc_prof, sizeof(unsigned long long) * 16);
-  unsigned long long zero[16] = {0};
+  cudaMemcpyFromSymbol(out24, dp_tc_prof, sizeof(unsigned long long) * 24);
+  unsigned long long zero[24] = {0};
   cudaMemcpyToSymbol(dp_tc_prof, zero, sizeof(zero));
   return 0;
 }

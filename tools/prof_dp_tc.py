@@ -27,7 +27,7 @@ y = (torch.rand(n, device="cuda", generator=g) < 0.5).float()
 theta = torch.randn(P, device="cuda", generator=g) * 0.1
 out = torch.empty(P + 1, dtype=torch.float64, device="cuda")
 ws = torch.empty(lib.eeyore_b200_dp_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
-buf = (C.c_ulonglong * 16)()
+buf = (C.c_ulonglong * 24)()
 prof = lib.eeyore_b200_dp_tc_profile
 prof.argtypes = [C.POINTER(C.c_ulonglong)]
 for it in range(3):
@@ -36,5 +36,10 @@ for it in range(3):
 tiles = (n // 128 + 147) // 148
 tot = sum(buf[:13])
 print(f"CTA 0: {tiles} tiles, {tot / tiles:.0f} cycles per tile")
+tot += sum(buf[13:20])
+print(f"  prologue {buf[20]} cycles, after the tile loop {buf[21]} cycles, tile loop {tot} cycles")
 for i, nm in enumerate(NAMES):
     print(f"  {nm:18s} {buf[i] / tiles:8.0f}  {100 * buf[i] / tot:5.1f}%")
+for i, nm in zip(range(13, 20), ["P2 ld+sigmoid+dot", "P2 pair barrier", "P2 exp/div", "P2 loop+split+store", "P2 fence+sync", "P2 MMA issue",
+                                  "P2 logs"]):
+    print(f"  {nm:18s} {buf[i] / tiles:8.0f}  {100 * buf[i] / tot:5.1f}%   (P2 + sync above is the remainder: butterfly)")
