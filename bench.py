@@ -518,7 +518,7 @@ def run_datapar(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    sampler = DataShardedHMC(model, theta_host.to(dev), x, y, step=w["step"], num_steps=L, seed=7)
+    sampler = DataShardedHMC(model, theta_host.to(dev), x, y, step=w["step"], num_steps=L, seed=7, exchange=args.exchange)
     clocks = ClockSampler(local, enabled=(rank == 0 and not os.environ.get("EEYORE_BENCH_NO_CLOCKS"))).start()
     for _ in range(args.warmup):
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
@@ -541,7 +541,7 @@ def run_datapar(args):
 
     out_theta = torch.empty(iters, P).pin_memory()
 
-    e2e_sampler = DataShardedHMC(model, theta_host, x, y, step=w["step"], num_steps=L, seed=11)
+    e2e_sampler = DataShardedHMC(model, theta_host, x, y, step=w["step"], num_steps=L, seed=11, exchange=args.exchange)
 
     def step_e2e():
         e2e_sampler.reset(theta_host)                        # chain state comes from the (pinned) host buffer
@@ -611,13 +611,16 @@ def run_datapar(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "rows_total": n_total, "rows_per_gpu": hi - lo,
                        "hmc_iterations_per_step": iters, "num_steps": L, "evals_counted_per_iteration": L,
-                       "exchange": "all-reduce of 1+P fp64 partial sums per evaluation (NCCL)" if world > 1 else "none (1 GPU)",
+                       "exchange": ("none (1 GPU)" if world == 1 else
+                                    "NCCL all-reduce of 1+P fp64 sums per evaluation" if sampler.exchange == "nccl" else
+                                    "1+P fp64 sums stored into every peer's inbox over NVLink (CUDA IPC) inside the fused post "
+                                    "kernel, sequence-numbered flags, totals added in rank order; no NCCL on the data path"),
                        "acceptance_rate": acc, "per_step_ms": per_step_ms,
                        "l2": "x shard (%.0f MB) exceeds the 126 MB L2" % ((hi - lo) * 68 / 1e6),
                        "data_resident": "x, y shards stay in HBM across steps; e2e copies the chain state in and the samples out"},
             "e2e": {"value": evals_step * args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": P * 4,
                     "d2h_bytes_per_step": iters * P * 4, "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": args.steps * iters * (2 + 4 * L),
+            "gpu_launches": args.steps * iters * (2 + (4 if sampler.exchange == "nccl" else 2) * L),
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
@@ -634,6 +637,9 @@ def run_datapar(args):
                                       "achieved_gbs": (hi - lo) * 68 / (kernel_ms * 1e-3) / 1e9}},
             "cpu_baseline": cpu,
         }))
+    sampler.check_status()
+    sampler.close()
+    e2e_sampler.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -650,6 +656,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="cfg5: override the total number of data rows")
     ap.add_argument("--lanes", type=int, default=0, help="threads cooperating on one chain (0 = library heuristic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="cfg5: exchange step of the data-sharded path (auto = peer stores over NVLink when there are several ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -538,7 +538,8 @@ int eeyore_b200_set_error_(int code, const char* msg);
 
 int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
                                void* workspace, void* stream) {
-  if (!theta || !x || !y || !out_sums || n_rows < 1) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: bad argument");
+  if (!theta || !x || !y || (!out_sums && !workspace) || n_rows < 1)
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: bad argument");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: x and y must be 16-byte aligned (TMA bulk copy)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -565,7 +566,8 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
   }
   dp_eval_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
                                                               (long)n_rows, partials);
-  dp_reduce_tc_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
+  if (out_sums)   // NULL: the caller folds the per-CTA rows itself (dp_post does, together with the exchange step)
+    dp_reduce_tc_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
   e = cudaGetLastError();
   if (!workspace) cudaFreeAsync(partials, st);
   if (e != cudaSuccess) return fail(e, "dp_loglik_grad");

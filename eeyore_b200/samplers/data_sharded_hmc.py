@@ -1,9 +1,12 @@
 """HMC for ONE chain whose data set is sharded over the GPUs of a box (BASELINE config 5).
 
 Every rank holds the same chain state (theta, momentum, Philox stream) and its own row shard.  One log-target
-evaluation = local fused forward+backward kernel over the shard (eeyore_b200/csrc/datapar.cu) -> all-reduce of
-1 + P partial sums in fp64 over NCCL -> prior added once; the leapfrog update and the accept test are then computed
-redundantly (and identically) on every rank, so no further exchange is needed.
+evaluation = two launches: the tcgen05 forward+backward kernel over the shard (csrc/datapar_tc.cu) and the fused "post"
+kernel (csrc/datapar.cu: dp_post_kernel) that folds the per-CTA sums, exchanges the 1 + P fp64 sums with the peers by
+direct NVLink stores into their CUDA-IPC-mapped inboxes (sequence-numbered flags, totals added in rank order, so
+bit-identical on every rank), adds the prior once and applies the leapfrog update.  The accept test is computed
+redundantly (and identically) on every rank, so no further exchange is needed.  exchange="nccl" keeps the plain
+all-reduce formulation (also used when a custom reduce_fn simulates the shards on one device).
 Mirrors eeyore/samplers/hmc.py:100-170 (leapfrog, hamiltonian, linear-space accept); device code: dp_hmc_* kernels.
 """
 import ctypes as C
@@ -24,7 +27,7 @@ def shard_rows(n_rows, world_size, rank, multiple=4):
 
 class DataShardedHMC:
     def __init__(self, model, theta0, x_shard, y_shard, step=0.1, num_steps=10, group=None, seed=0, chain=None,
-                 reduce_fn=None):
+                 reduce_fn=None, exchange="auto"):
         if not model.is_data_parallel():
             raise ValueError("DataShardedHMC serves the data-parallel architecture (MLP 16-64-64-1, float32, binary)")
         nv.require_cuda()
@@ -36,6 +39,9 @@ class DataShardedHMC:
         self.chain = chain if chain is not None else ChainList(keys=["sample", "target_val", "accepted"])
         self._reduce = reduce_fn or self._all_reduce
         dev, p = self.x.device, model.num_params()
+        if self.x.shape[0] < 1:
+            raise ValueError("every rank needs at least one row of the data set")
+        self._setup_exchange(exchange, reduce_fn is not None, dev)
         f32, f64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.float64, device=dev)
         self._sums = torch.empty(p + 1, **f64)
         self._work = torch.empty(int(nv.lib().eeyore_b200_dp_workspace_bytes()) // 8, **f64)   # per-CTA partial sums
@@ -60,23 +66,100 @@ class DataShardedHMC:
             self._acc_count.zero_()
         self._evaluate(self._theta_c, self._lt_c, self._grad_c)
 
+    # ---- exchange set-up ---------------------------------------------------------------------------------------------------
+    def _dist_world(self):
+        d = torch.distributed
+        if d.is_available() and d.is_initialized():
+            return d.get_world_size(self.group), d.get_rank(self.group)
+        return 1, 0
+
+    def _setup_exchange(self, exchange, has_reduce_fn, dev):
+        """exchange: "auto" | "p2p" | "local" | "nccl".  auto = nccl when a reduce_fn is given, else the fused path (peer
+        stores over NVLink for world > 1, purely local for one rank)."""
+        lib = nv.lib()
+        world, rank = self._dist_world()
+        if exchange == "auto":
+            exchange = "nccl" if has_reduce_fn else ("p2p" if world > 1 else "local")
+        if exchange not in ("p2p", "local", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p', 'local' or 'nccl'")
+        if exchange == "p2p" and world == 1:
+            exchange = "local"
+        if exchange == "local":
+            world, rank = 1, 0          # this rank's rows are the whole data set, whatever process group exists
+        self.exchange, self._world, self._rank = exchange, world, rank
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._n_parts = int(lib.eeyore_b200_dp_num_parts(self.x.shape[0]))
+        self._xbase, self._xopened, self._peers = None, [], None
+        if exchange == "p2p":
+            with torch.cuda.device(dev):
+                base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                nv.check(lib.eeyore_b200_dp_exchange_create(C.byref(base), handle))
+                handles = [None] * world
+                torch.distributed.all_gather_object(handles, bytes(handle), group=self.group)
+                peers = (C.c_void_p * 8)()
+                for r in range(world):
+                    if r == rank:
+                        peers[r] = base.value
+                    else:
+                        ptr = C.c_void_p()
+                        nv.check(lib.eeyore_b200_dp_exchange_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(ptr)))
+                        peers[r] = ptr.value
+                        self._xopened.append(ptr.value)
+                torch.distributed.barrier(group=self.group)          # every area is mapped before the first store
+            self._xbase, self._peers = base.value, peers
+            self._scratch_ptr = C.c_void_p(base.value + int(lib.eeyore_b200_dp_exchange_scratch_offset()))
+        elif exchange == "local":
+            self._scratch = torch.zeros(128, dtype=torch.float64, device=dev)
+            self._scratch_ptr = nv.ptr(self._scratch)
+
+    def close(self):
+        """Unmap the peers' exchange areas and free this rank's (collective: every rank calls it)."""
+        if getattr(self, "_xbase", None) is not None:
+            lib = nv.lib()
+            torch.cuda.synchronize(self.x.device)
+            if torch.distributed.is_initialized():
+                torch.distributed.barrier(group=self.group)
+            for ptr in self._xopened:
+                lib.eeyore_b200_dp_exchange_close(C.c_void_p(ptr))
+            if torch.distributed.is_initialized():
+                torch.distributed.barrier(group=self.group)
+            lib.eeyore_b200_dp_exchange_destroy(C.c_void_p(self._xbase))
+            self._xbase, self._xopened = None, []
+
+    def check_status(self):
+        """Raises if a peer never delivered its sums (the device code traps after a bounded spin)."""
+        if int(self._status.item()) != 0:
+            raise RuntimeError("data-sharded exchange timed out waiting for a peer rank")
+
     def _all_reduce(self, t):
         if torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(self.group) > 1:
             torch.distributed.all_reduce(t, group=self.group)
 
-    def _evaluate(self, theta, out_target, out_grad):
+    def _evaluate(self, theta, out_target, out_grad, step_mode=0):
+        """target and gradient at theta; step_mode 1 / 2 also applies the inner / last leapfrog update (fused path)."""
         m, lib = self.model, nv.lib()
         loc, scale = m.prior_on_device()
         st = nv.stream_ptr(self.x.device)
+        has_t, temp = (0, 0.0) if m.temperature is None else (1, float(m.temperature))
+        if self.exchange != "nccl":
+            nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0], None,
+                                                    nv.ptr(self._work), st))
+            nv.check(lib.eeyore_b200_dp_post(nv.ptr(self._work), self._n_parts, self._world, self._rank, self.n_evals + 1,
+                                             self._peers, self._scratch_ptr, nv.ptr(theta), nv.ptr(loc), nv.ptr(scale), has_t, temp,
+                                             nv.ptr(out_grad), nv.ptr(out_target), step_mode, self.step, nv.ptr(self._mom),
+                                             nv.ptr(self._theta_p), nv.ptr(self._kin1), nv.ptr(self._status), st))
+            self.n_evals += 1
+            return
         nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0],
                                                 nv.ptr(self._sums), nv.ptr(self._work), st))
         self._reduce(self._sums)                 # the one exchange step of the path: 1 + P doubles
-        nv.check(lib.eeyore_b200_dp_finish(nv.ptr(self._sums), nv.ptr(theta), nv.ptr(loc), nv.ptr(scale),
-                                           0 if m.temperature is None else 1,
-                                           0.0 if m.temperature is None else float(m.temperature),
+        nv.check(lib.eeyore_b200_dp_finish(nv.ptr(self._sums), nv.ptr(theta), nv.ptr(loc), nv.ptr(scale), has_t, temp,
                                            nv.ptr(out_target), nv.ptr(out_grad), st))
         self.n_evals += 1
+        if step_mode:
+            nv.check(lib.eeyore_b200_dp_hmc_step(nv.ptr(self._grad_p), self.step, 1 if step_mode == 2 else 0,
+                                                 nv.ptr(self._mom), nv.ptr(self._theta_p), nv.ptr(self._kin1), st))
 
     def set_noise_tape(self, z, u):
         m = self.model
@@ -95,9 +178,7 @@ class DataShardedHMC:
                                                   self._iter, nv.ptr(zt), nv.ptr(self._mom), nv.ptr(self._theta_p),
                                                   nv.ptr(self._kin0), st))
             for s in range(self.num_steps):
-                self._evaluate(self._theta_p, self._lt_p, self._grad_p)
-                nv.check(lib.eeyore_b200_dp_hmc_step(nv.ptr(self._grad_p), self.step, 1 if s == self.num_steps - 1 else 0,
-                                                     nv.ptr(self._mom), nv.ptr(self._theta_p), nv.ptr(self._kin1), st))
+                self._evaluate(self._theta_p, self._lt_p, self._grad_p, 2 if s == self.num_steps - 1 else 1)
             nv.check(lib.eeyore_b200_dp_hmc_accept(nv.ptr(self._theta_c), nv.ptr(self._grad_c), nv.ptr(self._lt_c),
                                                    nv.ptr(self._theta_p), nv.ptr(self._grad_p), nv.ptr(self._lt_p),
                                                    nv.ptr(self._kin0), nv.ptr(self._kin1), self.seed, self._iter, nv.ptr(ut),

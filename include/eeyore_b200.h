@@ -160,6 +160,9 @@ int eeyore_b200_dp_num_params(void);
 /* out_sums[0] = sum_i loglik_i, out_sums[1 + j] = d/dtheta_j sum_i loglik_i over this rank's rows (fp64, deterministic) */
 int eeyore_b200_dp_loglik_grad(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
                                void *workspace, void *stream);
+/* out_sums may be NULL when a workspace is given: the per-CTA rows ([dp_num_parts(n_rows)][P + 1] doubles) are then left
+ * in the workspace for dp_post, which folds them together with the exchange step. */
+int eeyore_b200_dp_num_parts(int64_t n_rows);
 /* the same sums from the FP32 CUDA-core formulation (no tensor cores): kept as an independent cross-check of the
  * tcgen05 kernel and as the A/B line of bench.py; not used by the product path */
 int eeyore_b200_dp_loglik_grad_ffma(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
@@ -170,6 +173,25 @@ int64_t eeyore_b200_dp_workspace_bytes(void);
  * (eeyore/models/bayesian_model.py:46-56) and applies the temperature */
 int eeyore_b200_dp_finish(const void *sums, const void *theta, const void *prior_loc, const void *prior_scale,
                           int has_temperature, double temperature, void *out_target, void *out_grad, void *stream);
+/* Fused tail of one evaluation (one launch): fixed-order fold of the workspace rows; for world > 1 the exchange step of
+ * the data-sharded path -- every rank stores its 1 + P sums into every peer's exchange area over NVLink (peer_bases[p] =
+ * rank p's area, mapped with dp_exchange_open), releases sequence-numbered flags and adds the world slots in rank order,
+ * so every rank holds bit-identical totals without NCCL; then the Normal log-prior, its gradient and the temperature
+ * (eeyore/models/bayesian_model.py:46-56, log_target_model.py:20-23) and, for step_mode 1 (inner) / 2 (last), the
+ * leapfrog update that follows the evaluation (eeyore/samplers/hmc.py:113-119).  seq = evaluation counter (>= 1, the same
+ * on every rank).  local_scratch = this rank's scratch (dp_exchange_scratch).  status[0] != 0 after a peer time-out. */
+int eeyore_b200_dp_post(const void *workspace, int n_parts, int world, int rank, uint64_t seq, void *const *peer_bases,
+                        void *local_scratch, const void *theta, const void *prior_loc, const void *prior_scale,
+                        int has_temperature, double temperature, void *out_grad, void *out_target, int step_mode,
+                        double step, void *momentum, void *theta_prop, void *kin1, int32_t *status, void *stream);
+/* exchange area of one rank: create (cudaMalloc, zeroed) + its 64-byte CUDA IPC handle; open / close a peer's area */
+int64_t eeyore_b200_dp_exchange_bytes(void);
+int eeyore_b200_dp_exchange_create(void **out_base, void *out_handle64);
+int eeyore_b200_dp_exchange_open(const void *handle64, void **out_ptr);
+int eeyore_b200_dp_exchange_close(void *peer_ptr);
+int eeyore_b200_dp_exchange_destroy(void *base);
+/* byte offset of the 128-double scratch block inside an exchange area */
+int64_t eeyore_b200_dp_exchange_scratch_offset(void);
 /* HMC.draw pieces for a replicated chain state (eeyore/samplers/hmc.py:100-170): momentum draw + first half step;
  * momentum / position update after each evaluation; accept test and commit.  z_tape / u_tape NULL = Philox. */
 int eeyore_b200_dp_hmc_begin(const void *theta_cur, const void *grad_cur, double step, uint64_t seed, uint64_t iter,
