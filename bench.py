@@ -39,7 +39,7 @@ WORKLOADS = {
                  flops_per_eval=368, dtype="f64"),
     # BASELINE.json configs[2] (SMMALA is builder-defined: absent from the reference snapshot)
     "cfg3": dict(name="cfg3: MLP 2-3-2-1 noisy-XOR-shaped N=200, SMMALA (Fisher metric, in-warp Cholesky), 16384 chains/GPU, fp64",
-                 dims=[2, 3, 2, 1], data="noisy_xor", loss="binary_classification", chains=16384, step=0.7, num_steps=1,
+                 dims=[2, 3, 2, 1], data="noisy_xor", loss="binary_classification", chains=16384, step=0.02, num_steps=1,
                  iters=20, thin=5, flops_per_eval=14480 + 160000 + 2667 + 800, dtype="f64", kind="smmala"),
     # BASELINE.json configs[4]: one chain, data sharded over the ranks, NCCL all-reduce per evaluation (strong scaling)
     "cfg5": dict(name="cfg5: MLP 16-64-64-1, 8388608 synthetic rows sharded over the GPUs, HMC L=10, fp32",
@@ -47,7 +47,7 @@ WORKLOADS = {
                  iters=2, thin=1, flops_per_eval=29056 * 8388608, rows=8388608, dtype="f32", kind="datapar"),
     # BASELINE.json configs[1]
     "cfg2": dict(name="cfg2: MLP 4-3-3 iris-shaped N=150, HMC L=10, 4096 chains/GPU, fp64", dims=[4, 3, 3], data="iris",
-                 loss="multiclass_classification", chains=4096, step=0.02, num_steps=10, iters=20, thin=5,
+                 loss="multiclass_classification", chains=4096, step=0.15, num_steps=10, iters=20, thin=5,
                  flops_per_eval=15408, dtype="f64"),
 }
 
