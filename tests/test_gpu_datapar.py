@@ -139,3 +139,42 @@ def test_full_tile_count_large_shard_linearity():
     parts = dp_sums(theta, x[:h], y[:h]) + dp_sums(theta, x[h:], y[h:])
     assert rel_err(npy(parts), npy(full)) < 1e-9
     assert torch.isfinite(full).all()
+
+
+def test_tcgen05_kernel_matches_the_cuda_core_kernel():
+    """Two independent formulations of the same sums (tcgen05 bf16-split MMAs vs FP32 FMA loops), ragged and full tiles."""
+    lib = nv.lib()
+    for n in (1, 64, 127, 128, 129, 5000, 70_001):
+        x, y = synth(n, seed=100 + n)
+        xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda().reshape(-1)
+        theta = torch.from_numpy((np.random.default_rng(n).normal(size=P) * 0.3).astype(np.float32)).cuda()
+        a = torch.empty(P + 1, dtype=torch.float64, device="cuda")
+        b = torch.empty_like(a)
+        nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(xd), nv.ptr(yd), n, nv.ptr(a), None, None))
+        nv.check(lib.eeyore_b200_dp_loglik_grad_ffma(nv.ptr(theta), nv.ptr(xd), nv.ptr(yd), n, nv.ptr(b), None, None))
+        assert abs(a[0].item() - b[0].item()) < 1e-6 * abs(b[0].item())
+        assert rel_err(npy(a[1:]), npy(b[1:])) < 3e-6
+        ll_ref = oracle.log_lik(SPEC, npy(theta).astype(np.float64)[None], x.astype(np.float64), y)[0]
+        assert abs(a[0].item() - ll_ref) < 1e-6 * abs(ll_ref)
+
+
+def test_fused_post_kernel_matches_the_unfused_tail():
+    """dp_post (fold + prior + leapfrog in one launch) against reduce / finish / step as separate kernels."""
+    n, T, L, step = 3000, 5, 4, 0.003
+    x, y = synth(n, seed=21)
+    theta0 = (np.random.default_rng(3).normal(size=P) * 0.2).astype(np.float32)
+    m = wide_model(temperature=0.7)
+    runs = {}
+    for mode in ("local", "nccl"):
+        s = DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), step=step, num_steps=L, seed=5,
+                           exchange=mode)
+        assert s.exchange == mode
+        runs[mode] = s.run(num_epochs=T, num_burnin_epochs=0)
+        s.check_status()
+        assert s.n_evals == 1 + T * L
+    (sa, ta, aa), (sb, tb, ab) = runs["local"], runs["nccl"]
+    assert torch.equal(aa, ab) and 0 < int(aa.sum())
+    assert rel_err(npy(sa), npy(sb)) < 1e-6
+    assert np.allclose(npy(ta), npy(tb), rtol=1e-9)
+    with pytest.raises(ValueError):
+        DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), exchange="smoke-signals")
