@@ -182,6 +182,58 @@ def run_sampler(name, kind, arch, dtype, n_iters, n_burnin, prior_scale, seed, *
     print(name, "acceptance", out["accepted"].mean())
 
 
+def power_posterior_goldens():
+    """The reference's PowerPosteriorSampler (tempered MH / MALA chains with neighbour swaps) on MLP 2-2-1 / XOR, fp64.
+    Recorded besides the proposal noise: every categorical neighbour draw (sample_categorical is wrapped on the instance)."""
+    from eeyore.samplers import PowerPosteriorSampler
+    for name, arch, spec_samplers, bs, n_iters, n_burnin, seed in (
+            ("pp_221_mix", "221", [["MetropolisHastings", {}], ["MALA", {"step": 0.3}], ["MetropolisHastings", {}],
+                                   ["MALA", {"step": 0.15}]], 3, 80, 10, 21),
+            ("pp_2321_mala", "2321", [["MALA", {"step": 0.4}], ["MALA", {"step": 0.3}], ["MALA", {"step": 0.2}],
+                                      ["MALA", {"step": 0.15}], ["MALA", {"step": 0.1}]], 1, 60, 0, 22)):
+        torch.manual_seed(seed)
+        a = ARCHS[arch]
+        data = load_data(a["data"], torch.float64)
+        loader = DataLoader(data, batch_size=len(data))
+        model = make_model(arch, torch.float64, prior_scale=math.sqrt(3.0))
+        theta0 = model.prior.sample() * 0.5
+        k = len(spec_samplers)
+        keys = ["sample", "target_val"]
+        with Tape() as tape:
+            s = PowerPosteriorSampler(model, loader, spec_samplers, theta0=theta0, between_step=bs, keys=keys)
+            js = []
+            orig = s.sample_categorical
+
+            def rec(i, _orig=orig, _js=js):
+                j = _orig(i)
+                _js.append(j)
+                return j
+
+            s.sample_categorical = rec
+            s.run(num_epochs=n_iters, num_burnin_epochs=n_burnin)
+        # call order per iteration: K x (z, u) within moves; then, when idx % bs == 0, K x (categorical, u)
+        nb = len(js) // k
+        z = np.stack(tape.z).reshape(n_iters, k, -1)
+        u_all = np.concatenate(tape.u)
+        u_w = np.zeros((n_iters, k)); u_b = np.zeros((nb, k))
+        pos = b_idx = 0
+        for t in range(n_iters):
+            u_w[t] = u_all[pos:pos + k]; pos += k
+            if t % bs == 0:
+                u_b[b_idx] = u_all[pos:pos + k]; pos += k; b_idx += 1
+        assert pos == len(u_all) and b_idx == nb, (pos, len(u_all), b_idx, nb)
+        out = dict(theta0=npy(theta0), z=z, u=u_w, j_tape=np.array(js, dtype=np.int64).reshape(nb, k), u_between=u_b,
+                   n_iters=n_iters, n_burnin=n_burnin, between_step=bs, b=0.5, temperatures=np.array(s.temperature),
+                   kinds=np.array([n for n, _ in spec_samplers]),
+                   steps=np.array([kw.get("step", 0.0) for _, kw in spec_samplers]),
+                   samples=np.stack([npy(s.samplers[i].chain.get_samples()) for i in range(k)]),
+                   target_vals=np.stack([npy(s.samplers[i].chain.get_target_vals()) for i in range(k)]),
+                   final_sample=np.stack([npy(s.samplers[i].current["sample"]) for i in range(k)]),
+                   final_target=np.array([float(s.samplers[i].current["target_val"]) for i in range(k)]))
+        np.savez_compressed(OUT / f"{name}.npz", **out)
+        print(name, "between sweeps", nb, "distinct final states", len({tuple(np.round(v, 6)) for v in out["final_sample"]}))
+
+
 def stats_goldens():
     out = {}
     chains = []
@@ -236,6 +288,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dp":
         datapar_goldens()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pp":
+        power_posterior_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tuner":
         s3 = math.sqrt(3.0)
         run_sampler("hmcda_xor2321_f64", "hmc", "2321", torch.float64, 90, 50, s3, 7, step=0.05, tuner_l=0.6)
@@ -259,3 +314,4 @@ if __name__ == "__main__":
     run_sampler("mh_xor2321_f64_nonsym", "mh", "2321", torch.float64, 300, 0, s3, 6, symmetric=False,
                 prop_scale=0.4)
     stats_goldens()
+    power_posterior_goldens()

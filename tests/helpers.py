@@ -40,3 +40,14 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.max(np.abs(b)), 1e-300)
     return float(np.max(np.abs(a - b)) / scale)
+
+
+def pp_setup(name):
+    """Power-posterior golden -> (spec, x, y, kinds, kwargs, arrays) in the oracle's calling convention."""
+    gd = load(name)
+    arch = "221" if "221" in name else "2321"
+    spec = spec_of(arch)
+    x, y = data_of(arch, np.float64)
+    kinds = ["mh" if str(k) == "MetropolisHastings" else "mala" for k in gd["kinds"]]
+    kwargs = [({} if k == "mh" else {"step": float(s)}) for k, s in zip(kinds, gd["steps"])]
+    return gd, spec, x, y, kinds, kwargs

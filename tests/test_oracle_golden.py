@@ -152,3 +152,23 @@ def test_hmc_with_dual_averaging_tuner(name, l, e0, eub):
     out, gd = _check_run(name, oracle.hmc_run, step=e0, num_steps=1, tuner=tuner)
     assert abs(out["final"]["step"][0] - float(gd["final_step"])) < 1e-12 * float(gd["final_step"])
     assert int(out["final"]["num_steps"][0]) == int(gd["final_num_steps"])
+
+
+@pytest.mark.parametrize("name", ["pp_221_mix", "pp_2321_mala"])
+def test_power_posterior_matches_the_reference(name):
+    """Tempered MH / MALA chains with neighbour swaps (power_posterior_sampler.py) fed the reference's own noise,
+    categorical draws and accept uniforms: every level's saved chain within 1e-10."""
+    from helpers import pp_setup
+    from oracle.power_posterior import power_posterior_run
+    gd, spec, x, y, kinds, kwargs = pp_setup(name)
+    P = gd["theta0"].shape[0]
+    s3 = 3.0 ** 0.5
+    r = power_posterior_run(spec, x, y, np.zeros(P), np.full(P, s3), gd["theta0"][None], kinds, kwargs,
+                            gd["z"][:, :, None, :], gd["u"][:, :, None], gd["j_tape"][:, :, None], gd["u_between"][:, :, None],
+                            temperatures=list(gd["temperatures"]), between_step=int(gd["between_step"]), b=float(gd["b"]),
+                            n_burnin=int(gd["n_burnin"]))
+    assert r["sample"].shape[:2] == gd["samples"].shape[:2]
+    assert rel_err(r["sample"][:, :, 0], gd["samples"]) < 1e-10
+    assert np.allclose(r["target_val"][:, :, 0], gd["target_vals"], rtol=1e-10, atol=1e-12)
+    assert rel_err(r["final_sample"][:, 0], gd["final_sample"]) < 1e-10
+    assert 0 < r["swaps"].sum() < r["swaps"].size          # the run contains accepted and rejected swaps
