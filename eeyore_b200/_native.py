@@ -51,6 +51,8 @@ class RunParams(C.Structure):
         ("tuner_has_eub", C.c_int32), ("tuner_pad", C.c_int32), ("tuner_iter0", C.c_int64), ("tuner_burnin", C.c_int64),
         ("tuner_state", C.c_void_p),
         ("stream", C.c_void_p),
+        ("adapt_p", C.c_double * 3), ("adapt_t0", C.c_int32), ("adapt_pad", C.c_int32), ("adapt_iter0", C.c_int64),
+        ("adapt_state", C.c_void_p), ("adapt_cov0", C.c_void_p), ("adapt_status", C.c_void_p),
     ]
 
 
@@ -70,6 +72,9 @@ SIGNATURES = {
     "eeyore_b200_mala_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_hmc_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_smmala_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_am_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_ram_run": (_I, [_VP, C.POINTER(RunParams)]),
+    "eeyore_b200_adapt_state_len": (_I64, [_VP, _I]),
     "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "eeyore_b200_dp_num_params": (_I, []),
     "eeyore_b200_dp_loglik_grad": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),

@@ -205,6 +205,31 @@ int eeyore_b200_smmala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p)
   return EEYORE_B200_OK;
 }
 
+static int adaptive_common(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p, int kind, const char* name) {
+  if (!h || !p) return fail(EEYORE_B200_EINVAL, "null argument");
+  if (!h->net || !h->net->adaptive)
+    return fail(EEYORE_B200_EUNSUPPORTED, "AM / RAM are built for the compiled network specialisations with at most 32 parameters");
+  if (p->n_chains < 1 || p->n_rows < 1 || p->n_iters < 0) return fail(EEYORE_B200_EINVAL, "bad sizes");
+  if (!p->theta || !p->target || !p->x || !p->y || !p->prior_loc || !p->prior_scale || !p->adapt_state || !p->adapt_status)
+    return fail(EEYORE_B200_EINVAL, "null state / data pointer");
+  if (kind == 0 && !p->adapt_cov0) return fail(EEYORE_B200_EINVAL, "AM needs cov0");
+  if (p->rng_mode == EEYORE_B200_RNG_TAPE && (!p->z_tape || !p->u_tape))
+    return fail(EEYORE_B200_EINVAL, "tape mode needs z_tape and u_tape");
+  if (p->n_iters == 0) return EEYORE_B200_OK;
+  cudaError_t e = h->net->adaptive(kind, *p, use_bulk());
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  return EEYORE_B200_OK;
+}
+
+int eeyore_b200_am_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p) { return adaptive_common(h, p, 0, "am_run"); }
+int eeyore_b200_ram_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p) { return adaptive_common(h, p, 1, "ram_run"); }
+
+int64_t eeyore_b200_adapt_state_len(eeyore_b200_mlp_t h, int kind) {
+  if (!h) return -1;
+  const int64_t P = eeyore_b200_mlp_num_params(h);
+  return kind == 0 ? P + 2 * P * P + 1 : P * P;
+}
+
 }  // extern "C"
 
 // ---- Philox draw export and FMA-peak microbenchmark -------------------------------------------------------------

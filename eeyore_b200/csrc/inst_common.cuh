@@ -2,6 +2,7 @@
 #pragma once
 #include "chain_kernels.cuh"
 #include "smmala.cuh"
+#include "adaptive.cuh"
 #include "registry.h"
 
 namespace eb {
@@ -61,6 +62,16 @@ template <typename T, class NET> cudaError_t smmala_entry(const eeyore_b200_run_
   }
 }
 
+template <typename T, class NET> cudaError_t adaptive_entry(int kind, const eeyore_b200_run_params& p, int use_bulk) {
+  if constexpr (NET::P <= 32) {
+    AdaptArgs ad{p.adapt_p[0], p.adapt_p[1], p.adapt_p[2], p.adapt_t0, (long)p.adapt_iter0, p.adapt_state, p.adapt_cov0,
+                 p.adapt_status};
+    return launch_adaptive<T, NET>(kind, chain_args_from<T>(p, use_bulk, NET::P), ad, (cudaStream_t)p.stream);
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+
 template <typename T, class NET> NetEntry make_entry(int dtype) {
   NetEntry e{};
   e.n_layers = NET::NL;
@@ -70,6 +81,7 @@ template <typename T, class NET> NetEntry make_entry(int dtype) {
   e.sampler = &sampler_entry<T, NET>;
   e.forward = &forward_entry<T, NET>;
   e.smmala = NET::LOSS == LOSS_BINARY ? &smmala_entry<T, NET> : nullptr;
+  e.adaptive = NET::P <= 32 ? &adaptive_entry<T, NET> : nullptr;
   return e;
 }
 

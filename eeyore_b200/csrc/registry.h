@@ -31,6 +31,7 @@ struct NetEntry {
   cudaError_t (*sampler)(int kind, const eeyore_b200_run_params&, int lanes, int use_bulk);
   cudaError_t (*forward)(int64_t n_chains, const void* theta, const void* x, int64_t n_rows, void* out, cudaStream_t);
   cudaError_t (*smmala)(const eeyore_b200_run_params&, int use_bulk);
+  cudaError_t (*adaptive)(int kind, const eeyore_b200_run_params&, int use_bulk);   // AM / RAM (P <= 32), else nullptr
 };
 
 }  // namespace eb

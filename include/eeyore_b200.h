@@ -124,6 +124,20 @@ typedef struct eeyore_b200_run_params {
   int64_t tuner_burnin;    /* leading iterations of this call that still tune (num_burnin_iters - counter.idx, >= 0) */
   double *tuner_state;     /* in/out [4, C]: barh, logbare, step, num_steps */
   void *stream;
+  /* Adaptive random-walk samplers (am_run / ram_run only).
+   * AM  (eeyore/samplers/am.py:8-107):  adapt_p = {l, b, c}, adapt_t0 = t0, adapt_cov0 = cov0 [P, P];
+   *      adapt_state [C, P + 2 P^2 + 1] = running mean, sum of theta theta^T, covariance estimate, number of accepted moves
+   *      (zeros / zeros / cov0 / 0 at the start of a chain); u_tape holds TWO uniforms per iteration [n_iters, 2, C].
+   * RAM (eeyore/samplers/ram.py:7-70):  adapt_p = {a, g, -};  adapt_state [C, P^2] = lower Cholesky factor of the proposal.
+   * adapt_iter0 = counter.idx at the first iteration of the call.  adapt_status [C]: 0, or 1 + iteration at which the
+   * factorisation failed (the reference's torch.linalg.cholesky raises there); the chain stops moving from then on. */
+  double adapt_p[3];
+  int32_t adapt_t0;
+  int32_t adapt_pad;
+  int64_t adapt_iter0;
+  void *adapt_state;
+  const void *adapt_cov0;
+  int32_t *adapt_status;
 } eeyore_b200_run_params;
 
 /* number of states a run with these (n_iters, n_burnin, thin) saves */
@@ -131,6 +145,12 @@ int64_t eeyore_b200_num_saved(int64_t n_iters, int64_t n_burnin, int64_t thin);
 
 /* MetropolisHastings.draw x n_iters (eeyore/samplers/metropolis_hastings.py:41-73) */
 int eeyore_b200_mh_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+/* AM.draw x n_iters (eeyore/samplers/am.py:62-107) and RAM.draw x n_iters (eeyore/samplers/ram.py:39-70): one warp per
+ * chain, proposal factor adapted and re-factorised in shared memory; compiled network specialisations with P <= 32 */
+int eeyore_b200_am_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+int eeyore_b200_ram_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
+/* length (in elements of the model dtype) of one chain's adapt_state: kind 0 = AM, 1 = RAM */
+int64_t eeyore_b200_adapt_state_len(eeyore_b200_mlp_t h, int kind);
 /* MALA.draw x n_iters (eeyore/samplers/mala.py:46-82) */
 int eeyore_b200_mala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
 /* HMC.draw + HMC.leapfrog x n_iters (eeyore/samplers/hmc.py:100-170) */

@@ -9,7 +9,7 @@ the product path has no CPU fallback.
 
 Parity status
 -------------
-* mlp / mh / mala / hmc / cov / inse_mc_cov / multi_ess: **pinned** -- checked
+* mlp / mh / mala / hmc / am / ram / power posterior / cov / inse_mc_cov / multi_ess: **pinned** -- checked
   against golden vectors generated from the unmodified reference
   (``/root/reference``) by ``oracle/make_golden.py`` and committed under
   ``tests/golden/`` (see ``tests/test_oracle_golden.py``).
@@ -22,6 +22,6 @@ Every function cites the reference file:line it follows (paths relative to
 """
 
 from .mlp import MLPSpec, log_lik, log_prior, log_target, log_target_grad, forward  # noqa: F401
-from .samplers import mh_run, mala_run, hmc_run, smmala_run, fisher_metric, DATuner  # noqa: F401
+from .samplers import mh_run, mala_run, hmc_run, smmala_run, fisher_metric, DATuner, am_run, ram_run  # noqa: F401
 from .stats import cov, inse_mc_cov, multi_ess, acf, is_pos_def  # noqa: F401
 from .philox import philox4x32_10, chain_uniforms, chain_normals  # noqa: F401

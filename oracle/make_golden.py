@@ -182,6 +182,49 @@ def run_sampler(name, kind, arch, dtype, n_iters, n_burnin, prior_scale, seed, *
     print(name, "acceptance", out["accepted"].mean())
 
 
+def adaptive_goldens():
+    """The reference's AM (am.py) and RAM (ram.py) on MLP 2-2-1 and 2-3-2-1 / XOR, fp64.  AM draws a second uniform (the
+    mixture test, am.py:70) only when idx + 1 > t0: the recorded u is [T, 2] with 0.5 where none was consumed."""
+    from eeyore.samplers import AM, RAM
+    for name, kind, arch, n_iters, n_burnin, seed, kw in (
+            # without a transform the empirical covariance is singular until more than P distinct states have been visited
+            # (the reference's own examples pass transform=softabs): t0 is chosen large enough for the plain estimator
+            ("am_xor221_f64", "am", "221", 400, 30, 31, dict(l=0.05, b=0.6, c=0.3, t0=80)),
+            ("am_xor2321_f64", "am", "2321", 500, 0, 32, dict(l=0.2, b=0.4, c=0.15, t0=200)),
+            ("ram_xor221_f64", "ram", "221", 300, 30, 33, dict(a=0.234, g=0.7)),
+            ("ram_xor2321_f64", "ram", "2321", 200, 0, 34, dict(a=0.3, g=0.6))):
+        torch.manual_seed(seed)
+        a = ARCHS[arch]
+        data = load_data(a["data"], torch.float64)
+        loader = DataLoader(data, batch_size=len(data))
+        model = make_model(arch, torch.float64, prior_scale=math.sqrt(3.0))
+        theta0 = model.prior.sample() * 0.5
+        chain = ChainList(keys=["sample", "target_val", "accepted"])
+        with Tape() as tape:
+            s = (AM if kind == "am" else RAM)(model, theta0=theta0, dataloader=loader, chain=chain, **kw)
+            s.run(num_epochs=n_iters, num_burnin_epochs=n_burnin)
+        z = np.stack(tape.z)
+        u_all = np.concatenate(tape.u)
+        if kind == "am":
+            u = np.full((n_iters, 2), 0.5)
+            pos = 0
+            for idx in range(n_iters):
+                if idx + 1 > kw["t0"]:
+                    u[idx, 0] = u_all[pos]; pos += 1
+                u[idx, 1] = u_all[pos]; pos += 1
+            assert pos == len(u_all)
+        else:
+            u = u_all
+            assert len(u) == n_iters
+        out = dict(theta0=npy(theta0), z=z, u=u, n_iters=n_iters, n_burnin=n_burnin,
+                   samples=npy(chain.get_samples()), target_vals=npy(chain.get_target_vals()),
+                   accepted=np.array(chain.vals["accepted"], dtype=np.uint8), final_sample=npy(s.current["sample"]),
+                   final_factor=npy(s.cov if kind == "am" else s.chol_cov))
+        out.update(kw)
+        np.savez_compressed(OUT / f"{name}.npz", **out)
+        print(name, "acceptance", out["accepted"].mean())
+
+
 def power_posterior_goldens():
     """The reference's PowerPosteriorSampler (tempered MH / MALA chains with neighbour swaps) on MLP 2-2-1 / XOR, fp64.
     Recorded besides the proposal noise: every categorical neighbour draw (sample_categorical is wrapped on the instance)."""
@@ -288,6 +331,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dp":
         datapar_goldens()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "adaptive":
+        adaptive_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pp":
         power_posterior_goldens()
         sys.exit(0)
@@ -315,3 +361,4 @@ if __name__ == "__main__":
                 prop_scale=0.4)
     stats_goldens()
     power_posterior_goldens()
+    adaptive_goldens()

@@ -282,3 +282,74 @@ def smmala_run(spec: MLPSpec, x, y, loc, scale, theta0, z, u, step, n_burnin=0, 
         _collect(store, t, n_burnin, thin, sample=theta, target_val=lt, grad_val=g,
                  accepted=acc.astype(np.uint8))
     return _finish(store, dict(sample=theta, target_val=lt, grad_val=g))
+
+
+def am_run(spec: MLPSpec, x, y, loc, scale, theta0, z, u, n_burnin=0, cov0=None, l=0.05, b=1.0, c=1.0, t0=2,
+           temperature=None, thin=1):
+    """Adaptive Metropolis, eeyore/samplers/am.py:62-107 (offset = 0, no transform).  theta0 [C, P]; z [T, C, P];
+    u [T, 2, C]: u[:, 0] is the mixture uniform (consumed only when idx + 1 > t0, am.py:69-70), u[:, 1] the accept uniform.
+    A covariance estimate that is not positive definite raises (torch.linalg.cholesky does, am.py:74)."""
+    theta = np.array(np.atleast_2d(theta0), copy=True)
+    dt = theta.dtype
+    nc, p = theta.shape
+    cov0 = np.eye(p, dtype=dt) if cov0 is None else np.asarray(cov0, dtype=dt)
+    cov = np.broadcast_to(cov0, (nc, p, p)).copy()
+    mean = np.zeros((nc, p), dtype=dt)
+    cov_sum = np.zeros((nc, p, p), dtype=dt)
+    n_acc = np.zeros(nc, dtype=np.int64)
+    lt = log_target(spec, theta, x, y, loc, scale, temperature)
+    store = {}
+    for idx in range(z.shape[0]):
+        zt = z[idx].astype(dt)
+        if idx + 1 > t0:                                                       # :69
+            chol = np.linalg.cholesky(cov)                                     # raises LinAlgError like torch (:74)
+            adapt = dt.type(b) * np.einsum("cij,cj->ci", chol, zt)
+            prop = theta + np.where((u[idx, 0] < l)[:, None], dt.type(c) * zt, adapt)
+        else:
+            prop = theta + dt.type(c) * zt                                     # :76
+        lt_p = log_target(spec, prop, x, y, loc, scale, temperature)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            acc = np.log(u[idx, 1].astype(dt)) < lt_p - lt                     # :81
+        theta = np.where(acc[:, None], prop, theta)
+        lt = np.where(acc, lt_p, lt)
+        if idx > 0:
+            n_acc += acc                                                       # :87-88
+        k = dt.type(idx + 1)
+        mean = ((k - 1) * mean + theta) / k                                    # recursive_mean, :93-95
+        cov_sum = cov_sum + theta[:, :, None] * theta[:, None, :]              # :96
+        if idx + 1 >= t0:                                                      # :97-102
+            kk = dt.type(idx)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rec = (cov_sum - (kk + 1) * (mean[:, :, None] * mean[:, None, :])) / kk
+            cov = np.where((n_acc == 0)[:, None, None], cov0[None], rec)
+        _collect(store, idx, n_burnin, thin, sample=theta, target_val=lt, accepted=acc.astype(np.uint8))
+    return _finish(store, dict(sample=theta, target_val=lt, cov=cov, running_mean=mean, cov_sum=cov_sum, num_accepted=n_acc))
+
+
+def ram_run(spec: MLPSpec, x, y, loc, scale, theta0, z, u, n_burnin=0, cov0=None, a=0.234, g=0.7, temperature=None, thin=1):
+    """Robust adaptive Metropolis, eeyore/samplers/ram.py:39-70 (offset = 0).  theta0 [C, P]; z [T, C, P]; u [T, C]."""
+    theta = np.array(np.atleast_2d(theta0), copy=True)
+    dt = theta.dtype
+    nc, p = theta.shape
+    cov0 = np.eye(p, dtype=dt) if cov0 is None else np.asarray(cov0, dtype=dt)
+    chol = np.broadcast_to(np.linalg.cholesky(cov0), (nc, p, p)).copy()        # :31-32
+    lt = log_target(spec, theta, x, y, loc, scale, temperature)
+    eye = np.eye(p, dtype=dt)
+    store = {}
+    for idx in range(z.shape[0]):
+        zt = z[idx].astype(dt)
+        prop = theta + np.einsum("cij,cj->ci", chol, zt)                       # :46
+        lt_p = log_target(spec, prop, x, y, loc, scale, temperature)
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            log_rate = lt_p - lt
+            acc = np.log(u[idx].astype(dt)) < log_rate                         # :51
+            ex = np.exp(log_rate)
+        alpha = np.where(ex < 1, ex, dt.type(1))                               # python min(1, nan) == 1
+        theta = np.where(acc[:, None], prop, theta)
+        lt = np.where(acc, lt_p, lt)
+        h = min(1, p * (idx + 1) ** (-g))                                      # :61
+        coef = (dt.type(h) * (alpha - dt.type(a)))[:, None, None]
+        inner = eye[None] + coef * (zt[:, :, None] * zt[:, None, :]) / np.einsum("ci,ci->c", zt, zt)[:, None, None]
+        chol = np.linalg.cholesky(chol @ inner @ np.transpose(chol, (0, 2, 1)))  # :62-66
+        _collect(store, idx, n_burnin, thin, sample=theta, target_val=lt, accepted=acc.astype(np.uint8))
+    return _finish(store, dict(sample=theta, target_val=lt, chol_cov=chol))

@@ -44,7 +44,7 @@ def test_run_params_struct_layout_matches_header():
         if not decl:
             continue
         for part in decl.split(","):
-            names.append(re.findall(r"\*?\s*([a-z_0-9]+)\s*$", part.strip())[0])
+            names.append(re.findall(r"\*?\s*([a-z_0-9]+)\s*(?:\[\d+\])?\s*$", part.strip())[0])
     assert names == [f[0] for f in nv.RunParams._fields_]
 
 

@@ -172,3 +172,27 @@ def test_power_posterior_matches_the_reference(name):
     assert np.allclose(r["target_val"][:, :, 0], gd["target_vals"], rtol=1e-10, atol=1e-12)
     assert rel_err(r["final_sample"][:, 0], gd["final_sample"]) < 1e-10
     assert 0 < r["swaps"].sum() < r["swaps"].size          # the run contains accepted and rejected swaps
+
+
+@pytest.mark.parametrize("name", ["am_xor221_f64", "am_xor2321_f64", "ram_xor221_f64", "ram_xor2321_f64"])
+def test_adaptive_metropolis_matches_the_reference(name):
+    """AM (am.py:62-107) and RAM (ram.py:39-70) fed the reference's noise: identical accept vectors, states < 1e-10 ...
+    up to the adaptation's own conditioning (the factor is re-derived from sums of outer products every iteration)."""
+    gd = load(name)
+    arch = "221" if "221" in name else "2321"
+    spec = spec_of(arch)
+    x, y = data_of(arch, np.float64)
+    P = gd["theta0"].shape[0]
+    s3 = 3.0 ** 0.5
+    if name.startswith("am"):
+        r = oracle.am_run(spec, x, y, np.zeros(P), np.full(P, s3), gd["theta0"][None], gd["z"][:, None], gd["u"][:, :, None],
+                          n_burnin=int(gd["n_burnin"]), l=float(gd["l"]), b=float(gd["b"]), c=float(gd["c"]), t0=int(gd["t0"]))
+        factor = r["final"]["cov"][0]
+    else:
+        r = oracle.ram_run(spec, x, y, np.zeros(P), np.full(P, s3), gd["theta0"][None], gd["z"][:, None], gd["u"][:, None],
+                           n_burnin=int(gd["n_burnin"]), a=float(gd["a"]), g=float(gd["g"]))
+        factor = r["final"]["chol_cov"][0]
+    assert np.array_equal(r["accepted"][:, 0], gd["accepted"])
+    assert rel_err(r["sample"][:, 0], gd["samples"]) < 1e-9
+    assert np.allclose(r["target_val"][:, 0], gd["target_vals"], rtol=1e-9, atol=1e-11)
+    assert rel_err(factor, gd["final_factor"]) < 1e-7
