@@ -86,6 +86,20 @@ class MLP(BayesianModel):
             self._handle = h
         return self._handle
 
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(model) as the reference's multi-chain samplers do (power_posterior_sampler.py:71-83): the copy gets
+        its own native handle (created lazily) instead of sharing or pickling the ctypes pointer."""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_handle":
+                new.__dict__[k] = None
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def __del__(self):
         try:
             if self._handle is not None:

@@ -177,3 +177,14 @@ def test_chainlist_and_chainfile_roundtrip(tmp_path):
     assert lists.acceptance() == [ch.acceptance_rate()] * 2
     st = ch.state(-1)
     assert st["accepted"] == 0 and torch.equal(st["sample"], torch.zeros(5, dtype=torch.float64))
+
+
+def test_model_deepcopy_gets_its_own_native_handle():
+    """The reference deep-copies the model per tempered chain (power_posterior_sampler.py:71-83)."""
+    import copy
+    m = MLP(loss=loss_functions["binary_classification"], hparams=Hyperparameters([2, 2, 1]), dtype=torch.float64)
+    h = m.handle()
+    c = copy.deepcopy(m)
+    c.temperature = 0.25
+    assert m.temperature is None and c.num_params() == 9
+    assert c.handle().value != h.value
