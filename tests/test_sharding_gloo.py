@@ -2,7 +2,8 @@
  (i) chain sharding -- no data-path collective: a rank running chains [lo, hi) with chain_offset = lo reproduces exactly
      those chains of the single-rank run (device code executed through tests/hostsim);
  (ii) data sharding -- one exchange step per evaluation: the all-reduced partial (loglik, gradient) sums over row shards
-     equal the unsharded evaluation (the oracle stands in for the per-rank kernel on CPU)."""
+     equal the unsharded evaluation (the oracle stands in for the per-rank kernel on CPU);
+ (iii) the rank-ordered inbox summation that replaces the all-reduce on the GPUs (csrc/datapar.cu: dp_post_kernel)."""
 import ctypes as C
 import os
 import socket
@@ -83,6 +84,18 @@ def _worker(rank, world, port, ret):
         _, g_full = oracle.log_target_grad(spec, th, xs, ys, *zero_prior)
         assert abs(sums[0].item() - ll_full) < 1e-9 * abs(ll_full)
         assert np.max(np.abs(sums[1:].numpy() - g_full[0])) < 1e-9 * np.max(np.abs(g_full[0]))
+        # (iii) the peer-store exchange of dp_post_kernel, emulated: every rank's sums land in slot [src] of every rank's inbox
+        # (an all-gather stands in for the NVLink stores) and each rank adds the slots in rank order -> bit-identical totals
+        mine = torch.from_numpy(np.concatenate([ll, gl[0]]))
+        inbox = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(inbox, mine)
+        total = torch.zeros_like(mine)
+        for src in range(world):
+            total += inbox[src]
+        both = [torch.empty_like(total) for _ in range(world)]
+        dist.all_gather(both, total)
+        assert all(torch.equal(both[0], b) for b in both)              # replicated chain state stays in lock step
+        assert torch.allclose(total, sums, rtol=1e-13, atol=0)
         ret[rank] = True
     finally:
         dist.destroy_process_group()
