@@ -7,11 +7,16 @@
 // Why tensor cores here and nowhere else: the two hidden layers are dense 64-wide contractions over 128-row tiles
 // (29,056 FLOP per row); the chain-batched kernels have no such contraction.
 //
-// fp32 parity on bf16 tensor cores: every operand x is split exactly into three bf16 pieces x = x1 + x2 + x3
-// (8 + 8 + 8 significant bits) and every product A B is evaluated as the six leading piece products
-//   A1 B1 + A1 B2 + A2 B1 + A1 B3 + A3 B1 + A2 B2        (dropped terms <= 2^-24 relative)
-// accumulated in fp32 in TMEM.  The B pieces are laid out side by side along N, so one product costs three MMAs
-// (A1 x [B1 B2 B3], A2 x [B1 B2], A3 x [B1]) into three 64-column accumulator groups that the epilogue adds up.
+// fp32 parity on 16-bit tensor cores: operands are split exactly into 16-bit pieces and a product A B is the sum of the
+// leading piece products, accumulated in fp32 in TMEM.  The B pieces are laid out side by side along N, so one A piece is
+// read once for all the B pieces it meets (one MMA per A piece, one 64-column accumulator group per B piece).
+//   * x, W0, Delta1 (MMA1, MMA5: unbounded data, small GEMMs): three bf16 pieces (8 + 8 + 8 bits), six products
+//       A1 B1 + A1 B2 + A2 B1 + A1 B3 + A3 B1 + A2 B2  = three MMAs (A1 x [B1 B2 B3], A2 x [B1 B2], A3 x [B1]);
+//   * H1, Delta2, W1 (MMA2, MMA3, MMA4: the three big GEMMs; magnitudes bounded by the parameters): two fp16 pieces
+//     (11 + 11 bits) after an exact power-of-two scaling chosen in the prologue (H1 * 2^10; W1 and Delta2 so that the largest
+//     possible magnitude is below 2^14), three products A1 B1 + A1 B2 + A2 B1 = two MMAs (A1 x [B1 B2], A2 x [B1]).
+//     A fp16 x bf16 MMA is illegal (tools/tc_probe.cu), so each GEMM is wholly one format.
+//   Emulated on the CPU and measured on the GPU: gradient within 3e-7 of the fp64 oracle for either split (bar 1e-5).
 //
 // Per 128-row tile (persistent CTAs, one per SM, 256 threads; thread = (row, half of the 64 features)):
 //   P0  x tile (coalesced loads, prefetched one tile ahead) -> bf16 pieces in smem  MMA1  Z1 = X W0^T
@@ -38,29 +43,32 @@ using namespace tc;
 constexpr uint32_t TC_CS = 2048;                 // chunk stride of [128 x C] activation buffers (128 rows * 16 B)
 constexpr uint32_t TC_ACT = 8 * TC_CS;           // one bf16 piece of a [128 x 64] activation: 16 KB
 constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] x tile: 4 KB
-constexpr uint32_t TC_WCS = 192 * 16;            // chunk stride of the piece-stacked weight buffers ([192 x K])
+constexpr uint32_t TC_WCS = 192 * 16;            // chunk stride of the 3-piece-stacked weight buffer W0 ([192 x K])
+constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-stacked weight buffers W1 ([128 x K])
+constexpr float TC_SH = 1024.f;                  // scale of H1 before the fp16 split (keeps the low piece normal)
 // TMEM columns (fp32)
-constexpr uint32_t TM_Z = 0;                     // Z1, then Z2, then D1 (3 groups of 64): one region, the phases are sequential
-constexpr uint32_t TM_W1 = 192;                  // [ones(8) | dW1 (3 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
-constexpr uint32_t TM_H1 = 392;                  // H1 in fp32 (P1 -> P3)
-constexpr uint32_t TM_W0 = 456;                  // [ones(8) | dW0 (3 x 16)]
+constexpr uint32_t TM_Z = 0;                     // Z1 (3 groups of 64), then Z2, then D1 (2 groups): one region, sequential phases
+constexpr uint32_t TM_W1 = 192;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
+constexpr uint32_t TM_H1 = 328;                  // H1 in fp32 (P1 -> P3)
+constexpr uint32_t TM_W0 = 392;                  // [ones(8) | dW0 (3 x 16)]
 constexpr int TC_FLUSH = 4;
 constexpr int TC_THREADS = DP_THREADS;           // 8 warps: every one an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
 
 struct TcSmem {
-  alignas(1024) uint16_t ones_h[1024];           // 2 KB of bf16 1.0: the N-chunk in front of the H1 pieces
-  alignas(16) uint16_t h1[3 * TC_ACT / 2];       // H1 pieces
-  alignas(16) uint16_t ones_x[1024];             // the N-chunk in front of the x pieces
-  alignas(16) uint16_t xp[3 * TC_XP / 2];        // x pieces
-  alignas(16) uint16_t dl[3 * TC_ACT / 2];       // Delta2 pieces
-  alignas(16) uint16_t dl1[3 * TC_ACT / 2];      // Delta1 pieces
-  alignas(16) uint16_t w0s[2 * TC_WCS / 2];      // rows 64 p + o, cols j      (B of MMA1)
-  alignas(16) uint16_t w1a[8 * TC_WCS / 2];      // rows 64 p + o, cols i      (B of MMA2)
-  alignas(16) uint16_t w1b[8 * TC_WCS / 2];      // rows 64 p + i, cols o      (B of MMA3)
+  alignas(1024) uint16_t ones_h[1024];           // 2 KB of fp16 1.0: the N-chunk in front of the H1 pieces
+  alignas(16) uint16_t h1[2 * TC_ACT / 2];       // H1 pieces (fp16 x 2, scaled by TC_SH)
+  alignas(16) uint16_t ones_x[1024];             // 2 KB of bf16 1.0: the N-chunk in front of the x pieces
+  alignas(16) uint16_t xp[3 * TC_XP / 2];        // x pieces (bf16 x 3)
+  alignas(16) uint16_t dl[2 * TC_ACT / 2];       // Delta2 pieces (fp16 x 2, scaled)
+  alignas(16) uint16_t dl1[3 * TC_ACT / 2];      // Delta1 pieces (bf16 x 3)
+  alignas(16) uint16_t w0s[2 * TC_WCS / 2];      // bf16 x 3: rows 64 p + o, cols j      (B of MMA1)
+  alignas(16) uint16_t w1a[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols i      (B of MMA2)
+  alignas(16) uint16_t w1b[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + i, cols o      (B of MMA3)
   alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
   alignas(16) float exch[2][DP_R];
   alignas(8) unsigned long long bar[6];          // 1..5: MMA groups
   float b2;
+  float red_max[2][DP_THREADS / 32];             // prologue: max |W1|, max |w2| per warp
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
@@ -122,6 +130,59 @@ __device__ __forceinline__ void split3_scalar(float x, uint16_t& p1, uint16_t& p
   p3 = (uint16_t)pack_bf16x2(s, 0.f);
 }
 
+// fp16 pair {hi half: b, lo half: a} (round to nearest even) and back
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {
+  float2 r;
+  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(h));
+  return r;
+}
+// 8 consecutive fp32 values (already scaled) -> two 16-byte rows of fp16 pieces: v = p1 + p2 + O(2^-22 v) (exact residual)
+__device__ __forceinline__ void split2h(const float* v, uint4& p1, uint4& p2) {
+  uint32_t a[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x0 = v[2 * j], x1 = v[2 * j + 1];
+    const uint32_t h = pack_f16x2(x0, x1);
+    const float2 hf2 = unpack_f16x2(h);
+    a[j] = h;
+    b[j] = pack_f16x2(x0 - hf2.x, x1 - hf2.y);
+  }
+  p1 = make_uint4(a[0], a[1], a[2], a[3]);
+  p2 = make_uint4(b[0], b[1], b[2], b[3]);
+}
+__device__ __forceinline__ void split2h_scalar(float x, uint16_t& p1, uint16_t& p2) {
+  const uint32_t h = pack_f16x2(x, 0.f);
+  const float r = x - unpack_f16x2(h).x;
+  p1 = (uint16_t)h;
+  p2 = (uint16_t)pack_f16x2(r, 0.f);
+}
+// 32 features of one row (scaled by `scale`), starting at chunk `chunk0` -> the two fp16 piece buffers
+__device__ __forceinline__ void store_pieces32h(unsigned char* base, int chunk0, int r, const float* v, float scale) {
+  unsigned char* p = base + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)chunk0 * TC_CS;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = v[8 * c + j] * scale;
+    uint4 p1, p2;
+    split2h(w, p1, p2);
+    *reinterpret_cast<uint4*>(p + c * TC_CS) = p1;
+    *reinterpret_cast<uint4*>(p + c * TC_CS + TC_ACT) = p2;
+  }
+}
+// 2^e (|e| < 127) and the exponent of the power of two that brings `vmax` into [2^13, 2^14)
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }
+__device__ __forceinline__ int scale_exp(float vmax) {
+  if (!(vmax > 0.f) || !(vmax < 3.0e38f)) return 0;       // all zero, or inf / nan (which propagate anyway)
+  const int e = 13 - (((__float_as_int(vmax) >> 23) & 0xff) - 127);
+  return e < -40 ? -40 : (e > 40 ? 40 : e);
+}
+
 // 32 features of one row, starting at chunk `chunk0` (8 features per chunk) -> the three piece buffers
 __device__ __forceinline__ void store_pieces32(unsigned char* base, uint32_t piece_bytes, int chunk0, int r, const float* v) {
   unsigned char* p = base + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)chunk0 * TC_CS;
@@ -144,6 +205,16 @@ __device__ __forceinline__ void load_sum3(uint32_t taddr, float* v) {
   tmem_ld_wait();
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(c[j]) + __uint_as_float(b[j])) + __uint_as_float(a[j]);
+}
+
+// the same for the two accumulator groups of a two-piece product
+__device__ __forceinline__ void load_sum2(uint32_t taddr, float* v) {
+  uint32_t a[32], b[32];
+  tmem_ld32(taddr, a);
+  tmem_ld32(taddr + 64, b);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(b[j]) + __uint_as_float(a[j]);
 }
 
 // hi + lo += x, error-free (Knuth two-sum): a pair of fp32 registers carries ~46 significant bits.  The tile loop uses
@@ -169,19 +240,19 @@ __device__ __forceinline__ void butterfly_step(float* t, int lane) {
   }
 }
 
-// one A piece per MMA against the first (3 - a) B pieces; D groups are 64 (or N_PIECE) columns wide
-//   a_desc[a]: descriptors of the three A pieces;  b_desc: descriptor of [B1 B2 B3] (pieces adjacent along N)
-template <int M, int N_LEAD, int N_PIECE, int A_MN, int B_MN>
+// one A piece per MMA against the first (NP - a) B pieces; D groups are N_PIECE columns wide
+//   a_desc[a]: descriptors of the A pieces;  b_desc: descriptor of [B1 B2 ..] (pieces adjacent along N);  FMT 0 = fp16, 1 = bf16
+template <int NP, int FMT, int M, int N_LEAD, int N_PIECE, int A_MN, int B_MN>
 __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_desc, uint64_t b_desc, uint32_t a_step,
                                             uint32_t b_step, int k_steps, uint32_t accumulate = 0u) {
-  constexpr uint32_t id0 = idesc_bf16(M, N_LEAD + 3 * N_PIECE, A_MN, B_MN);
-  constexpr uint32_t id1 = idesc_bf16(M, N_LEAD + 2 * N_PIECE, A_MN, B_MN);
-  constexpr uint32_t id2 = idesc_bf16(M, N_LEAD + 1 * N_PIECE, A_MN, B_MN);
+  constexpr uint32_t id0 = idesc_f16kind(M, N_LEAD + NP * N_PIECE, A_MN, B_MN, FMT, FMT);
+  constexpr uint32_t id1 = idesc_f16kind(M, N_LEAD + (NP - 1) * N_PIECE, A_MN, B_MN, FMT, FMT);
+  constexpr uint32_t id2 = idesc_f16kind(M, N_LEAD + 1 * N_PIECE, A_MN, B_MN, FMT, FMT);
   for (int k = 0; k < k_steps; ++k) {
     const uint64_t bd = desc_advance(b_desc, k * b_step);
     mma_bf16(d_tmem, desc_advance(a_desc[0], k * a_step), bd, id0, (k > 0) ? 1u : accumulate);
     mma_bf16(d_tmem, desc_advance(a_desc[1], k * a_step), bd, id1, 1u);
-    mma_bf16(d_tmem, desc_advance(a_desc[2], k * a_step), bd, id2, 1u);
+    if constexpr (NP == 3) mma_bf16(d_tmem, desc_advance(a_desc[2], k * a_step), bd, id2, 1u);
   }
 }
 
@@ -208,19 +279,42 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     for (int k = 0; k < 3; ++k)
       *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS)) = p[k];
   }
+  // power-of-two scales of the fp16 operands, from the parameter magnitudes (identical in every CTA and on every rank)
+  {
+    float m1 = 0.f, m2 = 0.f;
+    for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) m1 = fmaxf(m1, fabsf(theta[DP_OFF_W1 + e]));
+    if (tid < DP_H) m2 = fabsf(theta[DP_OFF_W2 + tid]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) { s.red_max[0][warp] = m1; s.red_max[1][warp] = m2; }
+  }
+  __syncthreads();
+  float w1max = 0.f, w2max = 0.f;
+#pragma unroll
+  for (int w = 0; w < TC_THREADS / 32; ++w) { w1max = fmaxf(w1max, s.red_max[0][w]); w2max = fmaxf(w2max, s.red_max[1][w]); }
+  const int e_w = scale_exp(w1max);                 // W1 * 2^e_w      in [2^13, 2^14)
+  const int e_d = scale_exp(0.25f * w2max);         // |Delta2| <= max|w2| / 4:  Delta2 * 2^e_d below 2^14
+  const float s_w = pow2i(e_w), s_d = pow2i(e_d);
+  const float inv_z2 = pow2i(-e_w) * (1.0f / TC_SH);            // Z2 = (H1 sh)(W1 sw)^T
+  const float inv_d1 = pow2i(-e_w) * pow2i(-e_d);               // D1 = (Delta2 sd)(W1 sw)
+  const float inv_w1 = pow2i(-e_d) * (1.0f / TC_SH);            // dW1 = (Delta2 sd)^T (H1 sh)
+  const float inv_b1 = pow2i(-e_d);                             // db1 = (Delta2 sd)^T 1
   for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) {   // W1[o][i]
     const int o = e / DP_H, i = e % DP_H;
-    uint16_t p[3];
-    split3_scalar(theta[DP_OFF_W1 + e], p[0], p[1], p[2]);
+    uint16_t p[2];
+    split2h_scalar(theta[DP_OFF_W1 + e] * s_w, p[0], p[1]);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1a) + cm_off(64 * k + o, i, TC_WCS)) = p[k];
-      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * k + i, o, TC_WCS)) = p[k];
+    for (int k = 0; k < 2; ++k) {
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1a) + cm_off(64 * k + o, i, TC_WCS2)) = p[k];
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * k + i, o, TC_WCS2)) = p[k];
     }
   }
   for (int e = tid; e < 1024; e += TC_THREADS) {
-    s.ones_h[e] = 0x3F80;
-    s.ones_x[e] = 0x3F80;
+    s.ones_h[e] = 0x3C00;     // fp16 1.0
+    s.ones_x[e] = 0x3F80;     // bf16 1.0
   }
   if (tid < DP_H) {
     s.b0[tid] = theta[DP_OFF_B0 + tid];
@@ -242,21 +336,24 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
 
   // descriptors (built once; K steps advance the start address)
-  uint64_t dXa[3], dH1a[3], dDLa[3], dDLm[3], dDL1m[3];
+  uint64_t dXa[3], dH1a[2], dDLa[2], dDLm[2], dDL1m[3];
   {
     const uint32_t ax = smem_u32(s.xp), ah = smem_u32(s.h1), ad = smem_u32(s.dl), ad1 = smem_u32(s.dl1);
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
       dXa[p] = smem_desc(ax + p * TC_XP, TC_CS, 128);      // K-major A (M = row, K = input feature)
+      dDL1m[p] = smem_desc(ad1 + p * TC_ACT, 128, TC_CS);  // MN-major A (M = unit, K = row)
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
       dH1a[p] = smem_desc(ah + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = hidden unit)
       dDLa[p] = smem_desc(ad + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = output unit)
       dDLm[p] = smem_desc(ad + p * TC_ACT, 128, TC_CS);    // MN-major A (M = unit, K = row)
-      dDL1m[p] = smem_desc(ad1 + p * TC_ACT, 128, TC_CS);
     }
   }
   const uint64_t dW0 = smem_desc(smem_u32(s.w0s), TC_WCS, 128);      // K-major B (N = 64 p + o, K = j)
-  const uint64_t dW1a = smem_desc(smem_u32(s.w1a), TC_WCS, 128);     // K-major B (N = 64 p + o, K = i)
-  const uint64_t dW1b = smem_desc(smem_u32(s.w1b), TC_WCS, 128);     // K-major B (N = 64 p + i, K = o)
+  const uint64_t dW1a = smem_desc(smem_u32(s.w1a), TC_WCS2, 128);    // K-major B (N = 64 p + o, K = i)
+  const uint64_t dW1b = smem_desc(smem_u32(s.w1b), TC_WCS2, 128);    // K-major B (N = 64 p + i, K = o)
   const uint64_t dH1m = smem_desc(smem_u32(s.ones_h), 128, TC_CS);   // MN-major B (N = [1 x8 | H1 pieces], K = row)
   const uint64_t dXm = smem_desc(smem_u32(s.ones_x), 128, TC_CS);    // MN-major B (N = [1 x8 | x pieces], K = row)
 
@@ -311,7 +408,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);                        // MMA1: Z1 = X W0^T
+        mma_product<3, 1, 128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);                  // MMA1: Z1 = X W0^T (bf16 x 3)
         mma_commit(&s.bar[1]);
       }
       __syncwarp();
@@ -332,7 +429,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         hbits[j] = __float_as_uint(v[j]);
       }
       tmem_st32(tm_lane + TM_H1 + 32 * hf, hbits);
-      store_pieces32(reinterpret_cast<unsigned char*>(s.h1), TC_ACT, 4 * hf, r, v);
+      store_pieces32h(reinterpret_cast<unsigned char*>(s.h1), 4 * hf, r, v, TC_SH);
       tmem_st_wait();
     }
     fence_async_smem();
@@ -341,7 +438,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS, 4);     // MMA2: Z2 = H1 W1^T
+        mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS2, 4);   // MMA2: Z2 = H1 W1^T (fp16 x 2)
         mma_commit(&s.bar[2]);
       }
       __syncwarp();
@@ -354,11 +451,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     float t[32], p_head = 0.5f, d_head = 0.f;
     {
       float h[32];
-      load_sum3(tm_lane + TM_Z + 32 * hf, h);
+      load_sum2(tm_lane + TM_Z + 32 * hf, h);
       float apart = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        h[j] = tc_sigmoid(h[j] + s.b1[32 * hf + j]);
+        h[j] = tc_sigmoid(fmaf(h[j], inv_z2, s.b1[32 * hf + j]));
         apart = fmaf(h[j], s.w2[32 * hf + j], apart);
       }
       TC_STAMP(13);
@@ -378,7 +475,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         t[j] = d * h[j];                                                   // dW2 terms
         h[j] = d * s.w2[32 * hf + j] * (1.f - h[j]) * h[j];                // Delta2
       }
-      store_pieces32(reinterpret_cast<unsigned char*>(s.dl), TC_ACT, 4 * hf, r, h);
+      store_pieces32h(reinterpret_cast<unsigned char*>(s.dl), 4 * hf, r, h, s_d);
     }
     TC_STAMP(16);
     fence_async_smem();
@@ -387,9 +484,9 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<128, 0, 64, 0, 0>(tm + TM_Z, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS, 4);     // MMA3: D1 = Delta2 W1
+        mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS2, 4);   // MMA3: D1 = Delta2 W1
         mma_commit(&s.bar[3]);
-        mma_product<64, 8, 64, 1, 1>(tm + TM_W1, dDLm, dH1m, 256, 256, 8, keep);             // MMA4: Delta2^T [1 H1]
+        mma_product<2, 0, 64, 8, 64, 1, 1>(tm + TM_W1, dDLm, dH1m, 256, 256, 8, keep);       // MMA4: Delta2^T [1 H1]
         mma_commit(&s.bar[4]);
       }
       __syncwarp();
@@ -420,14 +517,14 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     fence_after_sync();
     {
       float v[32];
-      load_sum3(tm_lane + TM_Z + 32 * hf, v);
+      load_sum2(tm_lane + TM_Z + 32 * hf, v);
       uint32_t hbits[32];
       tmem_ld32(tm_lane + TM_H1 + 32 * hf, hbits);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float h1 = __uint_as_float(hbits[j]);
-        v[j] = v[j] * (1.f - h1) * h1;
+        v[j] = (v[j] * inv_d1) * (1.f - h1) * h1;
       }
       TC_STAMP(7);
       store_pieces32(reinterpret_cast<unsigned char*>(s.dl1), TC_ACT, 4 * hf, r, v);
@@ -438,7 +535,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);             // MMA5: Delta1^T [1 X]
+        mma_product<3, 1, 64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);       // MMA5: Delta1^T [1 X] (bf16 x 3)
         mma_commit(&s.bar[5]);
       }
       __syncwarp();
@@ -450,13 +547,13 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     fence_after_sync();
     if (fold) {
       float v[32];
-      load_sum3(tm_lane + TM_W1 + 8 + 32 * hf, v);
+      load_sum2(tm_lane + TM_W1 + 8 + 32 * hf, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc2(g1[i], g1e[i], v[i]);
+      for (int i = 0; i < 32; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
       uint32_t o4[4];
       tmem_ld4(tm_lane + TM_W1, o4);
       tmem_ld_wait();
-      acc2(gb1, gb1e, __uint_as_float(o4[0]));
+      acc2(gb1, gb1e, __uint_as_float(o4[0]) * inv_b1);
     }
     TC_STAMP(10);
     mbar_wait(&s.bar[5], par);   // also: MMA5 has finished reading the x pieces and Delta1

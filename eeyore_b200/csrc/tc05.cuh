@@ -94,6 +94,13 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with explicit operand formats (0 = fp16, 1 = bf16); probed on B200: A and B must have the SAME format
+// (a fp16 x bf16 MMA raises "illegal instruction")
+__host__ __device__ constexpr uint32_t idesc_f16kind(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
