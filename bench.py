@@ -594,8 +594,14 @@ def run_datapar(args):
         torch.cuda.synchronize()
         return k0.elapsed_time(k1) / reps
 
+    amax = torch.zeros(1, dtype=torch.float32, device=dev)
+    nv.check(lib.eeyore_b200_dp_absmax(nv.ptr(x), x.numel(), nv.ptr(amax), nv.stream_ptr(dev)))
+
+    def tc_kernel(th, xx, yy, nn, out, wsp, st):          # max |x| of the shard computed once, as DataShardedHMC does
+        return lib.eeyore_b200_dp_loglik_grad_x(th, xx, yy, nn, nv.ptr(amax), out, wsp, st)
+
     barrier()
-    kernel_ms = max_over_ranks(time_kernel(lib.eeyore_b200_dp_loglik_grad))
+    kernel_ms = max_over_ranks(time_kernel(tc_kernel))
     ffma_ms = max_over_ranks(time_kernel(lib.eeyore_b200_dp_loglik_grad_ffma, reps=5))
     if rank == 0:
         peak32 = ctypes.c_double()

@@ -78,6 +78,8 @@ SIGNATURES = {
     "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "eeyore_b200_dp_num_params": (_I, []),
     "eeyore_b200_dp_loglik_grad": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
+    "eeyore_b200_dp_loglik_grad_x": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "eeyore_b200_dp_absmax": (_I, [_VP, _I64, _VP, _VP]),
     "eeyore_b200_dp_loglik_grad_ffma": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     "eeyore_b200_dp_num_parts": (_I, [_I64]),
     "eeyore_b200_dp_post": (_I, [_VP, _I, _I, _I, _U64, C.POINTER(_VP), _VP, _VP, _VP, _VP, _I, _D, _VP, _VP, _I, _D, _VP, _VP,

@@ -10,13 +10,13 @@
 // fp32 parity on 16-bit tensor cores: operands are split exactly into 16-bit pieces and a product A B is the sum of the
 // leading piece products, accumulated in fp32 in TMEM.  The B pieces are laid out side by side along N, so one A piece is
 // read once for all the B pieces it meets (one MMA per A piece, one 64-column accumulator group per B piece).
-//   * x, W0, Delta1 (MMA1, MMA5: unbounded data, small GEMMs): three bf16 pieces (8 + 8 + 8 bits), six products
-//       A1 B1 + A1 B2 + A2 B1 + A1 B3 + A3 B1 + A2 B2  = three MMAs (A1 x [B1 B2 B3], A2 x [B1 B2], A3 x [B1]);
-//   * H1, Delta2, W1 (MMA2, MMA3, MMA4: the three big GEMMs; magnitudes bounded by the parameters): two fp16 pieces
-//     (11 + 11 bits) after an exact power-of-two scaling chosen in the prologue (H1 * 2^10; W1 and Delta2 so that the largest
-//     possible magnitude is below 2^14), three products A1 B1 + A1 B2 + A2 B1 = two MMAs (A1 x [B1 B2], A2 x [B1]).
-//     A fp16 x bf16 MMA is illegal (tools/tc_probe.cu), so each GEMM is wholly one format.
-//   Emulated on the CPU and measured on the GPU: gradient within 3e-7 of the fp64 oracle for either split (bar 1e-5).
+//   Every operand is two fp16 pieces (11 + 11 bits, exact residual) after an exact power-of-two scaling that brings its
+//   largest possible magnitude just below 2^14: W0, W1 from max |W| (prologue), x from the shard's max |x| (a device scalar
+//   supplied by the caller or computed by a reduction kernel), H1 by 2^10, Delta2 from |Delta2| <= max|w2| / 4, Delta1 from
+//   |Delta1| <= 4 max|w2| max|W1|.  A product is A1 B1 + A1 B2 + A2 B1 (dropped term <= 2^-22) = two MMAs (A1 x [B1 B2],
+//   A2 x [B1]); the scales are undone in the epilogues (folded into an existing multiply).  The first version used three
+//   bf16 pieces and six products (no scaling needed): same accuracy, 1.75x the tensor time and 1.5x the operand bytes.
+//   Emulated on the CPU and measured on the GPU: gradient within 3e-7 of the fp64 oracle (bar 1e-5).
 //
 // Per 128-row tile (persistent CTAs, one per SM, 256 threads; thread = (row, half of the 64 features)):
 //   P0  x tile (coalesced loads, prefetched one tile ahead) -> bf16 pieces in smem  MMA1  Z1 = X W0^T
@@ -43,32 +43,31 @@ using namespace tc;
 constexpr uint32_t TC_CS = 2048;                 // chunk stride of [128 x C] activation buffers (128 rows * 16 B)
 constexpr uint32_t TC_ACT = 8 * TC_CS;           // one bf16 piece of a [128 x 64] activation: 16 KB
 constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] x tile: 4 KB
-constexpr uint32_t TC_WCS = 192 * 16;            // chunk stride of the 3-piece-stacked weight buffer W0 ([192 x K])
-constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-stacked weight buffers W1 ([128 x K])
+constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-stacked weight buffers ([128 x K])
 constexpr float TC_SH = 1024.f;                  // scale of H1 before the fp16 split (keeps the low piece normal)
 // TMEM columns (fp32)
-constexpr uint32_t TM_Z = 0;                     // Z1 (3 groups of 64), then Z2, then D1 (2 groups): one region, sequential phases
-constexpr uint32_t TM_W1 = 192;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
-constexpr uint32_t TM_H1 = 328;                  // H1 in fp32 (P1 -> P3)
-constexpr uint32_t TM_W0 = 392;                  // [ones(8) | dW0 (3 x 16)]
+constexpr uint32_t TM_Z = 0;                     // Z1, then Z2, then D1 (2 groups of 64): one region, the phases are sequential
+constexpr uint32_t TM_W1 = 128;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
+constexpr uint32_t TM_H1 = 264;                  // H1 in fp32 (P1 -> P3)
+constexpr uint32_t TM_W0 = 328;                  // [ones(8) | dW0 (2 x 16)]
 constexpr int TC_FLUSH = 4;
 constexpr int TC_THREADS = DP_THREADS;           // 8 warps: every one an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
 
 struct TcSmem {
   alignas(1024) uint16_t ones_h[1024];           // 2 KB of fp16 1.0: the N-chunk in front of the H1 pieces
   alignas(16) uint16_t h1[2 * TC_ACT / 2];       // H1 pieces (fp16 x 2, scaled by TC_SH)
-  alignas(16) uint16_t ones_x[1024];             // 2 KB of bf16 1.0: the N-chunk in front of the x pieces
-  alignas(16) uint16_t xp[3 * TC_XP / 2];        // x pieces (bf16 x 3)
+  alignas(16) uint16_t ones_x[1024];             // 2 KB of fp16 1.0: the N-chunk in front of the x pieces
+  alignas(16) uint16_t xp[2 * TC_XP / 2];        // x pieces (fp16 x 2, scaled)
   alignas(16) uint16_t dl[2 * TC_ACT / 2];       // Delta2 pieces (fp16 x 2, scaled)
-  alignas(16) uint16_t dl1[3 * TC_ACT / 2];      // Delta1 pieces (bf16 x 3)
-  alignas(16) uint16_t w0s[2 * TC_WCS / 2];      // bf16 x 3: rows 64 p + o, cols j      (B of MMA1)
+  alignas(16) uint16_t dl1[2 * TC_ACT / 2];      // Delta1 pieces (fp16 x 2, scaled)
+  alignas(16) uint16_t w0s[2 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols j      (B of MMA1)
   alignas(16) uint16_t w1a[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols i      (B of MMA2)
   alignas(16) uint16_t w1b[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + i, cols o      (B of MMA3)
   alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
   alignas(16) float exch[2][DP_R];
   alignas(8) unsigned long long bar[6];          // 1..5: MMA groups
   float b2;
-  float red_max[2][DP_THREADS / 32];             // prologue: max |W1|, max |w2| per warp
+  float red_max[3][DP_THREADS / 32];             // prologue: max |W1|, max |w2|, max |W0| per warp
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
@@ -93,41 +92,6 @@ __device__ __forceinline__ float tc_sigmoid(float z) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return r;
-}
-
-// d = {hi half: b, lo half: a} as bf16 (round to nearest even)
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
-  return d;
-}
-// 8 consecutive fp32 values -> three 16-byte rows of bf16 pieces (exact: v = p1 + p2 + p3 + O(2^-25 v))
-__device__ __forceinline__ void split3(const float* v, uint4& p1, uint4& p2, uint4& p3) {
-  uint32_t a[4], b[4], c[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float x0 = v[2 * j], x1 = v[2 * j + 1];
-    const uint32_t h = pack_bf16x2(x0, x1);
-    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
-    const uint32_t m = pack_bf16x2(r0, r1);
-    const float s0 = r0 - __uint_as_float(m << 16), s1 = r1 - __uint_as_float(m & 0xffff0000u);
-    a[j] = h;
-    b[j] = m;
-    c[j] = pack_bf16x2(s0, s1);
-  }
-  p1 = make_uint4(a[0], a[1], a[2], a[3]);
-  p2 = make_uint4(b[0], b[1], b[2], b[3]);
-  p3 = make_uint4(c[0], c[1], c[2], c[3]);
-}
-// scalar version for the weight staging
-__device__ __forceinline__ void split3_scalar(float x, uint16_t& p1, uint16_t& p2, uint16_t& p3) {
-  const uint32_t h = pack_bf16x2(x, 0.f);
-  const float r = x - __uint_as_float(h << 16);
-  const uint32_t m = pack_bf16x2(r, 0.f);
-  const float s = r - __uint_as_float(m << 16);
-  p1 = (uint16_t)h;
-  p2 = (uint16_t)m;
-  p3 = (uint16_t)pack_bf16x2(s, 0.f);
 }
 
 // fp16 pair {hi half: b, lo half: a} (round to nearest even) and back
@@ -183,31 +147,7 @@ __device__ __forceinline__ int scale_exp(float vmax) {
   return e < -40 ? -40 : (e > 40 ? 40 : e);
 }
 
-// 32 features of one row, starting at chunk `chunk0` (8 features per chunk) -> the three piece buffers
-__device__ __forceinline__ void store_pieces32(unsigned char* base, uint32_t piece_bytes, int chunk0, int r, const float* v) {
-  unsigned char* p = base + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)chunk0 * TC_CS;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 p1, p2, p3;
-    split3(v + 8 * c, p1, p2, p3);
-    *reinterpret_cast<uint4*>(p + c * TC_CS) = p1;
-    *reinterpret_cast<uint4*>(p + c * TC_CS + piece_bytes) = p2;
-    *reinterpret_cast<uint4*>(p + c * TC_CS + 2 * piece_bytes) = p3;
-  }
-}
-
-// v[j] = sum of the three accumulator groups (64 columns apart) at columns col0 + j, j < 32
-__device__ __forceinline__ void load_sum3(uint32_t taddr, float* v) {
-  uint32_t a[32], b[32], c[32];
-  tmem_ld32(taddr, a);
-  tmem_ld32(taddr + 64, b);
-  tmem_ld32(taddr + 128, c);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(c[j]) + __uint_as_float(b[j])) + __uint_as_float(a[j]);
-}
-
-// the same for the two accumulator groups of a two-piece product
+// v[j] = sum of the two accumulator groups (64 columns apart) of a two-piece product at columns col0 + j, j < 32
 __device__ __forceinline__ void load_sum2(uint32_t taddr, float* v) {
   uint32_t a[32], b[32];
   tmem_ld32(taddr, a);
@@ -259,7 +199,7 @@ __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_d
 // partials: [gridDim.x][DP_P + 1] doubles: [0] = log-likelihood, [1 + j] = d loglik / d theta_j
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, const float* __restrict__ y, long n_rows,
-                  double* __restrict__ partials) {
+                  const float* __restrict__ x_absmax, double* __restrict__ partials) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -271,33 +211,45 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
 #endif
 
   // ---- one-time staging: weights as bf16 pieces, constants, barriers, TMEM ------------------------------------------
-  for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) {  // W0[o][j]
-    const int o = e / DP_D0, j = e % DP_D0;
-    uint16_t p[3];
-    split3_scalar(theta[e], p[0], p[1], p[2]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS)) = p[k];
-  }
   // power-of-two scales of the fp16 operands, from the parameter magnitudes (identical in every CTA and on every rank)
   {
-    float m1 = 0.f, m2 = 0.f;
+    float m1 = 0.f, m2 = 0.f, m0 = 0.f;
     for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) m1 = fmaxf(m1, fabsf(theta[DP_OFF_W1 + e]));
+    for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) m0 = fmaxf(m0, fabsf(theta[e]));
     if (tid < DP_H) m2 = fabsf(theta[DP_OFF_W2 + tid]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
       m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
     }
-    if (lane == 0) { s.red_max[0][warp] = m1; s.red_max[1][warp] = m2; }
+    if (lane == 0) { s.red_max[0][warp] = m1; s.red_max[1][warp] = m2; s.red_max[2][warp] = m0; }
   }
   __syncthreads();
-  float w1max = 0.f, w2max = 0.f;
+  float w1max = 0.f, w2max = 0.f, w0max = 0.f;
 #pragma unroll
-  for (int w = 0; w < TC_THREADS / 32; ++w) { w1max = fmaxf(w1max, s.red_max[0][w]); w2max = fmaxf(w2max, s.red_max[1][w]); }
+  for (int w = 0; w < TC_THREADS / 32; ++w) {
+    w1max = fmaxf(w1max, s.red_max[0][w]);
+    w2max = fmaxf(w2max, s.red_max[1][w]);
+    w0max = fmaxf(w0max, s.red_max[2][w]);
+  }
   const int e_w = scale_exp(w1max);                 // W1 * 2^e_w      in [2^13, 2^14)
   const int e_d = scale_exp(0.25f * w2max);         // |Delta2| <= max|w2| / 4:  Delta2 * 2^e_d below 2^14
-  const float s_w = pow2i(e_w), s_d = pow2i(e_d);
+  const int e_w0 = scale_exp(w0max);
+  const int e_x = scale_exp(x_absmax[0]);           // the shard's max |x|
+  const int e_d1 = scale_exp(4.0f * w2max * w1max); // |Delta1| <= 64 max|Delta2| max|W1| / 4
+  const float s_w = pow2i(e_w), s_d = pow2i(e_d), s_w0 = pow2i(e_w0), s_x = pow2i(e_x), s_d1 = pow2i(e_d1);
+  const float inv_z1 = pow2i(-e_x) * pow2i(-e_w0);              // Z1 = (X sx)(W0 sw0)^T
+  const float inv_w0 = pow2i(-e_d1) * pow2i(-e_x);              // dW0 = (Delta1 sd1)^T (X sx)
+  const float inv_b0 = pow2i(-e_d1);                            // db0 = (Delta1 sd1)^T 1
+  for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) {  // W0[o][j]
+    const int o = e / DP_D0, j = e % DP_D0;
+    uint16_t p[2];
+    split2h_scalar(theta[e] * s_w0, p[0], p[1]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS2)) = p[k];
+  }
   const float inv_z2 = pow2i(-e_w) * (1.0f / TC_SH);            // Z2 = (H1 sh)(W1 sw)^T
   const float inv_d1 = pow2i(-e_w) * pow2i(-e_d);               // D1 = (Delta2 sd)(W1 sw)
   const float inv_w1 = pow2i(-e_d) * (1.0f / TC_SH);            // dW1 = (Delta2 sd)^T (H1 sh)
@@ -314,7 +266,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   }
   for (int e = tid; e < 1024; e += TC_THREADS) {
     s.ones_h[e] = 0x3C00;     // fp16 1.0
-    s.ones_x[e] = 0x3F80;     // bf16 1.0
+    s.ones_x[e] = 0x3C00;
   }
   if (tid < DP_H) {
     s.b0[tid] = theta[DP_OFF_B0 + tid];
@@ -336,22 +288,19 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
 
   // descriptors (built once; K steps advance the start address)
-  uint64_t dXa[3], dH1a[2], dDLa[2], dDLm[2], dDL1m[3];
+  uint64_t dXa[2], dH1a[2], dDLa[2], dDLm[2], dDL1m[2];
   {
     const uint32_t ax = smem_u32(s.xp), ah = smem_u32(s.h1), ad = smem_u32(s.dl), ad1 = smem_u32(s.dl1);
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
+    for (int p = 0; p < 2; ++p) {
       dXa[p] = smem_desc(ax + p * TC_XP, TC_CS, 128);      // K-major A (M = row, K = input feature)
       dDL1m[p] = smem_desc(ad1 + p * TC_ACT, 128, TC_CS);  // MN-major A (M = unit, K = row)
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
       dH1a[p] = smem_desc(ah + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = hidden unit)
       dDLa[p] = smem_desc(ad + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = output unit)
       dDLm[p] = smem_desc(ad + p * TC_ACT, 128, TC_CS);    // MN-major A (M = unit, K = row)
     }
   }
-  const uint64_t dW0 = smem_desc(smem_u32(s.w0s), TC_WCS, 128);      // K-major B (N = 64 p + o, K = j)
+  const uint64_t dW0 = smem_desc(smem_u32(s.w0s), TC_WCS2, 128);     // K-major B (N = 64 p + o, K = j)
   const uint64_t dW1a = smem_desc(smem_u32(s.w1a), TC_WCS2, 128);    // K-major B (N = 64 p + o, K = i)
   const uint64_t dW1b = smem_desc(smem_u32(s.w1b), TC_WCS2, 128);    // K-major B (N = 64 p + i, K = o)
   const uint64_t dH1m = smem_desc(smem_u32(s.ones_h), 128, TC_CS);   // MN-major B (N = [1 x8 | H1 pieces], K = row)
@@ -394,13 +343,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     TC_STAMP(0);
     const float yv = ynext;
     {
-      const float v[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      uint4 p1, p2, p3;
-      split3(v, p1, p2, p3);
+      const float v[8] = {xa.x * s_x, xa.y * s_x, xa.z * s_x, xa.w * s_x, xb.x * s_x, xb.y * s_x, xb.z * s_x, xb.w * s_x};
+      uint4 p1, p2;
+      split2h(v, p1, p2);
       unsigned char* dst = reinterpret_cast<unsigned char*>(s.xp) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + hf * TC_CS;
       *reinterpret_cast<uint4*>(dst) = p1;
       *reinterpret_cast<uint4*>(dst + TC_XP) = p2;
-      *reinterpret_cast<uint4*>(dst + 2 * TC_XP) = p3;
     }
     fence_async_smem();
     fence_before_sync();
@@ -408,7 +356,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<3, 1, 128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);                  // MMA1: Z1 = X W0^T (bf16 x 3)
+        mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);                  // MMA1: Z1 = X W0^T
         mma_commit(&s.bar[1]);
       }
       __syncwarp();
@@ -421,11 +369,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     fence_after_sync();
     {
       float v[32];
-      load_sum3(tm_lane + TM_Z + 32 * hf, v);
+      load_sum2(tm_lane + TM_Z + 32 * hf, v);
       uint32_t hbits[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = tc_sigmoid(v[j] + s.b0[32 * hf + j]);
+        v[j] = tc_sigmoid(fmaf(v[j], inv_z1, s.b0[32 * hf + j]));
         hbits[j] = __float_as_uint(v[j]);
       }
       tmem_st32(tm_lane + TM_H1 + 32 * hf, hbits);
@@ -527,7 +475,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         v[j] = (v[j] * inv_d1) * (1.f - h1) * h1;
       }
       TC_STAMP(7);
-      store_pieces32(reinterpret_cast<unsigned char*>(s.dl1), TC_ACT, 4 * hf, r, v);
+      store_pieces32h(reinterpret_cast<unsigned char*>(s.dl1), 4 * hf, r, v, s_d1);
     }
     fence_async_smem();
     fence_before_sync();
@@ -535,7 +483,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        mma_product<3, 1, 64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);       // MMA5: Delta1^T [1 X] (bf16 x 3)
+        mma_product<2, 0, 64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);       // MMA5: Delta1^T [1 X]
         mma_commit(&s.bar[5]);
       }
       __syncwarp();
@@ -560,15 +508,14 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     TC_STAMP(11);
     fence_after_sync();
     if (fold) {
-      uint32_t a[8], b[8], c[8], o4[4];
+      uint32_t a[8], b[8], o4[4];
       tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, a);
       tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, b);
-      tmem_ld8(tm_lane + TM_W0 + 8 + 32 + 8 * hf, c);
       tmem_ld4(tm_lane + TM_W0, o4);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc2(g0[i], g0e[i], (__uint_as_float(c[i]) + __uint_as_float(b[i])) + __uint_as_float(a[i]));
-      acc2(gb0, gb0e, __uint_as_float(o4[0]));
+      for (int i = 0; i < 8; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
+      acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
     }
     TC_STAMP(12);
     // the next tile's P0 ends with fence_before_sync + __syncthreads before any MMA overwrites these TMEM columns
@@ -616,6 +563,19 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   TC_STAMP(21);
 }
 
+// out[0] = max |x[i]| (out zeroed by the caller): non-negative floats order like their bit patterns, NaN sorts above inf
+__global__ void dp_absmax_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float a = fabsf(x[i]);
+    m = (a > m || a != a) ? a : m;
+  }
+  unsigned int b = __float_as_uint(m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), b);
+}
+
 // out[e] = sum over CTAs of partials[cta][e], fixed order
 __global__ void dp_reduce_tc_kernel(const double* __restrict__ partials, int n_parts, double* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -633,12 +593,12 @@ extern "C" {
 
 int eeyore_b200_set_error_(int code, const char* msg);
 
-int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
-                               void* workspace, void* stream) {
+int eeyore_b200_dp_loglik_grad_x(const void* theta, const void* x, const void* y, int64_t n_rows, const void* x_absmax,
+                                 void* out_sums, void* workspace, void* stream) {
   if (!theta || !x || !y || (!out_sums && !workspace) || n_rows < 1)
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: bad argument");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
-    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: x and y must be 16-byte aligned (TMA bulk copy)");
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_loglik_grad: x and y must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   auto fail = [](cudaError_t e, const char* where) {
     std::string m = std::string(where) + ": " + cudaGetErrorString(e);
@@ -655,6 +615,13 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
     e = cudaMallocAsync((void**)&partials, sizeof(double) * (size_t)grid * (DP_P + 1), st);
     if (e != cudaSuccess) return fail(e, "dp_loglik_grad(alloc)");
   }
+  float* absmax = (float*)x_absmax;          // caller-owned device scalar (max |x| of the shard), or NULL: computed here
+  if (!x_absmax) {
+    e = cudaMallocAsync((void**)&absmax, sizeof(float), st);
+    if (e != cudaSuccess) return fail(e, "dp_loglik_grad(alloc)");
+    cudaMemsetAsync(absmax, 0, sizeof(float), st);
+    dp_absmax_kernel<<<sms * 4, 256, 0, st>>>((const float*)x, (long)n_rows * DP_D0, absmax);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(dp_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
@@ -662,24 +629,34 @@ int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, 
     attr_set = true;
   }
   dp_eval_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
-                                                              (long)n_rows, partials);
+                                                              (long)n_rows, absmax, partials);
   if (out_sums)   // NULL: the caller folds the per-CTA rows itself (dp_post does, together with the exchange step)
     dp_reduce_tc_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
   e = cudaGetLastError();
   if (!workspace) cudaFreeAsync(partials, st);
+  if (!x_absmax) cudaFreeAsync(absmax, st);
   if (e != cudaSuccess) return fail(e, "dp_loglik_grad");
   return EEYORE_B200_OK;
 }
 
-#ifdef DP_TC_PROFILE
-/* debug builds only: cycles spent per phase by one warp of CTA 0, accumulated since the last call */
-int eeyore_b200_dp_tc_profile(unsigned long long* out24) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out24, dp_tc_prof, sizeof(unsigned long long) * 24);
-  unsigned long long zero[24] = {0};
-  cudaMemcpyToSymbol(dp_tc_prof, zero, sizeof(zero));
-  return 0;
+int eeyore_b200_dp_loglik_grad(const void* theta, const void* x, const void* y, int64_t n_rows, void* out_sums,
+                               void* workspace, void* stream) {
+  return eeyore_b200_dp_loglik_grad_x(theta, x, y, n_rows, nullptr, out_sums, workspace, stream);
 }
-#endif
+
+int eeyore_b200_dp_absmax(const void* x, int64_t n_values, void* out_absmax, void* stream) {
+  if (!x || !out_absmax || n_values < 1) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_absmax: bad argument");
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaMemsetAsync(out_absmax, 0, sizeof(float), (cudaStream_t)stream);
+  dp_absmax_kernel<<<sms * 4, 256, 0, (cudaStream_t)stream>>>((const float*)x, (long)n_values, (float*)out_absmax);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    std::string m = std::string("dp_absmax: ") + cudaGetErrorString(e);
+    return eeyore_b200_set_error_(EEYORE_B200_ECUDA, m.c_str());
+  }
+  return EEYORE_B200_OK;
+}
 
 }  // extern "C"

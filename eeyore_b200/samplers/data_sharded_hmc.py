@@ -42,6 +42,9 @@ class DataShardedHMC:
         if self.x.shape[0] < 1:
             raise ValueError("every rank needs at least one row of the data set")
         self._setup_exchange(exchange, reduce_fn is not None, dev)
+        self._x_absmax = torch.zeros(1, dtype=torch.float32, device=dev)       # max |x| of the shard, once per data set
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().eeyore_b200_dp_absmax(nv.ptr(self.x), self.x.numel(), nv.ptr(self._x_absmax), nv.stream_ptr(dev)))
         f32, f64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.float64, device=dev)
         self._sums = torch.empty(p + 1, **f64)
         self._work = torch.empty(int(nv.lib().eeyore_b200_dp_workspace_bytes()) // 8, **f64)   # per-CTA partial sums
@@ -143,16 +146,16 @@ class DataShardedHMC:
         st = nv.stream_ptr(self.x.device)
         has_t, temp = (0, 0.0) if m.temperature is None else (1, float(m.temperature))
         if self.exchange != "nccl":
-            nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0], None,
-                                                    nv.ptr(self._work), st))
+            nv.check(lib.eeyore_b200_dp_loglik_grad_x(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0],
+                                                      nv.ptr(self._x_absmax), None, nv.ptr(self._work), st))
             nv.check(lib.eeyore_b200_dp_post(nv.ptr(self._work), self._n_parts, self._world, self._rank, self.n_evals + 1,
                                              self._peers, self._scratch_ptr, nv.ptr(theta), nv.ptr(loc), nv.ptr(scale), has_t, temp,
                                              nv.ptr(out_grad), nv.ptr(out_target), step_mode, self.step, nv.ptr(self._mom),
                                              nv.ptr(self._theta_p), nv.ptr(self._kin1), nv.ptr(self._status), st))
             self.n_evals += 1
             return
-        nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0],
-                                                nv.ptr(self._sums), nv.ptr(self._work), st))
+        nv.check(lib.eeyore_b200_dp_loglik_grad_x(nv.ptr(theta), nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0],
+                                                  nv.ptr(self._x_absmax), nv.ptr(self._sums), nv.ptr(self._work), st))
         self._reduce(self._sums)                 # the one exchange step of the path: 1 + P doubles
         nv.check(lib.eeyore_b200_dp_finish(nv.ptr(self._sums), nv.ptr(theta), nv.ptr(loc), nv.ptr(scale), has_t, temp,
                                            nv.ptr(out_target), nv.ptr(out_grad), st))

@@ -180,6 +180,11 @@ int eeyore_b200_dp_num_params(void);
 /* out_sums[0] = sum_i loglik_i, out_sums[1 + j] = d/dtheta_j sum_i loglik_i over this rank's rows (fp64, deterministic) */
 int eeyore_b200_dp_loglik_grad(const void *theta, const void *x, const void *y, int64_t n_rows, void *out_sums,
                                void *workspace, void *stream);
+/* the same with the shard's max |x| supplied as a device scalar (fp32, e.g. from dp_absmax, computed once per data set):
+ * the tcgen05 kernel scales x by a power of two before splitting it into fp16 pieces; x_absmax NULL = computed per call */
+int eeyore_b200_dp_loglik_grad_x(const void *theta, const void *x, const void *y, int64_t n_rows, const void *x_absmax,
+                                 void *out_sums, void *workspace, void *stream);
+int eeyore_b200_dp_absmax(const void *x, int64_t n_values, void *out_absmax, void *stream);
 /* out_sums may be NULL when a workspace is given: the per-CTA rows ([dp_num_parts(n_rows)][P + 1] doubles) are then left
  * in the workspace for dp_post, which folds them together with the exchange step. */
 int eeyore_b200_dp_num_parts(int64_t n_rows);

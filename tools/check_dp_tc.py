@@ -62,7 +62,13 @@ def main():
     y = (torch.rand(n, device="cuda", generator=g) < 0.5).float()
     theta = torch.randn(P, device="cuda", generator=g) * 0.1
     ws = torch.empty(lib.eeyore_b200_dp_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
-    for name, fn in (("tcgen05", tc), ("ffma", ff)):
+    amax = torch.zeros(1, dtype=torch.float32, device="cuda")
+    nv.check(lib.eeyore_b200_dp_absmax(nv.ptr(x), x.numel(), nv.ptr(amax), None))
+
+    def tc_scaled(th, xx, yy, nn, out, wsp, st):      # max |x| computed once, as DataShardedHMC does
+        return lib.eeyore_b200_dp_loglik_grad_x(th, xx, yy, nn, nv.ptr(amax), out, wsp, st)
+
+    for name, fn in (("tcgen05", tc_scaled), ("ffma", ff)):
         for _ in range(3):
             sums(fn, theta, x, y, ws)
         torch.cuda.synchronize()
