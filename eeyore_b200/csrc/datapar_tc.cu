@@ -18,12 +18,14 @@
 //   bf16 pieces and six products (no scaling needed): same accuracy, 1.75x the tensor time and 1.5x the operand bytes.
 //   Emulated on the CPU and measured on the GPU: gradient within 3e-7 of the fp64 oracle (bar 1e-5).
 //
+// Two tiles are in flight per CTA (contexts A and B with their own operand buffers, accumulator region and mbarriers): the
+// phases alternate A, B, A, B ..., so the MMAs of one tile run on the tensor pipe under the epilogue of the other.
 // Per 128-row tile (persistent CTAs, one per SM, 256 threads; thread = (row, half of the 64 features)):
 //   P0  x tile (coalesced loads, prefetched one tile ahead) -> bf16 pieces in smem  MMA1  Z1 = X W0^T
-//   P1  H1 = sigmoid(Z1 + b0) -> pieces (smem) + fp32 copy parked in TMEM           MMA2  Z2 = H1 W1^T
+//   P1  H1 = sigmoid(Z1 + b0) -> pieces (smem)                                       MMA2  Z2 = H1 W1^T
 //   P2  H2, head, log-lik, delta3, dW2 (warp butterfly), Delta2 -> pieces           MMA3  D1 = Delta2 W1
 //                                                                                    MMA4  [db1 dW1] = Delta2^T [1 H1]
-//   P3  Delta1 = D1 H1 (1 - H1) -> pieces (second buffer: MMA4 may still be reading)  MMA5  [db0 dW0] = Delta1^T [1 X]
+//   P3  Delta1 = D1 H1 (1 - H1) -> pieces (over Delta2, after MMA4; H1 re-read from its pieces)  MMA5  [db0 dW0] = Delta1^T [1 X]
 // (A ninth, issue-only warp was measured slower: three warps on one scheduler cap the kernel at 168 registers -> spills.)
 //   P4  every TC_FLUSH tiles: weight-gradient accumulators TMEM -> fp64 registers (fp32 accumulation spans <= 512 rows)
 // One shared-memory copy of each activation serves both orientations: the SWIZZLE_NONE core-matrix layout of tc05.cuh
@@ -46,26 +48,28 @@ constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] 
 constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-stacked weight buffers ([128 x K])
 constexpr float TC_SH = 1024.f;                  // scale of H1 before the fp16 split (keeps the low piece normal)
 // TMEM columns (fp32)
-constexpr uint32_t TM_Z = 0;                     // Z1, then Z2, then D1 (2 groups of 64): one region, the phases are sequential
-constexpr uint32_t TM_W1 = 128;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
-constexpr uint32_t TM_H1 = 264;                  // H1 in fp32 (P1 -> P3)
-constexpr uint32_t TM_W0 = 328;                  // [ones(8) | dW0 (2 x 16)]
-constexpr int TC_FLUSH = 4;
+constexpr uint32_t TM_Z = 0;                     // per context (c * 128): Z1, then Z2, then D1 (2 groups of 64)
+constexpr uint32_t TM_W1 = 256;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
+constexpr uint32_t TM_W0 = 392;                  // [ones(8) | dW0 (2 x 16)]     (432 of 512 columns)
+constexpr int TC_FLUSH = 2;                      // PAIRS of tiles between two folds (4 tiles)
 constexpr int TC_THREADS = DP_THREADS;           // 8 warps: every one an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
 
-struct TcSmem {
+struct TcCtx {                                   // operand buffers of one tile in flight
   alignas(1024) uint16_t ones_h[1024];           // 2 KB of fp16 1.0: the N-chunk in front of the H1 pieces
   alignas(16) uint16_t h1[2 * TC_ACT / 2];       // H1 pieces (fp16 x 2, scaled by TC_SH)
   alignas(16) uint16_t ones_x[1024];             // 2 KB of fp16 1.0: the N-chunk in front of the x pieces
   alignas(16) uint16_t xp[2 * TC_XP / 2];        // x pieces (fp16 x 2, scaled)
-  alignas(16) uint16_t dl[2 * TC_ACT / 2];       // Delta2 pieces (fp16 x 2, scaled)
-  alignas(16) uint16_t dl1[2 * TC_ACT / 2];      // Delta1 pieces (fp16 x 2, scaled)
+  alignas(16) uint16_t dl[2 * TC_ACT / 2];       // Delta2 pieces, then Delta1 pieces (fp16 x 2, scaled)
+};
+
+struct TcSmem {
+  TcCtx ctx[2];
   alignas(16) uint16_t w0s[2 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols j      (B of MMA1)
   alignas(16) uint16_t w1a[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols i      (B of MMA2)
   alignas(16) uint16_t w1b[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + i, cols o      (B of MMA3)
   alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
   alignas(16) float exch[2][DP_R];
-  alignas(8) unsigned long long bar[6];          // 1..5: MMA groups
+  alignas(8) unsigned long long bar[2][6];       // per context, 1..5: MMA groups
   float b2;
   float red_max[3][DP_THREADS / 32];             // prologue: max |W1|, max |w2|, max |W0| per warp
   uint32_t tmem_base;
@@ -265,8 +269,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     }
   }
   for (int e = tid; e < 1024; e += TC_THREADS) {
-    s.ones_h[e] = 0x3C00;     // fp16 1.0
-    s.ones_x[e] = 0x3C00;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      s.ctx[c].ones_h[e] = 0x3C00;     // fp16 1.0
+      s.ctx[c].ones_x[e] = 0x3C00;
+    }
   }
   if (tid < DP_H) {
     s.b0[tid] = theta[DP_OFF_B0 + tid];
@@ -276,7 +283,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   if (tid == 0) {
     s.b2 = theta[DP_OFF_B2];
 #pragma unroll
-    for (int b = 0; b < 6; ++b) mbar_init(&s.bar[b], 1);
+    for (int b = 0; b < 12; ++b) mbar_init(&s.bar[0][0] + b, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&s.tmem_base);
@@ -287,26 +294,19 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   const uint32_t tm = s.tmem_base;
   const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
 
-  // descriptors (built once; K steps advance the start address)
-  uint64_t dXa[2], dH1a[2], dDLa[2], dDLm[2], dDL1m[2];
-  {
-    const uint32_t ax = smem_u32(s.xp), ah = smem_u32(s.h1), ad = smem_u32(s.dl), ad1 = smem_u32(s.dl1);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      dXa[p] = smem_desc(ax + p * TC_XP, TC_CS, 128);      // K-major A (M = row, K = input feature)
-      dDL1m[p] = smem_desc(ad1 + p * TC_ACT, 128, TC_CS);  // MN-major A (M = unit, K = row)
-      dH1a[p] = smem_desc(ah + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = hidden unit)
-      dDLa[p] = smem_desc(ad + p * TC_ACT, TC_CS, 128);    // K-major A (M = row, K = output unit)
-      dDLm[p] = smem_desc(ad + p * TC_ACT, 128, TC_CS);    // MN-major A (M = unit, K = row)
-    }
-  }
-  const uint64_t dW0 = smem_desc(smem_u32(s.w0s), TC_WCS2, 128);     // K-major B (N = 64 p + o, K = j)
-  const uint64_t dW1a = smem_desc(smem_u32(s.w1a), TC_WCS2, 128);    // K-major B (N = 64 p + o, K = i)
-  const uint64_t dW1b = smem_desc(smem_u32(s.w1b), TC_WCS2, 128);    // K-major B (N = 64 p + i, K = o)
-  const uint64_t dH1m = smem_desc(smem_u32(s.ones_h), 128, TC_CS);   // MN-major B (N = [1 x8 | H1 pieces], K = row)
-  const uint64_t dXm = smem_desc(smem_u32(s.ones_x), 128, TC_CS);    // MN-major B (N = [1 x8 | x pieces], K = row)
+  // shared-memory bases (32-bit shared addresses) of the operand buffers; descriptors are built where the MMAs are issued
+  const uint32_t a_ctx0 = smem_u32(&s.ctx[0]);
+  constexpr uint32_t CTXB = (uint32_t)sizeof(TcCtx);
+  constexpr uint32_t OFF_H1 = (uint32_t)offsetof(TcCtx, h1), OFF_ONESH = (uint32_t)offsetof(TcCtx, ones_h);
+  constexpr uint32_t OFF_XP = (uint32_t)offsetof(TcCtx, xp), OFF_ONESX = (uint32_t)offsetof(TcCtx, ones_x);
+  constexpr uint32_t OFF_DL = (uint32_t)offsetof(TcCtx, dl);
+  const uint32_t a_w0 = smem_u32(s.w0s), a_w1a = smem_u32(s.w1a), a_w1b = smem_u32(s.w1b);
+  auto descs2 = [](uint32_t base, uint32_t piece_bytes, uint32_t lbo, uint32_t sbo, uint64_t (&d)[2]) {
+    d[0] = smem_desc(base, lbo, sbo);
+    d[1] = smem_desc(base + piece_bytes, lbo, sbo);
+  };
 
-  // persistent FP64 accumulators: lanes 0..15 of every warp own unit o = 16 q + lane (M = 64 accumulator layout)
+  // weight-gradient sums: lanes 0..15 of every warp own unit o = 16 q + lane (M = 64 accumulator layout)
   float g1[32], g1e[32], g0[8], g0e[8];   // (sum, error term) pairs, see acc2
 #pragma unroll
   for (int i = 0; i < 32; ++i) g1[i] = g1e[i] = 0.f;
@@ -314,212 +314,234 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   for (int i = 0; i < 8; ++i) g0[i] = g0e[i] = 0.f;
   float gb1 = 0.f, gb1e = 0.f, gb0 = 0.f, gb0e = 0.f, gw2 = 0.f, gw2e = 0.f, gb2 = 0.f, gb2e = 0.f, ll = 0.f, lle = 0.f;
 
-  // this thread's 8 features of its row and the row's label, loaded one tile ahead (rows are 64 B: two 16-byte loads)
-  float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-  float ynext = 0.f;
-  auto prefetch_x = [&](long tile) {
+  // this thread's 8 features of its row and the row's label for both contexts, loaded one pair of tiles ahead
+  float4 xa0 = make_float4(0.f, 0.f, 0.f, 0.f), xb0 = xa0, xa1 = xa0, xb1 = xa0;
+  float yn0 = 0.f, yn1 = 0.f;
+  auto prefetch_x = [&](long tile, float4& xa, float4& xb, float& yn) {
     const long gr = tile * DP_R + r;
     xa = xb = make_float4(0.f, 0.f, 0.f, 0.f);
-    ynext = 0.f;
+    yn = 0.f;
     if (tile < n_tiles && gr < n_rows) {
       const float4* src = reinterpret_cast<const float4*>(x + gr * DP_D0 + 8 * hf);
       xa = __ldg(src);
       xb = __ldg(src + 1);
-      ynext = __ldg(y + gr);
+      yn = __ldg(y + gr);
     }
   };
 
-  long tile = blockIdx.x;
-  prefetch_x(tile);
+  long tile0 = blockIdx.x;                       // context c works on tile0 + c * gridDim.x
+  prefetch_x(tile0, xa0, xb0, yn0);
+  prefetch_x(tile0 + gridDim.x, xa1, xb1, yn1);
   uint32_t par = 0;
-  int it = 0;
+  int pair = 0;
   TC_STAMP(20);
-  for (; tile < n_tiles; tile += gridDim.x, par ^= 1u, ++it) {
-    const long row0 = tile * DP_R;
-    const int rows = (int)min((long)DP_R, n_rows - row0);
-    const bool fold = ((it + 1) % TC_FLUSH == 0) || (tile + gridDim.x >= n_tiles);
-    const uint32_t keep = (it % TC_FLUSH != 0) ? 1u : 0u;   // weight-gradient sums continue from the previous tile
-    // ---- P0: x tile -> bf16 pieces (rows beyond the data are zero) ---------------------------------------------------------
-    TC_STAMP(0);
-    const float yv = ynext;
-    {
-      const float v[8] = {xa.x * s_x, xa.y * s_x, xa.z * s_x, xa.w * s_x, xb.x * s_x, xb.y * s_x, xb.z * s_x, xb.w * s_x};
-      uint4 p1, p2;
-      split2h(v, p1, p2);
-      unsigned char* dst = reinterpret_cast<unsigned char*>(s.xp) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + hf * TC_CS;
-      *reinterpret_cast<uint4*>(dst) = p1;
-      *reinterpret_cast<uint4*>(dst + TC_XP) = p2;
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        fence_after_sync();
-        mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z, dXa, dW0, 0, 0, 1);                  // MMA1: Z1 = X W0^T
-        mma_commit(&s.bar[1]);
+  for (; tile0 < n_tiles; tile0 += 2L * gridDim.x, par ^= 1u, ++pair) {
+    const int n_ctx = (tile0 + gridDim.x < n_tiles) ? 2 : 1;            // uniform over the CTA
+    const bool fold = ((pair + 1) % TC_FLUSH == 0) || (tile0 + 2L * gridDim.x >= n_tiles);
+    float yv0 = 0.f, yv1 = 0.f;
+    // ---- P0: x tile -> fp16 pieces (rows beyond the data are zero) -----------------------------------------------------------
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {
+      TcCtx& cx = s.ctx[c];
+      if (pair > 0) mbar_wait(&s.bar[c][5], par ^ 1u);       // MMA5 of this context's previous tile has read xp and dl
+      const float4 xa = c ? xa1 : xa0, xb = c ? xb1 : xb0;
+      if (c) yv1 = yn1; else yv0 = yn0;
+      {
+        const float v[8] = {xa.x * s_x, xa.y * s_x, xa.z * s_x, xa.w * s_x, xb.x * s_x, xb.y * s_x, xb.z * s_x, xb.w * s_x};
+        uint4 p1, p2;
+        split2h(v, p1, p2);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(cx.xp) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + hf * TC_CS;
+        *reinterpret_cast<uint4*>(dst) = p1;
+        *reinterpret_cast<uint4*>(dst + TC_XP) = p2;
       }
-      __syncwarp();
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {
+          fence_after_sync();
+          uint64_t dA[2];
+          descs2(a_ctx0 + c * CTXB + OFF_XP, TC_XP, TC_CS, 128, dA);                      // K-major A (M = row, K = feature)
+          mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z + 128 * c, dA, smem_desc(a_w0, TC_WCS2, 128), 0, 0, 1);   // MMA1
+          mma_commit(&s.bar[c][1]);
+        }
+        __syncwarp();
+      }
     }
-    prefetch_x(tile + gridDim.x);
+    prefetch_x(tile0 + 2L * gridDim.x, xa0, xb0, yn0);
+    prefetch_x(tile0 + 3L * gridDim.x, xa1, xb1, yn1);
     TC_STAMP(1);
     // ---- P1: H1 = sigmoid(Z1 + b0) ------------------------------------------------------------------------------------
-    mbar_wait(&s.bar[1], par);
-    TC_STAMP(2);
-    fence_after_sync();
-    {
-      float v[32];
-      load_sum2(tm_lane + TM_Z + 32 * hf, v);
-      uint32_t hbits[32];
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {
+      TcCtx& cx = s.ctx[c];
+      mbar_wait(&s.bar[c][1], par);
+      fence_after_sync();
+      {
+        float v[32];
+        load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = tc_sigmoid(fmaf(v[j], inv_z1, s.b0[32 * hf + j]));
-        hbits[j] = __float_as_uint(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = tc_sigmoid(fmaf(v[j], inv_z1, s.b0[32 * hf + j]));
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), 4 * hf, r, v, TC_SH);
       }
-      tmem_st32(tm_lane + TM_H1 + 32 * hf, hbits);
-      store_pieces32h(reinterpret_cast<unsigned char*>(s.h1), 4 * hf, r, v, TC_SH);
-      tmem_st_wait();
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        fence_after_sync();
-        mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z, dH1a, dW1a, 2 * TC_CS, 2 * TC_WCS2, 4);   // MMA2: Z2 = H1 W1^T (fp16 x 2)
-        mma_commit(&s.bar[2]);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {
+          fence_after_sync();
+          uint64_t dA[2];
+          descs2(a_ctx0 + c * CTXB + OFF_H1, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = hidden unit)
+          mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1a, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
+          mma_commit(&s.bar[c][2]);                                                       // MMA2: Z2 = H1 W1^T
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     TC_STAMP(3);
     // ---- P2: H2, head, log-likelihood, delta3, dW2, Delta2 -------------------------------------------------------------
-    mbar_wait(&s.bar[2], par);
-    TC_STAMP(4);
-    fence_after_sync();
-    float t[32], p_head = 0.5f, d_head = 0.f;
-    {
-      float h[32];
-      load_sum2(tm_lane + TM_Z + 32 * hf, h);
-      float apart = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {
+      TcCtx& cx = s.ctx[c];
+      const long row0 = (tile0 + (long)c * gridDim.x) * DP_R;
+      const int rows = (int)min((long)DP_R, n_rows - row0);
+      const float yv = c ? yv1 : yv0;
+      mbar_wait(&s.bar[c][2], par);
+      fence_after_sync();
+      float t[32], p_head = 0.5f, d_head = 0.f;
+      {
+        float h[32];
+        load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, h);
+        float apart = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        h[j] = tc_sigmoid(fmaf(h[j], inv_z2, s.b1[32 * hf + j]));
-        apart = fmaf(h[j], s.w2[32 * hf + j], apart);
-      }
-      TC_STAMP(13);
-      s.exch[hf][r] = apart;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share rows 32 q .. 32 q + 31
-      TC_STAMP(14);
-      const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
-      float d = 0.f;
-      if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
-        p_head = 1.0f / (1.0f + expf(-a));
-        d = (p_head == 0.0f || p_head == 1.0f) ? NAN : (yv - p_head);
-      }
-      d_head = d;
-      TC_STAMP(15);
+        for (int j = 0; j < 32; ++j) {
+          h[j] = tc_sigmoid(fmaf(h[j], inv_z2, s.b1[32 * hf + j]));
+          apart = fmaf(h[j], s.w2[32 * hf + j], apart);
+        }
+        s.exch[hf][r] = apart;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share rows 32 q .. 32 q + 31
+        const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
+        float d = 0.f;
+        if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
+          p_head = 1.0f / (1.0f + expf(-a));
+          d = (p_head == 0.0f || p_head == 1.0f) ? NAN : (yv - p_head);
+        }
+        d_head = d;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        t[j] = d * h[j];                                                   // dW2 terms
-        h[j] = d * s.w2[32 * hf + j] * (1.f - h[j]) * h[j];                // Delta2
+        for (int j = 0; j < 32; ++j) {
+          t[j] = d * h[j];                                                   // dW2 terms
+          h[j] = d * s.w2[32 * hf + j] * (1.f - h[j]) * h[j];                // Delta2
+        }
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), 4 * hf, r, h, s_d);
       }
-      store_pieces32h(reinterpret_cast<unsigned char*>(s.dl), 4 * hf, r, h, s_d);
-    }
-    TC_STAMP(16);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        fence_after_sync();
-        mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z, dDLa, dW1b, 2 * TC_CS, 2 * TC_WCS2, 4);   // MMA3: D1 = Delta2 W1
-        mma_commit(&s.bar[3]);
-        mma_product<2, 0, 64, 8, 64, 1, 1>(tm + TM_W1, dDLm, dH1m, 256, 256, 8, keep);       // MMA4: Delta2^T [1 H1]
-        mma_commit(&s.bar[4]);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {
+          fence_after_sync();
+          const uint32_t keep = (c > 0 || pair % TC_FLUSH != 0) ? 1u : 0u;   // sums continue from the previous tile
+          uint64_t dA[2], dM[2];
+          descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = unit)
+          descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
+          mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1b, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
+          mma_commit(&s.bar[c][3]);                                                       // MMA3: D1 = Delta2 W1
+          mma_product<2, 0, 64, 8, 64, 1, 1>(tm + TM_W1, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESH, 128, TC_CS), 256, 256, 8, keep);
+          mma_commit(&s.bar[c][4]);                                                       // MMA4: Delta2^T [1 H1]
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
-    TC_STAMP(17);
-    TC_STAMP(18);
-    // in the shadow of MMA3: the log-likelihood term and the column sums for dW2
-    if (hf == 0) {   // one branch-free log per row for hard labels; soft labels take the general form
-      const float qv = (yv == 1.0f) ? p_head : 1.0f - p_head;
-      float term = (yv == 1.0f && p_head == 1.0f) || (yv == 0.0f && p_head == 0.0f) ? NAN : logf(qv);
-      if (yv != 0.0f && yv != 1.0f) term = logf(p_head) * yv + logf(1.0f - p_head) * (1.0f - yv);
-      if (r < rows) {
-        acc2(ll, lle, term);
-        acc2(gb2, gb2e, d_head);
+      // while the MMAs run: the log-likelihood term and the column sums for dW2
+      if (hf == 0) {   // one branch-free log per row for hard labels; soft labels take the general form
+        const float qv = (yv == 1.0f) ? p_head : 1.0f - p_head;
+        float term = (yv == 1.0f && p_head == 1.0f) || (yv == 0.0f && p_head == 0.0f) ? NAN : logf(qv);
+        if (yv != 0.0f && yv != 1.0f) term = logf(p_head) * yv + logf(1.0f - p_head) * (1.0f - yv);
+        if (r < rows) {
+          acc2(ll, lle, term);
+          acc2(gb2, gb2e, d_head);
+        }
       }
+      butterfly_step<16>(t, lane);
+      butterfly_step<8>(t, lane);
+      butterfly_step<4>(t, lane);
+      butterfly_step<2>(t, lane);
+      butterfly_step<1>(t, lane);
+      acc2(gw2, gw2e, t[0]);                                                 // unit 32 hf + lane, rows of quadrant q
     }
-    TC_STAMP(19);
-    butterfly_step<16>(t, lane);
-    butterfly_step<8>(t, lane);
-    butterfly_step<4>(t, lane);
-    butterfly_step<2>(t, lane);
-    butterfly_step<1>(t, lane);
-    acc2(gw2, gw2e, t[0]);                                                 // unit 32 hf + lane, rows of quadrant q
     TC_STAMP(5);
-    // ---- P3: Delta1 = D1 H1 (1 - H1) ------------------------------------------------------------------------------------
-    mbar_wait(&s.bar[3], par);
-    TC_STAMP(6);
-    fence_after_sync();
-    {
-      float v[32];
-      load_sum2(tm_lane + TM_Z + 32 * hf, v);
-      uint32_t hbits[32];
-      tmem_ld32(tm_lane + TM_H1 + 32 * hf, hbits);
-      tmem_ld_wait();
+    // ---- P3: Delta1 = D1 H1 (1 - H1), written over Delta2 once MMA4 has read it -------------------------------------------
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {
+      TcCtx& cx = s.ctx[c];
+      mbar_wait(&s.bar[c][3], par);
+      fence_after_sync();
+      {
+        float v[32];
+        load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, v);
+        // H1 of this row from its two fp16 pieces (exact up to 2^-22): no fp32 copy is kept
+        const unsigned char* hp = reinterpret_cast<const unsigned char*>(cx.h1) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u +
+                                  (uint32_t)(4 * hf) * TC_CS;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float h1 = __uint_as_float(hbits[j]);
-        v[j] = (v[j] * inv_d1) * (1.f - h1) * h1;
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 p1 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS);
+          const uint4 p2 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS + TC_ACT);
+          const uint32_t w1[4] = {p1.x, p1.y, p1.z, p1.w}, w2v[4] = {p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 a = unpack_f16x2(w1[k]), b = unpack_f16x2(w2v[k]);
+            const float h0 = (a.x + b.x) * (1.0f / TC_SH), h1v = (a.y + b.y) * (1.0f / TC_SH);
+            v[8 * ch + 2 * k] = (v[8 * ch + 2 * k] * inv_d1) * (1.f - h0) * h0;
+            v[8 * ch + 2 * k + 1] = (v[8 * ch + 2 * k + 1] * inv_d1) * (1.f - h1v) * h1v;
+          }
+        }
+        mbar_wait(&s.bar[c][4], par);                        // MMA4 has read Delta2 (and H1)
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), 4 * hf, r, v, s_d1);
       }
-      TC_STAMP(7);
-      store_pieces32h(reinterpret_cast<unsigned char*>(s.dl1), 4 * hf, r, v, s_d1);
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        fence_after_sync();
-        mma_product<2, 0, 64, 8, 16, 1, 1>(tm + TM_W0, dDL1m, dXm, 256, 256, 8, keep);       // MMA5: Delta1^T [1 X]
-        mma_commit(&s.bar[5]);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {
+          fence_after_sync();
+          const uint32_t keep = (c > 0 || pair % TC_FLUSH != 0) ? 1u : 0u;
+          uint64_t dM[2];
+          descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
+          mma_product<2, 0, 64, 8, 16, 1, 1>(tm + TM_W0, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESX, 128, TC_CS), 256, 256, 8, keep);
+          mma_commit(&s.bar[c][5]);                                                       // MMA5: Delta1^T [1 X]
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     TC_STAMP(9);
-    // ---- P4: every TC_FLUSH tiles fold the weight-gradient sums into the FP64 accumulators -----------------------------------
-    mbar_wait(&s.bar[4], par);
-    TC_STAMP(8);
-    fence_after_sync();
+    // ---- P4: every TC_FLUSH pairs fold the weight-gradient sums into the (sum, error) accumulators ---------------------------
     if (fold) {
-      float v[32];
-      load_sum2(tm_lane + TM_W1 + 8 + 32 * hf, v);
+      mbar_wait(&s.bar[n_ctx - 1][5], par);                  // the last MMA issued: everything before it is complete
+      fence_after_sync();
+      {
+        float v[32];
+        load_sum2(tm_lane + TM_W1 + 8 + 32 * hf, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
-      uint32_t o4[4];
-      tmem_ld4(tm_lane + TM_W1, o4);
-      tmem_ld_wait();
-      acc2(gb1, gb1e, __uint_as_float(o4[0]) * inv_b1);
-    }
-    TC_STAMP(10);
-    mbar_wait(&s.bar[5], par);   // also: MMA5 has finished reading the x pieces and Delta1
-    TC_STAMP(11);
-    fence_after_sync();
-    if (fold) {
-      uint32_t a[8], b[8], o4[4];
-      tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, a);
-      tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, b);
-      tmem_ld4(tm_lane + TM_W0, o4);
-      tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
+        uint32_t o4[4];
+        tmem_ld4(tm_lane + TM_W1, o4);
+        tmem_ld_wait();
+        acc2(gb1, gb1e, __uint_as_float(o4[0]) * inv_b1);
+      }
+      {
+        uint32_t a[8], b[8], o4[4];
+        tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, a);
+        tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, b);
+        tmem_ld4(tm_lane + TM_W0, o4);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
-      acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
+        for (int i = 0; i < 8; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
+        acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
+      }
+      fence_before_sync();                                   // ordered before the next pair's MMAs by its first __syncthreads
     }
     TC_STAMP(12);
-    // the next tile's P0 ends with fence_before_sync + __syncthreads before any MMA overwrites these TMEM columns
   }
+  // every MMA has completed: the last fold waited for the last one issued
 
   // ---- write this CTA's partial sums ---------------------------------------------------------------------------------
   fence_before_sync();
@@ -538,7 +560,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     }
   }
   // dW2: unit 32 hf + lane, partial over the rows of quadrant q; log-likelihood and db2: fixed-order block sums
-  double* red = reinterpret_cast<double*>(s.dl);   // the activation buffers are free now
+  double* red = reinterpret_cast<double*>(s.ctx[0].dl);   // the activation buffers are free now
   red[tid] = (double)gw2 + (double)gw2e;
   red[DP_THREADS + tid] = (double)ll + (double)lle;
   red[2 * DP_THREADS + tid] = (double)gb2 + (double)gb2e;
