@@ -423,7 +423,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
         float d = 0.f;
         if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
-          p_head = 1.0f / (1.0f + expf(-a));
+          p_head = __fdividef(1.0f, 1.0f + __expf(-a));        // 2 ulp; exact 0 / 1 at saturation like the reference
           d = (p_head == 0.0f || p_head == 1.0f) ? NAN : (yv - p_head);
         }
         d_head = d;
@@ -454,8 +454,8 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       // while the MMAs run: the log-likelihood term and the column sums for dW2
       if (hf == 0) {   // one branch-free log per row for hard labels; soft labels take the general form
         const float qv = (yv == 1.0f) ? p_head : 1.0f - p_head;
-        float term = (yv == 1.0f && p_head == 1.0f) || (yv == 0.0f && p_head == 0.0f) ? NAN : logf(qv);
-        if (yv != 0.0f && yv != 1.0f) term = logf(p_head) * yv + logf(1.0f - p_head) * (1.0f - yv);
+        float term = (yv == 1.0f && p_head == 1.0f) || (yv == 0.0f && p_head == 0.0f) ? NAN : __logf(qv);
+        if (yv != 0.0f && yv != 1.0f) term = __logf(p_head) * yv + __logf(1.0f - p_head) * (1.0f - yv);
         if (r < rows) {
           acc2(ll, lle, term);
           acc2(gb2, gb2e, d_head);
@@ -680,5 +680,16 @@ int eeyore_b200_dp_absmax(const void* x, int64_t n_values, void* out_absmax, voi
   }
   return EEYORE_B200_OK;
 }
+
+#ifdef DP_TC_PROFILE
+/* debug builds only: cycles spent per phase by one warp of CTA 0, accumulated since the last call */
+int eeyore_b200_dp_tc_profile(unsigned long long* out24) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out24, dp_tc_prof, sizeof(unsigned long long) * 24);
+  unsigned long long zero[24] = {0};
+  cudaMemcpyToSymbol(dp_tc_prof, zero, sizeof(zero));
+  return 0;
+}
+#endif
 
 }  // extern "C"

@@ -34,12 +34,9 @@ for it in range(3):
     nv.check(lib.eeyore_b200_dp_loglik_grad(nv.ptr(theta), nv.ptr(x), nv.ptr(y), n, nv.ptr(out), nv.ptr(ws), None))
     prof(buf)
 tiles = (n // 128 + 147) // 148
-tot = sum(buf[:13])
-print(f"CTA 0: {tiles} tiles, {tot / tiles:.0f} cycles per tile")
-tot += sum(buf[13:20])
-print(f"  prologue {buf[20]} cycles, after the tile loop {buf[21]} cycles, tile loop {tot} cycles")
-for i, nm in enumerate(NAMES):
-    print(f"  {nm:18s} {buf[i] / tiles:8.0f}  {100 * buf[i] / tot:5.1f}%")
-for i, nm in zip(range(13, 20), ["P2 ld+sigmoid+dot", "P2 pair barrier", "P2 exp/div", "P2 loop+split+store", "P2 fence+sync", "P2 MMA issue",
-                                  "P2 logs"]):
-    print(f"  {nm:18s} {buf[i] / tiles:8.0f}  {100 * buf[i] / tot:5.1f}%   (P2 + sync above is the remainder: butterfly)")
+labels = {1: "P0 (both contexts) + MMA1 issue", 3: "P1 (wait MMA1, sigmoid, split) x2", 5: "P2 (wait MMA2, head, Delta2, logs, butterfly) x2",
+          9: "P3 (wait MMA3/4, Delta1) x2", 12: "fold (every 2 pairs)"}
+tot = sum(buf[i] for i in labels)
+print(f"CTA 0: {tiles} tiles, {tot / tiles:.0f} cycles per tile; prologue {buf[20]} cycles, after the loop {buf[21]} cycles")
+for i, nm in labels.items():
+    print(f"  {nm:52s} {buf[i] / tiles:8.0f} per tile  {100 * buf[i] / tot:5.1f}%")
