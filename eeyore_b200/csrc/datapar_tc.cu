@@ -98,6 +98,19 @@ __device__ __forceinline__ float tc_sigmoid(float z) {
   return r;
 }
 
+// The same value with the reciprocal on the FMA pipe (integer seed, error <= 12 %, three Newton steps -> 4e-8).  With two
+// tiles in flight the epilogues are the critical path and the MUFU pipe (two ops per sigmoid) is their busiest unit: every
+// other unit takes this route (measured: 0 % 0.539 ms, 50 % 0.525 ms, 75 % 0.534 ms per 2M rows).
+__device__ __forceinline__ float tc_sigmoid_fma(float z) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  const float d = fminf(1.0f + e, 1.0e30f);
+  float r = __uint_as_float(0x7EF311C7u - __float_as_uint(d));
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return r;
+}
 // fp16 pair {hi half: b, lo half: a} (round to nearest even) and back
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   uint32_t d;
@@ -381,7 +394,8 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         float v[32];
         load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tc_sigmoid(fmaf(v[j], inv_z1, s.b0[32 * hf + j]));
+        for (int j = 0; j < 32; ++j)
+          v[j] = (j & 1) ? tc_sigmoid_fma(fmaf(v[j], inv_z1, s.b0[32 * hf + j])) : tc_sigmoid(fmaf(v[j], inv_z1, s.b0[32 * hf + j]));
         store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), 4 * hf, r, v, TC_SH);
       }
       fence_async_smem();
@@ -415,7 +429,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         float apart = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          h[j] = tc_sigmoid(fmaf(h[j], inv_z2, s.b1[32 * hf + j]));
+          h[j] = (j & 1) ? tc_sigmoid_fma(fmaf(h[j], inv_z2, s.b1[32 * hf + j])) : tc_sigmoid(fmaf(h[j], inv_z2, s.b1[32 * hf + j]));
           apart = fmaf(h[j], s.w2[32 * hf + j], apart);
         }
         s.exch[hf][r] = apart;
