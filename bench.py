@@ -613,11 +613,11 @@ def run_datapar(args):
             tensor_peak, peak_src = 1590.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
         flops_launch = 29056.0 * (hi - lo)
         achieved = flops_launch / (kernel_ms * 1e-3) / 1e12
-        # bf16 MMA work actually issued per 128-row tile: six piece products per GEMM; the M = 64 weight-gradient MMAs run
-        # at the cost of M = 128; ones columns for the bias sums
+        # fp16 MMA work actually issued per 128-row tile: three piece products per GEMM as two MMAs (N = 128 and 64, plus the
+        # 8 ones columns of the weight-gradient GEMMs); the M = 64 weight-gradient MMAs run at the cost of M = 128
         tiles = (hi - lo + 127) // 128
-        mma_flops_tile = 2 * 128 * 16 * (192 + 128 + 64) + 2 * (2 * 128 * 64 * (192 + 128 + 64)) \
-            + 2 * 128 * 128 * (200 + 136 + 72) + 2 * 128 * 128 * (56 + 40 + 24)
+        mma_flops_tile = 2 * 128 * 16 * (128 + 64) + 2 * (2 * 128 * 64 * (128 + 64)) \
+            + 2 * 128 * 128 * (136 + 72) + 2 * 128 * 128 * (40 + 24)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             procs = host_cores()
@@ -647,11 +647,11 @@ def run_datapar(args):
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "dp_eval_tc_kernel (tcgen05 bf16 MMA, fp32 accumulate in TMEM)",
+                         "kernel": "dp_eval_tc_kernel (tcgen05 fp16 MMA on exact two-piece splits, fp32 accumulate in TMEM, two tiles in flight)",
                          "avg_launch_ms": kernel_ms, "algorithmic_flops_per_row": 29056,
-                         "bf16_mma_tflops_issued": tiles * mma_flops_tile / (kernel_ms * 1e-3) / 1e12,
-                         "note": "fp32 parity costs six bf16 piece products per GEMM: the tensor pipe executes %.1fx the "
-                                 "algorithmic FLOPs" % (mma_flops_tile / (29056.0 * 128)),
+                         "f16_mma_tflops_issued": tiles * mma_flops_tile / (kernel_ms * 1e-3) / 1e12,
+                         "note": "fp32 parity costs three fp16 piece products per GEMM (and M = 64 padding): the tensor pipe "
+                                 "executes %.1fx the algorithmic FLOPs" % (mma_flops_tile / (29056.0 * 128)),
                          "fp32_fma_view": {"peak": peak32.value, "frac": achieved / peak32.value,
                                            "peak_source": "measured live by eeyore_b200_fma_peak (this device)",
                                            "ffma_kernel_ms": ffma_ms, "speedup_over_ffma_kernel": ffma_ms / kernel_ms},
