@@ -21,13 +21,14 @@
 // Two tiles are in flight per CTA (contexts A and B with their own operand buffers, accumulator region and mbarriers): the
 // phases alternate A, B, A, B ..., so the MMAs of one tile run on the tensor pipe under the epilogue of the other.
 // Per 128-row tile (persistent CTAs, one per SM, 256 threads; thread = (row, half of the 64 features)):
-//   P0  x tile (coalesced loads, prefetched one tile ahead) -> bf16 pieces in smem  MMA1  Z1 = X W0^T
+//   P0  x tile (coalesced loads, prefetched one pair of tiles ahead) -> pieces      MMA1  Z1 = X W0^T
 //   P1  H1 = sigmoid(Z1 + b0) -> pieces (smem)                                       MMA2  Z2 = H1 W1^T
 //   P2  H2, head, log-lik, delta3, dW2 (warp butterfly), Delta2 -> pieces           MMA3  D1 = Delta2 W1
 //                                                                                    MMA4  [db1 dW1] = Delta2^T [1 H1]
 //   P3  Delta1 = D1 H1 (1 - H1) -> pieces (over Delta2, after MMA4; H1 re-read from its pieces)  MMA5  [db0 dW0] = Delta1^T [1 X]
+//   P4  every TC_FLUSH pairs of tiles: weight-gradient sums TMEM -> (sum, error) fp32 register pairs (fp32 accumulation in
+//       TMEM spans <= 512 rows)
 // (A ninth, issue-only warp was measured slower: three warps on one scheduler cap the kernel at 168 registers -> spills.)
-//   P4  every TC_FLUSH tiles: weight-gradient accumulators TMEM -> fp64 registers (fp32 accumulation spans <= 512 rows)
 // One shared-memory copy of each activation serves both orientations: the SWIZZLE_NONE core-matrix layout of tc05.cuh
 // is a K-major operand for the forward / back-propagation GEMMs and an MN-major operand for the weight-gradient GEMMs.
 #include <cuda_runtime.h>

@@ -1,16 +1,16 @@
 // Thin inline-PTX layer over the sm_100a tensor-core path (tcgen05 + TMEM) used by the data-parallel kernel of
-// BASELINE config 5 (datapar_tc.cu).  Only what that kernel needs: TMEM allocation, BF16 `tcgen05.mma` (fp32
-// accumulate) with both operands in shared memory (no-swizzle canonical layouts written by CUDA cores),
+// BASELINE config 5 (datapar_tc.cu).  Only what that kernel needs: TMEM allocation, kind::f16 `tcgen05.mma` (fp16 or bf16 operands,
+// fp32 accumulate) with both operands in shared memory (no-swizzle canonical layouts written by CUDA cores),
 // commit -> mbarrier, and TMEM <-> register transfers for the epilogues.
 //
-// Operand layout used throughout ("core-matrix" layout, SWIZZLE_NONE):  a [R x C] bf16 matrix is stored as
+// Operand layout used throughout ("core-matrix" layout, SWIZZLE_NONE):  a [R x C] 16-bit matrix is stored as
 //     byte(r, c) = (r / 8) * 128 + (c / 8) * CS + (r % 8) * 16 + (c % 8) * 2          (CS = chunk stride >= R * 16)
 // i.e. 8 x 16-byte core matrices, row groups contiguous.  The same buffer is
 //   * a K-major operand  (MN = r, K = c):  SBO = 128 (next 8 rows), LBO = CS (next 8 k);  one K=16 step advances 2 * CS
 //   * an MN-major operand (MN = c, K = r): SBO = CS  (next 8 mn),   LBO = 128 (next 8 k); one K=16 step advances 256
 // which is what lets one copy of an activation tile serve the forward GEMM and the weight-gradient GEMM.
 // (MN-major operands of 32-bit types exist only in the 128B/32B-atom swizzle, which is why the fp32 path is an
-// error-compensated split into bf16 pieces rather than 3xTF32: measured with tools/tc_probe.cu.)
+// error-compensated split into 16-bit pieces rather than 3xTF32: measured with tools/tc_probe.cu.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
