@@ -1,8 +1,10 @@
 // Stand-alone probe for the tcgen05 building blocks of datapar_tc.cu (run on the GPU box; not part of the library):
 // checks the SWIZZLE_NONE descriptors in the three operand-major combinations the kernel uses, the M=64 accumulator
-// layout in TMEM, and prints rough MMA / TMEM-load timings.
+// layout in TMEM, and prints rough MMA / TMEM-load timings.  `tc_probe --mixed` tries a fp16 x bf16 MMA (illegal).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/tc_probe tools/tc_probe.cu && ./tools/tc_probe
+#include <cuda_fp16.h>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 #include "../eeyore_b200/csrc/tc05.cuh"
@@ -38,7 +40,8 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(int mode, const float* gA
   const uint32_t csA = 2048, csB = (mode == 3 || mode == 5) ? 2048 : 1024;
   for (int e = tid; e < a_rows * a_cols; e += 256) {
     const int r = e / a_cols, c = e % a_cols;
-    *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.A) + cm_off(r, c, csA)) = (uint16_t)(__float_as_uint(gA[e]) >> 16);
+    *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.A) + cm_off(r, c, csA)) =
+        (mode == 6) ? __half_as_ushort(__float2half_rn(gA[e])) : (uint16_t)(__float_as_uint(gA[e]) >> 16);
   }
   for (int e = tid; e < b_rows * b_cols; e += 256) {
     const int r = e / b_cols, c = e % b_cols;
@@ -79,6 +82,10 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(int mode, const float* gA
         mma_bf16(tm, ad, bd, id, k > 0);
         mma_bf16(tm + 64, ad, od, id1, k > 0);
       }
+    } else if (mode == 6) {  // mixed formats: A fp16 (K-major), B bf16 (K-major) -- raises "illegal instruction" on B200
+      const uint32_t id = idesc_f16kind(128, 64, 0, 0, 0, 1);
+      for (int k = 0; k < 4; ++k)
+        mma_bf16(tm, smem_desc(aA + k * 2 * csA, csA, 128), smem_desc(aB + k * 2 * csB, csB, 128), id, k > 0);
     } else if (mode == 4 || mode == 5) {  // timing only: 96 back-to-back MMAs
       const uint32_t id = (mode == 4) ? idesc_bf16(128, 64, 0, 0) : idesc_bf16(64, 64, 1, 1);
       const uint64_t a4 = smem_desc(aA, csA, 128), b4 = smem_desc(aB, 1024, 128);
@@ -163,7 +170,7 @@ static int run_mode(int mode, int swap_mn) {
     printf("mode %d swap %d: TIMEOUT waiting for the MMA commit\n", mode, swap_mn);
     return 3;
   }
-  if (mode >= 4) {
+  if (mode == 4 || mode == 5) {
     printf("mode %d: 96 MMAs issue->complete %lld cycles (%.1f per MMA); TMEM ld of 48 cols x 256 threads: %lld cycles\n", mode,
            cyc[0], cyc[0] / 96.0, cyc[1]);
     return 0;
@@ -177,7 +184,7 @@ static int run_mode(int mode, int swap_mn) {
       ++bad;
     }
   };
-  if (mode == 1) {
+  if (mode == 1 || mode == 6) {
     for (int r = 0; r < 128; ++r)
       for (int n = 0; n < 64; ++n) {
         float acc = 0;
@@ -210,7 +217,9 @@ static int run_mode(int mode, int swap_mn) {
   return bad ? 1 : 0;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "--mixed"))   // separate process: the illegal instruction kills the CUDA context
+    return run_mode(6, 0);
   int rc = 0;
   rc |= run_mode(1, 0);
   rc |= run_mode(2, 0);
