@@ -53,7 +53,13 @@ constexpr uint32_t TM_Z = 0;                     // per context (c * 128): Z1, t
 constexpr uint32_t TM_W1 = 256;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
 constexpr uint32_t TM_W0 = 392;                  // [ones(8) | dW0 (2 x 16)]     (432 of 512 columns)
 constexpr int TC_FLUSH = 2;                      // PAIRS of tiles between two folds (4 tiles)
-constexpr int TC_THREADS = DP_THREADS;           // 8 warps: every one an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
+#ifndef EB_TC_CG
+#define EB_TC_CG 2
+#endif
+constexpr int TC_CG = EB_TC_CG;                 // column groups: thread = (row, group of TC_FW of the 64 hidden units)
+constexpr int TC_FW = DP_H / TC_CG;              // hidden units per thread
+constexpr int TC_XW = DP_D0 / TC_CG;             // dW0 columns per thread
+constexpr int TC_THREADS = 128 * TC_CG;          // every warp an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
 
 struct TcCtx {                                   // operand buffers of one tile in flight
   alignas(1024) uint16_t ones_h[1024];           // 2 KB of fp16 1.0: the N-chunk in front of the H1 pieces
@@ -69,10 +75,10 @@ struct TcSmem {
   alignas(16) uint16_t w1a[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols i      (B of MMA2)
   alignas(16) uint16_t w1b[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + i, cols o      (B of MMA3)
   alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
-  alignas(16) float exch[2][DP_R];
+  alignas(16) float exch[TC_CG][DP_R];
   alignas(8) unsigned long long bar[2][6];       // per context, 1..5: MMA groups
   float b2;
-  float red_max[3][DP_THREADS / 32];             // prologue: max |W1|, max |w2|, max |W0| per warp
+  float red_max[3][TC_THREADS / 32];             // prologue: max |W1|, max |w2|, max |W0| per warp
   uint32_t tmem_base;
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "shared memory budget");
@@ -143,11 +149,11 @@ __device__ __forceinline__ void split2h_scalar(float x, uint16_t& p1, uint16_t& 
   p1 = (uint16_t)h;
   p2 = (uint16_t)pack_f16x2(r, 0.f);
 }
-// 32 features of one row (scaled by `scale`), starting at chunk `chunk0` -> the two fp16 piece buffers
+// TC_FW features of one row (scaled by `scale`), starting at chunk `chunk0` -> the two fp16 piece buffers
 __device__ __forceinline__ void store_pieces32h(unsigned char* base, int chunk0, int r, const float* v, float scale) {
   unsigned char* p = base + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)chunk0 * TC_CS;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < TC_FW / 8; ++c) {
     float w[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = v[8 * c + j] * scale;
@@ -167,12 +173,21 @@ __device__ __forceinline__ int scale_exp(float vmax) {
 
 // v[j] = sum of the two accumulator groups (64 columns apart) of a two-piece product at columns col0 + j, j < 32
 __device__ __forceinline__ void load_sum2(uint32_t taddr, float* v) {
-  uint32_t a[32], b[32];
-  tmem_ld32(taddr, a);
-  tmem_ld32(taddr + 64, b);
-  tmem_ld_wait();
+  if constexpr (TC_FW == 32) {
+    uint32_t a[32], b[32];
+    tmem_ld32(taddr, a);
+    tmem_ld32(taddr + 64, b);
+    tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(b[j]) + __uint_as_float(a[j]);
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(b[j]) + __uint_as_float(a[j]);
+  } else {
+    uint32_t a[16], b[16];
+    tmem_ld16(taddr, a);
+    tmem_ld16(taddr + 64, b);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(b[j]) + __uint_as_float(a[j]);
+  }
 }
 
 // hi + lo += x, error-free (Knuth two-sum): a pair of fp32 registers carries ~46 significant bits.  The tile loop uses
@@ -321,11 +336,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   };
 
   // weight-gradient sums: lanes 0..15 of every warp own unit o = 16 q + lane (M = 64 accumulator layout)
-  float g1[32], g1e[32], g0[8], g0e[8];   // (sum, error term) pairs, see acc2
+  float g1[TC_FW], g1e[TC_FW], g0[TC_XW], g0e[TC_XW];   // (sum, error term) pairs, see acc2
 #pragma unroll
-  for (int i = 0; i < 32; ++i) g1[i] = g1e[i] = 0.f;
+  for (int i = 0; i < TC_FW; ++i) g1[i] = g1e[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) g0[i] = g0e[i] = 0.f;
+  for (int i = 0; i < TC_XW; ++i) g0[i] = g0e[i] = 0.f;
   float gb1 = 0.f, gb1e = 0.f, gb0 = 0.f, gb0e = 0.f, gw2 = 0.f, gw2e = 0.f, gb2 = 0.f, gb2e = 0.f, ll = 0.f, lle = 0.f;
 
   // this thread's 8 features of its row and the row's label for both contexts, loaded one pair of tiles ahead
@@ -336,9 +351,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     xa = xb = make_float4(0.f, 0.f, 0.f, 0.f);
     yn = 0.f;
     if (tile < n_tiles && gr < n_rows) {
-      const float4* src = reinterpret_cast<const float4*>(x + gr * DP_D0 + 8 * hf);
-      xa = __ldg(src);
-      xb = __ldg(src + 1);
+      if (hf < 2) {                                    // the 16 input features are two 8-wide chunks
+        const float4* src = reinterpret_cast<const float4*>(x + gr * DP_D0 + 8 * hf);
+        xa = __ldg(src);
+        xb = __ldg(src + 1);
+      }
       yn = __ldg(y + gr);
     }
   };
@@ -360,7 +377,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       if (pair > 0) mbar_wait(&s.bar[c][5], par ^ 1u);       // MMA5 of this context's previous tile has read xp and dl
       const float4 xa = c ? xa1 : xa0, xb = c ? xb1 : xb0;
       if (c) yv1 = yn1; else yv0 = yn0;
-      {
+      if (hf < 2) {
         const float v[8] = {xa.x * s_x, xa.y * s_x, xa.z * s_x, xa.w * s_x, xb.x * s_x, xb.y * s_x, xb.z * s_x, xb.w * s_x};
         uint4 p1, p2;
         split2h(v, p1, p2);
@@ -392,12 +409,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       mbar_wait(&s.bar[c][1], par);
       fence_after_sync();
       {
-        float v[32];
-        load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, v);
+        float v[TC_FW];
+        load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = (j & 1) ? tc_sigmoid_fma(fmaf(v[j], inv_z1, s.b0[32 * hf + j])) : tc_sigmoid(fmaf(v[j], inv_z1, s.b0[32 * hf + j]));
-        store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), 4 * hf, r, v, TC_SH);
+        for (int j = 0; j < TC_FW; ++j)
+          v[j] = (j & 1) ? tc_sigmoid_fma(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j])) : tc_sigmoid(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]));
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), (TC_FW / 8) * hf, r, v, TC_SH);
       }
       fence_async_smem();
       fence_before_sync();
@@ -423,19 +440,22 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       const float yv = c ? yv1 : yv0;
       mbar_wait(&s.bar[c][2], par);
       fence_after_sync();
-      float t[32], p_head = 0.5f, d_head = 0.f;
+      float t[TC_FW], p_head = 0.5f, d_head = 0.f;
       {
-        float h[32];
-        load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, h);
+        float h[TC_FW];
+        load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, h);
         float apart = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          h[j] = (j & 1) ? tc_sigmoid_fma(fmaf(h[j], inv_z2, s.b1[32 * hf + j])) : tc_sigmoid(fmaf(h[j], inv_z2, s.b1[32 * hf + j]));
-          apart = fmaf(h[j], s.w2[32 * hf + j], apart);
+        for (int j = 0; j < TC_FW; ++j) {
+          h[j] = (j & 1) ? tc_sigmoid_fma(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j])) : tc_sigmoid(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]));
+          apart = fmaf(h[j], s.w2[TC_FW * hf + j], apart);
         }
         s.exch[hf][r] = apart;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share rows 32 q .. 32 q + 31
-        const float a = (s.exch[0][r] + s.exch[1][r]) + s.b2;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * TC_CG) : "memory");   // the warps that share rows 32 q .. 32 q + 31
+        float asum = s.exch[0][r];
+#pragma unroll
+        for (int cg = 1; cg < TC_CG; ++cg) asum += s.exch[cg][r];
+        const float a = asum + s.b2;
         float d = 0.f;
         if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
           p_head = __fdividef(1.0f, 1.0f + __expf(-a));        // 2 ulp; exact 0 / 1 at saturation like the reference
@@ -443,11 +463,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
         }
         d_head = d;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < TC_FW; ++j) {
           t[j] = d * h[j];                                                   // dW2 terms
-          h[j] = d * s.w2[32 * hf + j] * (1.f - h[j]) * h[j];                // Delta2
+          h[j] = d * s.w2[TC_FW * hf + j] * (1.f - h[j]) * h[j];             // Delta2
         }
-        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), 4 * hf, r, h, s_d);
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, h, s_d);
       }
       fence_async_smem();
       fence_before_sync();
@@ -476,7 +496,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
           acc2(gb2, gb2e, d_head);
         }
       }
-      butterfly_step<16>(t, lane);
+      if constexpr (TC_FW == 32) {
+        butterfly_step<16>(t, lane);
+      } else {                                       // 16 values: fold the two half-warps first (both keep the sums)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] += __shfl_xor_sync(0xffffffffu, t[i], 16);
+      }
       butterfly_step<8>(t, lane);
       butterfly_step<4>(t, lane);
       butterfly_step<2>(t, lane);
@@ -491,13 +516,13 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       mbar_wait(&s.bar[c][3], par);
       fence_after_sync();
       {
-        float v[32];
-        load_sum2(tm_lane + TM_Z + 128 * c + 32 * hf, v);
+        float v[TC_FW];
+        load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
         // H1 of this row from its two fp16 pieces (exact up to 2^-22): no fp32 copy is kept
         const unsigned char* hp = reinterpret_cast<const unsigned char*>(cx.h1) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u +
-                                  (uint32_t)(4 * hf) * TC_CS;
+                                  (uint32_t)((TC_FW / 8) * hf) * TC_CS;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < TC_FW / 8; ++ch) {
           const uint4 p1 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS);
           const uint4 p2 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS + TC_ACT);
           const uint32_t w1[4] = {p1.x, p1.y, p1.z, p1.w}, w2v[4] = {p2.x, p2.y, p2.z, p2.w};
@@ -510,7 +535,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
           }
         }
         mbar_wait(&s.bar[c][4], par);                        // MMA4 has read Delta2 (and H1)
-        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), 4 * hf, r, v, s_d1);
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, v, s_d1);
       }
       fence_async_smem();
       fence_before_sync();
@@ -533,23 +558,28 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
       mbar_wait(&s.bar[n_ctx - 1][5], par);                  // the last MMA issued: everything before it is complete
       fence_after_sync();
       {
-        float v[32];
-        load_sum2(tm_lane + TM_W1 + 8 + 32 * hf, v);
+        float v[TC_FW];
+        load_sum2(tm_lane + TM_W1 + 8 + TC_FW * hf, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
+        for (int i = 0; i < TC_FW; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
         uint32_t o4[4];
         tmem_ld4(tm_lane + TM_W1, o4);
         tmem_ld_wait();
         acc2(gb1, gb1e, __uint_as_float(o4[0]) * inv_b1);
       }
       {
-        uint32_t a[8], b[8], o4[4];
-        tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, a);
-        tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, b);
+        uint32_t a[TC_XW], b[TC_XW], o4[4];
+        if constexpr (TC_XW == 8) {
+          tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, *reinterpret_cast<uint32_t(*)[8]>(a));
+          tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, *reinterpret_cast<uint32_t(*)[8]>(b));
+        } else {
+          tmem_ld4(tm_lane + TM_W0 + 8 + 4 * hf, *reinterpret_cast<uint32_t(*)[4]>(a));
+          tmem_ld4(tm_lane + TM_W0 + 8 + 16 + 4 * hf, *reinterpret_cast<uint32_t(*)[4]>(b));
+        }
         tmem_ld4(tm_lane + TM_W0, o4);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
+        for (int i = 0; i < TC_XW; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
         acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
       }
       fence_before_sync();                                   // ordered before the next pair's MMAs by its first __syncthreads
@@ -566,9 +596,9 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   if (lane < 16) {
     const int o = 16 * q + lane;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) out[1 + DP_OFF_W1 + o * DP_H + 32 * hf + i] = (double)g1[i] + (double)g1e[i];
+    for (int i = 0; i < TC_FW; ++i) out[1 + DP_OFF_W1 + o * DP_H + TC_FW * hf + i] = (double)g1[i] + (double)g1e[i];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[1 + o * DP_D0 + 8 * hf + j] = (double)g0[j] + (double)g0e[j];
+    for (int j = 0; j < TC_XW; ++j) out[1 + o * DP_D0 + TC_XW * hf + j] = (double)g0[j] + (double)g0e[j];
     if (hf == 0) {
       out[1 + DP_OFF_B1 + o] = (double)gb1 + (double)gb1e;
       out[1 + DP_OFF_B0 + o] = (double)gb0 + (double)gb0e;
@@ -577,11 +607,11 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   // dW2: unit 32 hf + lane, partial over the rows of quadrant q; log-likelihood and db2: fixed-order block sums
   double* red = reinterpret_cast<double*>(s.ctx[0].dl);   // the activation buffers are free now
   red[tid] = (double)gw2 + (double)gw2e;
-  red[DP_THREADS + tid] = (double)ll + (double)lle;
-  red[2 * DP_THREADS + tid] = (double)gb2 + (double)gb2e;
+  red[TC_THREADS + tid] = (double)ll + (double)lle;
+  red[2 * TC_THREADS + tid] = (double)gb2 + (double)gb2e;
   __syncthreads();
   if (tid < DP_H) {
-    const int h2 = tid >> 5, l2 = tid & 31;
+    const int h2 = tid / TC_FW, l2 = tid % TC_FW;        // unit tid lives in column group h2, lane l2 of its warps
     double t = 0.0;
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) t += red[(4 * h2 + qq) * 32 + l2];
@@ -589,12 +619,12 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   }
   if (tid == 64) {
     double t = 0.0;
-    for (int i = 0; i < DP_R; ++i) t += red[DP_THREADS + i];      // hf == 0 threads are tid 0..127
+    for (int i = 0; i < DP_R; ++i) t += red[TC_THREADS + i];      // hf == 0 threads are tid 0..127
     out[0] = t;
   }
   if (tid == 96) {
     double t = 0.0;
-    for (int i = 0; i < DP_R; ++i) t += red[2 * DP_THREADS + i];
+    for (int i = 0; i < DP_R; ++i) t += red[2 * TC_THREADS + i];
     out[1 + DP_OFF_B2] = t;
   }
   TC_STAMP(21);
