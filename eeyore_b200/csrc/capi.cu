@@ -238,6 +238,10 @@ namespace eb {
 template <typename T>
 __global__ void philox_draws_kernel(long n_chains, int P, RngKey key, uint32_t iter, uint32_t chain0, T* z, T* u) {
   const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (sizeof(T) == 8) {   // the fp64 Box-Muller log reads the shared-memory tables
+    exp_table_init();
+    __syncthreads();
+  }
   if (c >= n_chains) return;
   const uint32_t gc = chain0 + (uint32_t)c;
   constexpr int PER = sizeof(T) == 8 ? 2 : 4;

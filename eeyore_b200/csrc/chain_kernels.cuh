@@ -174,7 +174,13 @@ EB_D DataView<T> stage_data(unsigned char* smem, const SmemLayout<T, NET>& lay, 
   }
   if (xb + yb > 0) mbar_wait(bar, 0);
   __syncthreads();
+  int hard = 1;
+  if constexpr (NET::LOSS == LOSS_BINARY) {
+    for (int i = tid; i < N; i += blockDim.x) hard &= (ys[i] == T(0) || ys[i] == T(1)) ? 1 : 0;
+    hard = __syncthreads_and(hard);
+  }
   DataView<T> d;
+  d.hard_labels = hard != 0;
   d.x = xs; d.y = ys; d.cls = cs; d.n_rows = N; d.ploc = ploc; d.pivar = pivar; d.lp_const = misc[0];
   d.temperature = a.temperature; d.has_temperature = a.has_temperature != 0;
   return d;

@@ -32,13 +32,16 @@ template <> EB_HD float fma_t<float>(float a, float b, float c) { return fmaf(a,
 template <> EB_HD double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
 // ---- fp64 fast paths ----------------------------------------------------------------------------------------------
-// The chain kernels are bound by the FP64 pipe, and most FP64 instructions of an evaluation are spent inside exp() and
-// the division of the sigmoid.  These versions keep ~1 ulp accuracy (parity tolerance is 1e-10) but
-//   * use a 64-entry 2^(j/64) table in shared memory + a degree-5 polynomial (the CUDA math library evaluates a
-//     degree-11 polynomial and materialises each 64-bit coefficient with two UMOVs per use, ~26% of all issued
-//     instructions in the first version of the kernels),
-//   * have no slow-path branches (arguments are clamped instead),
-//   * refine MUFU.RCP64H with one cubic step instead of the IEEE-exact division sequence.
+// The chain kernels are bound by the FP64 pipe (a warp-wide FP64 instruction occupies it for two cycles), and most FP64
+// instructions of an evaluation used to be spent inside exp(), the division of the sigmoid and log().  These versions keep
+// a few ulp accuracy (parity tolerance is 1e-10) with as few FP64 instructions and as short a dependency chain as possible:
+//   * exp: 2048-entry 2^(j/2048) table in shared memory + a degree-3 polynomial; the argument reduction is one exact
+//     FMA in base 2 (r = a * 2048/ln2 - n; the rounding of the constant costs |a| * 2^-53 relative);
+//   * sigmoid: 1 + e is formed by one FMA from the exponent-adjusted table entry, MUFU.RCP64H is refined with one cubic
+//     step, saturation is an integer test off the critical path: 10 FP64 instructions (CUDA libm + IEEE division: ~45);
+//   * log: fdlibm-style normalisation to [sqrt(1/2), sqrt(2)), a 1024-entry (1/c, -log(1/c)) table and a degree-4
+//     polynomial, no division: 7 FP64 instructions (fdlibm: 23 and a reciprocal).
+// Tables: tools/gen_math_tables.py (correctly rounded with mpmath).
 EB_HD int dbl_lo(double v) {
 #if defined(__CUDA_ARCH__)
   return __double2loint(v);
@@ -46,47 +49,83 @@ EB_HD int dbl_lo(double v) {
   uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)(b & 0xffffffffu);
 #endif
 }
-EB_HD double dbl_add_exponent(double v, int k) {
+EB_HD int dbl_hi(double v) {
 #if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+  return __double2hiint(v);
 #else
-  uint64_t b; memcpy(&b, &v, 8); b += (uint64_t)((int64_t)k << 52); memcpy(&v, &b, 8); return v;
+  uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)(b >> 32);
 #endif
 }
+EB_HD double dbl_from(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+EB_HD double dbl_add_exponent(double v, int k) { return dbl_from(dbl_hi(v) + (int)((unsigned)k << 20), dbl_lo(v)); }
 
-// Table of 2^(j/64).  Device: a per-CTA shared-memory copy filled by exp_table_init() in the kernel prologue (the lookup
-// index differs per lane, which the constant bank would serialise); host (tests/hostsim): the plain array.
-static const double kExp2TabHost[64] = {
+constexpr int kExpTabN = 2048, kLogTabN = 1024;
+// Host (tests/hostsim): the plain arrays.  Device: global-memory masters, copied by every CTA into shared memory in its
+// prologue (the lookup index differs per lane, which the constant bank would serialise).
+static const double kExp2TabHost[kExpTabN] = {
 #include "exp_table.inc"
 };
+#include "log_table.inc"
+static const double kLogInvHost[kLogTabN] = {EB_LOG_INV_TABLE};
+static const double kLogNlogHost[kLogTabN] = {EB_LOG_NLOG_TABLE};
 #if defined(__CUDACC__)
-static __constant__ double kExp2TabDev[64] = {
+static __device__ const double kExp2TabDev[kExpTabN] = {
 #include "exp_table.inc"
 };
+static __device__ const double kLogInvDev[kLogTabN] = {EB_LOG_INV_TABLE};
+static __device__ const double kLogNlogDev[kLogTabN] = {EB_LOG_NLOG_TABLE};
+// [2^(j/2048) (2048) | 1/c (1024) | -log(1/c) (1024)]: 32 KB of static shared memory in every kernel that evaluates fp64
+// sigmoids / logs
 EB_D double* exp_table_smem() {
-  __shared__ double tab[64];
+  __shared__ double tab[kExpTabN + 2 * kLogTabN];
   return tab;
 }
-// every thread of the CTA calls this once before the first fp64 sigmoid / softmax; followed by a __syncthreads()
+// every thread of the CTA calls this once before the first fp64 sigmoid / softmax / log; followed by a __syncthreads()
 EB_D void exp_table_init() {
   double* t = exp_table_smem();
-  for (int j = threadIdx.x; j < 64; j += blockDim.x) t[j] = kExp2TabDev[j];
+  for (int j = threadIdx.x; j < kExpTabN; j += blockDim.x) t[j] = kExp2TabDev[j];
+  for (int j = threadIdx.x; j < kLogTabN; j += blockDim.x) {
+    t[kExpTabN + j] = kLogInvDev[j];
+    t[kExpTabN + kLogTabN + j] = kLogNlogDev[j];
+  }
 }
 #endif
+EB_HD double exp2_tab(int j) {
+#if defined(__CUDA_ARCH__)
+  return exp_table_smem()[j];
+#else
+  return kExp2TabHost[j];
+#endif
+}
+EB_HD double log_inv_tab(int i) {
+#if defined(__CUDA_ARCH__)
+  return exp_table_smem()[kExpTabN + i];
+#else
+  return kLogInvHost[i];
+#endif
+}
+EB_HD double log_nlog_tab(int i) {
+#if defined(__CUDA_ARCH__)
+  return exp_table_smem()[kExpTabN + kLogTabN + i];
+#else
+  return kLogNlogHost[i];
+#endif
+}
 
-// exp(a) for |a| <= 700 (callers clamp): a = (64 k + j) ln2/64 + r, |r| <= ln2/128; exp(a) = 2^k * 2^(j/64) * P5(r).
-// 10 FP64-pipe instructions (the degree-11 single-polynomial version needed 15); ~1.5 ulp; NaN propagates.
-// constants with non-zero low words would otherwise be materialised by UMOV pairs at every use
-#define EB_MATH_CONSTS                                                                                             \
-  {92.332482616893657, -1.08304246932675596e-02, -2.98158582698529328e-12, 8.3333333333333332e-03,                \
-   4.1666666666666664e-02, 1.6666666666666666e-01,                                                                \
-   /* log: ln2_hi, ln2_lo, Lg1..Lg7 (Sun fdlibm e_log.c) */                                                       \
-   6.93147180369123816490e-01, 1.90821492927058770002e-10, 6.666666666666735130e-01, 3.999999999940941908e-01,    \
-   2.857142874366239149e-01, 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,        \
-   1.479819860511658591e-01}
-static const double kMathHost[15] = EB_MATH_CONSTS;
+// constants with non-zero low words live in the constant bank (DFMA takes c[][] operands; immediates would be
+// materialised by UMOV pairs at every use): 2048/ln2; a1, a2, a3 of 2^(r/2048) = 1 + a1 r + a2 r^2 + a3 r^3; ln2; 1/3
+#define EB_MATH_CONSTS                                                                                     \
+  {2954.639443740597, 0.0003384507717577858, 5.727446245172041e-08, 6.461528672932366e-12, 0.6931471805599453, \
+   0.3333333333333333}
+static const double kMathHost[6] = EB_MATH_CONSTS;
 #if defined(__CUDACC__)
-static __constant__ double kMathDev[15] = EB_MATH_CONSTS;
+static __constant__ double kMathDev[6] = EB_MATH_CONSTS;
 #endif
 EB_HD const double* math_consts() {
 #if defined(__CUDA_ARCH__)
@@ -96,25 +135,28 @@ EB_HD const double* math_consts() {
 #endif
 }
 
-EB_HD double exp_core(double a) {
+// The pieces of exp(a), |a| <= 708: a 2048/ln2 = n + r with |r| <= 1/2 (one exact FMA), n = 2048 k + j;
+// exp(a) = [2^k 2^(j/2048)] * q,  q = 2^(r/2048) = 1 + r (a1 + r (a2 + r a3))  (truncation 3.4e-17).  5 FP64 instructions.
+EB_HD void exp_pieces(double a, double& tjs, double& q) {
   const double* c = math_consts();
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
-  const double t = fma(a, c[0], magic);                            // 64 / ln 2
+  const double t = fma(a, c[0], magic);
   const double nf = t - magic;
   const int n = dbl_lo(t);
-  double r = fma(nf, c[1], a);                                     // -ln2_hi / 64 (32 significant bits: nf * hi is exact)
-  r = fma(nf, c[2], r);                                            // -ln2_lo / 64
+  const double r = fma(a, c[0], -nf);
+  double p = fma(r, c[3], c[2]);
+  p = fma(p, r, c[1]);
+  q = fma(r, p, 1.0);
+  tjs = dbl_add_exponent(exp2_tab(n & (kExpTabN - 1)), n >> 11);
+}
+EB_HD double exp_core(double a) {
+  double tjs, q;
+  exp_pieces(a, tjs, q);
 #if defined(__CUDA_ARCH__)
-  const double tj = exp_table_smem()[n & 63];
+  return __dmul_rn(tjs, q);   // never contracted into a consumer's add: GRAD / no-GRAD instantiations stay bit-identical
 #else
-  const double tj = kExp2TabHost[n & 63];
+  return tjs * q;
 #endif
-  double p = fma(r, c[3], c[4]);
-  p = fma(p, r, c[5]);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return dbl_add_exponent(tj * p, n >> 6);
 }
 
 // exp(a) for a <= 0 (softmax numerators): anything below e^-700 is far under one ulp of the sum it is added to.
@@ -137,49 +179,49 @@ EB_HD double rcp_ge1(double d) {
 #endif
 }
 
-// log(x) for positive, normal, finite x (probabilities in (0, 1]); branch-free restatement of the classic
-// fdlibm algorithm: x = 2^k (1 + f), sqrt(1/2) <= 1 + f < sqrt(2); s = f / (2 + f);
-// log(1 + f) = f - f^2/2 + s (f^2/2 + R(s^2)).  < 1 ulp.  Callers handle 0 / NaN.
+// log(x) for positive, normal, finite x (probabilities in (0, 1], uniforms, softmax sums).  x = 2^k m with
+// sqrt(1/2) <= m < sqrt(2) (the high-word trick of fdlibm's e_log.c); the window position of m selects c_i with
+// |m / c_i - 1| < 4.9e-4 (the bin around 1 has c = 1, so there is no cancellation for x -> 1);
+// log x = k ln2 - log(1/c_i) + log1p(r),  r = m (1/c_i) - 1 (one FMA),  log1p(r) = r - r^2/2 + r^3/3 - r^4/4  (5.5e-18).
+// Callers handle 0 / NaN.
 EB_HD double log_pos_normal(double x) {
   const double* c = math_consts();
-#if defined(__CUDA_ARCH__)
-  int hx = __double2hiint(x);
-  const int lx = __double2loint(x);
-#else
-  uint64_t b; memcpy(&b, &x, 8);
-  int hx = (int)(b >> 32);
-  const int lx = (int)(uint32_t)(b & 0xffffffffu);
-#endif
-  int k = (hx >> 20) - 1023;
-  hx &= 0x000fffff;
-  const int i = (hx + 0x95f64) & 0x100000;
-  k += i >> 20;
-#if defined(__CUDA_ARCH__)
-  const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
-#else
-  b = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (uint32_t)lx;
-  double m; memcpy(&m, &b, 8);
-#endif
-  const double f = m - 1.0;
-  const double s = f * rcp_ge1(2.0 + f);
-  const double dk = (double)k;
-  const double z = s * s;
-  const double w = z * z;
-  const double t1 = w * fma(w, fma(w, c[13], c[11]), c[9]);
-  const double t2 = z * fma(w, fma(w, fma(w, c[14], c[12]), c[10]), c[8]);
-  const double R = t2 + t1;
-  const double hfsq = 0.5 * f * f;
-  return fma(dk, c[6], -((hfsq - fma(s, hfsq + R, dk * c[7])) - f));
+  const int hs = dbl_hi(x) + 0x95f64;
+  const int f = hs & 0xfffff;
+  const double m = dbl_from(f + (0x3ff00000 - 0x95f64), dbl_lo(x));
+  const int i = f >> 10;
+  const double dk = (double)((hs >> 20) - 1023);
+  const double r = fma(m, log_inv_tab(i), -1.0);
+  const double base = fma(dk, c[4], log_nlog_tab(i));
+  const double s = r * r;
+  double q = fma(r, -0.25, c[5]);
+  q = fma(q, r, -0.5);
+  return base + fma(s, q, r);
 }
+
+// Exact tests on values that are known to be non-negative or NaN (probabilities): fp64 versions are integer compares
+// on the two words -- a DSETP would occupy the FP64 pipe like a DFMA.
+template <typename T> EB_HD bool prob_is_zero(T p) { return p == T(0); }
+template <typename T> EB_HD bool prob_is_one(T p) { return p == T(1); }
+template <typename T> EB_HD bool prob_is_nan(T p) { return p != p; }
+template <> EB_HD bool prob_is_zero<double>(double p) { return (dbl_hi(p) | dbl_lo(p)) == 0; }
+template <> EB_HD bool prob_is_one<double>(double p) { return dbl_hi(p) == 0x3ff00000 && dbl_lo(p) == 0; }
+template <> EB_HD bool prob_is_nan<double>(double p) { return (dbl_hi(p) & 0x7ff00000) == 0x7ff00000; }  // never inf
 
 // sigmoid as the reference evaluates it, 1 / (1 + exp(-g))  (torch.sigmoid, eeyore/models/mlp.py:48-49).
 template <typename T> EB_HD T sigmoid_t(T g) { return T(1) / (T(1) + exp_t<T>(-g)); }
-// fp64: exp(-g) is clamped to [e^-700, e^700]; below, 1 + e == 1 exactly as in the reference; above, the result is
-// ~1e-304 where the reference underflows towards 0 -- the head of the network restores the exact-zero case (head_loss).
+// fp64: d = 1 + exp(-g) by one FMA from the pieces of the exponential, then the refined reciprocal.  |g| > 708 (where the
+// exponent arithmetic would wrap) is replaced at the end by the saturated value -- 1 for g > 0 (1 + e == 1 exactly from
+// g > 36.7 on, as in the reference), 0 for g < -708 (the reference: below 3.3e-308, exactly 0 from -709.78 on); the test
+// is integer arithmetic on the high word, off the dependency chain, false for NaN (which propagates through the FMAs).
 template <> EB_HD double sigmoid_t<double>(double g) {
-  double a = -g;
-  a = (fabs(a) > 700.0) ? copysign(700.0, a) : a;  // NaN compares false and propagates
-  return rcp_ge1(1.0 + exp_core(a));
+  double tjs, q;
+  exp_pieces(-g, tjs, q);
+  const double s = rcp_ge1(fma(tjs, q, 1.0));
+  const int hi = dbl_hi(g);
+  const bool big = (int)((unsigned)(hi & 0x7fffffff) + 0xfffffu) > (0x40862000 + 0xfffff);   // signed: NaN high words wrap negative
+  const double sat = dbl_from(hi < 0 ? 0 : 0x3ff00000, 0);
+  return big ? sat : s;
 }
 
 // N sigmoids evaluated stage by stage ("vertically"): the N dependency chains are written interleaved so that the
@@ -189,47 +231,6 @@ template <typename T, int N> EB_HD void sigmoid_vec(const T (&g)[N], T (&out)[N]
 #pragma unroll
   for (int i = 0; i < N; ++i) out[i] = sigmoid_t<T>(g[i]);
 }
-#if defined(__CUDA_ARCH__)
-template <int N> EB_D void sigmoid_vec_f64(const double (&g)[N], double (&out)[N]) {
-  const double* c = math_consts();
-  const double magic = 6755399441055744.0;
-  double a[N], t[N], nf[N], r[N], p[N], tj[N], d[N], q[N], e[N];
-  int n[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) { a[i] = -g[i]; a[i] = (fabs(a[i]) > 700.0) ? copysign(700.0, a[i]) : a[i]; }
-#pragma unroll
-  for (int i = 0; i < N; ++i) t[i] = fma(a[i], c[0], magic);
-#pragma unroll
-  for (int i = 0; i < N; ++i) { nf[i] = t[i] - magic; n[i] = __double2loint(t[i]); }
-#pragma unroll
-  for (int i = 0; i < N; ++i) tj[i] = exp_table_smem()[n[i] & 63];
-#pragma unroll
-  for (int i = 0; i < N; ++i) r[i] = fma(nf[i], c[1], a[i]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) r[i] = fma(nf[i], c[2], r[i]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) p[i] = fma(r[i], c[3], c[4]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c[5]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 0.5);
-#pragma unroll
-  for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-  for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-  for (int i = 0; i < N; ++i) d[i] = 1.0 + dbl_add_exponent(tj[i] * p[i], n[i] >> 6);
-#pragma unroll
-  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q[i]) : "d"(d[i]));
-#pragma unroll
-  for (int i = 0; i < N; ++i) e[i] = fma(-d[i], q[i], 1.0);
-#pragma unroll
-  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) out[i] = fma(q[i], e[i], q[i]);
-}
-#endif
-
 
 // cos/sin(2 pi u)
 template <typename T> EB_HD void sincos2pi(T u, T* s, T* c);

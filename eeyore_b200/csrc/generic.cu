@@ -77,6 +77,7 @@ template <typename T> __device__ DataView<T> gen_stage(unsigned char* smem, cons
   }
   __syncthreads();
   DataView<T> d;
+  d.hard_labels = false;   // the runtime-shape row code keeps its soft-label branch
   d.x = xs; d.y = ys; d.cls = cs; d.n_rows = N; d.ploc = ploc; d.pivar = pivar; d.lp_const = misc[0];
   d.temperature = a.temperature; d.has_temperature = a.has_temperature != 0;
   return d;
@@ -196,6 +197,7 @@ template <typename T> int gen_pick_threads(const GenNet& n, int n_rows, int n_ve
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (sizeof(T) == 8) max_smem -= (int)(sizeof(double) * (kExpTabN + 2 * kLogTabN));   // the static fp64 math tables
   for (int th = 128; th >= 8; th >>= 1) {
     const GenLayout<T> lay(n, n_rows, th, n_vec_elems);
     if (lay.total <= (size_t)max_smem) { *smem_out = lay.total; return th; }

@@ -12,6 +12,7 @@
 // as a pre-flight check (the shipped library contains only the device instantiations).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 #ifndef EB_ROW_UNROLL
 #define EB_ROW_UNROLL 1
@@ -41,6 +42,7 @@ template <typename T> struct DataView {
   const T* y;       // [N] binary targets (LOSS_BINARY)
   const int* cls;   // [N] class index = argmax of the one-hot row (LOSS_MULTICLASS), constants.py:17
   int n_rows;
+  bool hard_labels; // every y is exactly 0 or 1 (LOSS_BINARY): the row code is then branch-free
   const T* ploc;    // [P] prior mean
   const T* pivar;   // [P] 1 / scale^2
   T lp_const;       // sum_j ( -log scale_j - log sqrt(2 pi) )
@@ -59,12 +61,7 @@ EB_HD void dense_fwd(const TH& th, const T (&in)[DIN], T (&out)[DOUT]) {
     pre[o] = a;
   }
   if constexpr (SIG) {
-#if defined(__CUDA_ARCH__) && defined(EB_SIGMOID_VEC)  // measured: 11.0e9 vs 11.4e9 evals/s (cfg4) -> off
-    if constexpr (sizeof(T) == 8) sigmoid_vec_f64<DOUT>(pre, out);
-    else sigmoid_vec<T, DOUT>(pre, out);
-#else
     sigmoid_vec<T, DOUT>(pre, out);
-#endif
   } else {
 #pragma unroll
     for (int o = 0; o < DOUT; ++o) out[o] = pre[o];
@@ -87,7 +84,7 @@ EB_HD void dense_bwd(const TH& th, const T (&in)[DIN], const T (&dout)[DOUT], GV
       T s = T(0);
 #pragma unroll
       for (int o = 0; o < DOUT; ++o) s = fma_t<T>(dout[o], th[OFF + o * DIN + i], s);
-      din[i] = s * (T(1) - in[i]) * in[i];
+      din[i] = s * fma_t<T>(-in[i], in[i], in[i]);   // out (1 - out) in one FMA
     }
   }
 }
@@ -95,29 +92,35 @@ EB_HD void dense_bwd(const TH& th, const T (&in)[DIN], const T (&dout)[DOUT], GV
 template <typename T> EB_HD T head_log(T q) { return log_t<T>(q); }
 // fp64: q is a probability in [0, 1]; 0 is patched by the caller, tiny values are normal numbers (>= 1e-304)
 template <> EB_HD double head_log<double>(double q) { return log_pos_normal(q > 0.0 ? q : 1.0); }
+// the same with the zero test supplied by the caller
+template <typename T> EB_HD T head_log_nz(T q, bool q_zero) { return head_log<T>(q); }
+template <> EB_HD double head_log_nz<double>(double q, bool q_zero) { return log_pos_normal(q_zero ? 1.0 : q); }
 
 // Head: returns this row's log-likelihood term and the seed d ll / d a_L.
-template <typename T, class NET> EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) {
+template <typename T, class NET, bool HARD = false>
+EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) {
   if constexpr (NET::LOSS == LOSS_BINARY) {
     T p = sigmoid_t<T>(a[0]);
-    // the reference's p is exactly 0 once exp(-a) overflows (a < -709.78 in fp64); the fp64 fast sigmoid clamps
-    if (sizeof(T) == 8 && a[0] < T(-709.782712893384)) p = T(0);
+    // (the reference's p is exactly 0 once exp(-a) overflows, a < -709.78 in fp64; the fp64 fast sigmoid saturates to 0
+    // from -708 on)
     if (p_out) *p_out = p;
     T term;
     // loss.py:2 evaluates log(p)*y + log(1-p)*(1-y); for y in {0,1} one product is 0 * log(.), which is NaN
     // exactly when that log is -inf -- reproduced without evaluating the second log and without
     // branching (one log of the selected argument; selects restore the special cases).
-    if (y == T(1) || y == T(0)) {
-      const T q = (y == T(1)) ? p : (T(1) - p);          // the probability of the observed label
-      const T other = (y == T(1)) ? (T(1) - p) : p;      // its complement: 0 there means 0 * log(0) = NaN
-      T lq = head_log<T>(q);
-      lq = (q == T(0)) ? -T(INFINITY) : lq;
-      term = (other == T(0) || q != q) ? qnan<T>() : lq;
+    const bool y1 = prob_is_one<T>(y), y0 = prob_is_zero<T>(y);
+    const bool p0 = prob_is_zero<T>(p), p1 = prob_is_one<T>(p);
+    if (HARD || y1 || y0) {
+      const T q = y1 ? p : (T(1) - p);                   // the probability of the observed label
+      const bool q_zero = y1 ? p0 : p1;                  // 1 - p == 0 exactly when p == 1
+      const bool other_zero = y1 ? p1 : p0;              // the complement: 0 there means 0 * log(0) = NaN
+      const T lq = head_log_nz<T>(q, q_zero);
+      term = (other_zero || prob_is_nan<T>(p)) ? qnan<T>() : (q_zero ? -T(INFINITY) : lq);
     } else {
       term = log_t<T>(p) * y + log_t<T>(T(1) - p) * (T(1) - y);
     }
     // autograd of the naive form gives (y/p - (1-y)/(1-p)) (1-p) p = y - p, and NaN when p hits 0 or 1
-    delta[0] = (p == T(0) || p == T(1)) ? qnan<T>() : (y - p);
+    delta[0] = (p0 || p1) ? qnan<T>() : (y - p);
     return term;
   } else {
     constexpr int K = NET::DL;
@@ -142,7 +145,7 @@ template <typename T, class NET> EB_HD T head_loss(T (&a)[NET::DL], T y, int cls
 }
 
 // One data row: forward, loss, (optionally) backward; accumulates into ll and g.
-template <typename T, class NET, bool GRAD, class TH, class GV>
+template <typename T, class NET, bool GRAD, bool HARD = false, class TH, class GV>
 EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g) {
   T h0[NET::D0];
 #pragma unroll
@@ -152,7 +155,7 @@ EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g)
   if constexpr (NET::NL == 2) {
     T a[NET::D2], dl[NET::D2];
     dense_fwd<T, NET::D1, NET::D2, NET::OFF1, false>(th, h1, a);
-    ll += head_loss<T, NET>(a, y, cls, dl, (T*)nullptr);
+    ll += head_loss<T, NET, HARD>(a, y, cls, dl, (T*)nullptr);
     if constexpr (GRAD) {
       T d1[NET::D1], d0[NET::D0];
       dense_bwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, dl, g, d1);
@@ -163,7 +166,7 @@ EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g)
     dense_fwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, h2);
     T a[NET::DL], dl[NET::DL];
     dense_fwd<T, NET::D2, NET::DL, NET::OFF2, false>(th, h2, a);
-    ll += head_loss<T, NET>(a, y, cls, dl, (T*)nullptr);
+    ll += head_loss<T, NET, HARD>(a, y, cls, dl, (T*)nullptr);
     if constexpr (GRAD) {
       T d2[NET::D2], d1[NET::D1], d0[NET::D0];
       dense_bwd<T, NET::D2, NET::DL, NET::OFF2, true>(th, h2, dl, g, d2);
@@ -200,22 +203,27 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
 #pragma unroll
     for (int j = 0; j < NET::P; ++j) g[j] = T(0);
   }
-  auto one_row = [&](int i) {
-    T y = T(0);
-    int cls = 0;
-    if constexpr (NET::LOSS == LOSS_BINARY) y = d.y[i]; else cls = d.cls[i];
-    accumulate_row<T, NET, GRAD>(th, d.x + i * NET::D0, y, cls, ll, g);
-  };
-  int i = sub;
+  // HARD: all labels are exactly 0 / 1 (uniform over the block, found once when the data set is staged), so the row code
+  // has no soft-label branch and is one basic block: with two rows per trip the instruction scheduler interleaves their
+  // dependency chains (the per-row critical path -- three sigmoid layers and a log in sequence -- is latency-bound).
+  auto rows = [&](auto hard_tag) {
+    constexpr bool HARD = decltype(hard_tag)::value;
+    auto one_row = [&](int i) {
+      T y = T(0);
+      int cls = 0;
+      if constexpr (NET::LOSS == LOSS_BINARY) y = d.y[i]; else cls = d.cls[i];
+      accumulate_row<T, NET, GRAD, HARD>(th, d.x + i * NET::D0, y, cls, ll, g);
+    };
+    int i = sub;
 #if EB_ROW_UNROLL >= 2
-  // two independent rows per trip: one basic block, so that the instruction scheduler can interleave their
-  // dependency chains (the per-row critical path -- three sigmoids and a log in sequence -- is latency-bound)
-  for (; i + G < d.n_rows; i += 2 * G) {
-    one_row(i);
-    one_row(i + G);
-  }
+    for (; i + G < d.n_rows; i += 2 * G) {
+      one_row(i);
+      one_row(i + G);
+    }
 #endif
-  for (; i < d.n_rows; i += G) one_row(i);
+    for (; i < d.n_rows; i += G) one_row(i);
+  };
+  if (NET::LOSS != LOSS_BINARY || d.hard_labels) rows(std::true_type{}); else rows(std::false_type{});
 #if defined(__CUDA_ARCH__)
   if constexpr (G > 1) {
     ll = group_allreduce<G>(ll);
@@ -226,13 +234,16 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
   }
 #endif
   // vector Normal prior: sum_j -(theta_j - loc_j)^2 / (2 scale_j^2) - log scale_j - log sqrt(2 pi); bayesian_model.py:46-50
-  T lp = d.lp_const;
+  T qs = T(0);
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) {
     const T dd = th[j] - d.ploc[j];
-    lp = fma_t<T>(-(dd * dd), T(0.5) * d.pivar[j], lp);
-    if constexpr (GRAD) g[j] = fma_t<T>(-dd, d.pivar[j], g[j]);
+    const T w = dd * d.pivar[j];
+    qs = fma_t<T>(dd, w, qs);
+    if constexpr (GRAD) g[j] -= w;
   }
+  const T lp_raw = fma_t<T>(T(-0.5), qs, d.lp_const);
+  T lp = lp_raw;
   if (d.has_temperature) {  // both terms scaled, bayesian_model.py:33-34,48-49
     ll *= d.temperature; lp *= d.temperature;
     if constexpr (GRAD) {

@@ -28,6 +28,8 @@ static DataView<T> make_view(const T* x, const T* y, int N, const T* loc, const 
   T c = T(0);
   for (int j = 0; j < NET::P; ++j) { pivar[j] = T(1) / (scale[j] * scale[j]); c += -log_t<T>(scale[j]) - T(kLogSqrt2Pi); }
   DataView<T> d;
+  d.hard_labels = true;
+  for (int i = 0; i < N; ++i) d.hard_labels = d.hard_labels && (ys[i] == T(0) || ys[i] == T(1));
   d.x = x; d.y = ys.data(); d.cls = cls.data(); d.n_rows = N; d.ploc = loc; d.pivar = pivar.data(); d.lp_const = c;
   d.temperature = (T)temp; d.has_temperature = has_t != 0;
   return d;
@@ -184,6 +186,8 @@ static DataView<T> gen_view(const GenNet& n, const T* x, const T* y, int N, cons
   T c = T(0);
   for (int j = 0; j < n.P; ++j) { pivar[j] = T(1) / (scale[j] * scale[j]); c += -log_t<T>(scale[j]) - T(kLogSqrt2Pi); }
   DataView<T> d;
+  d.hard_labels = true;
+  for (int i = 0; i < N; ++i) d.hard_labels = d.hard_labels && (ys[i] == T(0) || ys[i] == T(1));
   d.x = x; d.y = ys.data(); d.cls = cls.data(); d.n_rows = N; d.ploc = loc; d.pivar = pivar.data(); d.lp_const = c;
   d.temperature = (T)temp; d.has_temperature = has_t != 0;
   return d;
