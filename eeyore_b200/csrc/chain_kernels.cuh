@@ -79,8 +79,9 @@ template <typename T, class NET, int KIND> constexpr bool grad_in_smem() {
   return false;
 #endif
 }
+// two resident CTAs (255 registers) since the fp64 fast path interleaves two rows per lane (mlp_static.cuh: EB_ROW_BATCH)
 #ifndef EB_MINB_F64_SMALL
-#define EB_MINB_F64_SMALL 3
+#define EB_MINB_F64_SMALL 2
 #endif
 #ifndef EB_MINB_F64_LARGE
 #define EB_MINB_F64_LARGE 2

@@ -135,6 +135,26 @@ EB_HD const double* math_consts() {
 #endif
 }
 
+// 2^k 2^(j/2048) for n = 2048 k + j: the table entry with k added to its exponent field.
+EB_HD double exp2_tab_scaled(int n) {
+#if defined(__CUDA_ARCH__)
+  // five integer instructions spelled out (the compiler's own sequence for the same expression is seven; the dispatch
+  // port is as scarce as the FP64 pipe here)
+  int lo, hi;
+  asm("{\n\t.reg .u32 a;\n\t.reg .s32 k;\n\t"
+      "and.b32 a, %2, 2047;\n\t"
+      "mad.lo.u32 a, a, 8, %3;\n\t"
+      "ld.shared.v2.b32 {%0, %1}, [a];\n\t"
+      "shr.s32 k, %2, 11;\n\t"
+      "mad.lo.s32 %1, k, 1048576, %1;\n\t}"
+      : "=r"(lo), "=r"(hi)
+      : "r"(n), "r"((unsigned)__cvta_generic_to_shared(exp_table_smem())));
+  return __hiloint2double(hi, lo);
+#else
+  return dbl_add_exponent(exp2_tab(n & (kExpTabN - 1)), n >> 11);
+#endif
+}
+
 // The pieces of exp(a), |a| <= 708: a 2048/ln2 = n + r with |r| <= 1/2 (one exact FMA), n = 2048 k + j;
 // exp(a) = [2^k 2^(j/2048)] * q,  q = 2^(r/2048) = 1 + r (a1 + r (a2 + r a3))  (truncation 3.4e-17).  5 FP64 instructions.
 EB_HD void exp_pieces(double a, double& tjs, double& q) {
@@ -147,7 +167,7 @@ EB_HD void exp_pieces(double a, double& tjs, double& q) {
   double p = fma(r, c[3], c[2]);
   p = fma(p, r, c[1]);
   q = fma(r, p, 1.0);
-  tjs = dbl_add_exponent(exp2_tab(n & (kExpTabN - 1)), n >> 11);
+  tjs = exp2_tab_scaled(n);
 }
 EB_HD double exp_core(double a) {
   double tjs, q;
@@ -224,10 +244,81 @@ template <> EB_HD double sigmoid_t<double>(double g) {
   return big ? sat : s;
 }
 
+// The same without the saturation select: valid for |g| <= 708 and not NaN.  Callers (accumulate_row's fast path) track the
+// largest high word of the arguments and redo the row with sigmoid_t when the bound is violated.
+EB_HD double sigmoid_fast(double g) {
+  double tjs, q;
+  exp_pieces(-g, tjs, q);
+  return rcp_ge1(fma(tjs, q, 1.0));
+}
+// high word of |g|: as an unsigned number it orders finite values, infinity and NaN like the magnitude
+EB_HD int abs_hi(double g) { return dbl_hi(g) & 0x7fffffff; }
+constexpr int kAbsHi708 = 0x40862000;   // high word of 708.0
+constexpr int kAbsHi36 = 0x40420000;    // high word of 36.0: below, 0 < sigmoid < 1 strictly (1 + e^-36 > 1 in fp64)
+
+// M independent fast sigmoids written stage by stage, so that the instruction scheduler sees M interleaved dependency
+// chains (each alone is latency-bound: ten dependent FP64 operations, a table fetch and a MUFU).  Same arithmetic as
+// sigmoid_fast; `mx` collects the largest |g| high word.
+template <int M> EB_HD void sigmoid_fast_vec(const double (&g)[M], double (&out)[M], int& mx) {
+  const double* c = math_consts();
+  const double magic = 6755399441055744.0;
+  double t[M], r[M], p[M], tj[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) t[i] = fma(-g[i], c[0], magic);
+#pragma unroll
+  for (int i = 0; i < M; ++i) tj[i] = exp2_tab_scaled(dbl_lo(t[i]));
+#pragma unroll
+  for (int i = 0; i < M; ++i) r[i] = fma(-g[i], c[0], -(t[i] - magic));
+#pragma unroll
+  for (int i = 0; i < M; ++i) p[i] = fma(r[i], c[3], c[2]);
+#pragma unroll
+  for (int i = 0; i < M; ++i) p[i] = fma(p[i], r[i], c[1]);
+#pragma unroll
+  for (int i = 0; i < M; ++i) p[i] = fma(r[i], p[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < M; ++i) p[i] = fma(tj[i], p[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < M; ++i) out[i] = rcp_ge1(p[i]);
+#pragma unroll
+  for (int i = 0; i < M; ++i) { const int ah = abs_hi(g[i]); mx = ah > mx ? ah : mx; }
+}
+
 // N sigmoids evaluated stage by stage ("vertically"): the N dependency chains are written interleaved so that the
 // instruction scheduler keeps all of them in flight (a hidden layer's units are independent; each chain alone is
 // latency-bound: ~14 dependent FP64 operations plus a table lookup and a MUFU).
 template <typename T, int N> EB_HD void sigmoid_vec(const T (&g)[N], T (&out)[N]) {
+#if defined(EB_SIGMOID_VEC)
+  if constexpr (sizeof(T) == 8) {
+    // the same arithmetic as sigmoid_t<double>, written stage by stage; table entries are fetched as soon as n is known
+    const double* c = math_consts();
+    const double magic = 6755399441055744.0;
+    double t[N], r[N], p[N], tj[N];
+    int n[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fma(-g[i], c[0], magic);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { n[i] = dbl_lo(t[i]); tj[i] = exp2_tab(n[i] & (kExpTabN - 1)); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = fma(-g[i], c[0], -(t[i] - magic));
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(r[i], c[3], c[2]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c[1]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(r[i], p[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(dbl_add_exponent(tj[i], n[i] >> 11), p[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = rcp_ge1(p[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int hi = dbl_hi(g[i]);
+      const bool big = (int)((unsigned)(hi & 0x7fffffff) + 0xfffffu) > (0x40862000 + 0xfffff);
+      out[i] = big ? dbl_from(hi < 0 ? 0 : 0x3ff00000, 0) : p[i];
+    }
+    return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < N; ++i) out[i] = sigmoid_t<T>(g[i]);
 }
