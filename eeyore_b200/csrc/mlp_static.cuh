@@ -115,6 +115,8 @@ EB_HD void dense_bwd(const TH& th, const T (&in)[DIN], const T (&dout)[DOUT], GV
   }
 }
 
+template <typename T> EB_HD T rcp_sum_t(T s) { return T(1) / s; }
+template <> EB_HD double rcp_sum_t<double>(double s) { return rcp_ge1(s); }
 template <typename T> EB_HD T head_log(T q) { return log_t<T>(q); }
 // fp64: q is a probability in [0, 1]; 0 is patched by the caller, tiny values are normal numbers (>= 1e-304)
 template <> EB_HD double head_log<double>(double q) { return log_pos_normal(q > 0.0 ? q : 1.0); }
@@ -157,8 +159,8 @@ EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) 
     T s = T(0);
 #pragma unroll
     for (int k = 0; k < K; ++k) { e[k] = exp_nonpos_t<T>(a[k] - m); s += e[k]; }
-    const T inv = T(1) / s;
-    const T ls = head_log<T>(s);  // s >= 1
+    const T inv = rcp_sum_t<T>(s);   // s >= 1 (the maximal logit contributes e^0)
+    const T ls = head_log<T>(s);
     T term = T(0);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -393,14 +395,15 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
   // vector Normal prior: sum_j -(theta_j - loc_j)^2 / (2 scale_j^2) - log scale_j - log sqrt(2 pi); bayesian_model.py:46-50
   // (initialising the accumulators with the prior gradient instead would save an add per parameter, but keeps all of them
   // live through the peeled first row: measured as spills)
-  T qs = T(0);
+  T qp[4] = {T(0), T(0), T(0), T(0)};   // four partial sums: one chain of P dependent FMAs would be pure latency
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) {
     const T dd = th[j] - d.ploc[j];
     const T w = dd * d.pivar[j];
-    qs = fma_t<T>(dd, w, qs);
+    qp[j & 3] = fma_t<T>(dd, w, qp[j & 3]);
     if constexpr (GRAD) g[j] -= w;
   }
+  const T qs = (qp[0] + qp[1]) + (qp[2] + qp[3]);
   const T lp_raw = fma_t<T>(T(-0.5), qs, d.lp_const);
   T lp = lp_raw;
   if (d.has_temperature) {  // both terms scaled, bayesian_model.py:33-34,48-49

@@ -89,9 +89,9 @@ EB_HD bool mala_draw(const DataView<T>& d, int sub, T half_step, T sd, const Cur
   return log_t<T>(u) < log_rate;                                                          // :66
 }
 
-// hmc.py:126-170 with leapfrog :100-124.  z is the momentum draw p0.  The momentum lives in shared memory (element j at
-// p[j * ps], one copy per chain, lane `sub` owns entries j % G == sub) so that only theta' and the gradient accumulators
-// occupy registers during an evaluation.
+// hmc.py:126-170 with leapfrog :100-124.  z is the momentum draw p0.  The momentum vector `p` is a StridedVec over shared
+// memory (one copy per chain, lane `sub` owns entries j % G == sub), so that only theta' and the gradient accumulators
+// occupy registers during an evaluation -- or a RegVec where one lane owns the chain and the register budget allows.
 // The first gradient of the trajectory is the cached current gradient (the reference recomputes it at the same point
 // with the same data, hmc.py:104, so the value is identical); num_steps further evaluations follow.
 template <int G> EB_HD void group_sync() {
@@ -100,9 +100,9 @@ template <int G> EB_HD void group_sync() {
 #endif
 }
 
-template <typename T, class NET, int G, class GV, class TV>
+template <typename T, class NET, int G, class PV, class GV, class TV>
 EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_steps, const Cur<T>& cur, T lt_cur,
-                    const T (&z)[NET::P], T* p, int ps, T u, TV& thp, GV& gp, T& ltp, T* rate_out = nullptr) {
+                    const T (&z)[NET::P], PV& p, T u, TV& thp, GV& gp, T& ltp, T* rate_out = nullptr) {
   T kin = T(0);
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) kin = fma_t<T>(z[j], z[j], kin);
@@ -110,25 +110,25 @@ EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_st
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) {
     thp[j] = cur.th[j * cur.stride];
-    if (j % G == sub) p[j * ps] = fma_t<T>(half_eps, cur.g[j * cur.stride], z[j]);        // :105
+    if (j % G == sub) p[j] = fma_t<T>(half_eps, cur.g[j * cur.stride], z[j]);        // :105
   }
   group_sync<G>();
   ltp = lt_cur;
   for (int s = 0; s < num_steps; ++s) {
 #pragma unroll
-    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j * ps], thp[j]);           // :110, :117
+    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);           // :110, :117
     group_sync<G>();
     eval_target<T, NET, G, true>(d, sub, thp, ltp, gp);                                   // :113, :118
     const T w = (s == num_steps - 1) ? half_eps : eps;                                    // :114, :119
 #pragma unroll
     for (int j = 0; j < NET::P; ++j)
-      if (j % G == sub) p[j * ps] = fma_t<T>(w, gp[j], p[j * ps]);
+      if (j % G == sub) p[j] = fma_t<T>(w, gp[j], p[j]);
     group_sync<G>();
   }
   // momentum negation (:122) leaves the kinetic energy unchanged
   T kin1 = T(0);
 #pragma unroll
-  for (int j = 0; j < NET::P; ++j) kin1 = fma_t<T>(p[j * ps], p[j * ps], kin1);
+  for (int j = 0; j < NET::P; ++j) kin1 = fma_t<T>(p[j], p[j], kin1);
   const T h_prop = -ltp + T(0.5) * kin1;                                                  // :141
   T rate = exp_t<T>(h_cur - h_prop);
   rate = (rate > T(1)) ? T(1) : rate;                                                     // torch.min keeps NaN, :143-146

@@ -91,7 +91,7 @@ template <typename T, class NET> static void run_all(int kind, const eeyore_b200
       else if (kind == 1) acc = mala_draw<T, NET, 1>(d, 0, half_step, sd, cur, lt_cur, z, u, thp, gp, ltp);
       else {
         T rate;
-        acc = hmc_draw<T, NET, 1>(d, 0, cstep, chalf, num_steps, cur, lt_cur, z, mom, 1, u, thp, gp, ltp, &rate);
+        { StridedVec<T> pm{mom, 1}; acc = hmc_draw<T, NET, 1>(d, 0, cstep, chalf, num_steps, cur, lt_cur, z, pm, u, thp, gp, ltp, &rate); }
         if (tuned && t < p.tuner_burnin) {
           da_tune(tn, (double)rate, p.tuner_iter0 + t + 1, t != p.tuner_burnin - 1, tn_barh, tn_logbare, tn_step, num_steps);
           cstep = (T)tn_step; chalf = (T)(0.5 * tn_step);
