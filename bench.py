@@ -646,7 +646,7 @@ def run_datapar(args):
             "gpu_launches": args.steps * iters * (2 + (4 if sampler.exchange == "nccl" else 2) * L),
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / tensor_peak, "traffic": _cfg5_traffic(hi - lo), "peak_source": peak_src,
                          "kernel": "dp_eval_tc_kernel (tcgen05 fp16 MMA on exact two-piece splits, fp32 accumulate in TMEM, two tiles in flight)",
                          "avg_launch_ms": kernel_ms, "algorithmic_flops_per_row": 29056,
                          "f16_mma_tflops_issued": tiles * mma_flops_tile / (kernel_ms * 1e-3) / 1e12,
@@ -665,6 +665,16 @@ def run_datapar(args):
     e2e_sampler.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cfg5_traffic(rows_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of dp_eval_tc_kernel from the committed ncu --set full capture; only when
+    this launch processes the row count the capture was taken at (one GPU, 8,388,608 rows), else null."""
+    tfile = ROOT / "profiles" / "r01_traffic_cfg5.json"
+    if not tfile.exists():
+        return None
+    rec = json.loads(tfile.read_text())
+    return rec["dram_bytes_total"] if rec.get("rows_per_launch") == rows_per_launch else None
 
 
 def main():

@@ -93,6 +93,15 @@ template <typename T, class NET, int KIND> constexpr int min_blocks() {
   return NET::P <= 20 ? EB_MINB_F64_SMALL : (NET::P <= 32 ? EB_MINB_F64_LARGE : 2);
 }
 
+// Threads per CTA of the sampler kernels.  fp64 / small P runs two CTAs per SM for the register budget of the two-row fast
+// path; EB_SAMPLER_BLOCK_F64_SMALL > 128 puts more warps into those two CTAs (budget = 65536 / (2 * threads)).
+#ifndef EB_SAMPLER_BLOCK_F64_SMALL
+#define EB_SAMPLER_BLOCK_F64_SMALL 128
+#endif
+template <typename T, class NET, int KIND> constexpr int sampler_block() {
+  return (sizeof(T) == 8 && NET::P <= 20 && !grad_in_smem<T, NET, KIND>()) ? EB_SAMPLER_BLOCK_F64_SMALL : kBlock;
+}
+
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------------------------
 EB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -241,9 +250,10 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ChainArgs<T> a, T
 // (HMC) the momentum.  Global memory (coalesced in the chain-minor layout): the chain's current sample / gradient, read
 // once per iteration and written on accept.
 template <typename T, class NET, int G, int KIND>
-__global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_kernel(const ChainArgs<T> a) {
+__global__ void __launch_bounds__(sampler_block<T, NET, KIND>(), min_blocks<T, NET, KIND>()) sampler_kernel(const ChainArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int CPB = kBlock / G;
+  constexpr int KB = sampler_block<T, NET, KIND>();
+  constexpr int CPB = KB / G;
   constexpr int P = NET::P;
   constexpr bool IS_HMC = KIND == KIND_HMC || KIND == KIND_HMC_TUNED;
   constexpr bool GSM = grad_in_smem<T, NET, KIND>();
@@ -382,7 +392,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks<T, NET, KIND>()) sampler_ke
 
 // ---- launchers ----------------------------------------------------------------------------------------------------
 template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
-  constexpr int CPB = kBlock / G;
+  constexpr int KB = sampler_block<T, NET, KIND>();
+  constexpr int CPB = KB / G;
 #ifdef EB_THETA_IN_SMEM
   const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC || KIND == KIND_HMC_TUNED, true);
 #else
@@ -392,7 +403,7 @@ template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(c
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
   if (e != cudaSuccess) return e;
   const long blocks = (a.n_chains + CPB - 1) / CPB;
-  kern<<<(unsigned)blocks, kBlock, lay.total, st>>>(a);
+  kern<<<(unsigned)blocks, KB, lay.total, st>>>(a);
   return cudaGetLastError();
 }
 
