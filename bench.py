@@ -361,18 +361,27 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # Workloads whose per-launch working set fits the 126 MB L2 (configs 2 and 3) get the L2 flushed between timed steps (a
+    # 160 MB buffer is overwritten; the flush sits outside the per-step event pairs); config 4 streams 789 MB per launch.
+    esz0 = theta_host.element_size()
+    ws_bytes = C * (2 * (2 * P + 1) * esz0 + ((iters + thin - 1) // thin) * (P * esz0 + esz0 + 1) + 4)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev) if ws_bytes <= 126e6 else None
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     clocks.mark_begin()
-    ev[0].record()
     for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+        ev0[k].record()
         step_resident()
-        ev[k + 1].record()
+        ev1[k].record()
     barrier()
     clocks.mark_end()
     clocks.stop()
-    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
+    per_launch_ms = [ev0[k].elapsed_time(ev1[k]) for k in range(args.steps)]
+    t_local = (sum(per_launch_ms) if flush is not None else ev0[0].elapsed_time(ev1[-1])) * 1e-3
+    t_res = max_over_ranks(t_local)
     evals_step = C * iters * (1 if kind == "smmala" else L)
     value = world * evals_step * args.steps / t_res
     acc_rate = sampler.get_chain().acceptance().mean().item()
@@ -467,7 +476,10 @@ def run_ours(args):
                    "step_size": w["step"], "thin": thin, "evals_counted_per_iteration": L,
                    "evals_reference_executes_per_iteration": L + 1, "rng": "philox4x32-10 on device",
                    "acceptance_rate": acc_rate,
-                   "l2": "chain state + saved samples per launch (%.0f MB) exceed the 126 MB L2" % (hbm_bytes / 1e6)},
+                   "l2": ("chain state + saved samples per launch (%.0f MB) exceed the 126 MB L2" % (hbm_bytes / 1e6))
+                         if hbm_bytes > 126e6 else
+                         ("chain state + saved samples per launch are %.0f MB (below the 126 MB L2): 160 MB of device memory "
+                          "are overwritten between timed steps to flush it" % (hbm_bytes / 1e6))},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * t_e2e / args.steps, "chain_batches": nb,
                 "note": "public sampler API on %d chain batches / streams: each batch copies its theta in from pinned host "
