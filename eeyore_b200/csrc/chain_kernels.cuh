@@ -307,6 +307,14 @@ __global__ void __launch_bounds__(sampler_block<T, NET, KIND>(), min_blocks<T, N
     typename std::conditional<GSM, StridedVec<T>, RegVec<T, P>>::type gp;
     if constexpr (GSM) { gp.base = reinterpret_cast<T*>(smem + lay.off_grad) + threadIdx.x; gp.stride = kBlock; }
     T u, ltp;
+#ifndef EB_NO_PREFETCH_STATE   // measured on B200, config 4: 15.23e9 -> 15.40e9 evals/s
+    // issue the loads of the chain's current state before the noise is generated (hundreds of cycles of arithmetic that do
+    // not depend on them); hmc_draw reads the same addresses again and the compiler reuses the registers
+    if constexpr (IS_HMC && !TSM && !GSM) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) { thp[j] = cur.th[j * cur.stride]; gp[j] = cur.g[j * cur.stride]; }
+    }
+#endif
     if (a.rng_mode == 0) {
       philox_normals<T, P>(z, a.key, gchain, a.iter0 + (uint32_t)t);
       u = philox_uniform<T>(a.key, gchain, a.iter0 + (uint32_t)t);
