@@ -219,6 +219,12 @@ EB_HD double log_pos_normal(double x) {
   return base + fma(s, q, r);
 }
 
+// The far negative tail of the head's sigmoid, evaluated like the reference (libm exp, IEEE division): for a below -708 the
+// probability is subnormal (the fast reciprocal flushes it to 0) and exactly 0 from -709.78 on, where exp(-a) overflows.
+// Only the general (rare) path of the head calls this; its log must then accept subnormal arguments as well.
+EB_HD double sigmoid_ref_tail(double a) { return 1.0 / (1.0 + exp(-a)); }
+EB_HD double log_prob_any(double q) { return dbl_hi(q) < 0x00100000 ? log(q) : log_pos_normal(q); }   // q > 0
+
 // Exact tests on values that are known to be non-negative or NaN (probabilities): fp64 versions are integer compares
 // on the two words -- a DSETP would occupy the FP64 pipe like a DFMA.
 template <typename T> EB_HD bool prob_is_zero(T p) { return p == T(0); }

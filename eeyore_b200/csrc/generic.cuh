@@ -64,12 +64,12 @@ EB_HD void gen_accumulate_row(const GenNet& n, const TH& th, const T* xr, T y, i
   if (n.loss == LOSS_BINARY) {
     const T a0 = w.h[ho];
     T p = sigmoid_t<T>(a0);
-    if (sizeof(T) == 8 && a0 < T(-709.782712893384)) p = T(0);
+    if constexpr (sizeof(T) == 8) { if (a0 < T(-700)) p = sigmoid_ref_tail(a0); }   // as in mlp_static.cuh: head_loss
     T term;
     if (y == T(1) || y == T(0)) {
       const T q = (y == T(1)) ? p : (T(1) - p);
       const T other = (y == T(1)) ? (T(1) - p) : p;
-      T lq = head_log<T>(q);
+      T lq = head_log_nz<T>(q, q == T(0));
       lq = (q == T(0)) ? -T(INFINITY) : lq;
       term = (other == T(0) || q != q) ? qnan<T>() : lq;
     } else {

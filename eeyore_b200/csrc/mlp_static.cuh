@@ -122,15 +122,16 @@ template <typename T> EB_HD T head_log(T q) { return log_t<T>(q); }
 template <> EB_HD double head_log<double>(double q) { return log_pos_normal(q > 0.0 ? q : 1.0); }
 // the same with the zero test supplied by the caller
 template <typename T> EB_HD T head_log_nz(T q, bool q_zero) { return head_log<T>(q); }
-template <> EB_HD double head_log_nz<double>(double q, bool q_zero) { return log_pos_normal(q_zero ? 1.0 : q); }
+template <> EB_HD double head_log_nz<double>(double q, bool q_zero) { return log_prob_any(q_zero ? 1.0 : q); }
 
 // Head: returns this row's log-likelihood term and the seed d ll / d a_L.
 template <typename T, class NET, bool HARD = false>
 EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) {
   if constexpr (NET::LOSS == LOSS_BINARY) {
     T p = sigmoid_t<T>(a[0]);
-    // (the reference's p is exactly 0 once exp(-a) overflows, a < -709.78 in fp64; the fp64 fast sigmoid saturates to 0
-    // from -708 on)
+    // the reference's p is subnormal below a = -708 and exactly 0 once exp(-a) overflows (a < -709.78); the fp64 fast
+    // sigmoid saturates to 0 from -708 on, so this (general, rarely executed) path evaluates the tail like the reference
+    if constexpr (sizeof(T) == 8) { if (a[0] < T(-700)) p = sigmoid_ref_tail(a[0]); }
     if (p_out) *p_out = p;
     T term;
     // loss.py:2 evaluates log(p)*y + log(1-p)*(1-y); for y in {0,1} one product is 0 * log(.), which is NaN

@@ -287,3 +287,27 @@ def test_posterior_predictive_and_logistic_regression():
     assert np.allclose(npy(lt), ll_ref + lp_ref, rtol=1e-11)
     g_ref = np.concatenate([((y - s).T @ x), (y - s).sum(0)[:, None]], axis=1) - thl
     assert rel_err(npy(g), g_ref) < 1e-11
+
+
+def test_fast_and_general_forward_paths_agree_with_the_oracle_on_device():
+    """GPU twin of tests/test_hostsim.py::test_fast_and_general_forward_paths_agree_with_the_oracle: chains of one warp
+    straddle the bounds of the select-free fp64 fast path (|head pre-activation| = 36 and 708, hidden 708), so lanes of a
+    warp diverge between the fast and the general row code; values, gradients and the NaN / -inf pattern must match the
+    oracle on both sides (evaluation kernel, one lane and four lanes per chain)."""
+    from test_hostsim import _boundary_thetas
+    th = _boundary_thetas()
+    m = make_model("2321", "f64", 3.0 ** 0.5)
+    ds = dataset("2321", "f64")
+    spec = spec_of("2321")
+    loc, scale = np.zeros(20), np.full(20, 3.0 ** 0.5)
+    with np.errstate(all="ignore"):
+        lt_ref, g_ref = oracle.log_target_grad(spec, th, npy(ds.x), npy(ds.y), loc, scale)
+    for lanes in (1, 4):
+        lt, g = m.upto_grad_log_target_batch(torch.from_numpy(th), ds.x, ds.y, lanes=lanes)
+        lt, g = npy(lt), npy(g)
+        assert np.array_equal(np.isnan(lt), np.isnan(lt_ref)) and np.array_equal(np.isinf(lt), np.isinf(lt_ref))
+        fin = np.isfinite(lt_ref)
+        assert np.allclose(lt[fin], lt_ref[fin], rtol=1e-10, atol=0)
+        for c in np.nonzero(fin)[0]:
+            assert rel_err(g[c], g_ref[c]) < 1e-10, (lanes, c)
+        assert np.isnan(g[np.isnan(lt_ref)]).all()

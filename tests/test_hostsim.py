@@ -287,3 +287,44 @@ def test_runtime_shape_samplers_match_oracle(sim, kind):
     assert ref["accepted"].mean() > 0
     assert np.array_equal(out["acc"], ref["accepted"])
     assert rel_err(out["sample"], ref["sample"]) < 1e-10
+
+
+def _boundary_thetas():
+    """2-3-2-1 parameter vectors whose head pre-activation sweeps across the bounds of the fp64 fast path (|a| = 36: p may
+    round to exactly 1; |a| = 708: the exponent arithmetic of the fast exp would wrap) and whose hidden pre-activations
+    cross 708, next to ordinary ones -- so that within one batch of chains (and, on the GPU, within one warp) some rows take
+    the fast path and some the general one."""
+    rng = np.random.default_rng(5)
+    th = rng.normal(size=(96, 20)) * 0.7
+    heads = [0.0, 20.0, 35.9, 36.1, 36.8, 40.0, 700.0, 709.0, 720.0, -20.0, -35.9, -36.1, -40.0, -700.0, -707.9, -708.1, -745.0,
+             -800.0, 1e6, -1e6]
+    for k, b in enumerate(heads):
+        th[k, 17:19] = 0.0          # W2 = 0: the head pre-activation is the bias alone
+        th[k, 19] = b
+    for k, b in enumerate([30.0, 700.0, 707.0, 709.0, 5000.0, -700.0, -709.0, -5000.0]):
+        th[32 + k, 6] = b           # b0[0]: a hidden unit of the first layer saturates
+        th[40 + k, 15] = b          # b1[0]: one of the second layer
+    return th
+
+
+def test_fast_and_general_forward_paths_agree_with_the_oracle(sim):
+    """The fp64 row code has a select-free fast path and a general path that reproduces the reference's saturation / NaN
+    semantics (mlp_static.cuh: accumulate_row, accumulate_rows_fast).  Values, gradients and the NaN pattern must match the
+    oracle on both sides of every switch point; rows are also permuted so that the two-row batches pair differently."""
+    mg = load("model_goldens")
+    x, y = data_of("2321", np.float64, mg)
+    th = _boundary_thetas()
+    loc, scale = np.zeros(20), np.full(20, 3.0 ** 0.5)
+    spec = spec_of("2321")
+    with np.errstate(all="ignore"):
+        lt_ref, g_ref = oracle.log_target_grad(spec, th, x, y, loc, scale)
+    for perm in ([0, 1, 2, 3], [3, 1, 0, 2], [2, 3, 1, 0]):
+        lt, g = sim_eval(sim, "2321", "f64", th, x[perm], y[perm], loc, scale)
+        assert np.array_equal(np.isnan(lt), np.isnan(lt_ref))
+        assert np.array_equal(np.isinf(lt), np.isinf(lt_ref))
+        fin = np.isfinite(lt_ref)
+        assert fin.sum() > 60 and (~fin).sum() > 8
+        assert np.allclose(lt[fin], lt_ref[fin], rtol=1e-10, atol=0)
+        for c in np.nonzero(fin)[0]:
+            assert rel_err(g[c], g_ref[c]) < 1e-10, c
+        assert np.isnan(g[np.isnan(lt_ref)]).all()
