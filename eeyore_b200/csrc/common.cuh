@@ -122,10 +122,15 @@ EB_HD double log_nlog_tab(int i) {
 // materialised by UMOV pairs at every use): 2048/ln2; a1, a2, a3 of 2^(r/2048) = 1 + a1 r + a2 r^2 + a3 r^3; ln2; 1/3
 #define EB_MATH_CONSTS                                                                                     \
   {2954.639443740597, 0.0003384507717577858, 5.727446245172041e-08, 6.461528672932366e-12, 0.6931471805599453, \
-   0.3333333333333333}
-static const double kMathHost[6] = EB_MATH_CONSTS;
+   0.3333333333333333,                                                                                     \
+   /* [6..13] sin(pi r) = r (S0 + S1 z + ... + S7 z^7), [14..21] cos(pi r) = 1 + z (C1 + ... + C8 z^7), z = r^2 */ \
+   3.141592653589793, -5.16771278004997, 2.5501640398773455, -0.5992645293207921, 0.08214588661112823,     \
+   -0.0073704309457143504, 0.00046630280576761255, -2.1915353447830217e-05,                                \
+   -4.934802200544679, 4.0587121264167685, -1.3352627688545895, 0.2353306303588932, -0.02580689139001406,  \
+   0.0019295743094039231, -0.0001046381049248457, 4.303069587032947e-06}
+static const double kMathHost[22] = EB_MATH_CONSTS;
 #if defined(__CUDACC__)
-static __constant__ double kMathDev[6] = EB_MATH_CONSTS;
+static __constant__ double kMathDev[22] = EB_MATH_CONSTS;
 #endif
 EB_HD const double* math_consts() {
 #if defined(__CUDA_ARCH__)
@@ -329,6 +334,50 @@ template <typename T, int N> EB_HD void sigmoid_vec(const T (&g)[N], T (&out)[N]
   for (int i = 0; i < N; ++i) out[i] = sigmoid_t<T>(g[i]);
 }
 
+// sqrt(x) for positive, normal, finite x well inside the exponent range (Box-Muller radii: 1e-16 < x < 1500): reciprocal
+// square root seed (MUFU.RSQ64H), two coupled Newton steps on (g ~ sqrt x, h ~ 1 / (2 sqrt x)) and a final residual
+// correction; branch-free, 11 FP64 instructions, within 1 ulp.  (CUDA's sqrt() adds a range check and an out-of-line slow
+// path, which splits the basic block between the ten Box-Muller pairs of an iteration.)
+EB_HD double sqrt_pos(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  const double y = 1.0 / sqrt(x);
+#endif
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  return fma(fma(-g, g, x), h, g);
+}
+
+// sin(2 pi u), cos(2 pi u) for u in [0, 1): q = rint(4 u), r = 2 u - q / 2 in [-1/4, 1/4] (exact), Taylor polynomials of
+// sin(pi r) / cos(pi r) in r^2 (truncation 5e-17 / 2e-18), quadrant fix-up by integer sign flips.  Branch-free.
+EB_HD void sincos2pi_f64(double u, double* sn, double* cs) {
+  const double* c = math_consts();
+  const double magic = 6755399441055744.0;
+  const double t = fma(u, 4.0, magic);
+  const int iq = dbl_lo(t);
+  const double r = fma(t - magic, -0.5, u + u);
+  const double z = r * r;
+  double ps = fma(z, c[13], c[12]);
+  double pc = fma(z, c[21], c[20]);
+  ps = fma(ps, z, c[11]); pc = fma(pc, z, c[19]);
+  ps = fma(ps, z, c[10]); pc = fma(pc, z, c[18]);
+  ps = fma(ps, z, c[9]);  pc = fma(pc, z, c[17]);
+  ps = fma(ps, z, c[8]);  pc = fma(pc, z, c[16]);
+  ps = fma(ps, z, c[7]);  pc = fma(pc, z, c[15]);
+  ps = fma(ps, z, c[6]);  pc = fma(pc, z, c[14]);
+  const double S = ps * r, C = fma(pc, z, 1.0);
+  // quadrant iq mod 4: 0 (S, C), 1 (C, -S), 2 (-S, -C), 3 (-C, S)
+  const bool swap = (iq & 1) != 0;
+  const double a = swap ? C : S, b = swap ? S : C;
+  *sn = dbl_from(dbl_hi(a) ^ ((iq & 2) << 30), dbl_lo(a));
+  *cs = dbl_from(dbl_hi(b) ^ (((iq + 1) & 2) << 30), dbl_lo(b));
+}
+
 // cos/sin(2 pi u)
 template <typename T> EB_HD void sincos2pi(T u, T* s, T* c);
 template <> EB_HD void sincos2pi<float>(float u, float* s, float* c) {
@@ -338,13 +387,7 @@ template <> EB_HD void sincos2pi<float>(float u, float* s, float* c) {
   *s = sinf(6.283185307179586f * u); *c = cosf(6.283185307179586f * u);
 #endif
 }
-template <> EB_HD void sincos2pi<double>(double u, double* s, double* c) {
-#if defined(__CUDA_ARCH__)
-  sincospi(2.0 * u, s, c);
-#else
-  *s = sin(6.283185307179586 * u); *c = cos(6.283185307179586 * u);
-#endif
-}
+template <> EB_HD void sincos2pi<double>(double u, double* s, double* c) { sincos2pi_f64(u, s, c); }
 
 #if defined(__CUDACC__)
 // xor-butterfly all-reduce over the G lanes of a chain group (G a power of two <= 32).
