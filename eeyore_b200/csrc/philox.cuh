@@ -50,9 +50,14 @@ template <> struct Uni<float> {
 template <typename T> EB_HD T log_unit_t(T u) { return log_t<T>(u); }
 template <> EB_HD double log_unit_t<double>(double u) { return log_pos_normal(u); }
 
-// radius of the pair: -2 log u1 lies in (1e-16, 75) for the 53-bit (24-bit) uniforms of Uni<>
+// radius of the pair: -2 log u1 lies in [0, 75) for the 53-bit (24-bit) uniforms of Uni<>
 template <typename T> EB_HD T radius_t(T u1) { return sqrt_t<T>(T(-2) * log_unit_t<T>(u1)); }
-template <> EB_HD double radius_t<double>(double u1) { return sqrt_pos(-2.0 * log_pos_normal(u1)); }
+template <> EB_HD double radius_t<double>(double u1) {
+  // Uni<double>::from rounds its largest value (2^53 - 1/2) 2^-53 to exactly 1: log = 0, radius 0 (sqrt_pos itself needs x > 0)
+  const double x = -2.0 * log_pos_normal(u1);
+  const double r = sqrt_pos(x);
+  return (((dbl_hi(x) & 0x7fffffff) | dbl_lo(x)) == 0) ? 0.0 : r;
+}
 
 template <typename T> EB_HD void box_muller(T u1, T u2, T* z0, T* z1) {
   T r = radius_t<T>(u1);
