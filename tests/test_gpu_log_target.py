@@ -311,3 +311,23 @@ def test_fast_and_general_forward_paths_agree_with_the_oracle_on_device():
         for c in np.nonzero(fin)[0]:
             assert rel_err(g[c], g_ref[c]) < 1e-10, (lanes, c)
         assert np.isnan(g[np.isnan(lt_ref)]).all()
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_soft_labels_on_device(tag):
+    """GPU twin of tests/test_hostsim.py::test_soft_labels_take_the_general_path (targets in (0, 1), stats/loss.py:2), plus a
+    data set whose only soft label sits in the last row, so that the CTA-wide hard-label flag has to see every row."""
+    from test_hostsim import _soft_label_case
+    x, y, th = _soft_label_case()
+    dt, tdt = NP_DTYPES[tag], T_DTYPES[tag]
+    m = make_model("2321", tag, 2.0)
+    loc, scale = np.zeros(20), np.full(20, 2.0)
+    tol = 1e-10 if tag == "f64" else 2e-5
+    for yy in (y, np.array([[0.0], [1.0], [1.0], [0.0], [1.0], [0.0], [0.25]])):
+        lt_ref, g_ref = oracle.log_target_grad(spec_of("2321"), th, x, yy, loc, scale)
+        for lanes in (1, 4, 32):
+            lt, g = m.upto_grad_log_target_batch(torch.from_numpy(th.astype(dt)), torch.from_numpy(x.astype(dt)),
+                                                 torch.from_numpy(yy.astype(dt)), lanes=lanes)
+            assert np.allclose(npy(lt), lt_ref, rtol=tol, atol=0), lanes
+            for c in range(th.shape[0]):
+                assert rel_err(npy(g)[c], g_ref[c]) < tol, (lanes, c)

@@ -328,3 +328,23 @@ def test_fast_and_general_forward_paths_agree_with_the_oracle(sim):
         for c in np.nonzero(fin)[0]:
             assert rel_err(g[c], g_ref[c]) < 1e-10, c
         assert np.isnan(g[np.isnan(lt_ref)]).all()
+
+
+def _soft_label_case():
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(7, 2))
+    y = np.array([[0.0], [1.0], [0.3], [1.0], [0.75], [0.0], [0.5]])   # stats/loss.py:2 takes any float target
+    th = rng.normal(size=(40, 20)) * 0.9
+    return x, y, th
+
+
+def test_soft_labels_take_the_general_path(sim):
+    """Targets other than 0 / 1 (the reference's naive cross-entropy accepts them): the CTA-wide hard-label flag is off, every
+    row goes through the general code with both logs."""
+    x, y, th = _soft_label_case()
+    loc, scale = np.zeros(20), np.full(20, 2.0)
+    lt_ref, g_ref = oracle.log_target_grad(spec_of("2321"), th, x, y, loc, scale)
+    lt, g = sim_eval(sim, "2321", "f64", th, x, y, loc, scale)
+    assert np.allclose(lt, lt_ref, rtol=1e-10, atol=0)
+    for c in range(th.shape[0]):
+        assert rel_err(g[c], g_ref[c]) < 1e-10
