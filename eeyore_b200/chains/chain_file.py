@@ -52,6 +52,19 @@ class ChainFile(Chain):
             if arr.shape[0]:
                 np.savetxt(f, arr.reshape(arr.shape[0], -1), fmt=fmt[key], delimiter=",")
 
+    def extend_from_device(self, samples=None, target_vals=None, grad_vals=None, accepted=None, fmt=_DEFAULT_FMT):
+        """Append the saved states of one fused sampler launch ([n, P], [n], [n, P], [n] device tensors) to the files --
+        what n consecutive update() calls of the reference's loop (chain_file.py:28-45) would have written."""
+        block = {"sample": samples, "target_val": target_vals, "grad_val": grad_vals,
+                 "accepted": None if accepted is None else [int(a) for a in accepted.tolist()]}
+        missing = [k for k in self.vals if block.get(k) is None]
+        if missing:
+            raise KeyError(f"the native samplers do not record {missing}")
+        if any(f.closed for f in self.vals.values()):
+            self.reset(keys=list(self.vals.keys()))
+        self.write_block(block, fmt=fmt)
+        self.close()
+
     def line_to_val_element(self, line, key, dtype=torch.float64, device="cpu"):
         if key == "accepted":
             return int(line.strip())

@@ -251,12 +251,12 @@ template <typename T, class NET> cudaError_t launch_adaptive(int kind, const Cha
   cudaError_t e;
   if (kind == ADAPT_AM) {
     auto kern = adaptive_kernel<T, NET, ADAPT_AM>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = reserve_smem(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)blocks, kAdWarps * 32, smem, st>>>(a, ad);
   } else {
     auto kern = adaptive_kernel<T, NET, ADAPT_RAM>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = reserve_smem(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)blocks, kAdWarps * 32, smem, st>>>(a, ad);
   }

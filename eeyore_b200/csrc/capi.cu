@@ -18,6 +18,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static int cuda_fail(cudaError_t e, const char* where) {
   return fail(EEYORE_B200_ECUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
+static const char* kTooLarge =
+    "the data set does not fit the chain kernels' shared-memory staging (n_rows * (d0 + 1) values next to the kernel's "
+    "tables; about 190 KB per CTA) or the network is too large for the runtime-shape kernels; the data-parallel path "
+    "(eeyore_b200_dp_*) serves large data sets";
+// Philox counters are 32-bit words (csrc/philox.cuh: block, iteration, chain id, kind): offsets beyond 2^32 would alias streams
+static bool offsets_ok(const eeyore_b200_run_params* p) {
+  const uint64_t lim = 1ull << 32;
+  return p->chain_offset < lim && p->iter_offset < lim && p->chain_offset + (uint64_t)p->n_chains <= lim &&
+         p->iter_offset + (uint64_t)p->n_iters <= lim;
+}
+static bool lanes_ok(int lanes) { return lanes == 0 || lanes == 1 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32; }
 static int use_bulk() {
   static int v = -1;
   if (v < 0) { const char* s = getenv("EEYORE_B200_NO_BULK"); v = (s && s[0] == '1') ? 0 : 1; }
@@ -126,11 +137,12 @@ int eeyore_b200_log_target_grad(eeyore_b200_mlp_t h, int64_t n_chains, const voi
                                 void* out_logprior, int lanes_per_chain, void* stream) {
   if (!h || !theta || !x || !y || !prior_loc || !prior_scale) return fail(EEYORE_B200_EINVAL, "null argument");
   if (n_chains < 1 || n_rows < 1) return fail(EEYORE_B200_EINVAL, "n_chains and n_rows must be positive");
+  if (!lanes_ok(lanes_per_chain)) return fail(EEYORE_B200_EINVAL, "lanes_per_chain must be 0 (auto), 1, 4, 8, 16 or 32");
   EvalCall c{n_chains, theta, x, y, n_rows, prior_loc, prior_scale, has_temperature, temperature,
              out_target, out_grad, out_loglik, out_logprior,
              choose_lanes(n_chains, n_rows, lanes_per_chain), use_bulk(), (cudaStream_t)stream};
   cudaError_t e = h->net ? h->net->eval(c) : generic_eval(h->gen, h->dtype, c, nullptr);
-  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, "network too large for the runtime-shape kernels (per-thread vectors exceed shared memory)");
+  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, kTooLarge);
   if (e != cudaSuccess) return cuda_fail(e, "log_target_grad");
   return EEYORE_B200_OK;
 }
@@ -147,6 +159,7 @@ int eeyore_b200_forward(eeyore_b200_mlp_t h, int64_t n_chains, const void* theta
                (cudaStream_t)stream};
     e = generic_forward_(h, c, out);
   }
+  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, kTooLarge);
   if (e != cudaSuccess) return cuda_fail(e, "forward");
   return EEYORE_B200_OK;
 }
@@ -167,6 +180,9 @@ static int run_common(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p, int 
     return fail(EEYORE_B200_EINVAL, "tape mode needs z_tape and u_tape");
   if (kind == KIND_HMC && !p->tuner_state && p->num_steps < 1) return fail(EEYORE_B200_EINVAL, "num_steps must be >= 1");
   if (!(p->step > 0)) return fail(EEYORE_B200_EINVAL, "step must be positive");
+  if (!lanes_ok(p->lanes_per_chain)) return fail(EEYORE_B200_EINVAL, "lanes_per_chain must be 0 (auto), 1, 4, 8, 16 or 32");
+  if (p->rng_mode == EEYORE_B200_RNG_PHILOX && !offsets_ok(p))
+    return fail(EEYORE_B200_EINVAL, "chain_offset + n_chains and iter_offset + n_iters must stay below 2^32 (32-bit Philox counter words)");
   if (p->n_iters == 0) return EEYORE_B200_OK;
   const int lanes = choose_lanes(p->n_chains, p->n_rows, p->lanes_per_chain);
   if (kind == KIND_HMC && p->tuner_state != nullptr) {
@@ -179,8 +195,8 @@ static int run_common(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p, int 
   } else {
     if (kind == KIND_HMC_TUNED) return fail(EEYORE_B200_EUNSUPPORTED, "HMCDATuner needs a compiled network specialisation");
     e = generic_sampler(h->gen, h->dtype, kind, *p);
-    if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, "network too large for the runtime-shape kernels");
   }
+  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, kTooLarge);
   if (e != cudaSuccess) return cuda_fail(e, name);
   return EEYORE_B200_OK;
 }
@@ -199,8 +215,11 @@ int eeyore_b200_smmala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p)
   if (p->rng_mode == EEYORE_B200_RNG_TAPE && (!p->z_tape || !p->u_tape))
     return fail(EEYORE_B200_EINVAL, "tape mode needs z_tape and u_tape");
   if (!(p->step > 0)) return fail(EEYORE_B200_EINVAL, "step must be positive");
+  if (p->rng_mode == EEYORE_B200_RNG_PHILOX && !offsets_ok(p))
+    return fail(EEYORE_B200_EINVAL, "chain_offset + n_chains and iter_offset + n_iters must stay below 2^32 (32-bit Philox counter words)");
   if (p->n_iters == 0) return EEYORE_B200_OK;
   cudaError_t e = h->net->smmala(*p, use_bulk());
+  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, kTooLarge);
   if (e != cudaSuccess) return cuda_fail(e, "smmala_run");
   return EEYORE_B200_OK;
 }
@@ -215,8 +234,11 @@ static int adaptive_common(eeyore_b200_mlp_t h, const eeyore_b200_run_params* p,
   if (kind == 0 && !p->adapt_cov0) return fail(EEYORE_B200_EINVAL, "AM needs cov0");
   if (p->rng_mode == EEYORE_B200_RNG_TAPE && (!p->z_tape || !p->u_tape))
     return fail(EEYORE_B200_EINVAL, "tape mode needs z_tape and u_tape");
+  if (p->rng_mode == EEYORE_B200_RNG_PHILOX && !offsets_ok(p))
+    return fail(EEYORE_B200_EINVAL, "chain_offset + n_chains and iter_offset + n_iters must stay below 2^32 (32-bit Philox counter words)");
   if (p->n_iters == 0) return EEYORE_B200_OK;
   cudaError_t e = h->net->adaptive(kind, *p, use_bulk());
+  if (e == cudaErrorInvalidConfiguration) return fail(EEYORE_B200_EUNSUPPORTED, kTooLarge);
   if (e != cudaSuccess) return cuda_fail(e, name);
   return EEYORE_B200_OK;
 }

@@ -399,6 +399,19 @@ __global__ void __launch_bounds__(sampler_block<T, NET, KIND>(), min_blocks<T, N
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------------------
+// Raises the kernel's dynamic shared-memory limit to `bytes`.  cudaErrorInvalidConfiguration when the staged data set
+// (plus the kernel's static tables) exceeds what one CTA can have: capi.cu reports it as EEYORE_B200_EUNSUPPORTED.
+template <class K> cudaError_t reserve_smem(K kern, size_t bytes) {
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  if (bytes + fa.sharedSizeBytes > (size_t)max_optin) return cudaErrorInvalidConfiguration;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(const ChainArgs<T>& a, cudaStream_t st) {
   constexpr int KB = sampler_block<T, NET, KIND>();
   constexpr int CPB = KB / G;
@@ -408,7 +421,7 @@ template <typename T, class NET, int G, int KIND> cudaError_t launch_sampler_g(c
   const SmemLayout<T, NET> lay(a.n_rows, CPB, KIND == KIND_HMC || KIND == KIND_HMC_TUNED, grad_in_smem<T, NET, KIND>());
 #endif
   auto kern = sampler_kernel<T, NET, G, KIND>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+  cudaError_t e = reserve_smem(kern, lay.total);
   if (e != cudaSuccess) return e;
   const long blocks = (a.n_chains + CPB - 1) / CPB;
   kern<<<(unsigned)blocks, KB, lay.total, st>>>(a);
@@ -419,7 +432,7 @@ template <typename T, class NET, int G> cudaError_t launch_eval_g(const ChainArg
   constexpr int CPB = kBlock / G;
   const SmemLayout<T, NET> lay(a.n_rows, CPB, false);
   auto kern = eval_kernel<T, NET, G>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+  cudaError_t e = reserve_smem(kern, lay.total);
   if (e != cudaSuccess) return e;
   const long blocks = (a.n_chains + CPB - 1) / CPB;
   kern<<<(unsigned)blocks, kBlock, lay.total, st>>>(a);
@@ -453,7 +466,7 @@ template <typename T, class NET> cudaError_t launch_eval(int lanes, const ChainA
 template <typename T, class NET> cudaError_t launch_forward(const ChainArgs<T>& a, T* out, cudaStream_t st) {
   const size_t sm = sizeof(T) * (size_t)a.n_rows * NET::D0;
   auto kern = forward_kernel<T, NET>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaError_t e = reserve_smem(kern, sm);
   if (e != cudaSuccess) return e;
   const long blocks = (a.n_chains + kBlock - 1) / kBlock;
   kern<<<(unsigned)blocks, kBlock, sm, st>>>(a, out);

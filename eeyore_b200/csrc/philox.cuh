@@ -43,7 +43,9 @@ template <> struct Uni<double> {
   }
 };
 template <> struct Uni<float> {
-  static EB_HD float from(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f; }  // 2^-24
+  // 23-bit uniform in (0,1): (k + 1/2) 2^-23, k < 2^23 -- every value is exact in fp32 (a 24-bit k + 1/2 would round to
+  // even: neighbours collide and the largest one becomes exactly 1)
+  static EB_HD float from(uint32_t w) { return ((float)(w >> 9) + 0.5f) * 1.1920928955078125e-7f; }  // 2^-23
 };
 
 // log of a uniform in (0, 1): a positive normal number in both precisions

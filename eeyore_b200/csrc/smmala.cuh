@@ -7,7 +7,8 @@
 //   G = R R^T (Cholesky, R lower);  mean(theta) = theta + step/2 G^-1 grad;  theta' = mean + sqrt(step) R^-T z
 //   log q(b | a) = -(P/2) log(2 pi step) + sum_j log R_jj(a) - |R(a)^T (b - mean(a))|^2 / (2 step)
 //   accept <=> Cholesky of G(theta') succeeded and log u < lt' - lt - log q(theta'|theta) + log q(theta|theta')
-// Parity is checked against oracle/samplers.py:smmala_run (parity unpinned by the reference).
+// Parity is checked against tests/golden/smmala_*.npz (runs assembled from the reference's own pieces, oracle/make_golden.py:
+// smmala_goldens) and, at larger sizes, against oracle/samplers.py:smmala_run (itself pinned by those goldens).
 //
 // Work split inside the warp, per batch of 32 data rows:
 //   phase A (lane = data row): forward pass, Jacobian row J_i, log-lik term, gradient += (y_i - p_i) J_i;
@@ -353,7 +354,7 @@ template <typename T, class NET> cudaError_t launch_smmala(const ChainArgs<T>& a
   const SmemLayout<T, NET> lay(a.n_rows, kSmWarps, false);
   const size_t smem = align16(lay.total) + kSmWarps * sizeof(SmWarpMem<T, NET>);
   auto kern = smmala_kernel<T, NET>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = reserve_smem(kern, smem);
   if (e != cudaSuccess) return e;
   const long blocks = (a.n_chains + kSmWarps - 1) / kSmWarps;
   kern<<<(unsigned)blocks, kSmWarps * 32, smem, st>>>(a);

@@ -7,5 +7,8 @@ from .power_posterior_sampler import PowerPosteriorSampler
 from .ram import RAM
 from .sampler import Sampler
 from .serial_sampler import SerialSampler
-from .single_chain_serial_sampler import SingleChainSerialSampler
+from .native import NativeChainSampler
+
+# the reference's accessor base class (eeyore/samplers/single_chain_serial_sampler.py) is part of the native sampler base
+SingleChainSerialSampler = NativeChainSampler
 from .smmala import SMMALA

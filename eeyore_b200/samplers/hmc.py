@@ -16,6 +16,7 @@ class HMC(NativeChainSampler):
         self.tuner = tuner
         self._tuner_state = None
         self.step, self.num_steps = step, num_steps
+        self._step0, self._num_steps0 = None, None    # scalar values the per-chain tuner state starts from
         self.keys = ["sample", "target_val", "grad_val", "momentum", "hamiltonian", "accepted"]
         self._init_native(model, theta0, dataloader, data0, counter, chain, seed, lanes_per_chain, thin)
         if tuner is not None:                                    # hmc.py:17-28
@@ -56,18 +57,36 @@ class HMC(NativeChainSampler):
             ratio = one_step(self.step)
             guard += 1
 
+    def _scalar_step(self):
+        """(step, num_steps) as python scalars.  After a batched tuned run self.step / self.num_steps are per-chain tensors;
+        the scalars the tuner state was started from are kept aside for that case."""
+        if isinstance(self.step, torch.Tensor):
+            return self._step0, self._num_steps0
+        return float(self.step), int(self.num_steps)
+
+    def _on_new_state(self):
+        """set_current / reset.  One chain: the tuner state carries over, as the reference's HMCDATuner object does.
+        C chains: the per-chain dual-averaging state ([4, C]: barh, logbare, step, num_steps) belongs to the previous set
+        of chains -- drop it (a buffer of another C would be indexed out of bounds by the kernel) and go back to the scalar
+        step the tuner was started from."""
+        st = getattr(self, "_tuner_state", None)
+        if st is not None and (self._batched or st.shape[1] != self.num_chains):
+            if isinstance(self.step, torch.Tensor):
+                self.step, self.num_steps = self._step0, self._num_steps0
+            self._tuner_state = None
+
     def _tuner_buffers(self):
-        if self._tuner_state is None:
-            c = self.num_chains
+        c = self.num_chains
+        if self._tuner_state is None or self._tuner_state.shape != (4, c):
+            self._step0, self._num_steps0 = self._scalar_step()
             st = torch.zeros(4, c, dtype=torch.float64, device=self._theta.device)
-            st[2] = float(self.step)
-            st[3] = float(self.num_steps)
+            st[2] = self._step0
+            st[3] = float(self._num_steps0)
             self._tuner_state = st
         return self._tuner_state
 
     def _fill_params(self, p):
-        p.step, p.num_steps = float(self.step if not isinstance(self.step, torch.Tensor) else self.step.flatten()[0]), \
-            int(self.num_steps if not isinstance(self.num_steps, torch.Tensor) else self.num_steps.flatten()[0])
+        p.step, p.num_steps = self._scalar_step()
         if self.tuner is not None:
             t = self.tuner
             st = self._tuner_buffers()
@@ -98,7 +117,8 @@ class HMC(NativeChainSampler):
         from ..tuners import HMCDATuner
         t = None
         if self.tuner is not None:
-            t = HMCDATuner(self.tuner.l, e0=self.tuner.e0 if self.tuner.e0 is not None else float(self.step),
+            t = HMCDATuner(self.tuner.l, e0=self.tuner.e0 if self.tuner.e0 is not None else self._scalar_step()[0],
                            d=self.tuner.d, eub=self.tuner.eub)
-        return HMC(self.model, theta0=theta0, dataloader=self.dataloader, step=self.step, num_steps=self.num_steps,
+        step, num_steps = self._scalar_step()
+        return HMC(self.model, theta0=theta0, dataloader=self.dataloader, step=step, num_steps=num_steps,
                    tuner=t, lanes_per_chain=self.lanes_per_chain, thin=self.thin)

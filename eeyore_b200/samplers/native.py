@@ -5,21 +5,26 @@ structure-of-arrays device buffers; `current`, `chain` and `counter` are then up
 exactly as after the reference's python loop (eeyore/samplers/serial_sampler.py:35-52).
 """
 import ctypes as C
+from pathlib import Path
 
 import torch
 
 from .. import _native as nv
-from ..chains import ChainList, DeviceChains
+from ..chains import ChainFile, ChainList, DeviceChains
 from ..datasets import DataCounter
-from .single_chain_serial_sampler import SingleChainSerialSampler
+from .serial_sampler import SerialSampler
 
 
-class NativeChainSampler(SingleChainSerialSampler):
+class NativeChainSampler(SerialSampler):
+    """One sampler object = the state of C >= 1 chains on the device.  It also carries the accessor surface the reference
+    keeps in SingleChainSerialSampler (eeyore/samplers/single_chain_serial_sampler.py:5-41: get_model / get_chain /
+    get_param / get_sample / set_all / reset / to_chainfile); `eeyore_b200.samplers.SingleChainSerialSampler` is this
+    class."""
     _entry = None          # name of the C entry point
     _uses_grad = True
 
     def _init_native(self, model, theta0, dataloader, data0, counter, chain, seed, lanes_per_chain, thin):
-        super().__init__(counter or DataCounter.from_dataloader(dataloader))
+        SerialSampler.__init__(self, counter or DataCounter.from_dataloader(dataloader))
         self.model = model
         self.dataloader = dataloader
         self.thin = thin
@@ -39,10 +44,32 @@ class NativeChainSampler(SingleChainSerialSampler):
     def _default_chain_keys(self):
         return ["sample", "target_val", "accepted"]
 
+    # -- accessors (single_chain_serial_sampler.py:10-20,40-41) ---------------------------------------------------
+    def get_model(self):
+        return self.model
+
+    def get_param(self, idx):
+        return self.get_chain().get_param(idx)
+
+    def get_sample(self, idx):
+        return self.get_chain().get_sample(idx)
+
+    def set_all(self, theta, data=None):
+        return self.set_current(theta, data=data)
+
+    def to_chainfile(self, path=Path.cwd(), mode="a"):
+        chain = self.get_chain()
+        if isinstance(chain, DeviceChains):
+            chain.to_chainfiles(path, mode=mode)       # run%0Nd/<key>.csv, one directory per chain
+        else:
+            chain.to_chainfile(path=path, mode=mode)
+
     # -- state ---------------------------------------------------------------------------------------------------
     def _reset_chain(self):
-        if isinstance(self.chain, ChainList):
-            self.chain.reset(keys=list(self.chain.vals.keys()))
+        keys = list(self.chain.vals.keys())
+        if isinstance(self.chain, ChainFile):
+            self.chain.close()                         # reset() re-opens the files in the chain's own mode
+        self.chain.reset(keys=keys)
         self._device_blocks = []
 
     def _stage(self, x, y):
@@ -52,24 +79,48 @@ class NativeChainSampler(SingleChainSerialSampler):
     def set_current(self, theta, data=None):
         """<Sampler>.set_current of the reference (e.g. mala.py:26-29): evaluate target (and gradient) at theta.
         theta may be [P] (one chain, reference behaviour) or [C, P] (C independent chains)."""
-        x, y = data or next(iter(self.dataloader))
         m = self.model
-        th = m._to_dev(theta)
-        self._batched = th.dim() == 2
-        th = th.reshape(-1, m.num_params()).clone()
-        self.num_chains = th.shape[0]
-        xd, yd = self._stage(x, y)
-        self._data_dev = (xd, yd)
+        pn = m.num_params()
+        batched = theta.dim() == 2
+        c = theta.numel() // pn
+        # Same number of chains and same data as before (the repeated reset(theta) of a benchmark / restart loop): the
+        # device buffers are kept; theta lands in a [C, P] staging buffer (one contiguous, possibly host->device, copy)
+        # and the evaluation writes target / gradient in place.
+        reuse = (data is None and self._data_dev is not None and getattr(self, "_theta_soa", None) is not None
+                 and self.num_chains == c and self._batched == batched)
+        if reuse:
+            x = y = None
+            xd, yd = self._data_dev
+            self._stage_cp.copy_(theta.reshape(c, pn), non_blocking=True)
+            th = self._stage_cp
+            self._acc_count.zero_()
+        else:
+            x, y = data or next(iter(self.dataloader))
+            th = m._to_dev(theta).reshape(c, pn).clone()
+            self._batched, self.num_chains = batched, c
+            xd, yd = self._stage(x, y)
+            self._data_dev = (xd, yd)
+            self._stage_cp = th
+            self._acc_count = torch.zeros(c, dtype=torch.int32, device=th.device)
         lt, g = m._eval(th, xd, yd, want_grad=self._uses_grad)
-        self._set_state(th, lt, g)
-        self._acc_count = torch.zeros(self.num_chains, dtype=torch.int32, device=th.device)
+        self._set_state(th, lt, g, reuse)
         self._last_accepted = None
+        self._on_new_state()
         self._publish_current()
         return x, y
 
-    def _set_state(self, th, lt, g):
+    def _on_new_state(self):
+        """Hook: per-chain auxiliary state (tuner, adaptation) is invalid after set_current."""
+
+    def _set_state(self, th, lt, g, reuse=False):
         """Device state in the chain-minor layout ([P, C] storage; `_theta` / `_grad` are its [C, P] views) so that the
         sampler kernels read and write it coalesced."""
+        if reuse:
+            self._theta_soa.copy_(th.t())
+            if g is not None:
+                self._grad_soa.copy_(g.t())
+            self._lt.copy_(lt)
+            return
         self._theta_soa = th.t().contiguous()
         self._grad_soa = g.t().contiguous() if g is not None else None
         self._theta = self._theta_soa.t()
@@ -88,7 +139,12 @@ class NativeChainSampler(SingleChainSerialSampler):
         m._theta = self._theta[0].contiguous()  # the reference leaves the model parameters at the current state
 
     def reset(self, theta, data=None, reset_counter=True, reset_chain=True):
-        super().reset(theta.clone().detach(), data=data, reset_counter=reset_counter, reset_chain=reset_chain)
+        """single_chain_serial_sampler.py:33-38.  theta may live on the host (pinned memory makes the copy asynchronous)."""
+        if reset_counter:
+            self.counter.reset()
+        if reset_chain:
+            self._reset_chain()
+        self.set_all(theta.detach(), data=data)
 
     # -- noise ---------------------------------------------------------------------------------------------------
     def set_noise_tape(self, z, u):
@@ -162,7 +218,7 @@ class NativeChainSampler(SingleChainSerialSampler):
         return out
 
     def _wanted_keys(self):
-        if isinstance(self.chain, ChainList):
+        if isinstance(self.chain, (ChainList, ChainFile)):
             return tuple(self.chain.vals.keys())
         return ("sample", "target_val", "accepted")
 
@@ -171,7 +227,7 @@ class NativeChainSampler(SingleChainSerialSampler):
             return
         if self._batched:
             self._device_blocks.append(out)
-        else:
+        else:   # ChainList keeps the block in memory, ChainFile appends it to its <key>.csv files
             self.chain.extend_from_device(
                 samples=out["sample"][:, :, 0] if "sample" in out else None,
                 target_vals=out["target_val"][:, 0] if "target_val" in out else None,
@@ -189,12 +245,13 @@ class NativeChainSampler(SingleChainSerialSampler):
                             accept_count=self._acc_count, n_iters=self._iter_offset)
 
     def _run_fused(self, n_iters):
-        """Full-batch run: all remaining iterations in one launch (serial_sampler.py:35-52)."""
+        """Full-batch run: the n_iters iterations of one run() call in one launch (serial_sampler.py:35-52).  As in the
+        reference the counter is not rewound by run(): a second call continues the chain, and only iterations whose global
+        index is below num_burnin_iters are dropped."""
         if n_iters <= 0:
             return
         xd, yd = self._data_dev
-        n_burnin = max(0, min(n_iters, self.counter.num_burnin_iters - self.counter.idx))
-        before = self._acc_count.clone()
+        n_burnin = max(0, min(n_iters, (self.counter.num_burnin_iters or 0) - self.counter.idx))
         out = self._launch(n_iters, n_burnin, xd, yd, want=self._wanted_keys())
         self._store(out)
         if "accepted" in out:

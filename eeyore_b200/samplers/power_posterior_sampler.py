@@ -218,7 +218,7 @@ class PowerPosteriorSampler(SerialSampler):
         if any(s.thin != 1 for s in self.samplers):
             raise ValueError("thinning is not available in the power-posterior sampler")
         xd, yd = self.samplers[0]._data_dev
-        bs, end = self.between_step, c.num_iters
+        bs, end = self.between_step, c.idx + c.num_iters      # num_iters MORE draws per call, as the reference's loop
         want = tuple(self.keys)
         while c.idx < end:
             idx = c.idx

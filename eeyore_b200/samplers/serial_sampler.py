@@ -20,7 +20,9 @@ class SerialSampler(Sampler):
         self.counter.set_epoch_info(num_epochs, num_burnin_epochs)
         if self.counter.num_batches == 1 and hasattr(self, "_run_fused"):
             start = timer()
-            self._run_fused(self.counter.num_iters - self.counter.idx)
+            # like the reference's loop, every call performs num_epochs * num_batches draws; counter.idx keeps counting
+            # across calls, so a second run() continues the chain (burn-in gating by the global index, :46)
+            self._run_fused(self.counter.num_iters)
             if verbose:
                 print(f"Iterations {self.counter.idx} out of {self.counter.num_iters} (fused launch), "
                       f"duration {timedelta(seconds=timer() - start)}")

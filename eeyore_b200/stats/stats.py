@@ -111,9 +111,9 @@ def mc_se_from_cov(mc_cov_mat):
 
 
 def mc_se(x, method="inse", adjust=False, rowvar=False):
-    """eeyore/stats/mc_se.py: sqrt(diag(mc_cov) / n)."""
-    n = x.shape[1] if rowvar else x.shape[0]
-    return (mc_cov(x, method=method, adjust=adjust, rowvar=rowvar).diag() / n).sqrt()
+    """eeyore/stats/mc_se.py:4-5: mc_se_from_cov(mc_cov(x)) = sqrt(diag(mc_cov)) -- as in the reference there is no
+    division by n (ChainList.mc_se and ChainLists.mc_se give the same value whichever way they are called)."""
+    return mc_se_from_cov(mc_cov(x, method=method, adjust=adjust, rowvar=rowvar))
 
 
 def multi_ess(x, mc_cov_mat=None, method="inse", adjust=False):

@@ -109,7 +109,7 @@ typedef struct eeyore_b200_run_params {
   void *out_grad;          /* saved 'grad_val', same strides as out_samples; may be NULL */
   uint8_t *out_accepted;   /* [n_saved, C] saved 'accepted'; may be NULL */
   uint32_t *accept_count;  /* [C], incremented by the number of accepted proposals over all n_iters; may be NULL */
-  int32_t lanes_per_chain; /* threads cooperating on one chain (1,2,4,...,32); 0 = auto */
+  int32_t lanes_per_chain; /* threads cooperating on one chain: 1, 4, 8, 16 or 32; 0 = auto (else EINVAL) */
   int32_t reserved;
   /* HMC dual-averaging step-size tuner: HMCDATuner.tune hooked into HMC.draw during burn-in
    * (eeyore/tuners/hmcda_tuner.py:8-59, eeyore/samplers/hmc.py:158-163).  tuner_state == NULL disables it.

@@ -13,7 +13,9 @@ Parity status
   against golden vectors generated from the unmodified reference
   (``/root/reference``) by ``oracle/make_golden.py`` and committed under
   ``tests/golden/`` (see ``tests/test_oracle_golden.py``).
-* smmala, acf: **parity unpinned** -- the reference snapshot contains neither
+* smmala: the reference snapshot has no SMMALA sampler; pinned by tests/golden/smmala_*.npz, runs assembled from the
+  reference's own pieces only (make_golden.py:smmala_goldens) -- identical accept decisions, states < 1e-14
+* acf: **parity unpinned** -- the reference snapshot does not contain it
   (SURVEY.md section 0); the restatement follows SURVEY.md A.7 / A.10 and is
   builder-defined.
 

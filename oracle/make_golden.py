@@ -327,7 +327,110 @@ def datapar_goldens():
           [float(np.abs(grads[i] - grads64[i]).max() / np.abs(grads64[i]).max()) for i in range(3)])
 
 
+def model_goldens_f32_inputs_in_f64():
+    """The fp32 fixtures of model_goldens.npz (theta and data rounded to fp32) evaluated by the unmodified reference in
+    fp64: the yardstick BASELINE.json's 1e-5 fp32 bar is measured against (an fp32 evaluation by torch carries its own
+    ~1e-6 summation noise, which is not the kernel's error)."""
+    mg = np.load(OUT / "model_goldens.npz")
+    out = {}
+    for arch, a in ARCHS.items():
+        data = load_data(a["data"], torch.float32)
+        x64, y64 = data.x.double(), data.y.double()
+        for ps, pst in ((1.0, "p1"), (100.0, "p100"), (math.sqrt(3.0), "psqrt3")):
+            for temp, tt in ((None, ""), (0.7, "_T07")):
+                key = f"{arch}_f32_{pst}{tt}"
+                model = make_model(arch, torch.float64, prior_scale=float(np.float32(ps)), temperature=temp)
+                lts, grads, lls, lps = [], [], [], []
+                for th in torch.from_numpy(mg[key + "_theta"]).double():
+                    lt, g = model.upto_grad_log_target(th.clone().detach(), x64, y64)
+                    lts.append(lt.item()); grads.append(npy(g))
+                    lls.append(model.log_lik(x64, y64).item()); lps.append(model.log_prior().item())
+                out[key + "_lt64"] = np.array(lts); out[key + "_grad64"] = np.stack(grads)
+                out[key + "_ll64"] = np.array(lls); out[key + "_lp64"] = np.array(lps)
+    np.savez_compressed(OUT / "model_goldens_f32ref.npz", **out)
+    print("model_goldens_f32ref", len(out))
+
+
+def smmala_goldens():
+    """Independent pin of the (builder-defined) SMMALA: the snapshot has no SMMALA sampler, but it ships
+    every piece one is made of.  This run uses ONLY those pieces and torch -- none of the builder's restatement:
+      * log-target and gradient: the reference MLP, upto_grad_log_target (models/log_target_model.py:15-23);
+      * metric: expected Fisher information from per-row autograd derivatives of the reference MLP's output
+        (d p_i / d theta through MLP.forward, mlp.py:45-50): sum_i (dp_i)(dp_i)^T / (p_i (1 - p_i)) + prior precision;
+      * positive-definiteness test: eeyore.linalg.is_pos_def (linalg/is_pos_def.py:3-11); factor: torch.linalg.cholesky;
+      * proposal density: eeyore.kernels.MultivariateNormalKernel(loc, scale_tril).log_prob
+        (kernels/multivariate_normal_kernel.py:5-19, normalized_kernel.py:14-16), covariance step * G^-1;
+      * accept test: the MALA structure of samplers/mala.py:58-66, log(u) < log_rate.
+    The draw theta' = mean + sqrt(step) R^-T z (G = R R^T) is A.7's convention for mapping the recorded z to a proposal."""
+    from eeyore.kernels import MultivariateNormalKernel
+    from eeyore.linalg import is_pos_def
+    dt = torch.float64
+    s3 = math.sqrt(3.0)
+    rng = np.random.default_rng(3)
+    corners = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=np.float64)
+    nx = np.concatenate([c + 0.15 * rng.normal(size=(10, 2)) for c in corners])
+    ny = np.concatenate([np.full((10, 1), float(int(c[0]) ^ int(c[1]))) for c in corners])
+    xor = load_data("xor", dt)
+    cases = (("smmala_xor2321_f64", "2321", npy(xor.x), npy(xor.y), 0.9, 70, 10, 41),
+             ("smmala_nxor2321_f64", "2321", nx, ny, 0.12, 60, 0, 42),
+             ("smmala_xor221_f64", "221", npy(xor.x), npy(xor.y), 1.3, 90, 20, 43))
+    for name, arch, x_np, y_np, step, n_iters, n_burnin, seed in cases:
+        torch.manual_seed(seed)
+        model = make_model(arch, dt, prior_scale=s3)
+        P = model.num_params()
+        x, y = torch.from_numpy(x_np), torch.from_numpy(y_np)
+        prec = 1.0 / model.prior.scale ** 2
+
+        def state_at(theta):
+            lt, g = model.upto_grad_log_target(theta.clone().detach(), x, y)
+            p = model(x)[:, 0]
+            G = torch.diag(prec.clone())
+            for i in range(x.shape[0]):
+                dp = torch.cat([v.reshape(-1) for v in torch.autograd.grad(p[i], list(model.parameters()), retain_graph=True)])
+                G = G + torch.outer(dp, dp) / (p[i] * (1 - p[i])).detach()
+            G = (G + G.t()) / 2
+            lt, g, G = lt.detach(), g.detach(), G.detach()
+            if not (torch.isfinite(G).all() and is_pos_def(G)):
+                return None
+            R = torch.linalg.cholesky(G)
+            mean = theta + 0.5 * step * torch.linalg.solve(G, g)
+            cov = step * torch.linalg.inv(G)
+            kern = MultivariateNormalKernel(mean, torch.linalg.cholesky((cov + cov.t()) / 2))
+            return dict(theta=theta, lt=lt, g=g, R=R, mean=mean, kern=kern)
+
+        theta0 = model.prior.sample() * 0.5
+        cur = state_at(theta0)
+        assert cur is not None
+        zs, us, samples, lts, grads, accs = [], [], [], [], [], []
+        for t in range(n_iters):
+            z = torch.randn(P, dtype=dt)
+            u = torch.rand(1, dtype=dt)
+            prop_theta = cur["mean"] + math.sqrt(step) * torch.linalg.solve_triangular(cur["R"].t(), z[:, None], upper=True)[:, 0]
+            prop = state_at(prop_theta)
+            acc = False
+            if prop is not None:
+                log_rate = prop["lt"] - cur["lt"] - cur["kern"].log_prob(prop_theta) + prop["kern"].log_prob(cur["theta"])
+                acc = bool(torch.log(u) < log_rate)
+            if acc:
+                cur = prop
+            zs.append(npy(z)); us.append(u.item())
+            if t >= n_burnin:
+                samples.append(npy(cur["theta"])); lts.append(cur["lt"].item()); grads.append(npy(cur["g"])); accs.append(int(acc))
+        out = dict(x=x_np, y=y_np, theta0=npy(theta0), z=np.stack(zs), u=np.array(us), step=step, n_iters=n_iters,
+                   n_burnin=n_burnin, prior_scale=s3, samples=np.stack(samples), target_vals=np.array(lts),
+                   grad_vals=np.stack(grads), accepted=np.array(accs, dtype=np.uint8), final_sample=npy(cur["theta"]),
+                   final_target=cur["lt"].item())
+        np.savez_compressed(OUT / f"{name}.npz", **out)
+        print(name, "acceptance", out["accepted"].mean())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "smmala":
+        smmala_goldens()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "f32ref":
+        model_goldens_f32_inputs_in_f64()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dp":
         datapar_goldens()
         sys.exit(0)
@@ -362,3 +465,5 @@ if __name__ == "__main__":
     stats_goldens()
     power_posterior_goldens()
     adaptive_goldens()
+    model_goldens_f32_inputs_in_f64()
+    smmala_goldens()

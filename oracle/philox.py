@@ -46,7 +46,8 @@ def _u53(hi, lo):
 
 
 def _u24(w):
-    return ((w >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    """fp32 uniform in (0,1): (k + 1/2) 2^-23 with the top 23 bits k of the word (exact in fp32)."""
+    return ((w >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
 
 
 def _box_muller(u1, u2):

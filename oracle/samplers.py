@@ -13,8 +13,9 @@ standard-normal draw of iteration t (proposal noise for MH/MALA/SMMALA, initial
 momentum for HMC) and ``u[t, c]`` the uniform of the accept test, in the
 reference's per-iteration order (z first, then u).
 
-SMMALA is **builder-defined (parity unpinned)**: it is absent from the reference
-snapshot and follows SURVEY.md A.7.
+SMMALA is builder-defined: the reference snapshot has no SMMALA sampler and the restatement follows SURVEY.md A.7.  It
+is pinned by tests/golden/smmala_*.npz -- runs that oracle/make_golden.py:smmala_goldens assembles from the reference's
+own pieces only (MLP + autograd row derivatives, is_pos_def, MultivariateNormalKernel.log_prob, MALA's accept rule).
 """
 from __future__ import annotations
 
@@ -201,7 +202,7 @@ def _hmc_run_tuned(spec, x, y, loc, scale, theta, lt, g, z, u, n_burnin, tempera
 
 
 # --------------------------------------------------------------------------------------
-# SMMALA -- builder-defined, parity unpinned
+# SMMALA -- builder-defined algorithm, pinned by tests/golden/smmala_*.npz (make_golden.py:smmala_goldens)
 # --------------------------------------------------------------------------------------
 
 def fisher_metric(spec: MLPSpec, theta, x, y, loc, scale, temperature=None):

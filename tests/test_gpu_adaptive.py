@@ -74,7 +74,7 @@ def test_batched_chains_vs_oracle(kind, arch):
         s = RAM(m, theta0=torch.from_numpy(theta0), dataloader=loader, cov0=torch.from_numpy(cov0), a=0.3, g=0.65)
     s.set_noise_tape(torch.from_numpy(z), torch.from_numpy(u))
     s.run(num_epochs=40, num_burnin_epochs=10)
-    s.run(num_epochs=T, num_burnin_epochs=10)          # continues from iteration 40 (counter, adaptive state, tape)
+    s.run(num_epochs=T - 40, num_burnin_epochs=10)     # T - 40 more draws from iteration 40 on (counter, adaptive state, tape)
     ch = s.get_chain()
     assert np.array_equal(npy(ch.accepted_soa), ref["accepted"])
     got = np.transpose(npy(ch.get_samples()), (1, 0, 2))

@@ -1,6 +1,7 @@
 """GPU parity: chain-batched log_target / gradient kernel vs the reference's golden vectors and the oracle.
-Tolerances are BASELINE.json's: 1e-10 relative at fp64, 1e-5 at fp32 (2e-5 on gradients for the fp32 goldens, whose
-own summation-order noise is ~1e-6)."""
+Tolerances are BASELINE.json's: 1e-10 relative at fp64, 1e-5 at fp32.  The fp32 kernels are measured against fp64 truth:
+the unmodified reference evaluated in fp64 at the fp32 fixtures (tests/golden/model_goldens_f32ref.npz) -- torch's own fp32
+evaluation of the same fixtures (model_goldens.npz) is itself up to 2.7e-6 away from it."""
 import numpy as np
 import pytest
 import torch
@@ -22,13 +23,18 @@ def test_batched_eval_vs_reference_goldens(arch, tag, pst, tt, temp):
     m = make_model(arch, tag, PRIOR_SCALES[pst], temp)
     ds = dataset(arch, tag)
     theta = torch.from_numpy(mg[key + "_theta"]).to(T_DTYPES[tag])
-    tol = RTOL[tag] if tag == "f64" else 2e-5
+    tol = RTOL[tag]
+    if tag == "f64":
+        want_lt, want_g = mg[key + "_lt"], mg[key + "_grad"]
+    else:
+        ref64 = load("model_goldens_f32ref")
+        want_lt, want_g = ref64[key + "_lt64"], ref64[key + "_grad64"]
     for lanes in (0, 1, 4, 8, 16, 32):
         lt, g = m.upto_grad_log_target_batch(theta, ds.x, ds.y, lanes=lanes)
         lt, g = npy(lt), npy(g)
-        assert np.allclose(lt, mg[key + "_lt"], rtol=tol, atol=0), (lanes, lt, mg[key + "_lt"])
+        assert np.allclose(lt, want_lt, rtol=tol, atol=0), (lanes, lt, want_lt)
         for c in range(theta.shape[0]):
-            assert rel_err(g[c], mg[key + "_grad"][c]) < tol, (lanes, c)
+            assert rel_err(g[c], want_g[c]) < tol, (lanes, c)
         lt_only = npy(m.log_target_batch(theta, ds.x, ds.y, lanes=lanes))
         assert np.array_equal(lt_only, lt)
 
@@ -41,16 +47,21 @@ def test_single_chain_api_matches_reference(arch, tag):
     key = f"{arch}_{tag}_p100"
     m = make_model(arch, tag, 100.0)
     ds = dataset(arch, tag)
-    tol = RTOL[tag] if tag == "f64" else 2e-5
+    tol = RTOL[tag]
+    sfx = ""
+    if tag == "f32":                      # fp64 truth at the fp32 fixtures
+        mg_v, sfx = load("model_goldens_f32ref"), "64"
+    else:
+        mg_v = mg
     theta = torch.from_numpy(mg[key + "_theta"][0]).to(T_DTYPES[tag])
     lt = m.log_target(theta.clone().detach(), ds.x, ds.y)
-    assert lt.dim() == 0 and abs(lt.item() - mg[key + "_lt"][0]) <= tol * abs(mg[key + "_lt"][0])
+    assert lt.dim() == 0 and abs(lt.item() - mg_v[key + "_lt" + sfx][0]) <= tol * abs(mg_v[key + "_lt" + sfx][0])
     g = m.grad_log_target(lt)
-    assert g.shape == (m.num_params(),) and rel_err(npy(g), mg[key + "_grad"][0]) < tol
+    assert g.shape == (m.num_params(),) and rel_err(npy(g), mg_v[key + "_grad" + sfx][0]) < tol
     lt2, g2 = m.upto_grad_log_target(theta.clone().detach(), ds.x, ds.y)
     assert lt2.item() == lt.item() and torch.equal(g2, g)
-    assert abs(m.log_lik(ds.x, ds.y).item() - mg[key + "_ll"][0]) <= tol * abs(mg[key + "_ll"][0])
-    assert abs(m.log_prior().item() - mg[key + "_lp"][0]) <= tol * abs(mg[key + "_lp"][0])
+    assert abs(m.log_lik(ds.x, ds.y).item() - mg_v[key + "_ll" + sfx][0]) <= tol * abs(mg_v[key + "_ll" + sfx][0])
+    assert abs(m.log_prior().item() - mg_v[key + "_lp" + sfx][0]) <= tol * abs(mg_v[key + "_lp" + sfx][0])
     assert torch.equal(m.get_params(), theta.to(m.device))
     out = npy(m(ds.x))
     x, y = data_of(arch, NP_DTYPES[tag], mg)
@@ -91,12 +102,12 @@ def test_random_data_vs_oracle_ragged_rows(arch, tag, n_rows):
     m.prior = torch.distributions.Normal(torch.from_numpy(loc), torch.from_numpy(scale))
     lt_ref, g_ref = oracle.log_target_grad(spec, theta.astype(np.float64), x.astype(np.float64), y,
                                            loc.astype(np.float64), scale.astype(np.float64))
-    tol = RTOL[tag] if tag == "f64" else 1e-5
+    tol = RTOL[tag]                       # 1e-10 (fp64) / 1e-5 (fp32) against the fp64 oracle, as BASELINE.json states
     for lanes in (1, 4, 8, 16, 32):
         lt, g = m.upto_grad_log_target_batch(torch.from_numpy(theta), torch.from_numpy(x), torch.from_numpy(y), lanes=lanes)
-        assert np.allclose(npy(lt), lt_ref, rtol=tol * 10, atol=0), lanes
+        assert np.allclose(npy(lt), lt_ref, rtol=tol, atol=0), lanes
         for c in range(C):
-            assert rel_err(npy(g)[c], g_ref[c]) < tol * 10, (lanes, c)
+            assert rel_err(npy(g)[c], g_ref[c]) < tol, (lanes, c)
 
 
 def test_unaligned_data_pointer_takes_the_plain_load_path():
@@ -215,7 +226,7 @@ def test_runtime_shape_networks_vs_oracle(dims, bias, acts, loss, tag):
     lt, g = m.upto_grad_log_target_batch(torch.from_numpy(theta), torch.from_numpy(x), torch.from_numpy(y))
     lt_ref, g_ref = oracle.log_target_grad(spec, theta.astype(np.float64), x.astype(np.float64), y, loc.astype(np.float64),
                                            scale.astype(np.float64))
-    tol = 1e-10 if tag == "f64" else 2e-5
+    tol = RTOL[tag]
     assert np.allclose(npy(lt), lt_ref, rtol=tol, atol=0)
     for c in range(C):
         assert rel_err(npy(g)[c], g_ref[c]) < tol
@@ -322,9 +333,10 @@ def test_soft_labels_on_device(tag):
     dt, tdt = NP_DTYPES[tag], T_DTYPES[tag]
     m = make_model("2321", tag, 2.0)
     loc, scale = np.zeros(20), np.full(20, 2.0)
-    tol = 1e-10 if tag == "f64" else 2e-5
+    tol = RTOL[tag]
+    up = lambda a: a.astype(dt).astype(np.float64)        # the oracle sees the inputs as rounded to the kernel's dtype
     for yy in (y, np.array([[0.0], [1.0], [1.0], [0.0], [1.0], [0.0], [0.25]])):
-        lt_ref, g_ref = oracle.log_target_grad(spec_of("2321"), th, x, yy, loc, scale)
+        lt_ref, g_ref = oracle.log_target_grad(spec_of("2321"), up(th), up(x), up(yy), loc, scale)
         for lanes in (1, 4, 32):
             lt, g = m.upto_grad_log_target_batch(torch.from_numpy(th.astype(dt)), torch.from_numpy(x.astype(dt)),
                                                  torch.from_numpy(yy.astype(dt)), lanes=lanes)

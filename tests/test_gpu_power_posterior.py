@@ -93,3 +93,24 @@ def test_philox_mode_runs_and_validates():
         PowerPosteriorSampler(m, loader, [["HMC", {}], ["MALA", {}]], theta0=th0)
     with pytest.raises(ValueError):
         PowerPosteriorSampler(m, loader, spec_samplers, theta0=th0, temperature=[0.5, 1.0])
+
+
+def test_file_storage_matches_list_storage(tmp_path):
+    """PowerPosteriorSampler(storage='file') (power_posterior_sampler.py:57-63): chainN/<key>.csv per level, equal to the
+    in-memory chains of the same run."""
+    gd, spec, x, y, kinds, kwargs = pp_setup("pp_221_mix")
+    m, loader, _, _, P = make("221")
+    spec_samplers = [["MetropolisHastings", {}] if k == "mh" else ["MALA", {"step": kw["step"]}] for k, kw in zip(kinds, kwargs)]
+    runs = {}
+    for storage in ("list", "file"):
+        s = PowerPosteriorSampler(m, loader, spec_samplers, theta0=torch.from_numpy(gd["theta0"]),
+                                  between_step=int(gd["between_step"]), storage=storage, path=tmp_path, mode="w")
+        s.set_noise_tape(gd["z"], gd["u"], gd["j_tape"], gd["u_between"])
+        s.run(num_epochs=int(gd["n_iters"]), num_burnin_epochs=int(gd["n_burnin"]))
+        runs[storage] = s
+    for k in range(len(kinds)):
+        mem = runs["list"].samplers[k].get_chain()
+        disk = runs["file"].samplers[k].get_chain().to_chainlist(keys=["sample", "target_val"])
+        assert (tmp_path / f"chain{k + 1}" / "sample.csv").exists()
+        assert torch.equal(disk.get_samples(), mem.get_samples().cpu())
+        assert torch.equal(disk.get_target_vals(), mem.get_target_vals().cpu())

@@ -165,10 +165,12 @@ def test_philox_mode_hmc_matches_oracle_and_is_shard_invariant():
     s2.chain_offset = 40
     s2.run(num_epochs=T, num_burnin_epochs=0)
     assert torch.equal(s2.get_chain().samples_soa, got.samples_soa[:, :, 40:])
-    # continuing a run continues the stream: 4 + 5 iterations == 9 iterations
+    # as in the reference's loop, run() performs num_epochs MORE draws and the counter keeps counting: 4 + 5 iterations ==
+    # 9 iterations (same Philox stream)
     s3_ = HMC(m, theta0=torch.from_numpy(theta0), dataloader=loader(ds), step=step, num_steps=L, seed=seed)
     s3_.run(num_epochs=4, num_burnin_epochs=0)
-    s3_.run(num_epochs=9, num_burnin_epochs=0)
+    s3_.run(num_epochs=5, num_burnin_epochs=0)
+    assert s3_.counter.idx == 9
     assert torch.equal(s3_.get_chain().samples_soa, got.samples_soa)
 
 
@@ -279,6 +281,81 @@ def test_hmcda_tuner_many_chains_vs_oracle_and_split_runs():
     a.run(num_epochs=T, num_burnin_epochs=nb)
     b = HMC(m, theta0=torch.from_numpy(theta0), dataloader=loader(ds), tuner=HMCDATuner(l=l, e0=e0), seed=9)
     b.run(num_epochs=10, num_burnin_epochs=nb)      # 10 tuning iterations ...
-    b.run(num_epochs=T, num_burnin_epochs=nb)       # ... then the remaining 30 (15 still tuning)
+    b.run(num_epochs=T - 10, num_burnin_epochs=nb)  # ... then the remaining 30 (15 still tuning)
     assert torch.equal(a.get_chain().samples_soa, b.get_chain().samples_soa)
     assert torch.equal(a.step, b.step)
+
+
+def test_chainfile_backed_sampler_writes_what_a_chainlist_holds(tmp_path):
+    """A sampler constructed with chain=ChainFile(...) (eeyore/chains/chain_file.py:28-45): the fused run appends its saved
+    states to <key>.csv; reading the files back gives the ChainList of the same run, '%.18e' round-trip exact."""
+    from eeyore_b200.chains import ChainFile
+    gd = load("mala_xor221_f64")
+    m = make_model("221", "f64", float(gd["prior_scale"]))
+    ds = dataset("221", "f64")
+    keys = ["sample", "target_val", "grad_val", "accepted"]
+    runs = {}
+    for kind in ("list", "file"):
+        chain = ChainList(keys=keys) if kind == "list" else ChainFile(keys=keys, path=tmp_path / "mala", mode="w")
+        s = MALA(m, theta0=torch.from_numpy(gd["theta0"]), dataloader=loader(ds), chain=chain, step=1.74)
+        s.set_noise_tape(torch.from_numpy(gd["z"]), torch.from_numpy(gd["u"]))
+        s.run(num_epochs=200, num_burnin_epochs=20)
+        runs[kind] = s
+    back = runs["file"].get_chain().to_chainlist(keys=keys)
+    want = runs["list"].get_chain()
+    assert len(back) == len(want) == 180
+    assert torch.equal(back.get_samples(), want.get_samples().cpu())
+    assert torch.equal(back.get_target_vals(), want.get_target_vals().cpu())
+    assert torch.equal(back.get_grad_vals(), want.get_grad_vals().cpu())
+    assert back.vals["accepted"] == want.vals["accepted"]
+    assert np.array_equal(np.array(back.vals["accepted"], dtype=np.uint8), gd["accepted"][:180])
+    # a second run() appends (mode 'a' semantics of ChainFile.reset re-opening the files)
+    runs["file"].chain.mode = "a"
+    runs["file"].run(num_epochs=10, num_burnin_epochs=20)
+    assert len(runs["file"].get_chain().to_chainlist(keys=keys)) == 190
+
+
+def test_reset_reuses_the_device_buffers_and_restarts_the_chain():
+    """reset(theta_host) with the same number of chains keeps every device buffer (the e2e path of bench.py) and gives the
+    same chains as a freshly constructed sampler."""
+    m = make_model("2321", "f64", 3.0 ** 0.5)
+    ds = dataset("2321", "f64")
+    g = torch.Generator().manual_seed(3)
+    th_a = torch.randn(300, m.num_params(), dtype=torch.float64, generator=g)
+    th_b = torch.randn(300, m.num_params(), dtype=torch.float64, generator=g).pin_memory()
+    s = HMC(m, theta0=th_a, dataloader=loader(ds), step=0.3, num_steps=5, seed=21)
+    s.run(num_epochs=6, num_burnin_epochs=0)
+    ptrs = (s._theta_soa.data_ptr(), s._grad_soa.data_ptr(), s._lt.data_ptr())
+    s._iter_offset = 0
+    s.reset(th_b)
+    assert ptrs == (s._theta_soa.data_ptr(), s._grad_soa.data_ptr(), s._lt.data_ptr())
+    assert s.counter.idx == 0 and int(s.acceptance_counts().sum()) == 0
+    s.run(num_epochs=6, num_burnin_epochs=0)
+    fresh = HMC(m, theta0=th_b, dataloader=loader(ds), step=0.3, num_steps=5, seed=21)
+    fresh.run(num_epochs=6, num_burnin_epochs=0)
+    assert torch.equal(s.get_chain().samples_soa, fresh.get_chain().samples_soa)
+    assert torch.equal(s.acceptance_counts(), fresh.acceptance_counts())
+    # another number of chains re-allocates
+    s.reset(th_a[:17])
+    assert s.num_chains == 17 and s._theta_soa.shape == (m.num_params(), 17)
+
+
+def test_tuner_state_does_not_outlive_its_chains():
+    """reset() with another number of chains after a batched tuned run: the [4, C] dual-averaging buffer is rebuilt (it
+    would be indexed out of bounds otherwise) and the scalar initial step is restored; _spawn works after a batched run."""
+    from eeyore_b200.tuners import HMCDATuner
+    m = make_model("2321", "f64", 3.0 ** 0.5)
+    ds = dataset("2321", "f64")
+    th = torch.randn(96, m.num_params(), dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    s = HMC(m, theta0=th, dataloader=loader(ds), tuner=HMCDATuner(l=1.5, e0=0.25), seed=2)
+    s.run(num_epochs=30, num_burnin_epochs=20)
+    assert isinstance(s.step, torch.Tensor) and s.step.shape == (96,)
+    child = s._spawn(th[:8])
+    assert child.step == 0.25 and child.tuner.e0 == 0.25
+    s.reset(th[:40])
+    assert s.step == 0.25 and s._tuner_state is None
+    s.run(num_epochs=30, num_burnin_epochs=20)
+    assert s.step.shape == (40,) and s._tuner_state.shape == (4, 40)
+    ref = HMC(m, theta0=th[:40], dataloader=loader(ds), tuner=HMCDATuner(l=1.5, e0=0.25), seed=2)
+    ref.run(num_epochs=30, num_burnin_epochs=20)
+    assert torch.equal(ref.step, s.step)

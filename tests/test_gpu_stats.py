@@ -26,8 +26,11 @@ def test_reference_stats_goldens():
     assert abs(ess[0] - 564.6937234344964) < 1e-6            # SURVEY.md section 4 known answer
     lists = ChainLists(vals={"sample": [list(x[i].unbind(0)) for i in range(4)]})
     assert np.allclose(lists.multi_ess(), gd["multi_ess"], rtol=1e-9, atol=0)
-    se = npy(st.mc_se(x[0]))
-    assert np.allclose(se, np.sqrt(np.diag(gd["inse"][0]) / 1000), rtol=1e-10)
+    se = npy(st.mc_se(x[0]))                                 # eeyore/stats/mc_se.py: sqrt(diag(mc_cov)), no 1/n
+    assert np.allclose(se, np.sqrt(np.diag(gd["inse"][0])), rtol=1e-10)
+    ch = ChainList(vals={"sample": list(x[0].unbind(0))})    # the same value along every call path
+    assert np.allclose(npy(ch.mc_se()), se, rtol=1e-12)
+    assert np.allclose(npy(ch.mc_se(mc_cov_mat=ch.mc_cov())), se, rtol=1e-12)
 
 
 def test_config1_chain_multi_ess():

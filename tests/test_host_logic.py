@@ -188,3 +188,46 @@ def test_model_deepcopy_gets_its_own_native_handle():
     c.temperature = 0.25
     assert m.temperature is None and c.num_params() == 9
     assert c.handle().value != h.value
+
+
+def test_run_params_validation_happens_before_any_launch():
+    """Argument errors of the fused runs are reported (EINVAL) before the first CUDA call: Philox counter words are 32 bits,
+    so offsets that would alias streams are refused; lanes_per_chain has five legal widths."""
+    lib = nv.lib()
+    h = C.c_void_p()
+    dims = (C.c_int * 4)(2, 3, 2, 1); bias = (C.c_int * 3)(1, 1, 1); acts = (C.c_int * 3)(1, 1, 1)
+    assert lib.eeyore_b200_mlp_create(3, dims, bias, acts, 0, 1, C.byref(h)) == 0
+    dummy = C.c_void_p(16)            # never dereferenced: validation fails first
+
+    def params(**kw):
+        p = nv.RunParams()
+        p.n_chains, p.n_iters, p.n_rows, p.thin, p.step, p.num_steps = 8, 4, 4, 1, 0.1, 3
+        for k in ("theta", "target", "grad", "x", "y", "prior_loc", "prior_scale"):
+            setattr(p, k, dummy.value)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    for kw, needle in [(dict(chain_offset=1 << 32), b"2^32"), (dict(chain_offset=(1 << 32) - 4), b"2^32"),
+                       (dict(iter_offset=(1 << 32) - 2), b"2^32"), (dict(lanes_per_chain=2), b"lanes_per_chain"),
+                       (dict(lanes_per_chain=64), b"lanes_per_chain"), (dict(step=0.0), b"step")]:
+        p = params(**kw)
+        for entry in (lib.eeyore_b200_hmc_run, lib.eeyore_b200_mala_run, lib.eeyore_b200_mh_run):
+            assert entry(h, C.byref(p)) == nv.EINVAL, kw
+            assert needle in lib.eeyore_b200_last_error(), (kw, lib.eeyore_b200_last_error())
+    p = params(iter_offset=(1 << 32) - 2)
+    assert lib.eeyore_b200_smmala_run(h, C.byref(p)) == nv.EINVAL
+    # tape mode does not touch the Philox counters: large offsets are fine there (n_iters = 0 returns before any launch)
+    p = params(iter_offset=(1 << 40), rng_mode=nv.RNG_TAPE, z_tape=dummy.value, u_tape=dummy.value, n_iters=0)
+    assert lib.eeyore_b200_hmc_run(h, C.byref(p)) == 0
+    lib.eeyore_b200_mlp_destroy(h)
+
+
+def test_single_chain_serial_sampler_surface():
+    """The accessor surface of eeyore/samplers/single_chain_serial_sampler.py lives on the native sampler base."""
+    from eeyore_b200 import samplers
+    base = samplers.SingleChainSerialSampler
+    for name in ("get_model", "get_chain", "get_param", "get_sample", "set_current", "set_all", "reset", "to_chainfile",
+                 "run", "benchmark", "draw"):
+        assert callable(getattr(base, name)), name
+    assert issubclass(samplers.HMC, base) and issubclass(samplers.MALA, base) and issubclass(base, samplers.SerialSampler)

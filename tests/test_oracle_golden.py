@@ -196,3 +196,38 @@ def test_adaptive_metropolis_matches_the_reference(name):
     assert rel_err(r["sample"][:, 0], gd["samples"]) < 1e-9
     assert np.allclose(r["target_val"][:, 0], gd["target_vals"], rtol=1e-9, atol=1e-11)
     assert rel_err(factor, gd["final_factor"]) < 1e-7
+
+
+@pytest.mark.parametrize("name,arch", [("smmala_xor2321_f64", "2321"), ("smmala_nxor2321_f64", "2321"),
+                                       ("smmala_xor221_f64", "221")])
+def test_smmala_restatement_matches_the_reference_pieces_run(name, arch):
+    """oracle.smmala_run against a run assembled from the reference's own pieces (make_golden.py:smmala_goldens: reference
+    MLP + autograd row derivatives for the metric, is_pos_def, torch.linalg.cholesky, MultivariateNormalKernel.log_prob)."""
+    gd = load(name)
+    spec = spec_of(arch)
+    P = spec.num_params
+    ref = oracle.smmala_run(spec, gd["x"], gd["y"], np.zeros(P), np.full(P, float(gd["prior_scale"])), gd["theta0"][None],
+                            gd["z"][:, None, :], gd["u"][:, None], float(gd["step"]), n_burnin=int(gd["n_burnin"]))
+    assert np.array_equal(ref["accepted"][:, 0], gd["accepted"])
+    assert rel_err(ref["sample"][:, 0], gd["samples"]) < 1e-12
+    assert rel_err(ref["target_val"][:, 0], gd["target_vals"]) < 1e-12
+    assert rel_err(ref["grad_val"][:, 0], gd["grad_vals"]) < 1e-11
+
+
+def test_fp32_fixtures_evaluated_in_fp64_by_the_reference():
+    """model_goldens_f32ref.npz (the reference in fp64 at the fp32 fixtures): the oracle reproduces it at 1e-12, so the
+    1e-5 bar of the fp32 kernels can be measured against fp64 truth instead of torch's own fp32 rounding."""
+    mg, ref = load("model_goldens"), load("model_goldens_f32ref")
+    for arch in ARCHS:
+        x, y = data_of(arch, np.float32, mg)
+        spec = spec_of(arch)
+        P = spec.num_params
+        for pst, ps in PRIOR_SCALES.items():
+            for tt, temp in (("", None), ("_T07", 0.7)):
+                key = f"{arch}_f32_{pst}{tt}"
+                lt, g = oracle.log_target_grad(spec, mg[key + "_theta"].astype(np.float64), x.astype(np.float64),
+                                               y.astype(np.float64), np.zeros(P), np.full(P, float(np.float32(ps))), temp)
+                assert np.allclose(lt, ref[key + "_lt64"], rtol=1e-12, atol=0), key
+                assert rel_err(g, ref[key + "_grad64"]) < 1e-12, key
+                # and torch's fp32 evaluation of the same fixtures is itself within the fp32 bar of that truth
+                assert rel_err(mg[key + "_grad"], ref[key + "_grad64"]) < 2e-5, key
