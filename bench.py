@@ -1,8 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the sampler hot path (BASELINE.json metric: log-target+gradient evaluations per second).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg3|cfg5] [--impl ours|reference] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+The default line is config 4 (below); its `extra` object carries, measured in the same process at the same N, every other
+BASELINE configuration: cfg4_strong (524,288 chains in total, sharded), cfg4_thin1 (every iteration saved), cfg4_diagnostics
+(1,000 saved iterations per chain + on-device multi-ESS / ACF of every chain), cfg2, cfg3, cfg1 (one chain, wall time) and
+cfg5 (the data-sharded path with the peer-store exchange).
 
 Workload (default cfg4 = BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on):
 MLP 2-3-2-1 on XOR, HMC with 10 leapfrog steps, 524,288 independent fp64 chains PER GPU (chains are sharded across
@@ -288,68 +293,99 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of one bench run: rank / device / process group and the timing helpers every record uses."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.args = args
+        self.flush_buf = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def flush_l2(self, k=0):
+        """Overwrites 160 MB of device memory (the L2 is 126 MB)."""
+        if self.flush_buf is None:
+            self.flush_buf = self.torch.empty(160 << 20, dtype=self.torch.uint8, device=self.dev)
+        self.flush_buf.fill_(k & 0xFF)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def build_model(ctx, w):
+    torch = ctx.torch
     from torch.distributions import Normal
     from torch.utils.data import DataLoader
-
-    from eeyore_b200 import _native as nv
     from eeyore_b200.constants import loss_functions
     from eeyore_b200.datasets import XYDataset
     from eeyore_b200.models.mlp import MLP, Hyperparameters
-    from eeyore_b200.samplers import HMC
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    w = WORKLOADS[args.workload]
     dt = torch.float64 if w["dtype"] == "f64" else torch.float32
     x, y = synthetic_data(w)
     ds = XYDataset(torch.from_numpy(x).to(dt), torch.from_numpy(y).to(dt))
     nl = len(w["dims"]) - 1
     binary = w["loss"] == "binary_classification"
     hp = Hyperparameters(w["dims"], nl * [True], (nl - 1) * [torch.sigmoid] + [torch.sigmoid if binary else None])
-    model = MLP(loss=loss_functions[w["loss"]], hparams=hp, dtype=dt, device=dev)
+    model = MLP(loss=loss_functions[w["loss"]], hparams=hp, dtype=dt, device=ctx.dev)
     P = model.num_params()
     model.prior = Normal(torch.zeros(P, dtype=dt), S3 * torch.ones(P, dtype=dt))
-    C = args.chains or w["chains"]
-    iters, L, thin = args.iters or w["iters"], w["num_steps"], w["thin"]
+    return model, DataLoader(ds, batch_size=len(ds)), dt, x, y
+
+
+def make_sampler(w, model, loader, theta0, seed, thin, lanes=0, chain=None):
+    if w.get("kind") == "smmala":
+        from eeyore_b200.samplers import SMMALA
+        return SMMALA(model, theta0=theta0, dataloader=loader, step=w["step"], seed=seed, thin=thin, chain=chain)
+    from eeyore_b200.samplers import HMC
+    return HMC(model, theta0=theta0, dataloader=loader, step=w["step"], num_steps=w["num_steps"], seed=seed, thin=thin,
+               lanes_per_chain=lanes, chain=chain)
+
+
+def bench_chains(ctx, wname, steps, warmup, chains=None, thin=None, iters=None, e2e=True, clocks=None, scaling="weak",
+                 dtype=None):
+    """One chain-sharded workload: `value` with the chain state resident in HBM (one fused launch per step) and `e2e`
+    through the public sampler API with pinned HOST buffers: per step the chain states are copied host->device, the sampler
+    runs, and everything a ChainList would hold afterwards -- the saved samples, their targets and accept flags, the final
+    states and accept counts -- is copied device->host."""
+    torch = ctx.torch
+    args = ctx.args
+    w = dict(WORKLOADS[wname])
+    if dtype:
+        w["dtype"] = dtype
+    model, loader, dt, x, y = build_model(ctx, w)
+    P = model.num_params()
+    C = chains or args.chains or w["chains"]
+    iters = iters or args.iters or w["iters"]
+    thin = thin or w["thin"]
+    L = w["num_steps"]
+    kind = w.get("kind", "hmc")
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     gen = torch.Generator().manual_seed(1000 + rank)
     theta_host = (torch.randn(C, P, generator=gen, dtype=dt) * {"xor": 1.0, "noisy_xor": 0.5}.get(w["data"], 0.3)).pin_memory()
-    loader = DataLoader(ds, batch_size=len(ds))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
-    # ---- device-resident arm: state stays in HBM, one fused launch per step --------------------------------------
-    kind = w.get("kind", "hmc")
-
-    def make_sampler(theta0, seed):
-        if kind == "smmala":
-            from eeyore_b200.samplers import SMMALA
-            return SMMALA(model, theta0=theta0, dataloader=loader, step=w["step"], seed=seed, thin=thin)
-        return HMC(model, theta0=theta0, dataloader=loader, step=w["step"], num_steps=L, seed=seed, thin=thin,
-                   lanes_per_chain=args.lanes)
-
-    sampler = make_sampler(theta_host.to(dev), 12345)
+    sampler = make_sampler(w, model, loader, theta_host.to(dev), 12345, thin, args.lanes)
     sampler.chain_offset = rank * C          # global chain ids => results independent of the sharding
 
     def step_resident():
@@ -357,163 +393,322 @@ def run_ours(args):
         sampler.counter.reset()
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
 
-    clocks = ClockSampler(local, enabled=(rank == 0)).start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
-    barrier()
-    # Workloads whose per-launch working set fits the 126 MB L2 (configs 2 and 3) get the L2 flushed between timed steps (a
-    # 160 MB buffer is overwritten; the flush sits outside the per-step event pairs); config 4 streams 789 MB per launch.
-    esz0 = theta_host.element_size()
-    ws_bytes = C * (2 * (2 * P + 1) * esz0 + ((iters + thin - 1) // thin) * (P * esz0 + esz0 + 1) + 4)
-    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev) if ws_bytes <= 126e6 else None
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    clocks.mark_begin()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(k & 0xFF)
-        ev0[k].record()
-        step_resident()
-        ev1[k].record()
-    barrier()
-    clocks.mark_end()
-    clocks.stop()
-    per_launch_ms = [ev0[k].elapsed_time(ev1[k]) for k in range(args.steps)]
-    t_local = (sum(per_launch_ms) if flush is not None else ev0[0].elapsed_time(ev1[-1])) * 1e-3
-    t_res = max_over_ranks(t_local)
-    evals_step = C * iters * (1 if kind == "smmala" else L)
-    value = world * evals_step * args.steps / t_res
-    acc_rate = sampler.get_chain().acceptance().mean().item()
-
-    # ---- end-to-end arm: host buffers in, host results out, through the public API --------------------------------
-    out_theta = torch.empty(C, P, dtype=dt).pin_memory()
-    out_lt = torch.empty(C, dtype=dt).pin_memory()
-    out_acc = torch.empty(C, dtype=torch.int32).pin_memory()
-
-    # The chains are independent, so the step is cut into `nb` chain batches, each on its own stream: batch b + 1's
-    # host->device copy and batch b - 1's device->host copy run under batch b's kernel.  Philox is keyed by the global chain
-    # id, so the results do not depend on the batching.
-    nb = max(1, min(args.e2e_batches, C // 1024 if C >= 1024 else 1))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(nb)]
-    bounds = [(b * C // nb, (b + 1) * C // nb) for b in range(nb)]
-
-    def step_e2e():
-        cur = torch.cuda.current_stream()
-        keep = []
-        for (lo, hi), st in zip(bounds, streams):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                s = make_sampler(theta_host[lo:hi], 999)
-                s.chain_offset = rank * C + lo
-                s.run(num_epochs=iters, num_burnin_epochs=0)
-                out_theta[lo:hi].copy_(s.current["sample"], non_blocking=True)
-                out_lt[lo:hi].copy_(s.current["target_val"], non_blocking=True)
-                out_acc[lo:hi].copy_(s.acceptance_counts(), non_blocking=True)
-            keep.append(s)                       # buffers stay alive until their stream has drained
-        for st in streams:
-            cur.wait_stream(st)
-        cur.synchronize()
-        return out_lt[0].item()
-
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    e2e_value = world * evals_step * args.steps / t_e2e
-    h2d = (theta_host.numel() + x.size + y.size) * theta_host.element_size()
-    d2h = sum(t.numel() * t.element_size() for t in (out_theta, out_lt, out_acc))
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (sampler_kernel<..., KIND_HMC>) -------------------------------------------
-    import ctypes
-    peak = ctypes.c_double()
-    nv.check(nv.lib().eeyore_b200_fma_peak(nv.DTYPE_IDS[dt], 2000, ctypes.byref(peak)))
-    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
-    flops_launch = w["flops_per_eval"] * evals_step
-    achieved = flops_launch / avg_launch_s / 1e12
+    ctx.barrier()
     esz = theta_host.element_size()
     n_saved = (iters + thin - 1) // thin
     hbm_bytes = C * (2 * (2 * P + 1) * esz + n_saved * (P * esz + esz + 1) + 4)
+    flush = hbm_bytes <= 126e6     # working set below the L2 size: flush between timed steps (outside the event pairs)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ctx.barrier()
+    if clocks:
+        clocks.mark_begin()
+    for k in range(steps):
+        if flush:
+            ctx.flush_l2(k)
+        ev0[k].record()
+        step_resident()
+        ev1[k].record()
+    ctx.barrier()
+    if clocks:
+        clocks.mark_end()
+    per_launch_ms = [ev0[k].elapsed_time(ev1[k]) for k in range(steps)]
+    t_local = (sum(per_launch_ms) if flush else ev0[0].elapsed_time(ev1[-1])) * 1e-3
+    t_res = ctx.max_over_ranks(t_local)
+    evals_step = C * iters * (1 if kind == "smmala" else L)
+    value = world * evals_step * steps / t_res
+    acc_rate = sampler.get_chain().acceptance().mean().item()
+    rec = {
+        "value": value, "unit": "evals/s", "ms_per_step": 1e3 * t_res / steps, "scaling": scaling, "dtype": w["dtype"],
+        "config": {"workload": w["name"], "chains_per_gpu": C, "chains_total": C * world, "iterations_per_step": iters,
+                   "num_steps": L, "step_size": w["step"], "thin": thin, "evals_counted_per_iteration": 1 if kind == "smmala" else L,
+                   "acceptance_rate": acc_rate,
+                   "l2": ("chain state + saved samples per launch (%.0f MB) exceed the 126 MB L2" % (hbm_bytes / 1e6)) if not flush else
+                         ("chain state + saved samples per launch are %.0f MB (below the 126 MB L2): 160 MB of device memory are "
+                          "overwritten between timed steps to flush it" % (hbm_bytes / 1e6))},
+        "gpu_launches": steps,
+        "_per_launch_ms": per_launch_ms, "_evals_step": evals_step, "_hbm_bytes": hbm_bytes, "_P": P, "_C": C, "_dt": dt,
+    }
+    del sampler
+
+    if e2e:
+        # The chains are independent, so the step is cut into `nb` chain batches, each with its own persistent sampler and
+        # stream: batch b + 1's host->device copy and batch b - 1's device->host copies run under batch b's kernel.  Philox is
+        # keyed by the global chain id, so the results do not depend on the batching.  reset(theta_host) re-uses every device
+        # buffer of the sampler (no construction inside the timed region).
+        nb = max(1, min(args.e2e_batches, C // 32768))
+        bounds = [(b * C // nb, (b + 1) * C // nb) for b in range(nb)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nb)]
+        samplers = []
+        for (lo, hi) in bounds:
+            s = make_sampler(w, model, loader, theta_host[lo:hi], 999, thin, args.lanes)
+            s.chain_offset = rank * C + lo
+            samplers.append(s)
+        pin = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype).pin_memory()
+        out_samples = [pin(n_saved, P, hi - lo) for lo, hi in bounds]
+        out_targets = [pin(n_saved, hi - lo) for lo, hi in bounds]
+        out_accepted = [pin(n_saved, hi - lo, dtype=torch.uint8) for lo, hi in bounds]
+        out_theta, out_lt, out_acc = pin(C, P), pin(C), pin(C, dtype=torch.int32)
+
+        def step_e2e():
+            cur = torch.cuda.current_stream()
+            for b, ((lo, hi), st, s) in enumerate(zip(bounds, streams, samplers)):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    s.reset(theta_host[lo:hi])
+                    s.run(num_epochs=iters, num_burnin_epochs=0)
+                    blk = s._device_blocks[-1]
+                    out_samples[b].copy_(blk["sample"], non_blocking=True)
+                    out_targets[b].copy_(blk["target_val"], non_blocking=True)
+                    out_accepted[b].copy_(blk["accepted"], non_blocking=True)
+                    out_theta[lo:hi].copy_(s.current["sample"], non_blocking=True)
+                    out_lt[lo:hi].copy_(s.current["target_val"], non_blocking=True)
+                    out_acc[lo:hi].copy_(s.acceptance_counts(), non_blocking=True)
+            for st in streams:
+                cur.wait_stream(st)
+            cur.synchronize()
+            return out_lt[0].item()
+
+        for _ in range(max(2, warmup // 2)):
+            step_e2e()
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            step_e2e()
+        e1.record()
+        ctx.barrier()
+        t_e2e = ctx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        h2d = theta_host.numel() * esz
+        d2h = sum(t.numel() * t.element_size() for t in (out_theta, out_lt, out_acc, *out_samples, *out_targets, *out_accepted))
+        rec["e2e"] = {"value": world * evals_step * steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / steps, "chain_batches": nb,
+                      "returns": "every saved sample [n_saved, P, C], its target and accept flag, the final states / targets / "
+                                 "accept counts: what the ChainList objects of the run hold",
+                      "note": "public sampler API (reset + run) on %d persistent per-batch samplers / streams; copies of one batch "
+                              "overlap the kernels of the others" % nb}
+        rec["gpu_launches_e2e"] = (4 * nb) * steps   # per batch: eval + two transposes of reset, the fused run
+        del samplers
+    torch.cuda.empty_cache()
+    return rec
+
+
+def chain_roofline(ctx, rec, w):
+    """FMA roofline of the dominant kernel of a chain workload (sampler_kernel / smmala_kernel): algorithmic FLOPs per launch /
+    average launch time against the live-measured FMA peak of this device."""
+    import ctypes
+    from eeyore_b200 import _native as nv
+    dt = rec["_dt"]
+    peak = ctypes.c_double()
+    nv.check(nv.lib().eeyore_b200_fma_peak(nv.DTYPE_IDS[dt], 2000, ctypes.byref(peak)))
+    avg_launch_s = float(np.mean(rec["_per_launch_ms"])) * 1e-3
+    achieved = w["flops_per_eval"] * rec["_evals_step"] / avg_launch_s / 1e12
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
-    traffic = None
-    tfile = ROOT / "profiles" / "r01_traffic_cfg4.json"
-    if args.workload == "cfg4" and not args.chains and not args.iters and tfile.exists():
-        traffic = json.loads(tfile.read_text())["dram_bytes_total"]   # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
-    roofline = {"bound": "fp64_fma" if w["dtype"] == "f64" else "fp32_fma", "achieved": achieved, "peak": peak.value,
-                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
-                "peak_source": "measured live by eeyore_b200_fma_peak (dependent-free FMA chains, this device)",
-                "algorithmic_flops_per_eval": w["flops_per_eval"], "avg_launch_ms": avg_launch_s * 1e3,
-                "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / avg_launch_s / 1e9,
-                             "peak_gbs": hbm_peak,
-                             "peak_source": "MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"}}
-
-    # ---- CPU baseline: the oracle port on one core, bounded sample -------------------------------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpp, it = cpu_sample_sizes(args.workload)
-        cpp *= 16
-        t = _cpu_worker((args.workload, cpp, it, 0))
-        cpu = {"value": cpp * it * (1 if kind == "smmala" else L) / t, "unit": "evals/s", "cores": 1, "kind": "port",
-               "sample": f"{cpp} chains x {it} HMC iterations (L={L}) of the numpy oracle port, one process, {t:.1f} s"}
-
-    print(json.dumps({
-        "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-        "config": {"workload": w["name"], "chains_per_gpu": C, "hmc_iterations_per_step": iters, "num_steps": L,
-                   "step_size": w["step"], "thin": thin, "evals_counted_per_iteration": L,
-                   "evals_reference_executes_per_iteration": L + 1, "rng": "philox4x32-10 on device",
-                   "acceptance_rate": acc_rate,
-                   "l2": ("chain state + saved samples per launch (%.0f MB) exceed the 126 MB L2" % (hbm_bytes / 1e6))
-                         if hbm_bytes > 126e6 else
-                         ("chain state + saved samples per launch are %.0f MB (below the 126 MB L2): 160 MB of device memory "
-                          "are overwritten between timed steps to flush it" % (hbm_bytes / 1e6))},
-        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * t_e2e / args.steps, "chain_batches": nb,
-                "note": "public sampler API on %d chain batches / streams: each batch copies its theta in from pinned host "
-                        "memory, runs, and copies states / targets / accept counts out; copies overlap other batches' kernels" % nb},
-        "gpu_launches": args.steps,
-        "gpu_launches_e2e": 2 * nb * args.steps,
-        "clocks": clocks.summary(),
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-    }))
-    if world > 1:
-        dist.destroy_process_group()
+    out = {"bound": "fp64_fma" if dt == ctx.torch.float64 else "fp32_fma", "achieved": achieved, "peak": peak.value,
+           "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
+           "peak_source": "measured live by eeyore_b200_fma_peak (dependent-free FMA chains, this device)",
+           "algorithmic_flops_per_eval": w["flops_per_eval"], "avg_launch_ms": avg_launch_s * 1e3,
+           "hbm_view": {"algorithmic_bytes_per_launch": rec["_hbm_bytes"], "achieved_gbs": rec["_hbm_bytes"] / avg_launch_s / 1e9,
+                        "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"}}
+    return out
 
 
-def run_datapar(args):
-    """BASELINE config 5: one replicated chain, rows sharded over the ranks (strong scaling), NCCL all-reduce of the
-    1 + P partial sums after every local evaluation.  One step = `iters` HMC iterations (L evaluations each, every
-    evaluation over ALL rows)."""
-    import torch
-    import torch.distributed as dist
+def strip(rec):
+    return {k: v for k, v in rec.items() if not k.startswith("_")}
+
+
+def bench_diagnostics(ctx, reps=2):
+    """BASELINE config 4's second half: HMC sampling followed by on-device multi-ESS and autocorrelation of EVERY chain.
+    The saved-sample ring of all chains at once would be 84 GB (524,288 x 1,000 x 20 fp64), so the chains go through in
+    chunks: sample a chunk for n iterations (thin = 1, every chain's samples contiguous: sample_layout 'cnp'), run the
+    diagnostics kernel on it, keep [ESS, ACF] (C x (1 + 11 x 20) values), drop the ring.  Reported: the two stage times."""
+    torch = ctx.torch
+    from eeyore_b200 import stats as st
+    from eeyore_b200.chains import ChainList
+    args = ctx.args
+    w = WORKLOADS["cfg4"]
+    model, loader, dt, x, y = build_model(ctx, w)
+    P = model.num_params()
+    C = args.chains or w["chains"]
+    n, max_lag, chunk = args.diag_samples, 10, min(args.diag_chunk, C)
+    n_chunks = (C + chunk - 1) // chunk
+    gen = torch.Generator().manual_seed(2000 + ctx.rank)
+    theta_host = torch.randn(C, P, generator=gen, dtype=dt).pin_memory()
+    ess = torch.empty(C, dtype=dt, device=ctx.dev)
+    acf = torch.empty(C, max_lag + 1, P, dtype=dt, device=ctx.dev)
+    status = torch.empty(C, dtype=torch.int32, device=ctx.dev)
+    samplers = []
+    for k in range(n_chunks):
+        lo, hi = k * chunk, min(C, (k + 1) * chunk)
+        s = make_sampler(w, model, loader, theta_host[lo:hi], 4242, 1, args.lanes, chain=ChainList(keys=["sample", "accepted"]))
+        s.chain_offset = ctx.rank * C + lo
+        s.sample_layout = "cnp"
+        samplers.append(s)
+
+    def one_pass(timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_chunks + 1)]
+        ev[0].record()
+        for k, s in enumerate(samplers):
+            lo, hi = k * chunk, min(C, (k + 1) * chunk)
+            s._device_blocks = []
+            s.counter.reset()
+            s.run(num_epochs=n, num_burnin_epochs=0)
+            ev[2 * k + 1].record()
+            ring = s._device_blocks[-1]["sample"]                   # [n, P, c] view of the chain-major [c, n, P] buffer
+            out = st.chain_stats(ring, layout="npc", want=("ess",), max_lag=max_lag, check=False)
+            ess[lo:hi], acf[lo:hi], status[lo:hi] = out["ess"], out["acf"], out["status"]
+            s._device_blocks = []
+            del ring, out
+            ev[2 * k + 2].record()
+        torch.cuda.synchronize()
+        t_sample = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(n_chunks)) * 1e-3
+        t_stats = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(n_chunks)) * 1e-3
+        return t_sample, t_stats
+
+    one_pass(False)
+    ctx.barrier()
+    ts, tt = zip(*[one_pass(True) for _ in range(reps)])
+    ctx.barrier()
+    t_sample, t_stats = ctx.max_over_ranks(float(np.mean(ts))), ctx.max_over_ranks(float(np.mean(tt)))
+    ok = status == 0
+    # algorithmic work of the diagnostics of one chain: mean (n P), lags 0 and 1 (2 n P^2 each), one pass per further lag pair
+    # (2 n P^2, pair-summed), ACF (2 n P (max_lag + 1)); bytes: one read of the chain per pass
+    summary = {
+        "value": ctx.world * C / (t_sample + t_stats), "unit": "chains/s (sampled for %d iterations and diagnosed)" % n,
+        "chains_per_gpu": C, "chains_total": C * ctx.world, "samples_per_chain": n, "chunk_chains": chunk, "acf_max_lag": max_lag,
+        "sampling_s": t_sample, "diagnostics_s": t_stats, "diagnostics_over_sampling": t_stats / t_sample,
+        "sampling_evals_per_s": ctx.world * C * n * w["num_steps"] / t_sample,
+        "diagnosed_chains_per_s": ctx.world * C / t_stats,
+        "ring_bytes_per_chunk": chunk * n * P * 8,
+        "ess_mean": float(ess[ok].mean()) if bool(ok.any()) else None, "ess_min": float(ess[ok].min()) if bool(ok.any()) else None,
+        "chains_not_enough_samples": int((~ok).sum()),
+        "acf_lag1_mean": float(acf[:, 1].mean()), "acf_lag10_mean": float(acf[:, max_lag].mean()),
+        "kernel": "chain_stats_kernel<double, 5> (warp per chain, TMA-fed ring, register Cholesky / LU)",
+    }
+    del samplers, ess, acf
+    torch.cuda.empty_cache()
+    return summary
+
+
+def bench_cfg1(ctx):
+    """BASELINE configs[0] through the public API: MLP 2-2-1 on XOR, ONE MALA chain, 1,100 iterations (110 burn-in), fp64 --
+    one fused launch.  Wall time of sampler.run() including the synchronisation, best of three (the reference: 1.95 - 2.3 s)."""
+    torch = ctx.torch
+    from eeyore_b200.samplers import MALA
+    w = dict(name="cfg1", dims=[2, 2, 1], data="xor", loss="binary_classification", dtype="f64")
+    model, loader, dt, x, y = build_model(ctx, w)
+    theta0 = model.prior.sample()
+    best = None
+    for rep in range(4):
+        s = MALA(model, theta0=theta0, dataloader=loader, step=1.74, seed=rep)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s.run(num_epochs=1100, num_burnin_epochs=110)
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        if rep > 0:
+            best = t if best is None else min(best, t)
+    ch = s.get_chain()
+    return {"wall_ms_run_1100_iterations": 1e3 * best, "value": 1100 / best, "unit": "evals/s (one chain: latency, not throughput)",
+            "saved_samples": len(ch), "acceptance_rate": ch.acceptance_rate(), "launches": 1,
+            "multi_ess_of_the_chain": ch.multi_ess()}
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    torch = ctx.torch
+    clocks = ClockSampler(ctx.local, enabled=(ctx.rank == 0 and not os.environ.get("EEYORE_BENCH_NO_CLOCKS"))).start()
+    wname = args.workload
+    w = WORKLOADS[wname]
+    if w.get("kind") == "datapar":
+        line = bench_datapar(ctx, args.steps, args.warmup, clocks=clocks, full=True)
+    else:
+        head = bench_chains(ctx, wname, args.steps, args.warmup, clocks=clocks, dtype=args.dtype)
+        clocks.stop()
+        line = None
+        if ctx.rank == 0:
+            roof = chain_roofline(ctx, head, w)
+            tfile = ROOT / "profiles" / "r01_traffic_cfg4.json"
+            if wname == "cfg4" and not args.chains and not args.iters and not args.dtype and tfile.exists():
+                roof["traffic"] = json.loads(tfile.read_text())["dram_bytes_total"]   # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
+            line = {"metric": "log_target_grad_evals_per_sec", "value": head["value"], "unit": "evals/s", "n_gpus": ctx.world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+                    "config": dict(head["config"], evals_reference_executes_per_iteration=w["num_steps"] + 1,
+                                   rng="philox4x32-10 on device"),
+                    "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "gpu_launches_e2e": head["gpu_launches_e2e"],
+                    "clocks": clocks.summary(), "roofline": roof}
+    # ---- every other BASELINE configuration under the same clock (sub-records; the headline stays the line's own keys) ----
+    extra = {}
+    if args.extras and wname == "cfg4" and not args.dtype:
+        k = max(3, args.steps // 2)
+        wu = max(3, args.warmup // 2)
+        if ctx.world > 1:   # config 4 as BASELINE states it: 524,288 chains IN TOTAL, sharded over the GPUs
+            r = bench_chains(ctx, "cfg4", k, wu, chains=WORKLOADS["cfg4"]["chains"] // ctx.world, e2e=False, scaling="strong")
+            extra["cfg4_strong"] = strip(r)
+        else:
+            extra["cfg4_strong"] = {"note": "one GPU: identical to the headline (524,288 chains on this GPU)", "value": None}
+        r = bench_chains(ctx, "cfg4", k, wu, thin=1, e2e=False)
+        extra["cfg4_thin1"] = strip(r)
+        extra["cfg4_diagnostics"] = bench_diagnostics(ctx)
+        for name in ("cfg2", "cfg3"):
+            r = bench_chains(ctx, name, k, wu)
+            if ctx.rank == 0:
+                r["roofline"] = chain_roofline(ctx, r, WORKLOADS[name])
+            extra[name] = strip(r)
+        extra["cfg1"] = bench_cfg1(ctx)
+        extra["cfg5"] = bench_datapar(ctx, k, wu, clocks=None, full=False)
+    if ctx.rank == 0:
+        if ctx.world == 1 and not args.no_cpu_baseline and w.get("kind") != "datapar":
+            line["cpu_baseline"] = cpu_baseline_chains(wname)
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line))
+    ctx.close()
+
+
+def cpu_baseline_chains(wname):
+    """The oracle port on ONE host core, bounded sample; the unmodified reference itself cannot travel to the GPU box -- its
+    timing on the build container's CPU is quoted from profiles/r02_reference_cpu_timing.json."""
+    w = WORKLOADS[wname]
+    cpp, it = cpu_sample_sizes(wname)
+    cpp *= 16
+    t = _cpu_worker((wname, cpp, it, 0))
+    evals = cpp * it * (1 if w.get("kind") == "smmala" else w["num_steps"])
+    cpu = {"value": evals / t, "unit": "evals/s", "cores": 1, "kind": "port",
+           "sample": f"{cpp} chains x {it} iterations (L={w['num_steps']}) of the numpy oracle port, one process, {t:.1f} s"}
+    ref_file = ROOT / "profiles" / "r02_reference_cpu_timing.json"
+    if ref_file.exists():
+        ref = json.loads(ref_file.read_text())
+        cpu["note"] = ("the unmodified reference (torch autograd, /root/reference) cannot travel to the GPU box; timed in the build "
+                       "container (%s, %d cores, one thread): cfg1 MALA.run(1100, 110) %.2f s = %.0f evals/s; HMC 2-3-2-1 XOR %.0f "
+                       "evals/s; HMC 4-3-3 N=150 %.0f evals/s; 16-64-64-1 1M rows %.2f s per evaluation on %d threads "
+                       "(tools/time_reference.py)" % (
+                           ref["host"]["cpu"], ref["host"]["cores"], ref["cfg1_mala_221_1100_iters"]["seconds"],
+                           ref["cfg1_mala_221_1100_iters"]["evals_per_s"], ref["cfg4_hmc_2321_xor"]["evals_per_s_counting_L"],
+                           ref["cfg2_hmc_433_n150"]["evals_per_s_counting_L"],
+                           ref["cfg5_upto_grad_16_64_64_1_n1M"]["seconds_per_eval_1M_rows"],
+                           ref["cfg5_upto_grad_16_64_64_1_n1M"]["torch_threads"]))
+    return cpu
+
+
+def bench_datapar(ctx, steps, warmup, clocks=None, full=True):
+    """BASELINE config 5: one replicated chain, rows sharded over the ranks (strong scaling); the 1 + P partial sums of every
+    evaluation are exchanged by peer stores over NVLink inside the post kernel.  One step = `iters` HMC iterations (L
+    evaluations each, every evaluation over ALL rows).  full=False: the compact sub-record of the default line."""
+    torch, dist = ctx.torch, ctx.dist
     from torch.distributions import Normal
 
     from eeyore_b200.constants import loss_functions
     from eeyore_b200.models.mlp import MLP, Hyperparameters
     from eeyore_b200.samplers import DataShardedHMC, shard_rows
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOADS[args.workload]
+    args = ctx.args
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    w = WORKLOADS["cfg5"]
     n_total = args.rows or w["rows"]
     lo, hi = shard_rows(n_total, world, rank)
     gen = torch.Generator(device=dev).manual_seed(4)           # same stream on every rank; each keeps its slice
@@ -532,44 +727,33 @@ def run_datapar(args):
     model = MLP(loss=loss_functions[w["loss"]], hparams=hp, dtype=torch.float32, device=dev)
     P = model.num_params()
     model.prior = Normal(torch.zeros(P), S3 * torch.ones(P))
-    iters, L = args.iters or w["iters"], w["num_steps"]
+    iters, L = (args.iters if full else 0) or w["iters"], w["num_steps"]
     theta_host = (torch.randn(P, generator=torch.Generator().manual_seed(5)) * 0.1).pin_memory()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
     sampler = DataShardedHMC(model, theta_host.to(dev), x, y, step=w["step"], num_steps=L, seed=7, exchange=args.exchange)
-    clocks = ClockSampler(local, enabled=(rank == 0 and not os.environ.get("EEYORE_BENCH_NO_CLOCKS"))).start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    clocks.mark_begin()
+    ctx.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ctx.barrier()
+    if clocks:
+        clocks.mark_begin()
     ev[0].record()
-    for k in range(args.steps):
+    for k in range(steps):
         sampler.run(num_epochs=iters, num_burnin_epochs=0)
         ev[k + 1].record()
-    barrier()
-    clocks.mark_end()
-    clocks.stop()
-    t_res = max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
-    per_step_ms = [round(ev[k].elapsed_time(ev[k + 1]), 2) for k in range(args.steps)]
+    ctx.barrier()
+    if clocks:
+        clocks.mark_end()
+        clocks.stop()
+    t_res = ctx.max_over_ranks(ev[0].elapsed_time(ev[-1]) * 1e-3)
+    per_step_ms = [round(ev[k].elapsed_time(ev[k + 1]), 2) for k in range(steps)]
     evals_step = iters * L
-    value = evals_step * args.steps / t_res
+    value = evals_step * steps / t_res
     acc = sampler.acceptance_count() / max(1, sampler._iter)
+    launches_per_iter = sampler.launches_per_iteration()
 
     out_theta = torch.empty(iters, P).pin_memory()
-
     e2e_sampler = DataShardedHMC(model, theta_host, x, y, step=w["step"], num_steps=L, seed=11, exchange=args.exchange)
 
     def step_e2e():
@@ -579,15 +763,15 @@ def run_datapar(args):
         torch.cuda.current_stream().synchronize()
 
     step_e2e()
-    barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_e2e()
     e1.record()
-    barrier()
-    t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    # ---- the dominant kernel alone (dp_eval_tc_kernel + its 21-CTA reduction), CUDA events on the launching stream -------
+    ctx.barrier()
+    t_e2e = ctx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    # ---- the dominant kernel alone (dp_eval_tc_kernel), CUDA events on the launching stream ---------------------------------
     import ctypes
     from eeyore_b200 import _native as nv
     lib = nv.lib()
@@ -612,71 +796,75 @@ def run_datapar(args):
     def tc_kernel(th, xx, yy, nn, out, wsp, st):          # max |x| of the shard computed once, as DataShardedHMC does
         return lib.eeyore_b200_dp_loglik_grad_x(th, xx, yy, nn, nv.ptr(amax), out, wsp, st)
 
-    barrier()
-    kernel_ms = max_over_ranks(time_kernel(tc_kernel))
-    ffma_ms = max_over_ranks(time_kernel(lib.eeyore_b200_dp_loglik_grad_ffma, reps=5))
+    ctx.barrier()
+    kernel_ms = ctx.max_over_ranks(time_kernel(tc_kernel))
+    ffma_ms = ctx.max_over_ranks(time_kernel(lib.eeyore_b200_dp_loglik_grad_ffma, reps=5)) if full else None
+    line = None
     if rank == 0:
-        peak32 = ctypes.c_double()
-        nv.check(lib.eeyore_b200_fma_peak(nv.F32, 4000, ctypes.byref(peak32)))
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
             tensor_peak, peak_src = float(peaks["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst; the kernel is timed alone)"
         except Exception:
             tensor_peak, peak_src = 1590.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
-        flops_launch = 29056.0 * (hi - lo)
-        achieved = flops_launch / (kernel_ms * 1e-3) / 1e12
+        achieved = 29056.0 * (hi - lo) / (kernel_ms * 1e-3) / 1e12
         # fp16 MMA work actually issued per 128-row tile: three piece products per GEMM as two MMAs (N = 128 and 64, plus the
         # 8 ones columns of the weight-gradient GEMMs); the M = 64 weight-gradient MMAs run at the cost of M = 128
         tiles = (hi - lo + 127) // 128
         mma_flops_tile = 2 * 128 * 16 * (128 + 64) + 2 * (2 * 128 * 64 * (128 + 64)) \
             + 2 * 128 * 128 * (136 + 72) + 2 * 128 * 128 * (40 + 24)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            procs = host_cores()
-            pool = CpuPool(procs)
-            cpu_datapar_throughput(pool, procs, 1 << 16, n_total)
-            v, wall = cpu_datapar_throughput(pool, procs, 1 << 20, n_total)
-            pool.close()
-            cpu = {"value": v, "unit": "evals/s", "cores": procs, "kind": "port",
-                   "sample": f"one evaluation over {1 << 20} of the {n_total} rows split over {procs} processes of the numpy oracle "
-                             f"port, {wall:.1f} s, scaled linearly to {n_total} rows"}
-        print(json.dumps({
-            "metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "rows_total": n_total, "rows_per_gpu": hi - lo,
-                       "hmc_iterations_per_step": iters, "num_steps": L, "evals_counted_per_iteration": L,
-                       "exchange": ("none (1 GPU)" if world == 1 else
-                                    "NCCL all-reduce of 1+P fp64 sums per evaluation" if sampler.exchange == "nccl" else
-                                    "1+P fp64 sums stored into every peer's inbox over NVLink (CUDA IPC) inside the fused post "
-                                    "kernel, sequence-numbered flags, totals added in rank order; no NCCL on the data path"),
-                       "acceptance_rate": acc, "per_step_ms": per_step_ms,
-                       "l2": "x shard (%.0f MB) exceeds the 126 MB L2" % ((hi - lo) * 68 / 1e6),
-                       "data_resident": "x, y shards stay in HBM across steps; e2e copies the chain state in and the samples out"},
-            "e2e": {"value": evals_step * args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": P * 4,
-                    "d2h_bytes_per_step": iters * P * 4, "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": args.steps * iters * (2 + (4 if sampler.exchange == "nccl" else 2) * L),
-            "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tensor_peak, "traffic": _cfg5_traffic(hi - lo), "peak_source": peak_src,
-                         "kernel": "dp_eval_tc_kernel (tcgen05 fp16 MMA on exact two-piece splits, fp32 accumulate in TMEM, two tiles in flight)",
-                         "avg_launch_ms": kernel_ms, "algorithmic_flops_per_row": 29056,
-                         "f16_mma_tflops_issued": tiles * mma_flops_tile / (kernel_ms * 1e-3) / 1e12,
-                         "note": "fp32 parity costs three fp16 piece products per GEMM (and M = 64 padding): the tensor pipe "
-                                 "executes %.1fx the algorithmic FLOPs" % (mma_flops_tile / (29056.0 * 128)),
-                         "fp32_fma_view": {"peak": peak32.value, "frac": achieved / peak32.value,
-                                           "peak_source": "measured live by eeyore_b200_fma_peak (this device)",
-                                           "ffma_kernel_ms": ffma_ms, "speedup_over_ffma_kernel": ffma_ms / kernel_ms},
-                         "share_of_step": kernel_ms * evals_step / (1e3 * t_res / args.steps),
-                         "hbm_view": {"algorithmic_bytes_per_launch": (hi - lo) * 68,
-                                      "achieved_gbs": (hi - lo) * 68 / (kernel_ms * 1e-3) / 1e9}},
-            "cpu_baseline": cpu,
-        }))
+        exchange = ("none (1 GPU)" if world == 1 else
+                    "NCCL all-reduce of 1+P fp64 sums per evaluation" if sampler.exchange == "nccl" else
+                    "1+P fp64 sums stored into every peer's inbox over NVLink (CUDA IPC), sequence-numbered flags, totals added in "
+                    "rank order; no NCCL on the data path")
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                    "traffic": _cfg5_traffic(hi - lo), "peak_source": peak_src,
+                    "kernel": "dp_eval_tc_kernel (tcgen05 fp16 MMA on exact two-piece splits, fp32 accumulate in TMEM, two tiles in flight)",
+                    "avg_launch_ms": kernel_ms, "algorithmic_flops_per_row": 29056,
+                    "f16_mma_tflops_issued": tiles * mma_flops_tile / (kernel_ms * 1e-3) / 1e12,
+                    "share_of_step": kernel_ms * evals_step / (1e3 * t_res / steps),
+                    "hbm_view": {"algorithmic_bytes_per_launch": (hi - lo) * 68, "achieved_gbs": (hi - lo) * 68 / (kernel_ms * 1e-3) / 1e9}}
+        config = {"workload": w["name"], "rows_total": n_total, "rows_per_gpu": hi - lo, "hmc_iterations_per_step": iters,
+                  "num_steps": L, "evals_counted_per_iteration": L, "exchange": exchange, "trajectory": sampler.mode,
+                  "launches_per_hmc_iteration": launches_per_iter, "acceptance_rate": acc,
+                  "l2": "x shard (%.0f MB) exceeds the 126 MB L2" % ((hi - lo) * 68 / 1e6),
+                  "data_resident": "x, y shards stay in HBM across steps; e2e copies the chain state in and the samples out"}
+        e2e = {"value": evals_step * steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": P * 4, "d2h_bytes_per_step": iters * P * 4,
+               "ms_per_step": 1e3 * t_e2e / steps}
+        if full:
+            peak32 = ctypes.c_double()
+            nv.check(lib.eeyore_b200_fma_peak(nv.F32, 4000, ctypes.byref(peak32)))
+            roofline["note"] = ("fp32 parity costs three fp16 piece products per GEMM (and M = 64 padding): the tensor pipe executes "
+                                "%.1fx the algorithmic FLOPs" % (mma_flops_tile / (29056.0 * 128)))
+            roofline["fp32_fma_view"] = {"peak": peak32.value, "frac": achieved / peak32.value,
+                                         "peak_source": "measured live by eeyore_b200_fma_peak (this device)",
+                                         "ffma_kernel_ms": ffma_ms, "speedup_over_ffma_kernel": ffma_ms / kernel_ms}
+            config["per_step_ms"] = per_step_ms
+            cpu = None
+            if world == 1 and not args.no_cpu_baseline:
+                procs = host_cores()
+                pool = CpuPool(procs)
+                cpu_datapar_throughput(pool, procs, 1 << 16, n_total)
+                v, wall = cpu_datapar_throughput(pool, procs, 1 << 20, n_total)
+                pool.close()
+                cpu = {"value": v, "unit": "evals/s", "cores": procs, "kind": "port",
+                       "sample": f"one evaluation over {1 << 20} of the {n_total} rows split over {procs} processes of the numpy oracle "
+                                 f"port, {wall:.1f} s, scaled linearly to {n_total} rows"}
+            line = {"metric": "log_target_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": steps,
+                    "warmup": warmup, "ms_per_step": 1e3 * t_res / steps, "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "e2e": e2e,
+                    "gpu_launches": steps * iters * launches_per_iter, "clocks": clocks.summary() if clocks else None,
+                    "roofline": roofline, "cpu_baseline": cpu}
+        else:
+            line = {"value": value, "unit": "evals/s (each over all %d rows)" % n_total, "ms_per_step": 1e3 * t_res / steps,
+                    "ms_per_evaluation": 1e3 * t_res / steps / evals_step, "scaling": "strong", "dtype": "f32", "steps": steps,
+                    "config": config, "e2e": e2e, "kernel_ms": kernel_ms, "gpu_launches": steps * iters * launches_per_iter,
+                    "roofline": roofline}
     sampler.check_status()
     sampler.close()
     e2e_sampler.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del x, y
+    torch.cuda.empty_cache()
+    return line
 
 
 def _cfg5_traffic(rows_per_launch):
@@ -696,11 +884,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"], help="chain workloads: override the arithmetic type")
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--iters", type=int, default=0, help="override HMC iterations per step")
     ap.add_argument("--rows", type=int, default=0, help="cfg5: override the total number of data rows")
     ap.add_argument("--lanes", type=int, default=0, help="threads cooperating on one chain (0 = library heuristic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="default cfg4 line only, without the sub-records of the other BASELINE configurations")
+    ap.add_argument("--diag-samples", type=int, default=1000, help="saved iterations per chain of the diagnostics stage")
+    ap.add_argument("--diag-chunk", type=int, default=65536, help="chains per chunk of the diagnostics stage")
     ap.add_argument("--e2e-batches", type=int, default=8,
                     help="chain batches (streams) of the end-to-end arm: copies of one batch overlap the kernel of another")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
@@ -708,8 +901,6 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
-    elif WORKLOADS[args.workload].get("kind") == "datapar":
-        run_datapar(args)
     else:
         run_ours(args)
 

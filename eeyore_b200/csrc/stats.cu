@@ -1,5 +1,5 @@
 // On-device chain diagnostics: mean, sample covariance, initial-sequence Monte Carlo covariance (INSE), multivariate
-// ESS and autocorrelation, batched over chains (one CTA per chain, chain staged in shared memory).
+// ESS and autocorrelation, batched over chains.
 //
 // Replaces (reference paths):
 //   eeyore/stats/cov.py:5-15           sample covariance (n-1 denominator)
@@ -7,6 +7,23 @@
 //   eeyore/stats/inse_mc_cov.py:9-83   INSE estimator (adjust=False): the python double loop of torch.ger outer products
 //   eeyore/stats/multi_ess.py:6-14     n (det cov / det inse)^(1/p)
 // ACF is builder-defined (kanga is absent from the reference snapshot).
+//
+// Mapping (round 2; the first version gave a whole CTA to one chain and spent its time in CTA barriers and in serial
+// factorisations by one warp while seven waited):
+//   * ONE WARP PER CHAIN, no CTA-wide synchronisation anywhere; chains are independent, so a warp walks through its own
+//     data-dependent INSE loop (inse_mc_cov.py:20-73) at its own pace.
+//   * The chain is STREAMED, never staged whole: every pass (column means; lags 0 and 1; one pass per further lag pair)
+//     pulls the rows through a 32-row shared-memory ring, 8-row chunks fetched by TMA 1-D bulk copies (cp.async.bulk +
+//     mbarrier, issued by one lane three chunks ahead) when a chain's rows are contiguous -- the [C, n, P] layout the
+//     samplers write with sample_layout = "cnp" -- and by plain loads for any other strides.  Rows are centred once, on
+//     arrival; rows past the end read as zero, so lagged sums need no tail handling.  Any n works (no 200 KB limit).
+//   * Lagged cross-products sum_i x_i (x) x_{i+l}: the warp is two 16-lane row slices, each lane owns a TE x TE register
+//     tile of the P x P product (P = 20: 5 x 5, all 32 lanes busy, 10 shared-memory loads per 25 DFMA).  INSE only needs
+//     gamma_{2m} + gamma_{2m+1}, so for m >= 1 ONE pass multiplies x_i with the pair sum y_i = x_{i+2m} + x_{i+2m+1}
+//     (kept in a second ring, formed when a chunk arrives): half the FMAs of two separate lags.
+//   * Cholesky (the is_pos_def test) and LU with partial pivoting (torch.det) run in REGISTERS, one matrix row per lane,
+//     pivots and pivot rows exchanged by shuffles -- no shared-memory round trips in the dependent chain.
+// HBM traffic: each pass reads the chain once (n P sizeof(T) bytes per chain).  FLOPs: 2 n P^2 per lag pass.
 #include <cuda_runtime.h>
 #include <string>
 #include "common.cuh"
@@ -14,8 +31,13 @@
 
 namespace eb {
 
-constexpr int kStatThreads = 256;
-constexpr int kTile = 4;  // each thread owns a 4x4 tile of a lagged cross-product matrix
+constexpr int kStatWarps = 4;          // warps (= chains in flight) per CTA
+constexpr int kRB = 8;                 // rows per chunk
+constexpr int kNBuf = 4;               // chunks in the ring
+constexpr int kW = kRB * kNBuf;        // ring rows
+constexpr int kNearLag = (kNBuf - 2) * kRB - 1;   // largest lag whose partner rows are still in the ring (15)
+constexpr int kAcfGroup = 16;          // autocorrelation lags handled per pass
+constexpr unsigned kFull = 0xffffffffu;
 
 template <typename T> struct StatsArgs {
   const T* x;
@@ -26,295 +48,529 @@ template <typename T> struct StatsArgs {
   T* out_cov;    // [C,P,P]
   T* out_inse;   // [C,P,P]
   T* out_ess;    // [C]
-  int* out_status;  // [C] 0 ok, 1 = not enough samples (inse_mc_cov.py:44-45), 2 = non-finite input
+  int* out_status;  // [C] 0 ok, 1 = not enough samples (inse_mc_cov.py:44-45)
   int* out_lags;    // [C,2] (sn, last accepted m)
   int max_lag;
   T* out_acf;    // [C, max_lag+1, P]
-  T* scratch;    // global fallback for the centred chain ([grid, n, PS]) when it does not fit shared memory
-  int use_scratch;
 };
 
-__host__ __device__ inline int stat_ps(int P) { return ((P + kTile - 1) / kTile) * kTile + 1; }  // odd row stride
-
-// Lagged cross-product A[a][b] = sum_{i < n-lag} xc[i][a] * xc[i+lag][b], all threads of the CTA cooperate:
-// thread -> (tile, slice of the i range); per-slice partial tiles are reduced through shared memory.
-template <typename T>
-__device__ void lag_product(const T* __restrict__ xc, int n, int P, int PS, int lag, T* part, T* out, int tiles_1d,
-                            int slices) {
-  const int ntiles = tiles_1d * tiles_1d;
-  const int tid = threadIdx.x;
-  const int PP = tiles_1d * kTile;
-  if (tid < ntiles * slices) {
-    const int tile = tid % ntiles, slice = tid / ntiles;
-    const int a0 = (tile / tiles_1d) * kTile, b0 = (tile % tiles_1d) * kTile;
-    const int len = n - lag;
-    const int chunk = (len + slices - 1) / slices;
-    const int i0 = slice * chunk, i1 = min(len, i0 + chunk);
-    T acc[kTile][kTile];
-#pragma unroll
-    for (int r = 0; r < kTile; ++r)
-#pragma unroll
-      for (int c = 0; c < kTile; ++c) acc[r][c] = T(0);
-    for (int i = i0; i < i1; ++i) {
-      T va[kTile], vb[kTile];
-#pragma unroll
-      for (int r = 0; r < kTile; ++r) { va[r] = xc[(size_t)i * PS + a0 + r]; vb[r] = xc[(size_t)(i + lag) * PS + b0 + r]; }
-#pragma unroll
-      for (int r = 0; r < kTile; ++r)
-#pragma unroll
-        for (int c = 0; c < kTile; ++c) acc[r][c] = fma_t<T>(va[r], vb[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int r = 0; r < kTile; ++r)
-#pragma unroll
-      for (int c = 0; c < kTile; ++c) part[(size_t)slice * PP * PP + (a0 + r) * PP + b0 + c] = acc[r][c];
-  }
-  __syncthreads();
-  for (int e = tid; e < P * P; e += blockDim.x) {
-    const int a = e / P, b = e % P;
-    T s = T(0);
-    for (int sl = 0; sl < slices; ++sl) s += part[(size_t)sl * PP * PP + a * PP + b];
-    out[e] = s;
-  }
-  __syncthreads();
+// ---- mbarrier / bulk copy (one barrier per ring slot, owned by a warp) ---------------------------------------------------
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(bar)));
 }
+__device__ __forceinline__ void st_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(st_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(st_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void st_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Warp-level Cholesky of the P x P matrix m (row-major, stride P) into w; returns false when a pivot is not
-// positive (or NaN), i.e. torch.linalg.cholesky would raise (is_pos_def.py:5-9).  log_det (optional) = 2 sum log L_jj.
-template <typename T> __device__ bool warp_cholesky(const T* m, T* w, int P, T* det_out) {
-  const int lane = threadIdx.x & 31;
-  for (int e = lane; e < P * P; e += 32) w[e] = m[e];
-  __syncwarp();
-  bool ok = true;
-  T det = T(1);
-  for (int j = 0; j < P; ++j) {
-    T d = w[j * P + j];
-    for (int k = 0; k < j; ++k) d -= w[j * P + k] * w[j * P + k];
-    if (!(d > T(0))) { ok = false; break; }
-    const T l = sqrt_t<T>(d);
-    det *= d;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < P; i += 32) {
-      T s = w[i * P + j];
-      for (int k = 0; k < j; ++k) s -= w[i * P + k] * w[j * P + k];
-      w[i * P + j] = s / l;
-    }
-    if (lane == 0) w[j * P + j] = l;
-    __syncwarp();
+// ---- the ring: rows of ONE chain streamed through shared memory by the warp that owns it ---------------------------------
+template <typename T> struct Ring {
+  const T* base;        // first element of the chain
+  long s_iter, s_param;
+  int n, P;
+  bool bulk;            // rows contiguous and 16-byte aligned: chunks come by cp.async.bulk
+  T* X;                 // [kW][P] centred rows
+  T* Y;                 // [kW][P] pair sums y_g = x_g + x_{g+1}
+  const T* mean;        // [32] subtracted on arrival
+  uint64_t* bar;        // [kNBuf]
+  uint32_t phase;       // parity bit per slot
+  int next_issue, next_ready, last_chunk;
+  bool want_y;
+
+  __device__ __forceinline__ int rows_of(int k) const {
+    const int r = n - k * kRB;
+    return r < 0 ? 0 : (r > kRB ? kRB : r);
   }
-  if (det_out) *det_out = det;
+  __device__ __forceinline__ bool by_bulk(int k) const {
+    const int rows = rows_of(k);
+    return bulk && rows > 0 && ((rows * P * (int)sizeof(T)) & 15) == 0;
+  }
+  // all lanes; the slot's previous contents are dead (the callers' __syncwarp orders the last reads before this)
+  __device__ __forceinline__ void issue(int k, int lane) {
+    const int rows = rows_of(k);
+    if (rows <= 0) return;
+    T* dst = X + (k % kNBuf) * kRB * P;
+    if (by_bulk(k)) {
+      if (lane == 0) {
+        st_bulk_load(dst, base + (long)k * kRB * s_iter, (uint32_t)(rows * P * sizeof(T)), bar + (k % kNBuf));
+      }
+    } else {
+      const T* src = base + (long)k * kRB * s_iter;
+      for (int e = lane; e < rows * P; e += 32) {
+        const int i = e / P, j = e - i * P;
+        dst[e] = src[i * s_iter + j * s_param];
+      }
+    }
+  }
+  __device__ __forceinline__ void begin(int last, bool with_y, int lane) {
+    next_issue = 0; next_ready = 0; last_chunk = last; want_y = with_y;
+    st_fence_proxy_async();   // this lane's generic-proxy accesses to the ring memory, before the async-proxy (TMA) writes
+    __syncwarp();
+    for (; next_issue < kNBuf && next_issue <= last_chunk; ++next_issue) issue(next_issue, lane);
+  }
+  // chunks up to k arrived, centred, zero-filled past the end, pair sums formed
+  __device__ __forceinline__ void ready(int k, int lane) {
+    for (; next_ready <= k; ++next_ready) {
+      const int kk = next_ready, slot = kk % kNBuf, rows = rows_of(kk);
+      if (by_bulk(kk)) {
+        st_mbar_wait(bar + slot, (phase >> slot) & 1u);
+        phase ^= 1u << slot;
+      }
+      __syncwarp();
+      T* dst = X + slot * kRB * P;
+      for (int e = lane; e < kRB * P; e += 32) {
+        const int i = e / P, j = e - i * P;
+        dst[e] = (i < rows) ? dst[e] - mean[j] : T(0);
+      }
+      __syncwarp();
+      if (want_y) {   // y_g for g = first row of this chunk - 1 ... last row - 1 (row g + 1 is needed)
+        const int g0 = kk * kRB - 1;
+        for (int e = lane; e < kRB * P; e += 32) {
+          const int i = e / P, j = e - i * P, g = g0 + i;
+          if (g >= 0) Y[(g % kW) * P + j] = X[(g % kW) * P + j] + X[((g + 1) % kW) * P + j];
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // chunk `done` has been consumed: its slot takes the next chunk
+  __device__ __forceinline__ void release(int done, int lane) {
+    st_fence_proxy_async();
+    __syncwarp();
+    if (next_issue <= last_chunk && next_issue == done + kNBuf) { issue(next_issue, lane); ++next_issue; }
+  }
+  // centred value of row g, column j straight from global memory (partners beyond the ring)
+  __device__ __forceinline__ T far(int g, int j) const {
+    return (g < n) ? base[(long)g * s_iter + (long)j * s_param] - mean[j] : T(0);
+  }
+};
+
+template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(kFull, v, src); }
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int m) { return __shfl_xor_sync(kFull, v, m); }
+
+// ---- register factorisations: lane r holds row r of a PT x PT matrix --------------------------------------------------------
+// torch.linalg.cholesky succeeds <=> every pivot is positive (is_pos_def.py:5-9).  Right-looking; `a` is destroyed.
+template <typename T, int PT> __device__ __forceinline__ bool warp_chol_ok(T (&a)[PT]) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < PT; ++k) {
+    const T d = shfl_t(a[k], k);
+    if (!(d > T(0))) { ok = false; break; }     // uniform: d is a broadcast
+    const T rinv = T(1) / sqrt_t<T>(d);
+    const T lk = a[k] * rinv;                   // L[r][k] (rows r >= k)
+#pragma unroll
+    for (int c = k + 1; c < PT; ++c) a[c] = fma_t<T>(-lk, shfl_t(lk, c), a[c]);
+  }
   return ok;
 }
 
-// Warp-level determinant by LU with partial pivoting (torch.det, inse_mc_cov.py:47,66 and multi_ess.py:9-12).
-template <typename T> __device__ T warp_det_lu(const T* m, T* w, int P) {
-  const int lane = threadIdx.x & 31;
-  for (int e = lane; e < P * P; e += 32) w[e] = m[e];
-  __syncwarp();
+// determinant by LU with partial pivoting (torch.det; inse_mc_cov.py:47,66, multi_ess.py:9-12).  Rows stay in their lanes:
+// `pos` is the logical position of a lane's row, a pivot swaps positions only.  `a` is destroyed.
+template <typename T, int PT> __device__ __forceinline__ T warp_det_lu(T (&a)[PT], int lane) {
+  bool done = lane >= PT;
+  int pos = lane;
   T det = T(1);
-  for (int k = 0; k < P; ++k) {
-    // pivot search (all lanes redundantly; P <= 32)
-    int piv = k;
-    T best = fabs(w[k * P + k]);
-    for (int i = k + 1; i < P; ++i) {
-      const T v = fabs(w[i * P + k]);
-      if (v > best) { best = v; piv = i; }
+#pragma unroll
+  for (int k = 0; k < PT; ++k) {
+    // NaN sorts like +inf: it becomes the pivot and ends the loop uniformly (a NaN key would break the total order and the
+    // lanes would disagree about the pivot lane)
+    T v = done ? T(-1) : ((a[k] != a[k]) ? T(INFINITY) : fabs(a[k]));
+    int vp = pos, vl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // largest |a[k]|; ties -> lowest logical position (LAPACK idamax order)
+      const T v2 = shfl_xor_t(v, o);
+      const int p2 = __shfl_xor_sync(kFull, vp, o), l2 = __shfl_xor_sync(kFull, vl, o);
+      const bool take = (v2 > v) || (v2 == v && p2 < vp);
+      if (take) { v = v2; vp = p2; vl = l2; }
     }
-    __syncwarp();
-    if (piv != k) {
-      for (int c = lane; c < P; c += 32) { const T t = w[k * P + c]; w[k * P + c] = w[piv * P + c]; w[piv * P + c] = t; }
+    const T pv = shfl_t(a[k], vl);
+    if (vp != k) {                        // row interchange: the row at logical position k takes the pivot row's position
       det = -det;
+      if (!done && pos == k) pos = vp;
     }
-    __syncwarp();
-    const T pv = w[k * P + k];
+    if (lane == vl) pos = k;
     det *= pv;
-    if (pv == T(0) || pv != pv) break;
-    for (int i = k + 1 + lane; i < P; i += 32) {
-      const T f = w[i * P + k] / pv;
-      for (int c = k + 1; c < P; ++c) w[i * P + c] -= f * w[k * P + c];
-    }
-    __syncwarp();
+    if (pv == T(0) || pv != pv) break;    // uniform
+    const T rp = T(1) / pv;
+    const T f = (done || lane == vl) ? T(0) : a[k] * rp;
+#pragma unroll
+    for (int c = k + 1; c < PT; ++c) a[c] = fma_t<T>(-f, shfl_t(a[c], vl), a[c]);
+    if (lane == vl) done = true;
   }
   return det;
 }
 
-template <typename T> __global__ void __launch_bounds__(kStatThreads) chain_stats_kernel(const StatsArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = a.n, P = a.P, PS = stat_ps(P);
-  const int tiles_1d = (P + kTile - 1) / kTile, ntiles = tiles_1d * tiles_1d, PP = tiles_1d * kTile;
-  const int slices = max(1, min(kStatThreads / ntiles, 16));
-  const int tid = threadIdx.x;
-  // carve: matrices first, then the (optional) chain buffer
-  T* part = reinterpret_cast<T*>(smem_raw);            // [slices, PP, PP]
-  T* A0 = part + (size_t)slices * PP * PP;             // lag product (even lag)
-  T* A1 = A0 + P * P;                                  // lag product (odd lag)
-  T* Sig = A1 + P * P;                                 // running INSE estimate
-  T* Sig1 = Sig + P * P;                               // candidate
-  T* Cov = Sig1 + P * P;
-  T* work = Cov + P * P;                               // factorisation workspace
-  T* mean = work + P * P;                              // [PP]
-  T* ctrl = mean + PP;                                 // [4] broadcast slots
-  T* xs_sh = ctrl + 4;
-  const T inv_n = T(1) / T(n);
+// ---- lagged cross-products ---------------------------------------------------------------------------------------------------
+// lane = (h, ta, tb): row slice h (rows of parity h), tile (ta, tb) of TE x TE entries.
+template <typename T, int TE> struct Tile {
+  T v[TE][TE];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int r = 0; r < TE; ++r)
+#pragma unroll
+      for (int c = 0; c < TE; ++c) v[r][c] = T(0);
+  }
+  __device__ __forceinline__ void rank1(const T (&a)[TE], const T (&b)[TE]) {
+#pragma unroll
+    for (int r = 0; r < TE; ++r)
+#pragma unroll
+      for (int c = 0; c < TE; ++c) v[r][c] = fma_t<T>(a[r], b[c], v[r][c]);
+  }
+  // sum of the two row slices, then the h == 0 lanes store the tile into a row-major [4 TE][ld] matrix
+  __device__ __forceinline__ void store(T* mat, int ld, int ta, int tb, int h) {
+#pragma unroll
+    for (int r = 0; r < TE; ++r)
+#pragma unroll
+      for (int c = 0; c < TE; ++c) {
+        const T s = v[r][c] + shfl_xor_t(v[r][c], 16);
+        if (h == 0) mat[(ta * TE + r) * ld + tb * TE + c] = s;
+      }
+  }
+};
 
-  for (long c = blockIdx.x; c < a.C; c += gridDim.x) {
-    T* xc = a.use_scratch ? a.scratch + (size_t)blockIdx.x * n * PS : xs_sh;
-    // ---- stage the chain (zero-padded columns), mean, centring ------------------------------------------------
-    for (int e = tid; e < n * PS; e += blockDim.x) {
-      const int i = e / PS, j = e % PS;
-      xc[e] = (j < P) ? a.x[i * a.s_iter + c * a.s_chain + j * a.s_param] : T(0);
-    }
-    __syncthreads();
-    {
-      // column sums: thread -> (column, slice)
-      const int cs = max(1, kStatThreads / PP);
-      if (tid < PP * cs) {
-        const int j = tid % PP, sl = tid / PP;
-        const int chunk = (n + cs - 1) / cs;
-        T s = T(0);
-        for (int i = sl * chunk; i < min(n, (sl + 1) * chunk); ++i) s += xc[(size_t)i * PS + j];
-        part[sl * PP + j] = s;
-      }
-      __syncthreads();
-      if (tid < PP) {
-        T s = T(0);
-        for (int sl = 0; sl < cs; ++sl) s += part[sl * PP + tid];
-        mean[tid] = s * inv_n;
-      }
-      __syncthreads();
-      for (int e = tid; e < n * PS; e += blockDim.x) {
-        const int j = e % PS;
-        if (j < P) xc[e] -= mean[j];
-      }
-      __syncthreads();
-    }
-    if (a.out_mean) for (int j = tid; j < P; j += blockDim.x) a.out_mean[c * P + j] = mean[j];
+template <typename T, int TE> __device__ __forceinline__ void load_cols(const T* row, int col0, int P, T (&out)[TE]) {
+#pragma unroll
+  for (int r = 0; r < TE; ++r) out[r] = (col0 + r < P) ? row[col0 + r] : T(0);
+}
 
-    // ---- autocorrelation (builder-defined) -----------------------------------------------------
-    if (a.out_acf) {
-      const int K = a.max_lag + 1;
-      for (int e = tid; e < K * P; e += blockDim.x) {
-        const int k = e / P, j = e % P;
-        T num = T(0), den = T(0);
-        for (int t = 0; t < n; ++t) {
-          const T v = xc[(size_t)t * PS + j];
-          den = fma_t<T>(v, v, den);
-          if (t + k < n) num = fma_t<T>(v, xc[(size_t)(t + k) * PS + j], num);
+// column means: mean[j] = (1/n) sum_i x[i][j]   (the ring's own mean must be zero during this pass)
+template <typename T> __device__ void pass_mean(Ring<T>& rg, T* mean_out, int lane) {
+  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+  rg.begin(nci - 1, false, lane);
+  T s0 = T(0), s1 = T(0);
+  for (int ci = 0; ci < nci; ++ci) {
+    rg.ready(ci, lane);
+    if (lane < P) {
+      const T* x0 = rg.X + (ci % kNBuf) * kRB * P + lane;
+#pragma unroll
+      for (int t = 0; t < kRB; t += 2) { s0 += x0[t * P]; s1 += x0[(t + 1) * P]; }
+    }
+    rg.release(ci, lane);
+  }
+  __syncwarp();
+  if (lane < 32) mean_out[lane] = (lane < P) ? (s0 + s1) * (T(1) / T(n)) : T(0);
+  __syncwarp();
+}
+
+// A0 = sum_i x_i (x) x_i, A1 = sum_i x_i (x) x_{i+1}  (lags 0 and 1 in one pass)
+template <typename T, int TE>
+__device__ void pass_lag01(Ring<T>& rg, Tile<T, TE>& a0, Tile<T, TE>& a1, int lane) {
+  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+  const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
+  rg.begin(nci, false, lane);        // row n (a zero row) is the partner of row n - 1
+  a0.zero(); a1.zero();
+  for (int ci = 0; ci < nci; ++ci) {
+    rg.ready(ci + 1, lane);
+#pragma unroll
+    for (int t = 0; t < kRB / 2; ++t) {
+      const int i = ci * kRB + 2 * t + h;
+      const T* xi = rg.X + (i % kW) * P;
+      const T* xn = rg.X + ((i + 1) % kW) * P;
+      T xa[TE], b0[TE], b1[TE];
+      load_cols<T, TE>(xi, ta * TE, P, xa);
+      load_cols<T, TE>(xi, tb * TE, P, b0);
+      load_cols<T, TE>(xn, tb * TE, P, b1);
+      a0.rank1(xa, b0);
+      a1.rank1(xa, b1);
+    }
+    rg.release(ci, lane);
+  }
+}
+
+// A = sum_i x_i (x) x_{i+l}, l = 0 or 1: one lag per pass, for tiles too large to keep two in registers
+template <typename T, int TE> __device__ void pass_lag(Ring<T>& rg, int l, Tile<T, TE>& acc, int lane) {
+  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+  const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
+  rg.begin((nci * kRB - 1 + l) / kRB, false, lane);
+  acc.zero();
+  for (int ci = 0; ci < nci; ++ci) {
+    rg.ready((ci * kRB + kRB - 1 + l) / kRB, lane);
+#pragma unroll
+    for (int t = 0; t < kRB / 2; ++t) {
+      const int i = ci * kRB + 2 * t + h;
+      T xa[TE], xb[TE];
+      load_cols<T, TE>(rg.X + (i % kW) * P, ta * TE, P, xa);
+      load_cols<T, TE>(rg.X + ((i + l) % kW) * P, tb * TE, P, xb);
+      acc.rank1(xa, xb);
+    }
+    rg.release(ci, lane);
+  }
+}
+
+// B = sum_i x_i (x) (x_{i+l} + x_{i+l+1})
+template <typename T, int TE> __device__ void pass_pair(Ring<T>& rg, int l, Tile<T, TE>& b, int lane) {
+  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+  const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
+  const bool near = l <= kNearLag;
+  rg.begin(near ? (nci * kRB + l) / kRB : nci - 1, near, lane);
+  b.zero();
+  for (int ci = 0; ci < nci; ++ci) {
+    rg.ready(near ? (ci * kRB + kRB + l) / kRB : ci, lane);
+#pragma unroll
+    for (int t = 0; t < kRB / 2; ++t) {
+      const int i = ci * kRB + 2 * t + h;
+      T xa[TE], yb[TE];
+      load_cols<T, TE>(rg.X + (i % kW) * P, ta * TE, P, xa);
+      if (near) {
+        load_cols<T, TE>(rg.Y + ((i + l) % kW) * P, tb * TE, P, yb);
+      } else {   // partners beyond the ring: straight from global memory (slowly mixing chains only)
+#pragma unroll
+        for (int c = 0; c < TE; ++c) {
+          const int j = tb * TE + c;
+          yb[c] = (j < P) ? rg.far(i + l, j) + rg.far(i + l + 1, j) : T(0);
         }
-        a.out_acf[(c * K + k) * P + j] = num / den;
+      }
+      b.rank1(xa, yb);
+    }
+    rg.release(ci, lane);
+  }
+}
+
+// acc[k] = sum_i x_i[j] x_{i+k0+k}[j] for lane j, k < kAcfGroup
+template <typename T> __device__ void pass_acf(Ring<T>& rg, int k0, int kmax, T (&acc)[kAcfGroup], int lane) {
+  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+  const bool near = k0 == 0;
+  const int span = kmax < kAcfGroup - 1 ? kmax : kAcfGroup - 1;     // largest lag of the near group
+  rg.begin(near ? (nci * kRB - 1 + span) / kRB : nci - 1, false, lane);
+#pragma unroll
+  for (int k = 0; k < kAcfGroup; ++k) acc[k] = T(0);
+  const int j = lane < P ? lane : 0;
+  for (int ci = 0; ci < nci; ++ci) {
+    rg.ready(near ? (ci * kRB + kRB - 1 + span) / kRB : ci, lane);
+    for (int t = 0; t < kRB; ++t) {
+      const int i = ci * kRB + t;
+      const T xi = rg.X[(i % kW) * P + j];
+#pragma unroll
+      for (int k = 0; k < kAcfGroup; ++k) {
+        if (k0 + k <= kmax) {
+          const T xp = near ? rg.X[((i + k) % kW) * P + j] : rg.far(i + k0 + k, j);
+          acc[k] = fma_t<T>(xi, xp, acc[k]);
+        }
       }
     }
-    if (!a.out_cov && !a.out_inse && !a.out_ess) { __syncthreads(); continue; }
+    rg.release(ci, lane);
+  }
+}
 
-    // ---- lag 0: covariance and gamma_0 -------------------------------------------------------------------------
-    lag_product<T>(xc, n, P, PS, 0, part, A0, tiles_1d, slices);
-    for (int e = tid; e < P * P; e += blockDim.x) {
-      Cov[e] = A0[e] / T(n - 1);                       // cov.py:13-15
-      if (a.out_cov) a.out_cov[c * P * P + e] = Cov[e];
+// resident CTAs per SM: three (170 registers) while one lane's tiles are small, two (255 registers) beyond
+template <typename T, int TE> constexpr int stats_min_blocks() { return (TE * TE * (int)sizeof(T) <= 25 * 8) ? 3 : 2; }
+
+template <typename T, int TE>
+__global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) chain_stats_kernel(const StatsArgs<T> a) {
+  constexpr int PT = 4 * TE, LD = PT + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = a.n, P = a.P;
+  // per-warp carve (bytes, every piece 16-byte aligned)
+  const size_t ring_bytes = ((size_t)kW * P * sizeof(T) + 15) & ~size_t(15);
+  const size_t mat_bytes = ((size_t)PT * LD * sizeof(T) + 15) & ~size_t(15);
+  const size_t scratch_bytes = 2 * ring_bytes > 2 * mat_bytes ? 2 * ring_bytes : 2 * mat_bytes;   // rings, then A0 | A1
+  const size_t per_warp = scratch_bytes + mat_bytes + 32 * sizeof(T) + kNBuf * sizeof(uint64_t);
+  unsigned char* my = smem_raw + (size_t)warp * per_warp;
+  T* X = reinterpret_cast<T*>(my);
+  T* Y = reinterpret_cast<T*>(my + ring_bytes);
+  T* M0 = reinterpret_cast<T*>(my);                       // product matrices alias the (dead) rings between passes
+  T* M1 = reinterpret_cast<T*>(my + mat_bytes);
+  T* Sg = reinterpret_cast<T*>(my + scratch_bytes);        // running INSE estimate, row-major [PT][LD]
+  T* mean = reinterpret_cast<T*>(my + scratch_bytes + mat_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(my + scratch_bytes + mat_bytes + 32 * sizeof(T));
+  if (lane == 0) {
+#pragma unroll
+    for (int b = 0; b < kNBuf; ++b) st_mbar_init(bar + b);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  Ring<T> rg;
+  rg.s_iter = a.s_iter; rg.s_param = a.s_param; rg.n = n; rg.P = P;
+  rg.X = X; rg.Y = Y; rg.mean = mean; rg.bar = bar; rg.phase = 0;
+  const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
+  const T inv_n = T(1) / T(n);
+  const bool want_second = a.out_cov || a.out_inse || a.out_ess;
+
+  for (long c = (long)blockIdx.x * kStatWarps + warp; c < a.C; c += (long)gridDim.x * kStatWarps) {
+    rg.base = a.x + c * a.s_chain;
+    rg.bulk = a.s_param == 1 && a.s_iter == P && (reinterpret_cast<uintptr_t>(rg.base) & 15) == 0;
+    // ---- mean ------------------------------------------------------------------------------------------------------------
+    mean[lane] = T(0);
+    __syncwarp();
+    pass_mean<T>(rg, mean, lane);
+    if (a.out_mean && lane < P) a.out_mean[c * P + lane] = mean[lane];
+
+    // ---- autocorrelation (builder-defined) ------------------------------------------------------------------
+    if (a.out_acf) {
+      const int K = a.max_lag;
+      T den = T(1);
+      for (int k0 = 0; k0 <= K; k0 += kAcfGroup) {
+        T acc[kAcfGroup];
+        pass_acf<T>(rg, k0, K, acc, lane);
+        if (k0 == 0) den = acc[0];
+        if (lane < P) {
+#pragma unroll
+          for (int k = 0; k < kAcfGroup; ++k)
+            if (k0 + k <= K) a.out_acf[(c * (K + 1) + k0 + k) * P + lane] = acc[k] / den;
+        }
+      }
     }
-    __syncthreads();
+    if (!want_second) continue;
+
+    // ---- lags 0 and 1: covariance, gamma_0, Sigma_0 --------------------------------------------------------------------------
+    if constexpr (stats_min_blocks<T, TE>() == 3) {
+      Tile<T, TE> a0, a1;
+      pass_lag01<T, TE>(rg, a0, a1, lane);
+      __syncwarp();                       // the rings are dead: their memory takes the two product matrices
+      a0.store(M0, LD, ta, tb, h);
+      a1.store(M1, LD, ta, tb, h);
+      __syncwarp();
+    } else {                              // large tiles: one lag per pass; lag 0 waits in Sg (free until Sigma_0 is formed)
+      Tile<T, TE> acc;
+      pass_lag<T, TE>(rg, 0, acc, lane);
+      __syncwarp();
+      acc.store(Sg, LD, ta, tb, h);
+      __syncwarp();
+      pass_lag<T, TE>(rg, 1, acc, lane);
+      __syncwarp();
+      acc.store(M1, LD, ta, tb, h);
+      __syncwarp();
+      for (int e = lane; e < PT * LD; e += 32) M0[e] = Sg[e];
+      __syncwarp();
+    }
+    T row[PT];        // this lane's row of the candidate estimate
+    T det_cov;
+    {
+      T cv[PT];
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const bool in = lane < P && q < P;
+        const T a0rq = in ? M0[lane * LD + q] : T(0);
+        cv[q] = in ? a0rq / T(n - 1) : ((q == lane) ? T(1) : T(0));          // cov.py:13-15
+        if (a.out_cov && in) a.out_cov[(c * P + lane) * P + q] = cv[q];
+        // Gam = sym(gam0 + gam1), inse_mc_cov.py:32-33: pure additions before the scaling, so that elements (r, q) and (q, r)
+        // are bitwise equal (the reference's is_pos_def demands exact symmetry); Sigma_0 = -gam0 + 2 Gam (:35-36)
+        const T se = in ? a0rq + M1[lane * LD + q] : T(0);
+        const T st = in ? M0[q * LD + lane] + M1[q * LD + lane] : T(0);
+        const T gam = (se + st) * (T(0.5) * inv_n);
+        row[q] = in ? T(2) * gam - a0rq * inv_n : ((q == lane) ? T(1) : T(0));
+      }
+      det_cov = warp_det_lu<T, PT>(cv, lane);
+    }
     if (!a.out_inse && !a.out_ess) continue;
 
-    // ---- INSE (inse_mc_cov.py:20-73) ---------------------------------------------------------------------------
+    // ---- INSE (inse_mc_cov.py:20-73) ---------------------------------------------------------------------------------------
     const int ub = n / 2;
-    int sn = ub, m_last = -1, status = 0;
+    int sn = ub, m_last = -1;
     T last_det = T(0);
     bool phase2 = false;
     for (int m = 0; m < ub; ++m) {
-      if (m > 0) lag_product<T>(xc, n, P, PS, 2 * m, part, A0, tiles_1d, slices);
-      if (2 * m + 1 < n) lag_product<T>(xc, n, P, PS, 2 * m + 1, part, A1, tiles_1d, slices);
-      T* dst = phase2 ? Sig1 : Sig;
-      for (int e = tid; e < P * P; e += blockDim.x) {
-        const int r = e / P, q = e % P, et = q * P + r;
-        // Gam = sym(gam0 + gam1), :32-33.  Written with pure additions before the scaling so that FMA contraction
-        // cannot round element (r, q) and (q, r) differently: the reference's is_pos_def demands EXACT symmetry.
-        const T se = A0[e] + A1[e], st = A0[et] + A1[et];
-        const T gam = (se + st) * (T(0.5) * inv_n);
-        const T g0 = A0[e] * inv_n;
-        if (m == 0) dst[e] = T(2) * gam - g0;                          // :35-36 (A0 is exactly symmetric at lag 0)
-        else dst[e] = Sig[e] + T(2) * gam;                             // :37-38, :62
-      }
-      __syncthreads();
-      if (tid < 32) {
-        if (!phase2) {
-          T det;
-          const bool pd = warp_cholesky<T>(Sig, work, P, &det);         // is_pos_def(Sig), :40
-          if (tid == 0) ctrl[0] = pd ? T(1) : T(0);
-          if (pd) {
-            const T dlu = warp_det_lu<T>(Sig, work, P);                  // last_dtm = det(Sig), :47
-            if (tid == 0) ctrl[1] = dlu;
-          }
-        } else {
-          const T dlu = warp_det_lu<T>(Sig1, work, P);                   // :66
-          if (tid == 0) ctrl[1] = dlu;
+      if (m > 0) {
+        {
+          Tile<T, TE> b;
+          pass_pair<T, TE>(rg, 2 * m, b, lane);
+          __syncwarp();
+          b.store(M0, LD, ta, tb, h);
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+          const bool in = lane < P && q < P;
+          const T gam = in ? (M0[lane * LD + q] + M0[q * LD + lane]) * (T(0.5) * inv_n) : T(0);
+          const T base = in ? Sg[lane * LD + q] : ((q == lane) ? T(1) : T(0));
+          row[q] = in ? base + T(2) * gam : base;                          // :37-38, :62
         }
       }
-      __syncthreads();
       if (!phase2) {
-        if (ctrl[0] != T(0)) { sn = m; m_last = m; last_det = ctrl[1]; phase2 = true; }
+        if (lane < PT) {
+#pragma unroll
+          for (int q = 0; q < PT; ++q) Sg[lane * LD + q] = row[q];         // Sigma_m is kept whether or not it is PD yet
+        }
+        T w[PT];
+#pragma unroll
+        for (int q = 0; q < PT; ++q) w[q] = row[q];
+        if (warp_chol_ok<T, PT>(w)) {                                      // is_pos_def(Sig), :40
+#pragma unroll
+          for (int q = 0; q < PT; ++q) w[q] = row[q];
+          last_det = warp_det_lu<T, PT>(w, lane);                          // last_dtm = det(Sig), :47
+          sn = m; m_last = m; phase2 = true;
+        }
       } else {
-        const T cur = ctrl[1];
-        if (!(cur > last_det)) break;                                  // current_dtm <= last_dtm -> break, :68-69
-        for (int e = tid; e < P * P; e += blockDim.x) Sig[e] = Sig1[e];
+        T w[PT];
+#pragma unroll
+        for (int q = 0; q < PT; ++q) w[q] = row[q];
+        const T cur = warp_det_lu<T, PT>(w, lane);                         // :66
+        if (!(cur > last_det)) break;                                      // current_dtm <= last_dtm -> break, :68-69
+        if (lane < PT) {
+#pragma unroll
+          for (int q = 0; q < PT; ++q) Sg[lane * LD + q] = row[q];
+        }
         last_det = cur;
         m_last = m;
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (sn > ub - 1) status = 1;                                        // 'Not enough samples', :44-45
-    if (a.out_inse) for (int e = tid; e < P * P; e += blockDim.x) a.out_inse[c * P * P + e] = Sig[e];
-    // ---- multi-ESS (multi_ess.py:9-14) ---------------------------------------------------------------------------
-    if (tid < 32) {
-      const T dcov = warp_det_lu<T>(Cov, work, P);
-      if (tid == 0) {
-        const double ratio = (double)dcov / (double)last_det;
-        const T ess = (T)((double)n * pow(ratio, 1.0 / (double)P));
-        if (a.out_ess) a.out_ess[c] = status == 0 ? ess : qnan<T>();
-        if (a.out_status) a.out_status[c] = status;
-        if (a.out_lags) { a.out_lags[2 * c] = sn; a.out_lags[2 * c + 1] = m_last; }
-      }
+    const int status = sn > ub - 1 ? 1 : 0;                                // 'Not enough samples', :44-45
+    __syncwarp();
+    if (a.out_inse && lane < P)
+      for (int q = 0; q < P; ++q) a.out_inse[(c * P + lane) * P + q] = Sg[lane * LD + q];
+    // ---- multi-ESS (multi_ess.py:9-14) --------------------------------------------------------------------------------------
+    if (lane == 0) {
+      const double ratio = (double)det_cov / (double)last_det;
+      const T ess = (T)((double)n * pow(ratio, 1.0 / (double)P));
+      if (a.out_ess) a.out_ess[c] = status == 0 ? ess : qnan<T>();
+      if (a.out_status) a.out_status[c] = status;
+      if (a.out_lags) { a.out_lags[2 * c] = sn; a.out_lags[2 * c + 1] = m_last; }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
-template <typename T> size_t stats_smem_fixed(int P) {
-  const int tiles_1d = (P + kTile - 1) / kTile, ntiles = tiles_1d * tiles_1d, PP = tiles_1d * kTile;
-  int slices = kStatThreads / ntiles;
-  if (slices < 1) slices = 1;
-  if (slices > 16) slices = 16;
-  size_t part = (size_t)slices * PP * PP;
-  const size_t cs = (size_t)(kStatThreads / PP > 0 ? kStatThreads / PP : 1) * PP;
-  if (cs > part) part = cs;
-  return sizeof(T) * (part + 6 * (size_t)P * P + PP + 4);
+template <typename T> size_t stats_smem_bytes(int P, int TE) {
+  const int PT = 4 * TE, LD = PT + 1;
+  const size_t ring_bytes = ((size_t)kW * P * sizeof(T) + 15) & ~size_t(15);
+  const size_t mat_bytes = ((size_t)PT * LD * sizeof(T) + 15) & ~size_t(15);
+  const size_t scratch_bytes = 2 * ring_bytes > 2 * mat_bytes ? 2 * ring_bytes : 2 * mat_bytes;
+  return kStatWarps * (scratch_bytes + mat_bytes + 32 * sizeof(T) + kNBuf * sizeof(uint64_t));
 }
 
-template <typename T> cudaError_t launch_stats(StatsArgs<T> a, cudaStream_t st) {
-  int dev = 0, sms = 0, max_smem = 0;
+template <typename T, int TE> cudaError_t launch_stats_te(const StatsArgs<T>& a, cudaStream_t st) {
+  int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const int PS = stat_ps(a.P);
-  const size_t fixed = stats_smem_fixed<T>(a.P);
-  const size_t chain_bytes = sizeof(T) * (size_t)a.n * PS;
-  size_t smem = fixed + chain_bytes;
-  long grid = a.C < (long)sms * 8 ? a.C : (long)sms * 8;
-  a.use_scratch = 0;
-  a.scratch = nullptr;
-  cudaError_t e;
-  if (smem > (size_t)max_smem) {  // chain does not fit on chip: keep the centred chain in global memory (L2)
-    smem = fixed;
-    grid = a.C < (long)sms * 2 ? a.C : (long)sms * 2;
-    a.use_scratch = 1;
-    e = cudaMallocAsync((void**)&a.scratch, chain_bytes * grid, st);
-    if (e != cudaSuccess) return e;
-  }
-  e = cudaFuncSetAttribute(chain_stats_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = stats_smem_bytes<T>(a.P, TE);
+  auto kern = chain_stats_kernel<T, TE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  chain_stats_kernel<T><<<(unsigned)grid, kStatThreads, smem, st>>>(a);
-  e = cudaGetLastError();
-  if (a.use_scratch) cudaFreeAsync(a.scratch, st);
-  return e;
+  const long want = (a.C + kStatWarps - 1) / kStatWarps;
+  const long cap = (long)sms * 3 * 4;        // persistent-ish: a few CTAs per resident slot, warps stride over the chains
+  const long grid = want < cap ? want : cap;
+  kern<<<(unsigned)grid, kStatWarps * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T> cudaError_t launch_stats(const StatsArgs<T>& a, cudaStream_t st) {
+  switch ((a.P + 3) / 4) {
+    case 1: return launch_stats_te<T, 1>(a, st);
+    case 2: return launch_stats_te<T, 2>(a, st);
+    case 3: return launch_stats_te<T, 3>(a, st);
+    case 4: return launch_stats_te<T, 4>(a, st);
+    case 5: return launch_stats_te<T, 5>(a, st);
+    case 6: return launch_stats_te<T, 6>(a, st);
+    case 7: return launch_stats_te<T, 7>(a, st);
+    case 8: return launch_stats_te<T, 8>(a, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace eb
@@ -333,18 +589,19 @@ int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int 
   if (!samples || n_chains < 1 || n_samples < 2 || n_params < 1)
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "chain_stats: bad sizes or null samples");
   if (n_params > 32) return eeyore_b200_set_error_(EEYORE_B200_EUNSUPPORTED, "chain_stats: at most 32 parameters per chain");
+  if (n_samples >= (1LL << 30)) return eeyore_b200_set_error_(EEYORE_B200_EUNSUPPORTED, "chain_stats: at most 2^30 samples per chain");
   if (out_acf && (max_lag < 0 || max_lag >= n_samples))
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "acf: max_lag must be in [0, n_samples)");
   cudaError_t e;
   if (dtype == EEYORE_B200_F64) {
     StatsArgs<double> a{(const double*)samples, ss_iter, ss_chain, ss_param, (int)n_samples, n_params, n_chains,
                         (double*)out_mean, (double*)out_cov, (double*)out_inse, (double*)out_ess, out_status, out_lags,
-                        max_lag, (double*)out_acf, nullptr, 0};
+                        max_lag, (double*)out_acf};
     e = launch_stats<double>(a, (cudaStream_t)stream);
   } else if (dtype == EEYORE_B200_F32) {
     StatsArgs<float> a{(const float*)samples, ss_iter, ss_chain, ss_param, (int)n_samples, n_params, n_chains,
                        (float*)out_mean, (float*)out_cov, (float*)out_inse, (float*)out_ess, out_status, out_lags,
-                       max_lag, (float*)out_acf, nullptr, 0};
+                       max_lag, (float*)out_acf};
     e = launch_stats<float>(a, (cudaStream_t)stream);
   } else {
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dtype must be f32 or f64");

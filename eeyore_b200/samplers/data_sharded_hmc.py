@@ -211,5 +211,14 @@ class DataShardedHMC:
     def get_chain(self):
         return self.chain
 
+    @property
+    def mode(self):
+        return "one launch per evaluation + one fused post launch (fold, exchange, prior, leapfrog)"
+
+    def launches_per_iteration(self):
+        """Kernel launches of one HMC iteration: begin + accept + (evaluation, post) per leapfrog step; the NCCL formulation
+        adds the all-reduce and separate finish / step kernels."""
+        return 2 + (2 if self.exchange != "nccl" else 4) * self.num_steps
+
     def acceptance_count(self):
         return int(self._acc_count.item())

@@ -36,6 +36,10 @@ class NativeChainSampler(SerialSampler):
         self._tape = None
         self._data_dev = None
         self._device_blocks = []
+        # Storage order of the saved states of a batched run: "npc" = [n_saved, P, C] (chain-minor: the sampler's stores are
+        # coalesced) or "cnp" = [C, n_saved, P] (every chain contiguous: what the diagnostics kernel streams with bulk
+        # copies).  Either way DeviceChains sees the [n, P, C] indexing (a strided view for "cnp").
+        self.sample_layout = "npc"
         self.num_chains = 1
         self.current = {key: None for key in self.keys}
         if theta0 is not None:
@@ -167,11 +171,14 @@ class NativeChainSampler(SerialSampler):
         thin = max(1, int(self.thin))
         n_saved = int(nv.lib().eeyore_b200_num_saved(n_iters, n_burnin, thin))
         out = {}
+        chain_major = self.sample_layout == "cnp"
+        new_block = (lambda: torch.empty(c, n_saved, pn, dtype=m.dtype, device=dev).permute(1, 2, 0)) if chain_major else \
+            (lambda: torch.empty(n_saved, pn, c, dtype=m.dtype, device=dev))
         if n_saved > 0:
             if "sample" in want:
-                out["sample"] = torch.empty(n_saved, pn, c, dtype=m.dtype, device=dev)
+                out["sample"] = new_block()
             if "grad_val" in want and self._uses_grad:
-                out["grad_val"] = torch.empty(n_saved, pn, c, dtype=m.dtype, device=dev)
+                out["grad_val"] = new_block()
             if "target_val" in want:
                 out["target_val"] = torch.empty(n_saved, c, dtype=m.dtype, device=dev)
             out["accepted"] = torch.empty(n_saved, c, dtype=torch.uint8, device=dev)
@@ -198,10 +205,10 @@ class NativeChainSampler(SerialSampler):
         p.theta, p.target = self._theta_soa.data_ptr(), self._lt.data_ptr()
         p.grad = self._grad_soa.data_ptr() if self._uses_grad else None
         p.st_chain, p.st_param = 1, c
+        if "sample" in out or "grad_val" in out:
+            p.ss_iter, p.ss_param, p.ss_chain = (out.get("sample", out.get("grad_val"))).stride()
         if "sample" in out:
-            p.out_samples, p.ss_iter, p.ss_chain, p.ss_param = out["sample"].data_ptr(), pn * c, 1, c
-        elif "grad_val" in out:
-            p.ss_iter, p.ss_chain, p.ss_param = pn * c, 1, c
+            p.out_samples = out["sample"].data_ptr()
         if "grad_val" in out:
             p.out_grad = out["grad_val"].data_ptr()
         if "target_val" in out:
@@ -240,7 +247,8 @@ class NativeChainSampler(SerialSampler):
             return self.chain
         if not self._device_blocks:
             raise RuntimeError("no saved states yet")
-        cat = lambda k: (torch.cat([b[k] for b in self._device_blocks]) if k in self._device_blocks[0] else None)
+        blocks = self._device_blocks
+        cat = lambda k: (None if k not in blocks[0] else blocks[0][k] if len(blocks) == 1 else torch.cat([b[k] for b in blocks]))
         return DeviceChains(cat("sample"), cat("target_val"), cat("grad_val"), cat("accepted"),
                             accept_count=self._acc_count, n_iters=self._iter_offset)
 
