@@ -90,6 +90,9 @@ SIGNATURES = {
     "eeyore_b200_dp_exchange_close": (_I, [_VP]),
     "eeyore_b200_dp_exchange_destroy": (_I, [_VP]),
     "eeyore_b200_dp_exchange_scratch_offset": (_I64, []),
+    "eeyore_b200_dp_scratch_len": (_I64, []),
+    "eeyore_b200_dp_hmc_run": (_I, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _D, _D, _I,
+                                    _I64, _I64, _U64, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _U64, C.POINTER(_VP), _VP]),
     "eeyore_b200_dp_workspace_bytes": (_I64, []),
     "eeyore_b200_dp_finish": (_I, [_VP, _VP, _VP, _VP, _I, _D, _VP, _VP, _VP]),
     "eeyore_b200_dp_hmc_begin": (_I, [_VP, _VP, _D, _U64, _U64, _VP, _VP, _VP, _VP, _VP]),

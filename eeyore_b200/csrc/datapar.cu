@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "datapar.cuh"
+#include "datapar_post.cuh"
 #include "../../include/eeyore_b200.h"
 
 #ifndef DP_UNROLL_KMAJOR
@@ -32,7 +33,7 @@
 namespace eb {
 
 constexpr int DP_RS = DP_R + 4;      // row stride of feature-major buffers (floats); RS % 32 == 4
-constexpr double kLogSqrt2PiD = 0.9189385332046727;     // log(sqrt(2 pi))
+constexpr double kLogSqrt2PiD = kDpLogSqrt2Pi;
 
 struct DpSmem {
   alignas(16) unsigned long long bar[2];
@@ -494,51 +495,8 @@ __global__ void dp_hmc_accept_kernel(float* __restrict__ theta_cur, float* __res
 }
 
 
-// ---- fused "post" step of one evaluation --------------------------------------------------------------------------------
-// One launch (21 CTAs, one thread per entry of [loglik, dloglik]) does what used to be four steps:
-//   1. fixed-order sum of the per-CTA partial sums of the evaluation kernel                       (was dp_reduce_kernel)
-//   2. the exchange step of the data-sharded path: every rank stores its 1 + P sums straight into every peer's inbox over
-//      NVLink (peer pointers from CUDA IPC), releases a per-CTA flag with the evaluation's sequence number, waits for the
-//      same flag from every peer and adds the W inbox slots in rank order -> bit-identical totals on every rank
-//      (was an NCCL all-reduce of 42.5 KB, latency-bound, plus a launch gap on either side)
-//   3. Normal log-prior and its gradient, temperature (bayesian_model.py:46-56)                    (was dp_finish_kernel)
-//   4. optionally the leapfrog update that follows the evaluation (hmc.py:113-119)                 (was dp_hmc_step_kernel)
+// ---- fused "post" step of one evaluation (device code in datapar_post.cuh) ------------------------------------------------
 // Scalars (target, kinetic energy) are per-CTA partials folded in CTA order by the last CTA to finish (ticket counter).
-constexpr int DP_POST_THREADS = 256;
-constexpr int DP_POST_CTAS = (DP_P + 1 + DP_POST_THREADS - 1) / DP_POST_THREADS;   // 21
-constexpr int DP_XSLOT = DP_POST_CTAS * DP_POST_THREADS;                          // doubles per inbox slot (5376)
-constexpr int DP_XMAXW = 8;                                                        // ranks per box
-
-struct DpExchange {
-  int world, rank;
-  unsigned long long seq;                 // evaluation counter, identical on every rank, starts at 1
-  double* inbox[DP_XMAXW];                // inbox[p]: rank p's [2 parity][8 src][DP_XSLOT] doubles (peer-mapped)
-  unsigned long long* flags[DP_XMAXW];    // flags[p]: rank p's [2 parity][8 src][32 cta] sequence numbers
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ double block_sum_256(double v, double* red) {
-  // fixed order: lanes by xor-shuffle, then the 8 warp sums in warp order
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < DP_POST_THREADS / 32; ++w) t += red[w];
-  __syncthreads();
-  return t;   // valid in thread 0
-}
-
-// scratch: [0..31] log-prior partials, [32..63] kinetic partials, [64] summed log-likelihood, [65] ticket counter (as u64)
 __global__ void __launch_bounds__(DP_POST_THREADS)
 dp_post_kernel(const double* __restrict__ partials, int n_parts, DpExchange xc, const float* __restrict__ theta,
                const float* __restrict__ ploc, const float* __restrict__ pscale, int has_temp, double temp,
@@ -548,74 +506,21 @@ dp_post_kernel(const double* __restrict__ partials, int n_parts, DpExchange xc, 
   __shared__ double red[DP_POST_THREADS / 32];
   __shared__ int last_s;
   const int tid = threadIdx.x, cta = blockIdx.x;
-  const int e = cta * DP_POST_THREADS + tid;          // entry of [loglik, dloglik]; e <= DP_P is valid
-  double tot = 0.0;
-  if (e <= DP_P)
-    for (int c = 0; c < n_parts; ++c) tot += partials[(size_t)c * (DP_P + 1) + e];
-  if (xc.world > 1) {
-    const int par = (int)(xc.seq & 1ull);
-    const size_t slot = (size_t)(par * DP_XMAXW + xc.rank) * DP_XSLOT + e;
-    for (int p = 0; p < xc.world; ++p) xc.inbox[p][slot] = tot;      // coalesced 2 KB per CTA per peer, over NVLink
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      for (int p = 0; p < xc.world; ++p) st_release_sys(&xc.flags[p][(par * DP_XMAXW + xc.rank) * 32 + cta], xc.seq);
-      for (int src = 0; src < xc.world; ++src) {
-        const unsigned long long* f = &xc.flags[xc.rank][(par * DP_XMAXW + src) * 32 + cta];
-        long spins = 0;
-        while (ld_acquire_sys(f) < xc.seq) {
-          if (++spins > (1L << 28)) {   // seconds: a peer is gone; fail loudly instead of hanging the box
-            status[0] = 1;
-            __trap();
-          }
-        }
-      }
-    }
-    __syncthreads();
-    tot = 0.0;
-    for (int src = 0; src < xc.world; ++src)
-      tot += __ldcg(&xc.inbox[xc.rank][(size_t)(par * DP_XMAXW + src) * DP_XSLOT + e]);
-  }
-  double lp = 0.0, kin = 0.0;
-  if (e == 0) scratch[64] = tot;
-  if (e >= 1 && e <= DP_P) {
-    const int j = e - 1;
-    const double sc = (double)pscale[j], dd = (double)theta[j] - (double)ploc[j];
-    lp = -(dd * dd) / (2.0 * sc * sc) - log(sc) - kLogSqrt2PiD;
-    double g = tot - dd / (sc * sc);
-    if (has_temp) g *= temp;
-    const float gf = (float)g;
-    grad_out[j] = gf;
-    if (step_mode) {
-      const float w = (step_mode == 2) ? 0.5f * step : step;
-      const float pj = fmaf(w, gf, mom[j]);
-      mom[j] = pj;
-      if (step_mode == 1) theta_p[j] = fmaf(step, pj, theta_p[j]);
-      kin = (double)pj * (double)pj;
-    }
-  }
-  const double lp_cta = block_sum_256(lp, red);
-  const double kin_cta = block_sum_256(kin, red);
+  dp_post_entries(partials, n_parts, xc, xc.seq, theta, ploc, pscale, has_temp, temp, grad_out, step_mode, step, mom, theta_p,
+                  scratch, status, red, cta, tid);
   if (tid == 0) {
-    scratch[cta] = lp_cta;
-    scratch[32 + cta] = kin_cta;
     __threadfence();
-    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[65]), 1ull);
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[DP_SCRATCH_TICKET]), 1ull);
     last_s = (t == (unsigned long long)(gridDim.x - 1));
   }
   __syncthreads();
   if (last_s && tid == 0) {
     __threadfence();
-    double lpt = 0.0, kt = 0.0;
-    for (int c = 0; c < (int)gridDim.x; ++c) {
-      lpt += __ldcg(&scratch[c]);
-      kt += __ldcg(&scratch[32 + c]);
-    }
-    double ll = __ldcg(&scratch[64]);
-    if (has_temp) { ll *= temp; lpt *= temp; }
-    target_out[0] = ll + lpt;
-    if (step_mode == 2) kin_out[0] = 0.5 * kt;
-    *reinterpret_cast<unsigned long long*>(&scratch[65]) = 0ull;
+    double target, kin;
+    dp_post_scalars(scratch, has_temp, temp, target, kin);
+    target_out[0] = target;
+    if (step_mode == 2) kin_out[0] = kin;
+    *reinterpret_cast<unsigned long long*>(&scratch[DP_SCRATCH_TICKET]) = 0ull;
   }
 }
 
@@ -713,8 +618,10 @@ int eeyore_b200_dp_hmc_accept(void* theta_cur, void* grad_cur, void* target_cur,
 
 /* ---- peer exchange area of the data-sharded path (CUDA IPC; one per rank) ---------------------------------------------- */
 int64_t eeyore_b200_dp_exchange_bytes(void) {
-  return (int64_t)(2 * DP_XMAXW * DP_XSLOT * sizeof(double) + 2 * DP_XMAXW * 32 * sizeof(unsigned long long) + 128 * sizeof(double));
+  return (int64_t)(2 * DP_XMAXW * DP_XSLOT * sizeof(double) + 2 * DP_XMAXW * 32 * sizeof(unsigned long long) + DP_SCRATCH_LEN * sizeof(double));
 }
+
+int64_t eeyore_b200_dp_scratch_len(void) { return DP_SCRATCH_LEN; }
 
 int64_t eeyore_b200_dp_exchange_scratch_offset(void) {
   return (int64_t)(2 * DP_XMAXW * DP_XSLOT * sizeof(double) + 2 * DP_XMAXW * 32 * sizeof(unsigned long long));

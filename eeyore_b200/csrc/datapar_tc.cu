@@ -35,7 +35,9 @@
 #include <math.h>
 #include <stdint.h>
 #include <string>
+#include "philox.cuh"
 #include "datapar.cuh"
+#include "datapar_post.cuh"
 #include "tc05.cuh"
 #include "../../include/eeyore_b200.h"
 
@@ -229,12 +231,36 @@ __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_d
   }
 }
 
-// partials: [gridDim.x][DP_P + 1] doubles: [0] = log-likelihood, [1 + j] = d loglik / d theta_j
-__global__ void __launch_bounds__(TC_THREADS, 1)
-dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, const float* __restrict__ y, long n_rows,
-                  const float* __restrict__ x_absmax, double* __restrict__ partials) {
-  extern __shared__ __align__(1024) unsigned char tc_raw[];
-  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+// One-time set-up of a CTA: the blocks of fp16 ones, the mbarriers, the TMEM allocation.  Returns the TMEM base address.
+__device__ __forceinline__ uint32_t tc_setup(TcSmem& s) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 1024; e += TC_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      s.ctx[c].ones_h[e] = 0x3C00;     // fp16 1.0
+      s.ctx[c].ones_x[e] = 0x3C00;
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < 12; ++b) mbar_init(&s.bar[0][0] + b, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  return s.tmem_base;
+}
+
+// One evaluation over the rows of this CTA's tiles.  out: this CTA's row of the partial sums ([DP_P + 1] doubles: [0] =
+// log-likelihood, [1 + j] = d loglik / d theta_j).  theta is read through L2 (ld.global.cg): inside the persistent HMC kernel
+// it was written by other CTAs of the same launch.  `again`: not the first evaluation of this launch -- every MMA of the
+// previous one has completed, and the mbarriers (whose phases depend on the tile count) are re-initialised.
+__device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const float* theta, const float* __restrict__ x,
+                                             const float* __restrict__ y, const long n_rows, const float* __restrict__ x_absmax,
+                                             double* out, const bool again) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hf = warp >> 2;   // TMEM lane quadrant; which half of the 64 features
   const int r = 32 * q + lane;              // this thread's row of the tile (= TMEM lane)
@@ -247,9 +273,9 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   // power-of-two scales of the fp16 operands, from the parameter magnitudes (identical in every CTA and on every rank)
   {
     float m1 = 0.f, m2 = 0.f, m0 = 0.f;
-    for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) m1 = fmaxf(m1, fabsf(theta[DP_OFF_W1 + e]));
-    for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) m0 = fmaxf(m0, fabsf(theta[e]));
-    if (tid < DP_H) m2 = fabsf(theta[DP_OFF_W2 + tid]);
+    for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) m1 = fmaxf(m1, fabsf(__ldcg(theta + DP_OFF_W1 + e)));
+    for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) m0 = fmaxf(m0, fabsf(__ldcg(theta + e)));
+    if (tid < DP_H) m2 = fabsf(__ldcg(theta + DP_OFF_W2 + tid));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
@@ -278,7 +304,7 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) {  // W0[o][j]
     const int o = e / DP_D0, j = e % DP_D0;
     uint16_t p[2];
-    split2h_scalar(theta[e] * s_w0, p[0], p[1]);
+    split2h_scalar(__ldcg(theta + e) * s_w0, p[0], p[1]);
 #pragma unroll
     for (int k = 0; k < 2; ++k)
       *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS2)) = p[k];
@@ -290,37 +316,30 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) {   // W1[o][i]
     const int o = e / DP_H, i = e % DP_H;
     uint16_t p[2];
-    split2h_scalar(theta[DP_OFF_W1 + e] * s_w, p[0], p[1]);
+    split2h_scalar(__ldcg(theta + DP_OFF_W1 + e) * s_w, p[0], p[1]);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1a) + cm_off(64 * k + o, i, TC_WCS2)) = p[k];
       *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * k + i, o, TC_WCS2)) = p[k];
     }
   }
-  for (int e = tid; e < 1024; e += TC_THREADS) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      s.ctx[c].ones_h[e] = 0x3C00;     // fp16 1.0
-      s.ctx[c].ones_x[e] = 0x3C00;
-    }
-  }
   if (tid < DP_H) {
-    s.b0[tid] = theta[DP_OFF_B0 + tid];
-    s.b1[tid] = theta[DP_OFF_B1 + tid];
-    s.w2[tid] = theta[DP_OFF_W2 + tid];
+    s.b0[tid] = __ldcg(theta + DP_OFF_B0 + tid);
+    s.b1[tid] = __ldcg(theta + DP_OFF_B1 + tid);
+    s.w2[tid] = __ldcg(theta + DP_OFF_W2 + tid);
   }
   if (tid == 0) {
-    s.b2 = theta[DP_OFF_B2];
+    s.b2 = __ldcg(theta + DP_OFF_B2);
+    if (again) {
 #pragma unroll
-    for (int b = 0; b < 12; ++b) mbar_init(&s.bar[0][0] + b, 1);
-    mbar_fence_init();
+      for (int b = 0; b < 12; ++b) { mbar_inval(&s.bar[0][0] + b); mbar_init(&s.bar[0][0] + b, 1); }
+      mbar_fence_init();
+    }
   }
-  if (warp == 0) tmem_alloc<512>(&s.tmem_base);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tm = s.tmem_base;
   const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
 
   // shared-memory bases (32-bit shared addresses) of the operand buffers; descriptors are built where the MMAs are issued
@@ -591,8 +610,6 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
   // ---- write this CTA's partial sums ---------------------------------------------------------------------------------
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tm);
-  double* out = partials + (size_t)blockIdx.x * (DP_P + 1);
   if (lane < 16) {
     const int o = 16 * q + lane;
 #pragma unroll
@@ -628,6 +645,164 @@ dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, 
     out[1 + DP_OFF_B2] = t;
   }
   TC_STAMP(21);
+}
+
+// partials: [gridDim.x][DP_P + 1] doubles
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, const float* __restrict__ y, long n_rows,
+                  const float* __restrict__ x_absmax, double* __restrict__ partials) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  const uint32_t tm = tc_setup(s);
+  tc_eval_body(s, tm, theta, x, y, n_rows, x_absmax, partials + (size_t)blockIdx.x * (DP_P + 1), false);
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc<512>(tm);
+}
+
+// ---- the whole HMC run in ONE launch ---------------------------------------------------------------------------------------
+// eeyore/samplers/hmc.py:100-170 (leapfrog, hamiltonian, linear-space accept) and the epoch loop of
+// eeyore/samplers/serial_sampler.py:35-52 for the replicated chain of the data-sharded path.  Persistent CTAs, one per SM
+// (cooperative launch); the trajectory never leaves the SMs:
+//   per iteration:  momentum draw + first half step (post CTAs, thread = parameter)          -> grid barrier
+//     L times:      evaluation over this CTA's row tiles (tc_eval_body) -> per-CTA partial sums -> grid barrier
+//                   fold + peer-store exchange + prior + leapfrog (post CTAs, dp_post_entries) -> grid barrier
+//                   (every CTA then re-reads theta' through L2 and re-splits the weights)
+//                   accept test (every post CTA computes the same decision from the same scalars), commit, sample write-out
+// The TMEM allocation, the ones blocks and the launch itself are paid once per run instead of once per evaluation, and there is
+// no kernel boundary (launch gap) between an evaluation, its exchange and the next evaluation.
+struct DpRunArgs {
+  const float* x; const float* y; long n_rows; const float* x_absmax;
+  float* theta_cur; float* grad_cur; double* target_cur;         // in/out chain state
+  float* theta_p; float* grad_p; float* mom;                     // work vectors [P]
+  double* partials;                                              // [gridDim.x][P + 1]
+  double* scratch;                                               // DP_SCRATCH_LEN doubles (datapar_post.cuh)
+  unsigned long long* grid_ctr;                                  // zeroed by the host before the launch
+  int* status;
+  const float* ploc; const float* pscale; int has_temp; double temp;
+  float step; int num_steps;
+  long n_iters, n_burnin;
+  RngKey key; uint32_t iter0;
+  const float* z_tape; const float* u_tape;                      // [n_iters][P], [n_iters] or NULL
+  float* out_samples; double* out_target; uint8_t* out_acc;      // [n_saved][P], [n_saved], [n_saved] or NULL
+  uint32_t* acc_count;
+  DpExchange xc;                                                 // xc.seq = sequence number of the first evaluation
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all CTAs of the (co-resident) grid; `epoch` counts the arrivals expected so far
+__device__ __forceinline__ void grid_sync(unsigned long long* ctr, unsigned long long& epoch, int* status) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1ull);
+    long spins = 0;
+    while (ld_acquire_gpu(ctr) < epoch) {
+      __nanosleep(20);
+      if (++spins > (1L << 27)) {     // seconds: a CTA is gone; fail loudly instead of hanging the box
+        status[0] = 2;
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) dp_hmc_run_kernel(const DpRunArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
+  __shared__ double red[DP_POST_THREADS / 32];
+  __shared__ double bc[4];
+  __shared__ int acc_s;
+  static_assert(TC_THREADS == DP_POST_THREADS, "post layout: 256 threads per CTA");
+  const int tid = threadIdx.x, cta = blockIdx.x;
+  const bool post = cta < DP_POST_CTAS;                 // these CTAs also own the parameter entries
+  const int e = cta * DP_POST_THREADS + tid, j = e - 1; // entry of [loglik, dloglik]; parameter j
+  const bool own = post && e >= 1 && e <= DP_P;
+  const uint32_t tm = tc_setup(s);
+  unsigned long long epoch = 0;
+  unsigned long long seq = a.xc.seq;
+  double lt_cur = __ldcg(a.target_cur);
+  bool again = false;
+  uint32_t n_acc = 0;
+
+  for (long it = 0; it < a.n_iters; ++it) {
+    const uint32_t iter = a.iter0 + (uint32_t)it;
+    // ---- momentum draw, kinetic energy, first half step: p = z + step/2 grad; theta' = theta + step p   (hmc.py:134,105,110)
+    if (post) {
+      double k = 0.0;
+      if (own) {
+        float z;
+        if (a.z_tape) {
+          z = a.z_tape[(size_t)it * DP_P + j];
+        } else {   // the stream of dp_hmc_begin_kernel: four normals per Philox block
+          U4 w = philox4x32_10(U4{(uint32_t)(j >> 2), iter, 0u, 0u}, a.key.k0, a.key.k1);
+          float z0, z1;
+          if ((j & 2) == 0) box_muller<float>(Uni<float>::from(w.x), Uni<float>::from(w.y), &z0, &z1);
+          else box_muller<float>(Uni<float>::from(w.z), Uni<float>::from(w.w), &z0, &z1);
+          z = (j & 1) ? z1 : z0;
+        }
+        k = (double)z * (double)z;
+        const float pj = fmaf(0.5f * a.step, a.grad_cur[j], z);
+        a.mom[j] = pj;
+        a.theta_p[j] = fmaf(a.step, pj, a.theta_cur[j]);
+      }
+      const double kc = block_sum_256(k, red);
+      if (tid == 0) a.scratch[DP_SCRATCH_KIN0 + 32 * (int)(it & 1) + cta] = kc;
+    }
+    grid_sync(a.grid_ctr, epoch, a.status);
+    // ---- the trajectory ------------------------------------------------------------------------------------------------------
+    for (int st = 0; st < a.num_steps; ++st) {
+      tc_eval_body(s, tm, a.theta_p, a.x, a.y, a.n_rows, a.x_absmax, a.partials + (size_t)cta * (DP_P + 1), again);
+      again = true;
+      grid_sync(a.grid_ctr, epoch, a.status);
+      if (post)
+        dp_post_entries(a.partials, (int)gridDim.x, a.xc, seq, a.theta_p, a.ploc, a.pscale, a.has_temp, a.temp, a.grad_p,
+                        st == a.num_steps - 1 ? 2 : 1, a.step, a.mom, a.theta_p, a.scratch, a.status, red, cta, tid);
+      ++seq;
+      grid_sync(a.grid_ctr, epoch, a.status);
+    }
+    // ---- accept test in linear space (hmc.py:143-148), commit, sample write-out -----------------------------------------------
+    if (post) {
+      if (tid == 0) {
+        double lt_p, kin1, kin0 = 0.0;
+        dp_post_scalars(a.scratch, a.has_temp, a.temp, lt_p, kin1);
+        for (int c = 0; c < DP_POST_CTAS; ++c) kin0 += __ldcg(&a.scratch[DP_SCRATCH_KIN0 + 32 * (int)(it & 1) + c]);
+        kin0 *= 0.5;
+        const double h_cur = -lt_cur + kin0, h_prop = -lt_p + kin1;
+        double rate = exp(h_cur - h_prop);
+        rate = (rate > 1.0) ? 1.0 : rate;
+        const float u = a.u_tape ? a.u_tape[it] : philox_uniform<float>(a.key, 0u, iter);
+        acc_s = ((double)u < rate) ? 1 : 0;
+        bc[0] = lt_p;
+      }
+      __syncthreads();
+      const int acc = acc_s;
+      if (acc) lt_cur = bc[0];
+      n_acc += (uint32_t)acc;
+      const long k = it - a.n_burnin;
+      if (own) {
+        if (acc) { a.theta_cur[j] = a.theta_p[j]; a.grad_cur[j] = a.grad_p[j]; }
+        if (k >= 0 && a.out_samples) a.out_samples[(size_t)k * DP_P + j] = a.theta_cur[j];
+      }
+      if (cta == 0 && tid == 0 && k >= 0) {
+        if (a.out_target) a.out_target[k] = lt_cur;
+        if (a.out_acc) a.out_acc[k] = (uint8_t)acc;
+      }
+      __syncthreads();   // acc_s / bc are rewritten in the next iteration
+    }
+  }
+  if (cta == 0 && tid == 0) {
+    a.target_cur[0] = lt_cur;
+    if (a.acc_count) a.acc_count[0] += n_acc;
+  }
+  __syncthreads();
+  if ((tid >> 5) == 0) tmem_dealloc<512>(tm);
 }
 
 // out[0] = max |x[i]| (out zeroed by the caller): non-negative floats order like their bit patterns, NaN sorts above inf
@@ -703,6 +878,67 @@ int eeyore_b200_dp_loglik_grad_x(const void* theta, const void* x, const void* y
   if (!workspace) cudaFreeAsync(partials, st);
   if (!x_absmax) cudaFreeAsync(absmax, st);
   if (e != cudaSuccess) return fail(e, "dp_loglik_grad");
+  return EEYORE_B200_OK;
+}
+
+int eeyore_b200_dp_hmc_run(const void* x, const void* y, int64_t n_rows, const void* x_absmax, void* theta_cur, void* grad_cur,
+                           void* target_cur, void* theta_prop, void* grad_prop, void* momentum, void* workspace,
+                           void* local_scratch, void* grid_counter, int32_t* status, const void* prior_loc,
+                           const void* prior_scale, int has_temperature, double temperature, double step, int num_steps,
+                           int64_t n_iters, int64_t n_burnin, uint64_t seed, uint64_t iter_offset, const void* z_tape,
+                           const void* u_tape, void* out_samples, void* out_target, uint8_t* out_accepted,
+                           uint32_t* accept_count, int world, int rank, uint64_t seq, void* const* peer_bases, void* stream) {
+  if (!x || !y || n_rows < 1 || !x_absmax || !theta_cur || !grad_cur || !target_cur || !theta_prop || !grad_prop || !momentum ||
+      !workspace || !local_scratch || !grid_counter || !status || !prior_loc || !prior_scale)
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_hmc_run: null argument");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_hmc_run: x and y must be 16-byte aligned");
+  if (num_steps < 1 || n_iters < 0 || !(step > 0)) return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_hmc_run: bad step / num_steps / n_iters");
+  if (world < 1 || world > DP_XMAXW || rank < 0 || rank >= world || (world > 1 && (!peer_bases || seq == 0)))
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_hmc_run: bad world / rank / sequence number");
+  if (iter_offset + (uint64_t)n_iters > (1ull << 32))
+    return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dp_hmc_run: iter_offset + n_iters must stay below 2^32 (32-bit Philox counter words)");
+  if (n_iters == 0) return EEYORE_B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto fail = [](cudaError_t e, const char* where) {
+    std::string m = std::string(where) + ": " + cudaGetErrorString(e);
+    return eeyore_b200_set_error_(EEYORE_B200_ECUDA, m.c_str());
+  };
+  int dev = 0, sms = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop || sms < DP_POST_CTAS) return eeyore_b200_set_error_(EEYORE_B200_EUNSUPPORTED, "dp_hmc_run: cooperative launch unavailable");
+  static bool attr_set = false;
+  cudaError_t e;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(dp_hmc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+    if (e != cudaSuccess) return fail(e, "dp_hmc_run(attr)");
+    attr_set = true;
+  }
+  DpRunArgs a{};
+  a.x = (const float*)x; a.y = (const float*)y; a.n_rows = (long)n_rows; a.x_absmax = (const float*)x_absmax;
+  a.theta_cur = (float*)theta_cur; a.grad_cur = (float*)grad_cur; a.target_cur = (double*)target_cur;
+  a.theta_p = (float*)theta_prop; a.grad_p = (float*)grad_prop; a.mom = (float*)momentum;
+  a.partials = (double*)workspace; a.scratch = (double*)local_scratch; a.grid_ctr = (unsigned long long*)grid_counter;
+  a.status = status; a.ploc = (const float*)prior_loc; a.pscale = (const float*)prior_scale;
+  a.has_temp = has_temperature; a.temp = temperature; a.step = (float)step; a.num_steps = num_steps;
+  a.n_iters = (long)n_iters; a.n_burnin = (long)n_burnin;
+  a.key = RngKey{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)}; a.iter0 = (uint32_t)iter_offset;
+  a.z_tape = (const float*)z_tape; a.u_tape = (const float*)u_tape;
+  a.out_samples = (float*)out_samples; a.out_target = (double*)out_target; a.out_acc = out_accepted; a.acc_count = accept_count;
+  a.xc.world = world; a.xc.rank = rank; a.xc.seq = seq;
+  for (int p = 0; p < world && world > 1; ++p) {
+    a.xc.inbox[p] = reinterpret_cast<double*>(peer_bases[p]);
+    a.xc.flags[p] = reinterpret_cast<unsigned long long*>(a.xc.inbox[p] + 2 * DP_XMAXW * DP_XSLOT);
+  }
+  e = cudaMemsetAsync(grid_counter, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return fail(e, "dp_hmc_run(memset)");
+  void* params[] = {(void*)&a};
+  // every SM gets one CTA (195 KB of shared memory each): the grid barrier needs all of them resident, which the cooperative
+  // launch guarantees (it fails instead of dead-locking when the device is shared)
+  e = cudaLaunchCooperativeKernel((const void*)dp_hmc_run_kernel, dim3((unsigned)sms), dim3(TC_THREADS), params, sizeof(TcSmem), st);
+  if (e != cudaSuccess) return fail(e, "dp_hmc_run");
   return EEYORE_B200_OK;
 }
 

@@ -12,15 +12,16 @@
 // factorisations by one warp while seven waited):
 //   * ONE WARP PER CHAIN, no CTA-wide synchronisation anywhere; chains are independent, so a warp walks through its own
 //     data-dependent INSE loop (inse_mc_cov.py:20-73) at its own pace.
-//   * The chain is STREAMED, never staged whole: every pass (column means; lags 0 and 1; one pass per further lag pair)
-//     pulls the rows through a 32-row shared-memory ring, 8-row chunks fetched by TMA 1-D bulk copies (cp.async.bulk +
-//     mbarrier, issued by one lane three chunks ahead) when a chain's rows are contiguous -- the [C, n, P] layout the
-//     samplers write with sample_layout = "cnp" -- and by plain loads for any other strides.  Rows are centred once, on
-//     arrival; rows past the end read as zero, so lagged sums need no tail handling.  Any n works (no 200 KB limit).
-//   * Lagged cross-products sum_i x_i (x) x_{i+l}: the warp is two 16-lane row slices, each lane owns a TE x TE register
-//     tile of the P x P product (P = 20: 5 x 5, all 32 lanes busy, 10 shared-memory loads per 25 DFMA).  INSE only needs
-//     gamma_{2m} + gamma_{2m+1}, so for m >= 1 ONE pass multiplies x_i with the pair sum y_i = x_{i+2m} + x_{i+2m+1}
-//     (kept in a second ring, formed when a chunk arrives): half the FMAs of two separate lags.
+//   * The chain is STREAMED, never staged whole: every pass (column means; autocorrelation; lags 0 and 1; one pass per
+//     further lag pair) pulls the rows through a 64-row shared-memory ring, 16-row chunks fetched by TMA 1-D bulk copies
+//     (cp.async.bulk + mbarrier, issued by one lane three chunks ahead) when a chain's rows are contiguous -- the
+//     [C, n, P] layout the samplers write with sample_layout = "cnp" -- and by plain loads for any other strides.  Rows
+//     are centred once, on arrival; rows past the end read as zero, so lagged sums need no tail handling.  Any n works.
+//   * Lagged cross-products sum_i x_i (x) x_{i+l}: the warp is two 16-lane row slices (8 consecutive rows of a chunk each),
+//     each lane owns a TE x TE register tile of the P x P product (P = 20: 5 x 5, all 32 lanes busy).  Consecutive rows
+//     share their partner rows, so the B-side values slide through registers: lags 0 and 1 together cost 2 TE loads per
+//     row for 2 TE^2 FMAs.  INSE only needs gamma_{2m} + gamma_{2m+1}, so for m >= 1 ONE pass multiplies x_i with the pair
+//     sum x_{i+2m} + x_{i+2m+1} (formed from the sliding window): half the FMAs of two separate lags.
 //   * Cholesky (the is_pos_def test) and LU with partial pivoting (torch.det) run in REGISTERS, one matrix row per lane,
 //     pivots and pivot rows exchanged by shuffles -- no shared-memory round trips in the dependent chain.
 // HBM traffic: each pass reads the chain once (n P sizeof(T) bytes per chain).  FLOPs: 2 n P^2 per lag pass.
@@ -32,10 +33,11 @@
 namespace eb {
 
 constexpr int kStatWarps = 4;          // warps (= chains in flight) per CTA
-constexpr int kRB = 8;                 // rows per chunk
+constexpr int kRB = 16;                // rows per chunk; a half-warp (row slice) works on 8 consecutive rows of it
+constexpr int kHB = kRB / 2;
 constexpr int kNBuf = 4;               // chunks in the ring
-constexpr int kW = kRB * kNBuf;        // ring rows
-constexpr int kNearLag = (kNBuf - 2) * kRB - 1;   // largest lag whose partner rows are still in the ring (15)
+constexpr int kW = kRB * kNBuf;        // ring rows (64)
+constexpr int kNearLag = (kNBuf - 2) * kRB - 1;   // largest lag whose partner rows are still in the ring (31)
 constexpr int kAcfGroup = 16;          // autocorrelation lags handled per pass
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -77,73 +79,71 @@ __device__ __forceinline__ void st_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void st_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the ring: rows of ONE chain streamed through shared memory by the warp that owns it ---------------------------------
-template <typename T> struct Ring {
+// PC = the number of parameters when it is a multiple of four (compile-time strides: every shared-memory offset of the hot
+// loops is an immediate), 0 = run-time P.
+template <typename T, int PC> struct Ring {
   const T* base;        // first element of the chain
   long s_iter, s_param;
-  int n, P;
+  int n, p_rt;
   bool bulk;            // rows contiguous and 16-byte aligned: chunks come by cp.async.bulk
   T* X;                 // [kW][P] centred rows
-  T* Y;                 // [kW][P] pair sums y_g = x_g + x_{g+1}
   const T* mean;        // [32] subtracted on arrival
   uint64_t* bar;        // [kNBuf]
   uint32_t phase;       // parity bit per slot
   int next_issue, next_ready, last_chunk;
-  bool want_y;
 
+  __device__ __forceinline__ int P() const { return PC ? PC : p_rt; }
   __device__ __forceinline__ int rows_of(int k) const {
     const int r = n - k * kRB;
     return r < 0 ? 0 : (r > kRB ? kRB : r);
   }
-  __device__ __forceinline__ bool by_bulk(int k) const {
-    const int rows = rows_of(k);
-    return bulk && rows > 0 && ((rows * P * (int)sizeof(T)) & 15) == 0;
-  }
-  // all lanes; the slot's previous contents are dead (the callers' __syncwarp orders the last reads before this)
+  __device__ __forceinline__ bool by_bulk(int rows) const { return bulk && rows > 0 && ((rows * P() * (int)sizeof(T)) & 15) == 0; }
+  __device__ __forceinline__ const T* row(int g) const { return X + (g & (kW - 1)) * P(); }
+  // all lanes; the slot's previous contents are dead (the callers' fence + __syncwarp order the last accesses before this)
   __device__ __forceinline__ void issue(int k, int lane) {
     const int rows = rows_of(k);
     if (rows <= 0) return;
-    T* dst = X + (k % kNBuf) * kRB * P;
-    if (by_bulk(k)) {
-      if (lane == 0) {
-        st_bulk_load(dst, base + (long)k * kRB * s_iter, (uint32_t)(rows * P * sizeof(T)), bar + (k % kNBuf));
-      }
+    T* dst = X + (k & (kNBuf - 1)) * kRB * P();
+    if (by_bulk(rows)) {
+      if (lane == 0)
+        st_bulk_load(dst, base + (long)k * kRB * s_iter, (uint32_t)(rows * P() * sizeof(T)), bar + (k & (kNBuf - 1)));
     } else {
       const T* src = base + (long)k * kRB * s_iter;
-      for (int e = lane; e < rows * P; e += 32) {
-        const int i = e / P, j = e - i * P;
+      for (int e = lane; e < rows * P(); e += 32) {
+        const int i = e / P(), j = e - i * P();
         dst[e] = src[i * s_iter + j * s_param];
       }
     }
   }
-  __device__ __forceinline__ void begin(int last, bool with_y, int lane) {
-    next_issue = 0; next_ready = 0; last_chunk = last; want_y = with_y;
+  __device__ __forceinline__ void begin(int last, int lane) {
+    next_issue = 0; next_ready = 0; last_chunk = last;
     st_fence_proxy_async();   // this lane's generic-proxy accesses to the ring memory, before the async-proxy (TMA) writes
     __syncwarp();
     for (; next_issue < kNBuf && next_issue <= last_chunk; ++next_issue) issue(next_issue, lane);
   }
-  // chunks up to k arrived, centred, zero-filled past the end, pair sums formed
+  // chunks up to k arrived, centred, zero-filled past the end
   __device__ __forceinline__ void ready(int k, int lane) {
-    for (; next_ready <= k; ++next_ready) {
-      const int kk = next_ready, slot = kk % kNBuf, rows = rows_of(kk);
-      if (by_bulk(kk)) {
+    while (next_ready <= k) {
+      const int kk = next_ready++, slot = kk & (kNBuf - 1), rows = rows_of(kk);
+      if (by_bulk(rows)) {
         st_mbar_wait(bar + slot, (phase >> slot) & 1u);
         phase ^= 1u << slot;
       }
       __syncwarp();
-      T* dst = X + slot * kRB * P;
-      for (int e = lane; e < kRB * P; e += 32) {
-        const int i = e / P, j = e - i * P;
-        dst[e] = (i < rows) ? dst[e] - mean[j] : T(0);
+      T* dst = X + slot * kRB * P();
+      if (PC > 0 && rows == kRB) {          // full chunk, compile-time P: kRB P / 32 = P / 2 elements per lane
+#pragma unroll
+        for (int q = 0; q < PC / 2; ++q) {
+          const int e = lane + 32 * q;
+          dst[e] -= mean[e % (PC > 0 ? PC : 1)];
+        }
+      } else {
+        for (int e = lane; e < kRB * P(); e += 32) {
+          const int i = e / P(), j = e - i * P();
+          dst[e] = (i < rows) ? dst[e] - mean[j] : T(0);
+        }
       }
       __syncwarp();
-      if (want_y) {   // y_g for g = first row of this chunk - 1 ... last row - 1 (row g + 1 is needed)
-        const int g0 = kk * kRB - 1;
-        for (int e = lane; e < kRB * P; e += 32) {
-          const int i = e / P, j = e - i * P, g = g0 + i;
-          if (g >= 0) Y[(g % kW) * P + j] = X[(g % kW) * P + j] + X[((g + 1) % kW) * P + j];
-        }
-        __syncwarp();
-      }
     }
   }
   // chunk `done` has been consumed: its slot takes the next chunk
@@ -214,7 +214,8 @@ template <typename T, int PT> __device__ __forceinline__ T warp_det_lu(T (&a)[PT
 }
 
 // ---- lagged cross-products ---------------------------------------------------------------------------------------------------
-// lane = (h, ta, tb): row slice h (rows of parity h), tile (ta, tb) of TE x TE entries.
+// lane = (h, ta, tb): row slice h (8 consecutive rows of every 16-row chunk), tile (ta, tb) of TE x TE entries with STRIDED
+// ownership: the lane holds entries (ta + 4 r, tb + 4 c) -- for a fixed r the four ta lanes read four consecutive values.
 template <typename T, int TE> struct Tile {
   T v[TE][TE];
   __device__ __forceinline__ void zero() {
@@ -236,130 +237,141 @@ template <typename T, int TE> struct Tile {
 #pragma unroll
       for (int c = 0; c < TE; ++c) {
         const T s = v[r][c] + shfl_xor_t(v[r][c], 16);
-        if (h == 0) mat[(ta * TE + r) * ld + tb * TE + c] = s;
+        if (h == 0) mat[(ta + 4 * r) * ld + tb + 4 * c] = s;
       }
   }
 };
 
-template <typename T, int TE> __device__ __forceinline__ void load_cols(const T* row, int col0, int P, T (&out)[TE]) {
+// out[r] = row[t0 + 4 r] (zero past the last column when P is not a multiple of four)
+template <typename T, int TE, int PC> __device__ __forceinline__ void load_cols(const T* row, int t0, int P, T (&out)[TE]) {
 #pragma unroll
-  for (int r = 0; r < TE; ++r) out[r] = (col0 + r < P) ? row[col0 + r] : T(0);
+  for (int r = 0; r < TE; ++r) out[r] = (PC > 0 || t0 + 4 * r < P) ? row[t0 + 4 * r] : T(0);
 }
 
-// column means: mean[j] = (1/n) sum_i x[i][j]   (the ring's own mean must be zero during this pass)
-template <typename T> __device__ void pass_mean(Ring<T>& rg, T* mean_out, int lane) {
-  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
-  rg.begin(nci - 1, false, lane);
-  T s0 = T(0), s1 = T(0);
+// column means: mean[j] = (1/n) sum_i x[i][j]   (the ring's own mean must be zero during this pass).
+// Returns true when some column never changes (a chain that never moved, or a frozen parameter): its mean is then set to
+// that value exactly, the centred column is exactly zero, so is its row / column of every lagged product, and no Sigma_m can
+// be positive definite -- the caller reports 'Not enough samples' (inse_mc_cov.py:44-45) without walking through n / 2 lags.
+template <typename T, int PC> __device__ bool pass_mean(Ring<T, PC>& rg, T* mean_out, int lane) {
+  const int n = rg.n, P = rg.P(), nci = (n + kRB - 1) / kRB;
+  rg.begin(nci - 1, lane);
+  T s0 = T(0), s1 = T(0), first = T(0);
+  bool same = true;
   for (int ci = 0; ci < nci; ++ci) {
     rg.ready(ci, lane);
     if (lane < P) {
-      const T* x0 = rg.X + (ci % kNBuf) * kRB * P + lane;
+      const T* x0 = rg.X + (ci & (kNBuf - 1)) * kRB * P + lane;
+      if (ci == 0) first = x0[0];
+      const int rows = rg.rows_of(ci);
 #pragma unroll
-      for (int t = 0; t < kRB; t += 2) { s0 += x0[t * P]; s1 += x0[(t + 1) * P]; }
+      for (int t = 0; t < kRB; t += 2) {
+        const T v0 = x0[t * P], v1 = x0[(t + 1) * P];
+        s0 += v0; s1 += v1;
+        same = same && (t >= rows || v0 == first) && (t + 1 >= rows || v1 == first);
+      }
     }
     rg.release(ci, lane);
   }
   __syncwarp();
-  if (lane < 32) mean_out[lane] = (lane < P) ? (s0 + s1) * (T(1) / T(n)) : T(0);
+  const bool frozen = lane < P && same;
+  mean_out[lane] = (lane < P) ? (frozen ? first : (s0 + s1) * (T(1) / T(n))) : T(0);
   __syncwarp();
+  return __any_sync(kFull, frozen);
 }
 
-// A0 = sum_i x_i (x) x_i, A1 = sum_i x_i (x) x_{i+1}  (lags 0 and 1 in one pass)
-template <typename T, int TE>
-__device__ void pass_lag01(Ring<T>& rg, Tile<T, TE>& a0, Tile<T, TE>& a1, int lane) {
-  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+// A0 = sum_i x_i (x) x_i and A1 = sum_i x_i (x) x_{i+1} in one pass (DUAL), or one of them (lag l = 0 / 1) for tiles too large
+// to keep two in registers.  The B-side columns of row i + 1 are row i + 1's own B-side columns one step later: a sliding
+// register window, 2 TE shared-memory loads per row for up to 2 TE^2 FMAs.
+template <typename T, int TE, int PC, bool DUAL>
+__device__ void pass_lag01(Ring<T, PC>& rg, int l, Tile<T, TE>& a0, Tile<T, TE>& a1, int lane) {
+  const int n = rg.n, P = rg.P(), nci = (n + kRB - 1) / kRB;
   const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
-  rg.begin(nci, false, lane);        // row n (a zero row) is the partner of row n - 1
-  a0.zero(); a1.zero();
+  const bool next_row = DUAL || l == 1;
+  rg.begin(next_row ? nci : nci - 1, lane);     // row n (a zero row) is the partner of row n - 1
+  a0.zero();
+  if (DUAL) a1.zero();
   for (int ci = 0; ci < nci; ++ci) {
-    rg.ready(ci + 1, lane);
+    rg.ready(next_row ? ci + 1 : ci, lane);
+    const int r0 = ci * kRB + kHB * h;
+    const T* xr = rg.row(r0);                   // this slice's 8 rows are contiguous in the ring
+    T pb[TE];
+    load_cols<T, TE, PC>(xr, tb, P, pb);
 #pragma unroll
-    for (int t = 0; t < kRB / 2; ++t) {
-      const int i = ci * kRB + 2 * t + h;
-      const T* xi = rg.X + (i % kW) * P;
-      const T* xn = rg.X + ((i + 1) % kW) * P;
-      T xa[TE], b0[TE], b1[TE];
-      load_cols<T, TE>(xi, ta * TE, P, xa);
-      load_cols<T, TE>(xi, tb * TE, P, b0);
-      load_cols<T, TE>(xn, tb * TE, P, b1);
-      a0.rank1(xa, b0);
-      a1.rank1(xa, b1);
+    for (int t = 0; t < kHB; ++t) {
+      T xa[TE], nb[TE];
+      load_cols<T, TE, PC>(xr + t * P, ta, P, xa);
+      if (next_row) load_cols<T, TE, PC>((t + 1 < kHB) ? xr + (t + 1) * P : rg.row(r0 + kHB), tb, P, nb);
+      if (DUAL) { a0.rank1(xa, pb); a1.rank1(xa, nb); }
+      else a0.rank1(xa, l == 0 ? pb : nb);
+      if (next_row) {
+#pragma unroll
+        for (int c = 0; c < TE; ++c) pb[c] = nb[c];
+      } else if (t + 1 < kHB) {
+        load_cols<T, TE, PC>(xr + (t + 1) * P, tb, P, pb);
+      }
     }
     rg.release(ci, lane);
   }
 }
 
-// A = sum_i x_i (x) x_{i+l}, l = 0 or 1: one lag per pass, for tiles too large to keep two in registers
-template <typename T, int TE> __device__ void pass_lag(Ring<T>& rg, int l, Tile<T, TE>& acc, int lane) {
-  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
-  const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
-  rg.begin((nci * kRB - 1 + l) / kRB, false, lane);
-  acc.zero();
-  for (int ci = 0; ci < nci; ++ci) {
-    rg.ready((ci * kRB + kRB - 1 + l) / kRB, lane);
-#pragma unroll
-    for (int t = 0; t < kRB / 2; ++t) {
-      const int i = ci * kRB + 2 * t + h;
-      T xa[TE], xb[TE];
-      load_cols<T, TE>(rg.X + (i % kW) * P, ta * TE, P, xa);
-      load_cols<T, TE>(rg.X + ((i + l) % kW) * P, tb * TE, P, xb);
-      acc.rank1(xa, xb);
-    }
-    rg.release(ci, lane);
-  }
-}
-
-// B = sum_i x_i (x) (x_{i+l} + x_{i+l+1})
-template <typename T, int TE> __device__ void pass_pair(Ring<T>& rg, int l, Tile<T, TE>& b, int lane) {
-  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
+// B = sum_i x_i (x) (x_{i+l} + x_{i+l+1}): the pair sum is formed from the sliding window (TE adds per row)
+template <typename T, int TE, int PC> __device__ void pass_pair(Ring<T, PC>& rg, int l, Tile<T, TE>& b, int lane) {
+  const int n = rg.n, P = rg.P(), nci = (n + kRB - 1) / kRB;
   const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
   const bool near = l <= kNearLag;
-  rg.begin(near ? (nci * kRB + l) / kRB : nci - 1, near, lane);
+  rg.begin(near ? (nci * kRB + l) / kRB : nci - 1, lane);
   b.zero();
   for (int ci = 0; ci < nci; ++ci) {
     rg.ready(near ? (ci * kRB + kRB + l) / kRB : ci, lane);
+    const int r0 = ci * kRB + kHB * h;
+    const T* xr = rg.row(r0);
+    T pb[TE];
+    if (near) {
+      load_cols<T, TE, PC>(rg.row(r0 + l), tb, P, pb);
+    } else {   // partners beyond the ring: straight from global memory (slowly mixing chains only)
 #pragma unroll
-    for (int t = 0; t < kRB / 2; ++t) {
-      const int i = ci * kRB + 2 * t + h;
-      T xa[TE], yb[TE];
-      load_cols<T, TE>(rg.X + (i % kW) * P, ta * TE, P, xa);
+      for (int c = 0; c < TE; ++c) pb[c] = (tb + 4 * c < P) ? rg.far(r0 + l, tb + 4 * c) : T(0);
+    }
+#pragma unroll
+    for (int t = 0; t < kHB; ++t) {
+      T xa[TE], nb[TE], yb[TE];
+      load_cols<T, TE, PC>(xr + t * P, ta, P, xa);
       if (near) {
-        load_cols<T, TE>(rg.Y + ((i + l) % kW) * P, tb * TE, P, yb);
-      } else {   // partners beyond the ring: straight from global memory (slowly mixing chains only)
+        load_cols<T, TE, PC>(rg.row(r0 + l + t + 1), tb, P, nb);
+      } else {
 #pragma unroll
-        for (int c = 0; c < TE; ++c) {
-          const int j = tb * TE + c;
-          yb[c] = (j < P) ? rg.far(i + l, j) + rg.far(i + l + 1, j) : T(0);
-        }
+        for (int c = 0; c < TE; ++c) nb[c] = (tb + 4 * c < P) ? rg.far(r0 + l + t + 1, tb + 4 * c) : T(0);
       }
+#pragma unroll
+      for (int c = 0; c < TE; ++c) { yb[c] = pb[c] + nb[c]; pb[c] = nb[c]; }
       b.rank1(xa, yb);
     }
     rg.release(ci, lane);
   }
 }
 
-// acc[k] = sum_i x_i[j] x_{i+k0+k}[j] for lane j, k < kAcfGroup
-template <typename T> __device__ void pass_acf(Ring<T>& rg, int k0, int kmax, T (&acc)[kAcfGroup], int lane) {
-  const int n = rg.n, P = rg.P, nci = (n + kRB - 1) / kRB;
-  const bool near = k0 == 0;
-  const int span = kmax < kAcfGroup - 1 ? kmax : kAcfGroup - 1;     // largest lag of the near group
-  rg.begin(near ? (nci * kRB - 1 + span) / kRB : nci - 1, false, lane);
+// acc[k] = sum_i x_i[j] x_{i+k0+k}[j] for lane j, k < kAcfGroup: the 16 + 16 partner values of a chunk sit in registers
+// (one shared-memory load per row and lane for 16 FMAs)
+template <typename T, int PC> __device__ void pass_acf(Ring<T, PC>& rg, int k0, T (&acc)[kAcfGroup], int lane) {
+  const int n = rg.n, P = rg.P(), nci = (n + kRB - 1) / kRB;
+  const bool near = k0 + 2 * kAcfGroup - 1 < kW - kRB;    // the partner rows of a chunk (up to i0 + k0 + 31) are still in the ring
+  const int ahead = (k0 + 2 * kAcfGroup - 1) / kRB;        // chunks beyond ci that hold partner rows
+  rg.begin(near ? nci - 1 + ahead : nci - 1, lane);
 #pragma unroll
   for (int k = 0; k < kAcfGroup; ++k) acc[k] = T(0);
   const int j = lane < P ? lane : 0;
+  static_assert(kAcfGroup == kRB, "one partner window per chunk");
   for (int ci = 0; ci < nci; ++ci) {
-    rg.ready(near ? (ci * kRB + kRB - 1 + span) / kRB : ci, lane);
-    for (int t = 0; t < kRB; ++t) {
-      const int i = ci * kRB + t;
-      const T xi = rg.X[(i % kW) * P + j];
+    rg.ready(near ? ci + ahead : ci, lane);
+    const int i0 = ci * kRB;
+    T w[2 * kAcfGroup];
 #pragma unroll
-      for (int k = 0; k < kAcfGroup; ++k) {
-        if (k0 + k <= kmax) {
-          const T xp = near ? rg.X[((i + k) % kW) * P + j] : rg.far(i + k0 + k, j);
-          acc[k] = fma_t<T>(xi, xp, acc[k]);
-        }
-      }
+    for (int t = 0; t < 2 * kAcfGroup; ++t) w[t] = near ? rg.row(i0 + k0 + t)[j] : rg.far(i0 + k0 + t, j);
+#pragma unroll
+    for (int t = 0; t < kRB; ++t) {
+      const T xi = (k0 == 0) ? w[t] : rg.row(i0 + t)[j];
+#pragma unroll
+      for (int k = 0; k < kAcfGroup; ++k) acc[k] = fma_t<T>(xi, w[t + k], acc[k]);
     }
     rg.release(ci, lane);
   }
@@ -368,21 +380,21 @@ template <typename T> __device__ void pass_acf(Ring<T>& rg, int k0, int kmax, T 
 // resident CTAs per SM: three (170 registers) while one lane's tiles are small, two (255 registers) beyond
 template <typename T, int TE> constexpr int stats_min_blocks() { return (TE * TE * (int)sizeof(T) <= 25 * 8) ? 3 : 2; }
 
-template <typename T, int TE>
+template <typename T, int TE, bool EXACT>
 __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) chain_stats_kernel(const StatsArgs<T> a) {
-  constexpr int PT = 4 * TE, LD = PT + 1;
+  constexpr int PT = 4 * TE, LD = PT + 1, PC = EXACT ? PT : 0;
+  constexpr bool DUAL = stats_min_blocks<T, TE>() == 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = a.n, P = a.P;
+  const int n = a.n, P = PC ? PC : a.P;
   // per-warp carve (bytes, every piece 16-byte aligned)
   const size_t ring_bytes = ((size_t)kW * P * sizeof(T) + 15) & ~size_t(15);
   const size_t mat_bytes = ((size_t)PT * LD * sizeof(T) + 15) & ~size_t(15);
-  const size_t scratch_bytes = 2 * ring_bytes > 2 * mat_bytes ? 2 * ring_bytes : 2 * mat_bytes;   // rings, then A0 | A1
+  const size_t scratch_bytes = ring_bytes > 2 * mat_bytes ? ring_bytes : 2 * mat_bytes;   // the ring, then A0 | A1
   const size_t per_warp = scratch_bytes + mat_bytes + 32 * sizeof(T) + kNBuf * sizeof(uint64_t);
   unsigned char* my = smem_raw + (size_t)warp * per_warp;
   T* X = reinterpret_cast<T*>(my);
-  T* Y = reinterpret_cast<T*>(my + ring_bytes);
-  T* M0 = reinterpret_cast<T*>(my);                       // product matrices alias the (dead) rings between passes
+  T* M0 = reinterpret_cast<T*>(my);                       // product matrices alias the (dead) ring between passes
   T* M1 = reinterpret_cast<T*>(my + mat_bytes);
   T* Sg = reinterpret_cast<T*>(my + scratch_bytes);        // running INSE estimate, row-major [PT][LD]
   T* mean = reinterpret_cast<T*>(my + scratch_bytes + mat_bytes);
@@ -394,9 +406,9 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
   }
   __syncwarp();
 
-  Ring<T> rg;
-  rg.s_iter = a.s_iter; rg.s_param = a.s_param; rg.n = n; rg.P = P;
-  rg.X = X; rg.Y = Y; rg.mean = mean; rg.bar = bar; rg.phase = 0;
+  Ring<T, PC> rg;
+  rg.s_iter = a.s_iter; rg.s_param = a.s_param; rg.n = n; rg.p_rt = P;
+  rg.X = X; rg.mean = mean; rg.bar = bar; rg.phase = 0;
   const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
   const T inv_n = T(1) / T(n);
   const bool want_second = a.out_cov || a.out_inse || a.out_ess;
@@ -407,7 +419,7 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
     // ---- mean ------------------------------------------------------------------------------------------------------------
     mean[lane] = T(0);
     __syncwarp();
-    pass_mean<T>(rg, mean, lane);
+    const bool frozen = pass_mean<T, PC>(rg, mean, lane);
     if (a.out_mean && lane < P) a.out_mean[c * P + lane] = mean[lane];
 
     // ---- autocorrelation (builder-defined) ------------------------------------------------------------------
@@ -416,7 +428,7 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
       T den = T(1);
       for (int k0 = 0; k0 <= K; k0 += kAcfGroup) {
         T acc[kAcfGroup];
-        pass_acf<T>(rg, k0, K, acc, lane);
+        pass_acf<T, PC>(rg, k0, acc, lane);
         if (k0 == 0) den = acc[0];
         if (lane < P) {
 #pragma unroll
@@ -428,20 +440,20 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
     if (!want_second) continue;
 
     // ---- lags 0 and 1: covariance, gamma_0, Sigma_0 --------------------------------------------------------------------------
-    if constexpr (stats_min_blocks<T, TE>() == 3) {
+    if constexpr (DUAL) {
       Tile<T, TE> a0, a1;
-      pass_lag01<T, TE>(rg, a0, a1, lane);
-      __syncwarp();                       // the rings are dead: their memory takes the two product matrices
+      pass_lag01<T, TE, PC, true>(rg, 0, a0, a1, lane);
+      __syncwarp();                       // the ring is dead: its memory takes the two product matrices
       a0.store(M0, LD, ta, tb, h);
       a1.store(M1, LD, ta, tb, h);
       __syncwarp();
     } else {                              // large tiles: one lag per pass; lag 0 waits in Sg (free until Sigma_0 is formed)
       Tile<T, TE> acc;
-      pass_lag<T, TE>(rg, 0, acc, lane);
+      pass_lag01<T, TE, PC, false>(rg, 0, acc, acc, lane);
       __syncwarp();
       acc.store(Sg, LD, ta, tb, h);
       __syncwarp();
-      pass_lag<T, TE>(rg, 1, acc, lane);
+      pass_lag01<T, TE, PC, false>(rg, 1, acc, acc, lane);
       __syncwarp();
       acc.store(M1, LD, ta, tb, h);
       __syncwarp();
@@ -474,11 +486,11 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
     int sn = ub, m_last = -1;
     T last_det = T(0);
     bool phase2 = false;
-    for (int m = 0; m < ub; ++m) {
+    for (int m = 0; m < (frozen ? 0 : ub); ++m) {
       if (m > 0) {
         {
           Tile<T, TE> b;
-          pass_pair<T, TE>(rg, 2 * m, b, lane);
+          pass_pair<T, TE, PC>(rg, 2 * m, b, lane);
           __syncwarp();
           b.store(M0, LD, ta, tb, h);
           __syncwarp();
@@ -523,7 +535,7 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
     const int status = sn > ub - 1 ? 1 : 0;                                // 'Not enough samples', :44-45
     __syncwarp();
     if (a.out_inse && lane < P)
-      for (int q = 0; q < P; ++q) a.out_inse[(c * P + lane) * P + q] = Sg[lane * LD + q];
+      for (int q = 0; q < P; ++q) a.out_inse[(c * P + lane) * P + q] = frozen ? qnan<T>() : Sg[lane * LD + q];
     // ---- multi-ESS (multi_ess.py:9-14) --------------------------------------------------------------------------------------
     if (lane == 0) {
       const double ratio = (double)det_cov / (double)last_det;
@@ -540,16 +552,16 @@ template <typename T> size_t stats_smem_bytes(int P, int TE) {
   const int PT = 4 * TE, LD = PT + 1;
   const size_t ring_bytes = ((size_t)kW * P * sizeof(T) + 15) & ~size_t(15);
   const size_t mat_bytes = ((size_t)PT * LD * sizeof(T) + 15) & ~size_t(15);
-  const size_t scratch_bytes = 2 * ring_bytes > 2 * mat_bytes ? 2 * ring_bytes : 2 * mat_bytes;
+  const size_t scratch_bytes = ring_bytes > 2 * mat_bytes ? ring_bytes : 2 * mat_bytes;
   return kStatWarps * (scratch_bytes + mat_bytes + 32 * sizeof(T) + kNBuf * sizeof(uint64_t));
 }
 
-template <typename T, int TE> cudaError_t launch_stats_te(const StatsArgs<T>& a, cudaStream_t st) {
+template <typename T, int TE, bool EXACT> cudaError_t launch_stats_te(const StatsArgs<T>& a, cudaStream_t st) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = stats_smem_bytes<T>(a.P, TE);
-  auto kern = chain_stats_kernel<T, TE>;
+  auto kern = chain_stats_kernel<T, TE, EXACT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long want = (a.C + kStatWarps - 1) / kStatWarps;
@@ -561,14 +573,14 @@ template <typename T, int TE> cudaError_t launch_stats_te(const StatsArgs<T>& a,
 
 template <typename T> cudaError_t launch_stats(const StatsArgs<T>& a, cudaStream_t st) {
   switch ((a.P + 3) / 4) {
-    case 1: return launch_stats_te<T, 1>(a, st);
-    case 2: return launch_stats_te<T, 2>(a, st);
-    case 3: return launch_stats_te<T, 3>(a, st);
-    case 4: return launch_stats_te<T, 4>(a, st);
-    case 5: return launch_stats_te<T, 5>(a, st);
-    case 6: return launch_stats_te<T, 6>(a, st);
-    case 7: return launch_stats_te<T, 7>(a, st);
-    case 8: return launch_stats_te<T, 8>(a, st);
+    case 1: return a.P == 4 ? launch_stats_te<T, 1, true>(a, st) : launch_stats_te<T, 1, false>(a, st);
+    case 2: return a.P == 8 ? launch_stats_te<T, 2, true>(a, st) : launch_stats_te<T, 2, false>(a, st);
+    case 3: return a.P == 12 ? launch_stats_te<T, 3, true>(a, st) : launch_stats_te<T, 3, false>(a, st);
+    case 4: return a.P == 16 ? launch_stats_te<T, 4, true>(a, st) : launch_stats_te<T, 4, false>(a, st);
+    case 5: return a.P == 20 ? launch_stats_te<T, 5, true>(a, st) : launch_stats_te<T, 5, false>(a, st);
+    case 6: return a.P == 24 ? launch_stats_te<T, 6, true>(a, st) : launch_stats_te<T, 6, false>(a, st);
+    case 7: return a.P == 28 ? launch_stats_te<T, 7, true>(a, st) : launch_stats_te<T, 7, false>(a, st);
+    case 8: return a.P == 32 ? launch_stats_te<T, 8, true>(a, st) : launch_stats_te<T, 8, false>(a, st);
   }
   return cudaErrorInvalidValue;
 }

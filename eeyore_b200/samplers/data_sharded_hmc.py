@@ -27,7 +27,7 @@ def shard_rows(n_rows, world_size, rank, multiple=4):
 
 class DataShardedHMC:
     def __init__(self, model, theta0, x_shard, y_shard, step=0.1, num_steps=10, group=None, seed=0, chain=None,
-                 reduce_fn=None, exchange="auto"):
+                 reduce_fn=None, exchange="auto", trajectory="persistent"):
         if not model.is_data_parallel():
             raise ValueError("DataShardedHMC serves the data-parallel architecture (MLP 16-64-64-1, float32, binary)")
         nv.require_cuda()
@@ -36,6 +36,9 @@ class DataShardedHMC:
         self.y = model._to_dev(y_shard).reshape(-1)
         if self.x.data_ptr() % 16 or self.y.data_ptr() % 16:
             raise ValueError("row shards must start at 16-byte aligned addresses")
+        if trajectory not in ("persistent", "launches"):
+            raise ValueError("trajectory must be 'persistent' (the whole run in one cooperative launch) or 'launches'")
+        self.trajectory = trajectory
         self.chain = chain if chain is not None else ChainList(keys=["sample", "target_val", "accepted"])
         self._reduce = reduce_fn or self._all_reduce
         dev, p = self.x.device, model.num_params()
@@ -112,8 +115,9 @@ class DataShardedHMC:
             self._xbase, self._peers = base.value, peers
             self._scratch_ptr = C.c_void_p(base.value + int(lib.eeyore_b200_dp_exchange_scratch_offset()))
         elif exchange == "local":
-            self._scratch = torch.zeros(128, dtype=torch.float64, device=dev)
+            self._scratch = torch.zeros(int(lib.eeyore_b200_dp_scratch_len()), dtype=torch.float64, device=dev)
             self._scratch_ptr = nv.ptr(self._scratch)
+        self._grid_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def close(self):
         """Unmap the peers' exchange areas and free this rank's (collective: every rank calls it)."""
@@ -189,6 +193,35 @@ class DataShardedHMC:
                                                    nv.ptr(self._acc_count), st))
         self._iter += 1
 
+    @property
+    def persistent(self):
+        """The whole run as one cooperative launch (csrc/datapar_tc.cu: dp_hmc_run_kernel); the NCCL formulation and
+        trajectory='launches' keep one launch per evaluation."""
+        return self.trajectory == "persistent" and self.exchange != "nccl"
+
+    def _run_persistent(self, n_iters, n_burnin, samples, targets, accepted):
+        m, lib = self.model, nv.lib()
+        loc, scale = m.prior_on_device()
+        has_t, temp = (0, 0.0) if m.temperature is None else (1, float(m.temperature))
+        zt = ut = None
+        if self._tape is not None:
+            z, u, pos = self._tape
+            if pos + n_iters > z.shape[0]:
+                raise RuntimeError("noise tape exhausted")
+            zt, ut = z[pos:pos + n_iters].contiguous(), u[pos:pos + n_iters].contiguous()
+            self._tape[2] = pos + n_iters
+        n_saved = samples.shape[0]
+        with torch.cuda.device(self.x.device):
+            nv.check(lib.eeyore_b200_dp_hmc_run(
+                nv.ptr(self.x), nv.ptr(self.y), self.x.shape[0], nv.ptr(self._x_absmax), nv.ptr(self._theta_c), nv.ptr(self._grad_c),
+                nv.ptr(self._lt_c), nv.ptr(self._theta_p), nv.ptr(self._grad_p), nv.ptr(self._mom), nv.ptr(self._work),
+                self._scratch_ptr, nv.ptr(self._grid_ctr), nv.ptr(self._status), nv.ptr(loc), nv.ptr(scale), has_t, temp,
+                self.step, self.num_steps, n_iters, n_burnin, self.seed, self._iter, nv.ptr(zt), nv.ptr(ut),
+                nv.ptr(samples) if n_saved else None, nv.ptr(targets) if n_saved else None, nv.ptr(accepted) if n_saved else None,
+                nv.ptr(self._acc_count), self._world, self._rank, self.n_evals + 1, self._peers, nv.stream_ptr(self.x.device)))
+        self._iter += n_iters
+        self.n_evals += n_iters * self.num_steps
+
     def run(self, num_epochs, num_burnin_epochs, verbose=False, verbose_step=100):
         """sampler.run of the reference (serial_sampler.py:35-52) with one full-data batch per epoch."""
         dev, p = self.x.device, self.model.num_params()
@@ -196,12 +229,15 @@ class DataShardedHMC:
         samples = torch.empty(n_saved, p, dtype=torch.float32, device=dev)
         targets = torch.empty(n_saved, dtype=torch.float64, device=dev)
         accepted = torch.empty(n_saved, dtype=torch.uint8, device=dev)
-        for t in range(num_epochs):
-            k = t - num_burnin_epochs
-            if k >= 0:
-                self.draw(samples[k], targets[k:k + 1], accepted[k:k + 1])
-            else:
-                self.draw()
+        if self.persistent and num_epochs > 0:
+            self._run_persistent(num_epochs, num_burnin_epochs, samples, targets, accepted)
+        else:
+            for t in range(num_epochs):
+                k = t - num_burnin_epochs
+                if k >= 0:
+                    self.draw(samples[k], targets[k:k + 1], accepted[k:k + 1])
+                else:
+                    self.draw()
         if n_saved:
             self.chain.extend_from_device(samples=samples, target_vals=targets.to(torch.float32), accepted=accepted)
             self.current["accepted"] = int(accepted[-1].item())
@@ -213,11 +249,15 @@ class DataShardedHMC:
 
     @property
     def mode(self):
+        if self.persistent:
+            return "persistent: the whole run (every evaluation, exchange, leapfrog and accept step) in one cooperative launch"
         return "one launch per evaluation + one fused post launch (fold, exchange, prior, leapfrog)"
 
     def launches_per_iteration(self):
-        """Kernel launches of one HMC iteration: begin + accept + (evaluation, post) per leapfrog step; the NCCL formulation
-        adds the all-reduce and separate finish / step kernels."""
+        """Kernel launches of one HMC iteration.  persistent: none of its own (one launch per run()); otherwise begin + accept
+        + (evaluation, post) per leapfrog step; the NCCL formulation adds the all-reduce and separate finish / step kernels."""
+        if self.persistent:
+            return 0
         return 2 + (2 if self.exchange != "nccl" else 4) * self.num_steps
 
     def acceptance_count(self):

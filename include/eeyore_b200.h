@@ -215,8 +215,10 @@ int eeyore_b200_dp_exchange_create(void **out_base, void *out_handle64);
 int eeyore_b200_dp_exchange_open(const void *handle64, void **out_ptr);
 int eeyore_b200_dp_exchange_close(void *peer_ptr);
 int eeyore_b200_dp_exchange_destroy(void *base);
-/* byte offset of the 128-double scratch block inside an exchange area */
+/* byte offset of the scratch block (dp_scratch_len doubles) inside an exchange area */
 int64_t eeyore_b200_dp_exchange_scratch_offset(void);
+/* doubles a local scratch block must hold (zero-initialised by the caller) */
+int64_t eeyore_b200_dp_scratch_len(void);
 /* HMC.draw pieces for a replicated chain state (eeyore/samplers/hmc.py:100-170): momentum draw + first half step;
  * momentum / position update after each evaluation; accept test and commit.  z_tape / u_tape NULL = Philox. */
 int eeyore_b200_dp_hmc_begin(const void *theta_cur, const void *grad_cur, double step, uint64_t seed, uint64_t iter,
@@ -227,6 +229,24 @@ int eeyore_b200_dp_hmc_accept(void *theta_cur, void *grad_cur, void *target_cur,
                               const void *grad_prop, const void *target_prop, const void *kin0, const void *kin1,
                               uint64_t seed, uint64_t iter, const void *u_tape, void *out_sample, void *out_target,
                               uint8_t *out_accepted, uint32_t *accept_count, void *stream);
+
+/* sampler.run for the replicated chain of the data-sharded path in ONE cooperative launch (persistent CTAs, one per SM):
+ * n_iters x [HMC.draw: momentum draw, num_steps x (evaluation over this rank's rows on the tensor cores, grid barrier, fold +
+ * peer-store exchange + prior + leapfrog, grid barrier), accept test, commit, sample write-out]
+ * (eeyore/samplers/hmc.py:100-170 inside the loop of eeyore/samplers/serial_sampler.py:35-52).  theta_cur / grad_cur /
+ * target_cur (fp64 scalar) hold the current state on entry (dp_loglik_grad_x + dp_post at theta_cur) and on return.
+ * workspace: dp_workspace_bytes; local_scratch: dp_scratch_len doubles; grid_counter: 8 bytes of device memory.
+ * The first evaluation uses exchange sequence number `seq`, the k-th seq + k: the caller advances its counter by
+ * n_iters * num_steps.  Saved from iteration n_burnin on: out_samples [n_saved, P] fp32, out_target [n_saved] fp64,
+ * out_accepted [n_saved]; each may be NULL.  z_tape [n_iters, P] / u_tape [n_iters] NULL = Philox.
+ * status[0]: 1 = a peer never delivered its sums, 2 = grid barrier time-out (the kernel traps). */
+int eeyore_b200_dp_hmc_run(const void *x, const void *y, int64_t n_rows, const void *x_absmax, void *theta_cur, void *grad_cur,
+                           void *target_cur, void *theta_prop, void *grad_prop, void *momentum, void *workspace,
+                           void *local_scratch, void *grid_counter, int32_t *status, const void *prior_loc,
+                           const void *prior_scale, int has_temperature, double temperature, double step, int num_steps,
+                           int64_t n_iters, int64_t n_burnin, uint64_t seed, uint64_t iter_offset, const void *z_tape,
+                           const void *u_tape, void *out_samples, void *out_target, uint8_t *out_accepted,
+                           uint32_t *accept_count, int world, int rank, uint64_t seq, void *const *peer_bases, void *stream);
 
 /* Philox draws exactly as the samplers consume them (tests / reproducibility):
  * out_z [n_chains, P] normals and out_u [n_chains] uniform of iteration `iter`. */

@@ -178,3 +178,37 @@ def test_fused_post_kernel_matches_the_unfused_tail():
     assert np.allclose(npy(ta), npy(tb), rtol=1e-9)
     with pytest.raises(ValueError):
         DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), exchange="smoke-signals")
+
+
+@pytest.mark.parametrize("n", [3000, 70_001])
+def test_persistent_run_kernel_matches_the_per_evaluation_launches(n):
+    """sampler.run as ONE cooperative launch (dp_hmc_run_kernel: grid barriers between evaluation, fold / exchange /
+    leapfrog and the next evaluation) against the same run issued as one launch per evaluation + one post launch: the same
+    arithmetic in the same order, so samples, targets and accept decisions are bitwise equal -- tape and Philox noise,
+    burn-in, temperature, a second run() continuing the first."""
+    T, L, step = 6, 4, 0.003
+    x, y = synth(n, seed=31)
+    theta0 = (np.random.default_rng(4).normal(size=P) * 0.2).astype(np.float32)
+    rng = np.random.default_rng(5)
+    z, u = rng.normal(size=(2 * T, P)).astype(np.float32), rng.uniform(size=2 * T).astype(np.float32)
+    for temperature, tape in ((None, True), (0.7, False)):
+        m = wide_model(temperature=temperature)
+        runs = {}
+        for traj in ("persistent", "launches"):
+            s = DataShardedHMC(m, torch.from_numpy(theta0), torch.from_numpy(x), torch.from_numpy(y), step=step, num_steps=L, seed=5,
+                               trajectory=traj)
+            assert s.persistent == (traj == "persistent") and s.exchange == "local"
+            if tape:
+                s.set_noise_tape(torch.from_numpy(z), torch.from_numpy(u))
+            first = s.run(num_epochs=T, num_burnin_epochs=2)
+            second = s.run(num_epochs=T, num_burnin_epochs=0)
+            s.check_status()
+            torch.cuda.synchronize()
+            assert s.n_evals == 1 + 2 * T * L and s._iter == 2 * T
+            runs[traj] = (first, second, s.acceptance_count(), s.current["target_val"].item(), s._theta_c.clone(), s._grad_c.clone())
+        for (sa, ta, aa), (sb, tb, ab) in zip(runs["persistent"][:2], runs["launches"][:2]):
+            assert torch.equal(aa, ab) and torch.equal(sa, sb) and torch.equal(ta, tb)
+        assert runs["persistent"][0][0].shape == (T - 2, P) and runs["persistent"][1][0].shape == (T, P)
+        assert runs["persistent"][2] == runs["launches"][2] and 0 < runs["persistent"][2] <= 2 * T
+        assert runs["persistent"][3] == runs["launches"][3]
+        assert torch.equal(runs["persistent"][4], runs["launches"][4]) and torch.equal(runs["persistent"][5], runs["launches"][5])

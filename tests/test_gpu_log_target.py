@@ -60,8 +60,16 @@ def test_single_chain_api_matches_reference(arch, tag):
     assert g.shape == (m.num_params(),) and rel_err(npy(g), mg_v[key + "_grad" + sfx][0]) < tol
     lt2, g2 = m.upto_grad_log_target(theta.clone().detach(), ds.x, ds.y)
     assert lt2.item() == lt.item() and torch.equal(g2, g)
-    assert abs(m.log_lik(ds.x, ds.y).item() - mg_v[key + "_ll" + sfx][0]) <= tol * abs(mg_v[key + "_ll" + sfx][0])
-    assert abs(m.log_prior().item() - mg_v[key + "_lp" + sfx][0]) <= tol * abs(mg_v[key + "_lp" + sfx][0])
+    for name, got in (("_ll", m.log_lik(ds.x, ds.y).item()), ("_lp", m.log_prior().item())):
+        want = mg_v[key + name + sfx][0]
+        bar = tol
+        if tag == "f32":
+            # the naive BCE on fp32 probabilities (stats/loss.py:2) is ill-conditioned at saturated units: for the 2-2-1 fixture
+            # torch's own fp32 log_lik is 1.1e-5 from the fp64 truth.  In the reference dtype the bar is 1e-5 (north_star);
+            # against the fp64 truth: 1e-5, or twice the reference's own fp32 error where that is larger
+            assert abs(got - mg[key + name][0]) <= tol * abs(mg[key + name][0]), name
+            bar = max(tol, 2 * abs(mg[key + name][0] - want) / abs(want))
+        assert abs(got - want) <= bar * abs(want), name
     assert torch.equal(m.get_params(), theta.to(m.device))
     out = npy(m(ds.x))
     x, y = data_of(arch, NP_DTYPES[tag], mg)

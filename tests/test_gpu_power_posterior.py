@@ -104,7 +104,7 @@ def test_file_storage_matches_list_storage(tmp_path):
     runs = {}
     for storage in ("list", "file"):
         s = PowerPosteriorSampler(m, loader, spec_samplers, theta0=torch.from_numpy(gd["theta0"]),
-                                  between_step=int(gd["between_step"]), storage=storage, path=tmp_path, mode="w")
+                                  between_step=int(gd["between_step"]), storage=storage, path=tmp_path)   # mode 'a': every launch appends
         s.set_noise_tape(gd["z"], gd["u"], gd["j_tape"], gd["u_between"])
         s.run(num_epochs=int(gd["n_iters"]), num_burnin_epochs=int(gd["n_burnin"]))
         runs[storage] = s
