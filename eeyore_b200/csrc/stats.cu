@@ -22,9 +22,12 @@
 //     share their partner rows, so the B-side values slide through registers: lags 0 and 1 together cost 2 TE loads per
 //     row for 2 TE^2 FMAs.  INSE only needs gamma_{2m} + gamma_{2m+1}, so for m >= 1 ONE pass multiplies x_i with the pair
 //     sum x_{i+2m} + x_{i+2m+1} (formed from the sliding window): half the FMAs of two separate lags.
-//   * Cholesky (the is_pos_def test) and LU with partial pivoting (torch.det) run in REGISTERS, one matrix row per lane,
-//     pivots and pivot rows exchanged by shuffles -- no shared-memory round trips in the dependent chain.
-// HBM traffic: each pass reads the chain once (n P sizeof(T) bytes per chain).  FLOPs: 2 n P^2 per lag pass.
+//   * Cholesky (the is_pos_def test) and LU with partial pivoting (torch.det) work on a shared-memory copy, one matrix row
+//     per lane, the pivot row read as a broadcast; compact rolled loops (a fully unrolled register version was tried first:
+//     its straight-line code made instruction-cache misses the kernel's top stall).
+// Passes over a chain when everything is asked for: lags 0 + 1 (on rows shifted by a sample of the chain, with the means as a
+// by-product), autocorrelation, one per further lag pair.  HBM traffic: each pass reads the chain once (n P sizeof(T) bytes
+// per chain).  FLOPs: 2 n P^2 per lag, n P^2 per lag pair.
 #include <cuda_runtime.h>
 #include <string>
 #include "common.cuh"
@@ -132,11 +135,12 @@ template <typename T, int PC> struct Ring {
       __syncwarp();
       T* dst = X + slot * kRB * P();
       if (PC > 0 && rows == kRB) {          // full chunk, compile-time P: kRB P / 32 = P / 2 elements per lane
+        constexpr int NE = PC > 0 ? PC / 2 : 1;
+        T v[NE], mv[NE];
 #pragma unroll
-        for (int q = 0; q < PC / 2; ++q) {
-          const int e = lane + 32 * q;
-          dst[e] -= mean[e % (PC > 0 ? PC : 1)];
-        }
+        for (int q = 0; q < NE; ++q) { v[q] = dst[lane + 32 * q]; mv[q] = mean[(lane + 32 * q) % (PC > 0 ? PC : 1)]; }
+#pragma unroll
+        for (int q = 0; q < NE; ++q) dst[lane + 32 * q] = v[q] - mv[q];
       } else {
         for (int e = lane; e < kRB * P(); e += 32) {
           const int i = e / P(), j = e - i * P();
@@ -161,33 +165,40 @@ template <typename T, int PC> struct Ring {
 template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(kFull, v, src); }
 template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int m) { return __shfl_xor_sync(kFull, v, m); }
 
-// ---- register factorisations: lane r holds row r of a PT x PT matrix --------------------------------------------------------
-// torch.linalg.cholesky succeeds <=> every pivot is positive (is_pos_def.py:5-9).  Right-looking; `a` is destroyed.
-template <typename T, int PT> __device__ __forceinline__ bool warp_chol_ok(T (&a)[PT]) {
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < PT; ++k) {
-    const T d = shfl_t(a[k], k);
-    if (!(d > T(0))) { ok = false; break; }     // uniform: d is a broadcast
+// ---- factorisations of a P x P matrix in shared memory (row-major, row stride ld odd), one row per lane -------------------
+// Compact rolled loops in real functions: straight-line register versions (one copy per call site, ~80 KB of code each for
+// P = 20) made instruction-cache misses the top stall of the kernel.  Lane r updates row r; the pivot row is read by
+// every lane at the same address (a broadcast), so nothing goes through shuffles but the pivot search.
+// torch.linalg.cholesky succeeds <=> every pivot is positive (is_pos_def.py:5-9).  Right-looking; w is destroyed.
+template <typename T> __device__ __noinline__ bool warp_chol_ok(T* w, int P, int ld, int lane) {
+  T* my = w + (lane < P ? lane : 0) * ld;
+  for (int k = 0; k < P; ++k) {
+    const T d = w[k * ld + k];
+    if (!(d > T(0))) return false;              // uniform: every lane reads the same element
     const T rinv = T(1) / sqrt_t<T>(d);
-    const T lk = a[k] * rinv;                   // L[r][k] (rows r >= k)
-#pragma unroll
-    for (int c = k + 1; c < PT; ++c) a[c] = fma_t<T>(-lk, shfl_t(lk, c), a[c]);
+    const bool below = lane > k && lane < P;
+    const T lk = below ? my[k] * rinv : T(0);   // L[r][k]
+    if (below) my[k] = lk;
+    __syncwarp();
+    if (below)
+      for (int c = k + 1; c <= lane; ++c) my[c] = fma_t<T>(-lk, w[c * ld + k], my[c]);   // lower triangle only
+    __syncwarp();
   }
-  return ok;
+  return true;
 }
 
-// determinant by LU with partial pivoting (torch.det; inse_mc_cov.py:47,66, multi_ess.py:9-12).  Rows stay in their lanes:
-// `pos` is the logical position of a lane's row, a pivot swaps positions only.  `a` is destroyed.
-template <typename T, int PT> __device__ __forceinline__ T warp_det_lu(T (&a)[PT], int lane) {
-  bool done = lane >= PT;
+// determinant by LU with partial pivoting (torch.det; inse_mc_cov.py:47,66, multi_ess.py:9-12).  Rows stay where they are:
+// `pos` is the logical position of a lane's row, a pivot swaps positions only.  w is destroyed.
+template <typename T> __device__ __noinline__ T warp_det_lu(T* w, int P, int ld, int lane) {
+  bool done = lane >= P;
   int pos = lane;
   T det = T(1);
-#pragma unroll
-  for (int k = 0; k < PT; ++k) {
+  T* my = w + (lane < P ? lane : 0) * ld;
+  for (int k = 0; k < P; ++k) {
+    const T ak = done ? T(0) : my[k];
     // NaN sorts like +inf: it becomes the pivot and ends the loop uniformly (a NaN key would break the total order and the
     // lanes would disagree about the pivot lane)
-    T v = done ? T(-1) : ((a[k] != a[k]) ? T(INFINITY) : fabs(a[k]));
+    T v = done ? T(-1) : ((ak != ak) ? T(INFINITY) : fabs(ak));
     int vp = pos, vl = lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {   // largest |a[k]|; ties -> lowest logical position (LAPACK idamax order)
@@ -196,7 +207,8 @@ template <typename T, int PT> __device__ __forceinline__ T warp_det_lu(T (&a)[PT
       const bool take = (v2 > v) || (v2 == v && p2 < vp);
       if (take) { v = v2; vp = p2; vl = l2; }
     }
-    const T pv = shfl_t(a[k], vl);
+    const T* pr = w + vl * ld;
+    const T pv = pr[k];
     if (vp != k) {                        // row interchange: the row at logical position k takes the pivot row's position
       det = -det;
       if (!done && pos == k) pos = vp;
@@ -204,11 +216,12 @@ template <typename T, int PT> __device__ __forceinline__ T warp_det_lu(T (&a)[PT
     if (lane == vl) pos = k;
     det *= pv;
     if (pv == T(0) || pv != pv) break;    // uniform
-    const T rp = T(1) / pv;
-    const T f = (done || lane == vl) ? T(0) : a[k] * rp;
-#pragma unroll
-    for (int c = k + 1; c < PT; ++c) a[c] = fma_t<T>(-f, shfl_t(a[c], vl), a[c]);
+    if (!done && lane != vl) {
+      const T f = ak * (T(1) / pv);
+      for (int c = k + 1; c < P; ++c) my[c] = fma_t<T>(-f, pr[c], my[c]);
+    }
     if (lane == vl) done = true;
+    __syncwarp();
   }
   return det;
 }
@@ -281,34 +294,42 @@ template <typename T, int PC> __device__ bool pass_mean(Ring<T, PC>& rg, T* mean
 
 // A0 = sum_i x_i (x) x_i and A1 = sum_i x_i (x) x_{i+1} in one pass (DUAL), or one of them (lag l = 0 / 1) for tiles too large
 // to keep two in registers.  The B-side columns of row i + 1 are row i + 1's own B-side columns one step later: a sliding
-// register window, 2 TE shared-memory loads per row for up to 2 TE^2 FMAs.
+// register window, 2 TE shared-memory loads per row for up to 2 TE^2 FMAs.  csum (lanes with tb == 0; lag-0 pass only)
+// collects the column sums of the rows as they stand in the ring: the pass runs on rows shifted by a sample of the chain
+// instead of centred rows, and the caller corrects the products with the mean of the shifted rows -- one pass over the
+// chain less than "means first".  The row loop is unrolled by two only: with eight rows unrolled the loop bodies of the
+// passes (8 KB each) evicted each other from the instruction caches (a fifth of all stall samples).
 template <typename T, int TE, int PC, bool DUAL>
-__device__ void pass_lag01(Ring<T, PC>& rg, int l, Tile<T, TE>& a0, Tile<T, TE>& a1, int lane) {
+__device__ void pass_lag01(Ring<T, PC>& rg, int l, Tile<T, TE>& a0, Tile<T, TE>& a1, T (&csum)[TE], int lane) {
   const int n = rg.n, P = rg.P(), nci = (n + kRB - 1) / kRB;
   const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
   const bool next_row = DUAL || l == 1;
+  const bool sums = tb == 0 && (DUAL || l == 0);
   rg.begin(next_row ? nci : nci - 1, lane);     // row n (a zero row) is the partner of row n - 1
   a0.zero();
   if (DUAL) a1.zero();
+#pragma unroll
+  for (int r = 0; r < TE; ++r) csum[r] = T(0);
   for (int ci = 0; ci < nci; ++ci) {
     rg.ready(next_row ? ci + 1 : ci, lane);
     const int r0 = ci * kRB + kHB * h;
     const T* xr = rg.row(r0);                   // this slice's 8 rows are contiguous in the ring
+    const T* xlast = rg.row(r0 + kHB);          // the row after them may sit in the next slot (or wrap)
     T pb[TE];
     load_cols<T, TE, PC>(xr, tb, P, pb);
-#pragma unroll
+#pragma unroll 2
     for (int t = 0; t < kHB; ++t) {
       T xa[TE], nb[TE];
       load_cols<T, TE, PC>(xr + t * P, ta, P, xa);
-      if (next_row) load_cols<T, TE, PC>((t + 1 < kHB) ? xr + (t + 1) * P : rg.row(r0 + kHB), tb, P, nb);
+      if (next_row || t + 1 < kHB) load_cols<T, TE, PC>((t + 1 < kHB) ? xr + (t + 1) * P : xlast, tb, P, nb);
       if (DUAL) { a0.rank1(xa, pb); a1.rank1(xa, nb); }
       else a0.rank1(xa, l == 0 ? pb : nb);
-      if (next_row) {
+      if (sums) {
 #pragma unroll
-        for (int c = 0; c < TE; ++c) pb[c] = nb[c];
-      } else if (t + 1 < kHB) {
-        load_cols<T, TE, PC>(xr + (t + 1) * P, tb, P, pb);
+        for (int r = 0; r < TE; ++r) csum[r] += xa[r];
       }
+#pragma unroll
+      for (int c = 0; c < TE; ++c) pb[c] = nb[c];
     }
     rg.release(ci, lane);
   }
@@ -332,7 +353,7 @@ template <typename T, int TE, int PC> __device__ void pass_pair(Ring<T, PC>& rg,
 #pragma unroll
       for (int c = 0; c < TE; ++c) pb[c] = (tb + 4 * c < P) ? rg.far(r0 + l, tb + 4 * c) : T(0);
     }
-#pragma unroll
+#pragma unroll 2
     for (int t = 0; t < kHB; ++t) {
       T xa[TE], nb[TE], yb[TE];
       load_cols<T, TE, PC>(xr + t * P, ta, P, xa);
@@ -390,15 +411,17 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
   // per-warp carve (bytes, every piece 16-byte aligned)
   const size_t ring_bytes = ((size_t)kW * P * sizeof(T) + 15) & ~size_t(15);
   const size_t mat_bytes = ((size_t)PT * LD * sizeof(T) + 15) & ~size_t(15);
-  const size_t scratch_bytes = ring_bytes > 2 * mat_bytes ? ring_bytes : 2 * mat_bytes;   // the ring, then A0 | A1
-  const size_t per_warp = scratch_bytes + mat_bytes + 32 * sizeof(T) + kNBuf * sizeof(uint64_t);
+  const size_t scratch_bytes = ring_bytes > 3 * mat_bytes ? ring_bytes : 3 * mat_bytes;   // the ring, then A0 | A1 | work copy
+  const size_t per_warp = scratch_bytes + mat_bytes + 64 * sizeof(T) + kNBuf * sizeof(uint64_t);
   unsigned char* my = smem_raw + (size_t)warp * per_warp;
   T* X = reinterpret_cast<T*>(my);
   T* M0 = reinterpret_cast<T*>(my);                       // product matrices alias the (dead) ring between passes
   T* M1 = reinterpret_cast<T*>(my + mat_bytes);
+  T* Wk = reinterpret_cast<T*>(my + 2 * mat_bytes);
   T* Sg = reinterpret_cast<T*>(my + scratch_bytes);        // running INSE estimate, row-major [PT][LD]
   T* mean = reinterpret_cast<T*>(my + scratch_bytes + mat_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(my + scratch_bytes + mat_bytes + 32 * sizeof(T));
+  T* aux = mean + 32;                                       // column sums of the shifted rows
+  uint64_t* bar = reinterpret_cast<uint64_t*>(my + scratch_bytes + mat_bytes + 64 * sizeof(T));
   if (lane == 0) {
 #pragma unroll
     for (int b = 0; b < kNBuf; ++b) st_mbar_init(bar + b);
@@ -416,14 +439,7 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
   for (long c = (long)blockIdx.x * kStatWarps + warp; c < a.C; c += (long)gridDim.x * kStatWarps) {
     rg.base = a.x + c * a.s_chain;
     rg.bulk = a.s_param == 1 && a.s_iter == P && (reinterpret_cast<uintptr_t>(rg.base) & 15) == 0;
-    // ---- mean ------------------------------------------------------------------------------------------------------------
-    mean[lane] = T(0);
-    __syncwarp();
-    const bool frozen = pass_mean<T, PC>(rg, mean, lane);
-    if (a.out_mean && lane < P) a.out_mean[c * P + lane] = mean[lane];
-
-    // ---- autocorrelation (builder-defined) ------------------------------------------------------------------
-    if (a.out_acf) {
+    auto autocorrelation = [&]() {   // builder-defined; needs the true mean in `mean`
       const int K = a.max_lag;
       T den = T(1);
       for (int k0 = 0; k0 <= K; k0 += kAcfGroup) {
@@ -436,97 +452,137 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
             if (k0 + k <= K) a.out_acf[(c * (K + 1) + k0 + k) * P + lane] = acc[k] / den;
         }
       }
+    };
+    if (!want_second) {
+      // ---- mean (and autocorrelation) only --------------------------------------------------------------------------------
+      mean[lane] = T(0);
+      __syncwarp();
+      pass_mean<T, PC>(rg, mean, lane);
+      if (a.out_mean && lane < P) a.out_mean[c * P + lane] = mean[lane];
+      if (a.out_acf) autocorrelation();
+      continue;
     }
-    if (!want_second) continue;
 
-    // ---- lags 0 and 1: covariance, gamma_0, Sigma_0 --------------------------------------------------------------------------
-    if constexpr (DUAL) {
-      Tile<T, TE> a0, a1;
-      pass_lag01<T, TE, PC, true>(rg, 0, a0, a1, lane);
-      __syncwarp();                       // the ring is dead: its memory takes the two product matrices
-      a0.store(M0, LD, ta, tb, h);
-      a1.store(M1, LD, ta, tb, h);
-      __syncwarp();
-    } else {                              // large tiles: one lag per pass; lag 0 waits in Sg (free until Sigma_0 is formed)
-      Tile<T, TE> acc;
-      pass_lag01<T, TE, PC, false>(rg, 0, acc, acc, lane);
-      __syncwarp();
-      acc.store(Sg, LD, ta, tb, h);
-      __syncwarp();
-      pass_lag01<T, TE, PC, false>(rg, 1, acc, acc, lane);
-      __syncwarp();
-      acc.store(M1, LD, ta, tb, h);
-      __syncwarp();
-      for (int e = lane; e < PT * LD; e += 32) M0[e] = Sg[e];
+    // ---- lags 0 and 1 on SHIFTED rows u_i = x_i - s, s = the middle row of the chain (no separate pass for the means) ---------
+    // With S = sum_i u_i, d = S / n:   sum_i (u_i - d)(u_i - d)^T = A0u - n d d^T,
+    //   sum_{i<n-1} (u_i - d)(u_{i+1} - d)^T = A1u - d (S - u_0)^T - (S - u_{n-1}) d^T + (n - 1) d d^T;  mean = s + d.
+    // s is a sample of the chain, so |d| is of the order of the chain's spread: no cancellation to speak of.
+    mean[lane] = lane < P ? rg.base[(long)(n / 2) * a.s_iter + (long)lane * a.s_param] : T(0);
+    __syncwarp();
+    {
+      T csum[TE];
+      if constexpr (DUAL) {
+        Tile<T, TE> a0, a1;
+        pass_lag01<T, TE, PC, true>(rg, 0, a0, a1, csum, lane);
+        __syncwarp();                       // the ring is dead: its memory takes the two product matrices
+        a0.store(M0, LD, ta, tb, h);
+        a1.store(M1, LD, ta, tb, h);
+      } else {                              // large tiles: one lag per pass; lag 0 waits in Sg (free until Sigma_0 is formed)
+        Tile<T, TE> acc;
+        T unused[TE];
+        pass_lag01<T, TE, PC, false>(rg, 0, acc, acc, csum, lane);
+        __syncwarp();
+        acc.store(Sg, LD, ta, tb, h);
+        __syncwarp();
+        pass_lag01<T, TE, PC, false>(rg, 1, acc, acc, unused, lane);
+        __syncwarp();
+        acc.store(M1, LD, ta, tb, h);
+        __syncwarp();
+        for (int e = lane; e < PT * LD; e += 32) M0[e] = Sg[e];
+      }
+#pragma unroll
+      for (int r = 0; r < TE; ++r) {        // column sums: the two row slices, then the owner lanes publish them
+        const T cs = csum[r] + shfl_xor_t(csum[r], 16);
+        if (h == 0 && tb == 0) aux[ta + 4 * r] = cs;
+      }
       __syncwarp();
     }
-    T row[PT];        // this lane's row of the candidate estimate
+    // a column whose shifted values are all exactly zero never moved: no Sigma_m can be positive definite (its row and column
+    // of every lagged product are exactly zero) -- 'Not enough samples' (inse_mc_cov.py:44-45) without walking through n / 2 lags
+    const bool frozen = __any_sync(kFull, lane < P && M0[lane * LD + lane] == T(0));
+    {
+      const int jj = lane < P ? lane : 0;
+      const T sj = mean[jj], Sj = aux[jj], dj = Sj * inv_n;
+      const T u0 = rg.base[(long)jj * a.s_param] - sj;
+      const T uL = rg.base[(long)(n - 1) * a.s_iter + (long)jj * a.s_param] - sj;
+      for (int q = 0; q < P; ++q) {
+        const T dq = shfl_t(dj, q), Sq = shfl_t(Sj, q), u0q = shfl_t(u0, q);
+        if (lane < P) {
+          const T dd = dj * dq;
+          M0[lane * LD + q] -= T(n) * dd;
+          M1[lane * LD + q] += T(n - 1) * dd - dj * (Sq - u0q) - (Sj - uL) * dq;
+        }
+      }
+      __syncwarp();
+      if (lane < P) mean[lane] = sj + dj;
+      __syncwarp();
+      if (a.out_mean && lane < P) a.out_mean[c * P + lane] = mean[lane];
+    }
+    // Wk: work copy for the factorisations (the third matrix of the dead ring's memory)
     T det_cov;
     {
-      T cv[PT];
-#pragma unroll
-      for (int q = 0; q < PT; ++q) {
-        const bool in = lane < P && q < P;
-        const T a0rq = in ? M0[lane * LD + q] : T(0);
-        cv[q] = in ? a0rq / T(n - 1) : ((q == lane) ? T(1) : T(0));          // cov.py:13-15
-        if (a.out_cov && in) a.out_cov[(c * P + lane) * P + q] = cv[q];
-        // Gam = sym(gam0 + gam1), inse_mc_cov.py:32-33: pure additions before the scaling, so that elements (r, q) and (q, r)
-        // are bitwise equal (the reference's is_pos_def demands exact symmetry); Sigma_0 = -gam0 + 2 Gam (:35-36)
-        const T se = in ? a0rq + M1[lane * LD + q] : T(0);
-        const T st = in ? M0[q * LD + lane] + M1[q * LD + lane] : T(0);
-        const T gam = (se + st) * (T(0.5) * inv_n);
-        row[q] = in ? T(2) * gam - a0rq * inv_n : ((q == lane) ? T(1) : T(0));
+      if (lane < P) {
+        for (int q = 0; q < P; ++q) {
+          const T a0rq = M0[lane * LD + q];
+          const T cv = a0rq / T(n - 1);                                      // cov.py:13-15
+          Wk[lane * LD + q] = cv;
+          if (a.out_cov) a.out_cov[(c * P + lane) * P + q] = cv;
+          // Gam = sym(gam0 + gam1), inse_mc_cov.py:32-33: pure additions before the scaling, so that elements (r, q) and
+          // (q, r) are bitwise equal (the reference's is_pos_def demands exact symmetry); Sigma_0 = -gam0 + 2 Gam (:35-36)
+          const T se = a0rq + M1[lane * LD + q];
+          const T st = M0[q * LD + lane] + M1[q * LD + lane];
+          const T gam = (se + st) * (T(0.5) * inv_n);
+          Sg[lane * LD + q] = T(2) * gam - a0rq * inv_n;
+        }
       }
-      det_cov = warp_det_lu<T, PT>(cv, lane);
+      __syncwarp();
+      det_cov = warp_det_lu<T>(Wk, P, LD, lane);
     }
+    if (a.out_acf) autocorrelation();       // the ring takes its memory back (M0 / M1 have been consumed; Sg lives outside)
     if (!a.out_inse && !a.out_ess) continue;
 
     // ---- INSE (inse_mc_cov.py:20-73) ---------------------------------------------------------------------------------------
+    // Sg holds Sigma_{m-1} (the last accepted estimate in phase 2); the candidate Sigma_m = Sg + 2 Gam_m is formed element by
+    // element wherever it is needed (identical arithmetic each time)
     const int ub = n / 2;
     int sn = ub, m_last = -1;
     T last_det = T(0);
     bool phase2 = false;
+    auto candidate = [&](T* dst) {   // dst = Sg + 2 sym(B) / n for m >= 1 (:37-38, :62); Sg itself for m = 0
+      if (lane < P)
+        for (int q = 0; q < P; ++q) {
+          const T gam = (M0[lane * LD + q] + M0[q * LD + lane]) * (T(0.5) * inv_n);
+          dst[lane * LD + q] = Sg[lane * LD + q] + T(2) * gam;
+        }
+      __syncwarp();
+    };
+    auto copy_sg = [&](T* dst) {
+      if (lane < P)
+        for (int q = 0; q < P; ++q) dst[lane * LD + q] = Sg[lane * LD + q];
+      __syncwarp();
+    };
     for (int m = 0; m < (frozen ? 0 : ub); ++m) {
       if (m > 0) {
-        {
-          Tile<T, TE> b;
-          pass_pair<T, TE, PC>(rg, 2 * m, b, lane);
-          __syncwarp();
-          b.store(M0, LD, ta, tb, h);
-          __syncwarp();
-        }
-#pragma unroll
-        for (int q = 0; q < PT; ++q) {
-          const bool in = lane < P && q < P;
-          const T gam = in ? (M0[lane * LD + q] + M0[q * LD + lane]) * (T(0.5) * inv_n) : T(0);
-          const T base = in ? Sg[lane * LD + q] : ((q == lane) ? T(1) : T(0));
-          row[q] = in ? base + T(2) * gam : base;                          // :37-38, :62
-        }
+        Tile<T, TE> b;
+        pass_pair<T, TE, PC>(rg, 2 * m, b, lane);
+        __syncwarp();
+        b.store(M0, LD, ta, tb, h);
+        __syncwarp();
       }
       if (!phase2) {
-        if (lane < PT) {
-#pragma unroll
-          for (int q = 0; q < PT; ++q) Sg[lane * LD + q] = row[q];         // Sigma_m is kept whether or not it is PD yet
-        }
-        T w[PT];
-#pragma unroll
-        for (int q = 0; q < PT; ++q) w[q] = row[q];
-        if (warp_chol_ok<T, PT>(w)) {                                      // is_pos_def(Sig), :40
-#pragma unroll
-          for (int q = 0; q < PT; ++q) w[q] = row[q];
-          last_det = warp_det_lu<T, PT>(w, lane);                          // last_dtm = det(Sig), :47
+        if (m > 0) candidate(Sg);                                          // Sigma_m is kept whether or not it is PD yet
+        copy_sg(Wk);
+        if (warp_chol_ok<T>(Wk, P, LD, lane)) {                            // is_pos_def(Sig), :40
+          __syncwarp();
+          copy_sg(Wk);
+          last_det = warp_det_lu<T>(Wk, P, LD, lane);                      // last_dtm = det(Sig), :47
           sn = m; m_last = m; phase2 = true;
         }
       } else {
-        T w[PT];
-#pragma unroll
-        for (int q = 0; q < PT; ++q) w[q] = row[q];
-        const T cur = warp_det_lu<T, PT>(w, lane);                         // :66
+        candidate(Wk);
+        const T cur = warp_det_lu<T>(Wk, P, LD, lane);                     // :66
         if (!(cur > last_det)) break;                                      // current_dtm <= last_dtm -> break, :68-69
-        if (lane < PT) {
-#pragma unroll
-          for (int q = 0; q < PT; ++q) Sg[lane * LD + q] = row[q];
-        }
+        candidate(Sg);
         last_det = cur;
         m_last = m;
       }
@@ -552,8 +608,8 @@ template <typename T> size_t stats_smem_bytes(int P, int TE) {
   const int PT = 4 * TE, LD = PT + 1;
   const size_t ring_bytes = ((size_t)kW * P * sizeof(T) + 15) & ~size_t(15);
   const size_t mat_bytes = ((size_t)PT * LD * sizeof(T) + 15) & ~size_t(15);
-  const size_t scratch_bytes = ring_bytes > 2 * mat_bytes ? ring_bytes : 2 * mat_bytes;
-  return kStatWarps * (scratch_bytes + mat_bytes + 32 * sizeof(T) + kNBuf * sizeof(uint64_t));
+  const size_t scratch_bytes = ring_bytes > 3 * mat_bytes ? ring_bytes : 3 * mat_bytes;
+  return kStatWarps * (scratch_bytes + mat_bytes + 64 * sizeof(T) + kNBuf * sizeof(uint64_t));
 }
 
 template <typename T, int TE, bool EXACT> cudaError_t launch_stats_te(const StatsArgs<T>& a, cudaStream_t st) {
