@@ -548,6 +548,8 @@ def bench_diagnostics(ctx, reps=2):
         s.sample_layout = "cnp"
         samplers.append(s)
 
+    left = []
+
     def one_pass(timed):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_chunks + 1)]
         ev[0].record()
@@ -558,19 +560,36 @@ def bench_diagnostics(ctx, reps=2):
             s.run(num_epochs=n, num_burnin_epochs=0)
             ev[2 * k + 1].record()
             ring = s._device_blocks[-1]["sample"]                   # [n, P, c] view of the chain-major [c, n, P] buffer
-            out = st.chain_stats(ring, layout="npc", want=("ess",), max_lag=max_lag, check=False)
+            # chains whose INSE estimate is still not positive definite after 15 lag pairs (a third of a per cent: antithetic
+            # HMC chains, which end as 'Not enough samples' after n / 2 lag pairs) are left undecided here, their samples kept
+            # (160 KB each), and all of them are finished side by side in ONE launch after the last chunk
+            out = st.chain_stats(ring, layout="npc", want=("ess",), max_lag=max_lag, check=False, defer="leave")
             ess[lo:hi], acf[lo:hi], status[lo:hi] = out["ess"], out["acf"], out["status"]
+            todo = (out["status"] == 3).nonzero().flatten()
+            if todo.numel():
+                left.append((todo + lo, ring.permute(2, 0, 1)[todo]))
             s._device_blocks = []
             del ring, out
             ev[2 * k + 2].record()
+        e_tail0, e_tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_tail0.record()
+        n_left = 0
+        if left:
+            idx = torch.cat([i for i, _ in left])
+            n_left = int(idx.numel())
+            out = st.chain_stats(torch.cat([x_ for _, x_ in left]), layout="cnp", want=("ess",), max_lag=max_lag, check=False,
+                                 defer=False)
+            ess[idx], acf[idx], status[idx] = out["ess"], out["acf"], out["status"]
+            left.clear()
+        e_tail1.record()
         torch.cuda.synchronize()
         t_sample = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(n_chunks)) * 1e-3
-        t_stats = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(n_chunks)) * 1e-3
-        return t_sample, t_stats
+        t_stats = (sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(n_chunks)) + e_tail0.elapsed_time(e_tail1)) * 1e-3
+        return t_sample, t_stats, n_left, e_tail0.elapsed_time(e_tail1) * 1e-3
 
     one_pass(False)
     ctx.barrier()
-    ts, tt = zip(*[one_pass(True) for _ in range(reps)])
+    ts, tt, nl, tl = zip(*[one_pass(True) for _ in range(reps)])
     ctx.barrier()
     t_sample, t_stats = ctx.max_over_ranks(float(np.mean(ts))), ctx.max_over_ranks(float(np.mean(tt)))
     ok = status == 0
@@ -584,7 +603,8 @@ def bench_diagnostics(ctx, reps=2):
         "diagnosed_chains_per_s": ctx.world * C / t_stats,
         "ring_bytes_per_chunk": chunk * n * P * 8,
         "ess_mean": float(ess[ok].mean()) if bool(ok.any()) else None, "ess_min": float(ess[ok].min()) if bool(ok.any()) else None,
-        "chains_not_enough_samples": int((~ok).sum()),
+        "chains_not_enough_samples": int((~ok).sum()), "chains_finished_in_the_last_launch": int(nl[-1]),
+        "last_launch_s": float(np.mean(tl)),
         "acf_lag1_mean": float(acf[:, 1].mean()), "acf_lag10_mean": float(acf[:, max_lag].mean()),
         "kernel": "chain_stats_kernel<double, 5> (warp per chain, TMA-fed ring, register Cholesky / LU)",
     }

@@ -75,7 +75,7 @@ SIGNATURES = {
     "eeyore_b200_am_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_ram_run": (_I, [_VP, C.POINTER(RunParams)]),
     "eeyore_b200_adapt_state_len": (_I64, [_VP, _I]),
-    "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP]),
+    "eeyore_b200_chain_stats": (_I, [_I, _I64, _I64, _I, _VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP]),
     "eeyore_b200_dp_num_params": (_I, []),
     "eeyore_b200_dp_loglik_grad": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP]),
     "eeyore_b200_dp_loglik_grad_x": (_I, [_VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP]),

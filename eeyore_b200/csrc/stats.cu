@@ -57,6 +57,8 @@ template <typename T> struct StatsArgs {
   int* out_lags;    // [C,2] (sn, last accepted m)
   int max_lag;
   T* out_acf;    // [C, max_lag+1, P]
+  const long* index;   // optional [C]: the chains to process (inputs and outputs are addressed by index[k]); NULL = 0 .. C-1
+  int defer_m;         // >= 0: a chain whose estimate is not positive definite up to lag pair defer_m is left with status 3
 };
 
 // ---- mbarrier / bulk copy (one barrier per ring slot, owned by a warp) ---------------------------------------------------
@@ -436,7 +438,8 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
   const T inv_n = T(1) / T(n);
   const bool want_second = a.out_cov || a.out_inse || a.out_ess;
 
-  for (long c = (long)blockIdx.x * kStatWarps + warp; c < a.C; c += (long)gridDim.x * kStatWarps) {
+  for (long ck = (long)blockIdx.x * kStatWarps + warp; ck < a.C; ck += (long)gridDim.x * kStatWarps) {
+    const long c = a.index ? a.index[ck] : ck;
     rg.base = a.x + c * a.s_chain;
     rg.bulk = a.s_param == 1 && a.s_iter == P && (reinterpret_cast<uintptr_t>(rg.base) & 15) == 0;
     auto autocorrelation = [&]() {   // builder-defined; needs the true mean in `mean`
@@ -561,7 +564,9 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
         for (int q = 0; q < P; ++q) dst[lane * LD + q] = Sg[lane * LD + q];
       __syncwarp();
     };
+    bool deferred = false;
     for (int m = 0; m < (frozen ? 0 : ub); ++m) {
+      if (!phase2 && a.defer_m >= 0 && m > a.defer_m) { deferred = true; break; }
       if (m > 0) {
         Tile<T, TE> b;
         pass_pair<T, TE, PC>(rg, 2 * m, b, lane);
@@ -588,7 +593,9 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
       }
       __syncwarp();
     }
-    const int status = sn > ub - 1 ? 1 : 0;                                // 'Not enough samples', :44-45
+    // 1 = 'Not enough samples' (:44-45); 3 = undecided after defer_m lag pairs: the caller finishes these chains in a second
+    // launch (index list), where all of them run side by side instead of each holding up the warp that met it
+    const int status = deferred ? 3 : (sn > ub - 1 ? 1 : 0);
     __syncwarp();
     if (a.out_inse && lane < P)
       for (int q = 0; q < P; ++q) a.out_inse[(c * P + lane) * P + q] = frozen ? qnan<T>() : Sg[lane * LD + q];
@@ -653,7 +660,7 @@ int eeyore_b200_set_error_(int code, const char* msg);
 int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int n_params, const void* samples,
                             int64_t ss_iter, int64_t ss_chain, int64_t ss_param, void* out_mean, void* out_cov,
                             void* out_inse, void* out_ess, int32_t* out_status, int32_t* out_lags, int max_lag,
-                            void* out_acf, void* stream) {
+                            void* out_acf, const int64_t* chain_index, int defer_after, void* stream) {
   if (!samples || n_chains < 1 || n_samples < 2 || n_params < 1)
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "chain_stats: bad sizes or null samples");
   if (n_params > 32) return eeyore_b200_set_error_(EEYORE_B200_EUNSUPPORTED, "chain_stats: at most 32 parameters per chain");
@@ -664,12 +671,12 @@ int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int 
   if (dtype == EEYORE_B200_F64) {
     StatsArgs<double> a{(const double*)samples, ss_iter, ss_chain, ss_param, (int)n_samples, n_params, n_chains,
                         (double*)out_mean, (double*)out_cov, (double*)out_inse, (double*)out_ess, out_status, out_lags,
-                        max_lag, (double*)out_acf};
+                        max_lag, (double*)out_acf, (const long*)chain_index, defer_after};
     e = launch_stats<double>(a, (cudaStream_t)stream);
   } else if (dtype == EEYORE_B200_F32) {
     StatsArgs<float> a{(const float*)samples, ss_iter, ss_chain, ss_param, (int)n_samples, n_params, n_chains,
                        (float*)out_mean, (float*)out_cov, (float*)out_inse, (float*)out_ess, out_status, out_lags,
-                       max_lag, (float*)out_acf};
+                       max_lag, (float*)out_acf, (const long*)chain_index, defer_after};
     e = launch_stats<float>(a, (cudaStream_t)stream);
   } else {
     return eeyore_b200_set_error_(EEYORE_B200_EINVAL, "dtype must be f32 or f64");

@@ -22,7 +22,10 @@ def _device_of(x):
     return x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
-def chain_stats(x, layout="cnp", want=("mean", "cov", "inse", "ess"), max_lag=None, check=True):
+DEFER_AFTER = 15     # lag pairs a chain may take in the first launch before it is left to the second one
+
+
+def chain_stats(x, layout="cnp", want=("mean", "cov", "inse", "ess"), max_lag=None, check=True, defer=True):
     """Diagnostics of C chains in one launch.
 
     x: [C, n, P] (layout 'cnp', the ChainLists.get_samples orientation) or [n, P, C] (layout 'npc', the samplers'
@@ -57,14 +60,28 @@ def chain_stats(x, layout="cnp", want=("mean", "cov", "inse", "ess"), max_lag=No
     lags = torch.zeros(c, 2, dtype=torch.int32, device=dev)
     if max_lag is not None:
         out["acf"] = mk(c, max_lag + 1, p)
-    with torch.cuda.device(dev):
+    def launch(count, index, defer_after):
         nv.check(nv.lib().eeyore_b200_chain_stats(
-            nv.DTYPE_IDS[x.dtype], c, n, p, nv.ptr(x), ss_iter, ss_chain, ss_param,
+            nv.DTYPE_IDS[x.dtype], count, n, p, nv.ptr(x), ss_iter, ss_chain, ss_param,
             nv.ptr(out.get("mean")), nv.ptr(out.get("cov")), nv.ptr(out.get("inse")), nv.ptr(out.get("ess")),
             nv.ptr(status), nv.ptr(lags), -1 if max_lag is None else int(max_lag), nv.ptr(out.get("acf")),
-            nv.stream_ptr(dev)))
+            nv.ptr(index), defer_after, nv.stream_ptr(dev)))
+
+    # A chain whose INSE estimate never becomes positive definite walks through n / 2 lag pairs (and ends as 'Not enough
+    # samples'), a hundred times the work of an ordinary chain.  With many chains in the batch the first launch leaves such
+    # chains undecided (status 3) after DEFER_AFTER lag pairs, and a second launch finishes all of them side by side, one
+    # warp each, instead of each one holding up the warp that happened to meet it.
+    # defer = "leave": first launch only; the caller collects the status-3 chains (of several batches) and finishes them in one
+    # call with defer=False.
+    two_tier = bool(defer) and need_status and (c >= 4096 or defer == "leave")
+    with torch.cuda.device(dev):
+        launch(c, None, DEFER_AFTER if two_tier else -1)
+        if two_tier and defer != "leave":
+            todo = (status == 3).nonzero().flatten()
+            if todo.numel():
+                launch(int(todo.numel()), todo, -1)
     out["status"], out["lags"] = status, lags
-    if check and need_status and bool((status != 0).any()):
+    if check and need_status and bool((status == 1).any()):
         raise RuntimeError("Not enough samples")      # inse_mc_cov.py:44-45
     return out
 

@@ -158,19 +158,25 @@ int eeyore_b200_hmc_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
 /* SMMALA (absent from the reference snapshot; SURVEY.md A.7, builder-defined): Fisher metric, batched Cholesky */
 int eeyore_b200_smmala_run(eeyore_b200_mlp_t h, const eeyore_b200_run_params *p);
 
-/* Chain diagnostics on the device, one CTA per chain (samples element (s, c, j) at s*ss_iter + c*ss_chain + j*ss_param;
+/* Chain diagnostics on the device, one warp per chain (samples element (s, c, j) at s*ss_iter + c*ss_chain + j*ss_param;
  * n_params <= 32).  Any output pointer may be NULL.
  *   out_mean [C,P]     ChainList.mean                        (eeyore/chains/chain_list.py:69-71)
  *   out_cov  [C,P,P]   stats.cov                             (eeyore/stats/cov.py:5-15)
  *   out_inse [C,P,P]   stats.inse_mc_cov, adjust=False       (eeyore/stats/inse_mc_cov.py:9-83)
  *   out_ess  [C]       stats.multi_ess                       (eeyore/stats/multi_ess.py:6-14)
- *   out_status [C]     0 = ok, 1 = 'Not enough samples' (inse_mc_cov.py:44-45; the Python layer raises RuntimeError)
+ *   out_status [C]     0 = ok, 1 = 'Not enough samples' (inse_mc_cov.py:44-45; the Python layer raises RuntimeError),
+ *                      3 = undecided after defer_after lag pairs (only when defer_after >= 0)
+ *   chain_index        NULL, or n_chains device indices: only these chains are processed (inputs and outputs are addressed
+ *                      by the index).  A chain whose estimate never becomes positive definite walks through n / 2 lag
+ *                      pairs; with defer_after = m >= 0 such chains stop after lag pair m with status 3 and the caller
+ *                      finishes them in a second call (chain_index = those chains, defer_after = -1), where they all run side
+ *                      by side.  defer_after = -1: every chain is finished in this call.
  *   out_lags [C,2]     (first lag index with a positive-definite estimate, last accepted lag index)
  *   out_acf  [C, max_lag+1, P]  autocorrelation function (builder-defined; absent from the reference) */
 int eeyore_b200_chain_stats(int dtype, int64_t n_chains, int64_t n_samples, int n_params, const void *samples,
                             int64_t ss_iter, int64_t ss_chain, int64_t ss_param, void *out_mean, void *out_cov,
                             void *out_inse, void *out_ess, int32_t *out_status, int32_t *out_lags, int max_lag,
-                            void *out_acf, void *stream);
+                            void *out_acf, const int64_t *chain_index, int defer_after, void *stream);
 
 /* ---- data-parallel path (BASELINE config 5: MLP 16-64-64-1, fp32, rows sharded across GPUs) -----------------------
  * One parameter vector, millions of rows.  Each rank evaluates its row shard; the caller all-reduces out_sums
