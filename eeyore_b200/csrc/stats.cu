@@ -94,26 +94,39 @@ template <typename T, int PC> struct Ring {
   T* X;                 // [kW][P] centred rows
   const T* mean;        // [32] subtracted on arrival
   uint64_t* bar;        // [kNBuf]
-  uint32_t phase;       // parity bit per slot
+  uint32_t* phase;      // parity bit per slot (shared by every view of this warp's ring)
+  // A view streams rows shift, shift + 1, ... in chunks of kRB rows through `nslots` (a power of two) slots from slot0 on:
+  // the whole ring (shift 0, 4 slots) for lags whose partner rows stay within the window, or two half rings for far lags --
+  // the rows themselves through slots 0-1 and their partners (shift = lag) through slots 2-3.
+  int shift, slot0, nslots;
   int next_issue, next_ready, last_chunk;
 
   __device__ __forceinline__ int P() const { return PC ? PC : p_rt; }
+  __device__ __forceinline__ void view(int shift_, int slot0_, int nslots_) { shift = shift_; slot0 = slot0_; nslots = nslots_; }
+  __device__ __forceinline__ int slot_of(int k) const { return slot0 + (k & (nslots - 1)); }
   __device__ __forceinline__ int rows_of(int k) const {
-    const int r = n - k * kRB;
+    const int r = n - shift - k * kRB;
     return r < 0 ? 0 : (r > kRB ? kRB : r);
   }
-  __device__ __forceinline__ bool by_bulk(int rows) const { return bulk && rows > 0 && ((rows * P() * (int)sizeof(T)) & 15) == 0; }
-  __device__ __forceinline__ const T* row(int g) const { return X + (g & (kW - 1)) * P(); }
+  __device__ __forceinline__ const T* src_of(int k) const { return base + ((long)k * kRB + shift) * s_iter; }
+  __device__ __forceinline__ bool by_bulk(int k) const {
+    const int rows = rows_of(k);
+    return bulk && rows > 0 && ((rows * P() * (int)sizeof(T)) & 15) == 0 && (reinterpret_cast<uintptr_t>(src_of(k)) & 15) == 0;
+  }
+  // row g of the chain (g >= shift, within the window)
+  __device__ __forceinline__ const T* row(int g) const {
+    const int q = g - shift;
+    return X + ((slot0 + ((q / kRB) & (nslots - 1))) * kRB + (q & (kRB - 1))) * P();
+  }
   // all lanes; the slot's previous contents are dead (the callers' fence + __syncwarp order the last accesses before this)
   __device__ __forceinline__ void issue(int k, int lane) {
     const int rows = rows_of(k);
     if (rows <= 0) return;
-    T* dst = X + (k & (kNBuf - 1)) * kRB * P();
-    if (by_bulk(rows)) {
-      if (lane == 0)
-        st_bulk_load(dst, base + (long)k * kRB * s_iter, (uint32_t)(rows * P() * sizeof(T)), bar + (k & (kNBuf - 1)));
+    T* dst = X + slot_of(k) * kRB * P();
+    const T* src = src_of(k);
+    if (by_bulk(k)) {
+      if (lane == 0) st_bulk_load(dst, src, (uint32_t)(rows * P() * sizeof(T)), bar + slot_of(k));
     } else {
-      const T* src = base + (long)k * kRB * s_iter;
       for (int e = lane; e < rows * P(); e += 32) {
         const int i = e / P(), j = e - i * P();
         dst[e] = src[i * s_iter + j * s_param];
@@ -124,15 +137,15 @@ template <typename T, int PC> struct Ring {
     next_issue = 0; next_ready = 0; last_chunk = last;
     st_fence_proxy_async();   // this lane's generic-proxy accesses to the ring memory, before the async-proxy (TMA) writes
     __syncwarp();
-    for (; next_issue < kNBuf && next_issue <= last_chunk; ++next_issue) issue(next_issue, lane);
+    for (; next_issue < nslots && next_issue <= last_chunk; ++next_issue) issue(next_issue, lane);
   }
   // chunks up to k arrived, centred, zero-filled past the end
   __device__ __forceinline__ void ready(int k, int lane) {
     while (next_ready <= k) {
-      const int kk = next_ready++, slot = kk & (kNBuf - 1), rows = rows_of(kk);
-      if (by_bulk(rows)) {
-        st_mbar_wait(bar + slot, (phase >> slot) & 1u);
-        phase ^= 1u << slot;
+      const int kk = next_ready++, slot = slot_of(kk), rows = rows_of(kk);
+      if (by_bulk(kk)) {
+        st_mbar_wait(bar + slot, (*phase >> slot) & 1u);
+        *phase ^= 1u << slot;
       }
       __syncwarp();
       T* dst = X + slot * kRB * P();
@@ -156,9 +169,9 @@ template <typename T, int PC> struct Ring {
   __device__ __forceinline__ void release(int done, int lane) {
     st_fence_proxy_async();
     __syncwarp();
-    if (next_issue <= last_chunk && next_issue == done + kNBuf) { issue(next_issue, lane); ++next_issue; }
+    if (next_issue <= last_chunk && next_issue == done + nslots) { issue(next_issue, lane); ++next_issue; }
   }
-  // centred value of row g, column j straight from global memory (partners beyond the ring)
+  // centred value of row g, column j straight from global memory (autocorrelation lags beyond the window)
   __device__ __forceinline__ T far(int g, int j) const {
     return (g < n) ? base[(long)g * s_iter + (long)j * s_param] - mean[j] : T(0);
   }
@@ -337,40 +350,49 @@ __device__ void pass_lag01(Ring<T, PC>& rg, int l, Tile<T, TE>& a0, Tile<T, TE>&
   }
 }
 
-// B = sum_i x_i (x) (x_{i+l} + x_{i+l+1}): the pair sum is formed from the sliding window (TE adds per row)
+// B = sum_i x_i (x) (x_{i+l} + x_{i+l+1}): the pair sum is formed from the sliding window (TE adds per row).  Lags beyond the
+// ring window (slowly mixing chains, and chains whose estimate never becomes positive definite) stream the partner rows
+// through the second half of the ring (rp: a view shifted by l) -- the same loop at the same speed.
 template <typename T, int TE, int PC> __device__ void pass_pair(Ring<T, PC>& rg, int l, Tile<T, TE>& b, int lane) {
   const int n = rg.n, P = rg.P(), nci = (n + kRB - 1) / kRB;
   const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
   const bool near = l <= kNearLag;
-  rg.begin(near ? (nci * kRB + l) / kRB : nci - 1, lane);
+  Ring<T, PC> rp = rg;
+  if (near) {
+    rg.view(0, 0, kNBuf);
+    rg.begin((nci * kRB + l) / kRB, lane);
+  } else {
+    rg.view(0, 0, kNBuf / 2);
+    rp.view(l, kNBuf / 2, kNBuf / 2);
+    rg.begin(nci - 1, lane);
+    rp.begin(nci, lane);                 // partner rows of chunk ci: l + 16 ci ... l + 16 ci + 16 (the last one in chunk ci + 1)
+  }
   b.zero();
   for (int ci = 0; ci < nci; ++ci) {
-    rg.ready(near ? (ci * kRB + kRB + l) / kRB : ci, lane);
+    if (near) {
+      rg.ready((ci * kRB + kRB + l) / kRB, lane);
+    } else {
+      rg.ready(ci, lane);
+      rp.ready(ci + 1, lane);
+    }
+    const Ring<T, PC>& rb = near ? rg : rp;
     const int r0 = ci * kRB + kHB * h;
     const T* xr = rg.row(r0);
     T pb[TE];
-    if (near) {
-      load_cols<T, TE, PC>(rg.row(r0 + l), tb, P, pb);
-    } else {   // partners beyond the ring: straight from global memory (slowly mixing chains only)
-#pragma unroll
-      for (int c = 0; c < TE; ++c) pb[c] = (tb + 4 * c < P) ? rg.far(r0 + l, tb + 4 * c) : T(0);
-    }
+    load_cols<T, TE, PC>(rb.row(r0 + l), tb, P, pb);
 #pragma unroll 2
     for (int t = 0; t < kHB; ++t) {
       T xa[TE], nb[TE], yb[TE];
       load_cols<T, TE, PC>(xr + t * P, ta, P, xa);
-      if (near) {
-        load_cols<T, TE, PC>(rg.row(r0 + l + t + 1), tb, P, nb);
-      } else {
-#pragma unroll
-        for (int c = 0; c < TE; ++c) nb[c] = (tb + 4 * c < P) ? rg.far(r0 + l + t + 1, tb + 4 * c) : T(0);
-      }
+      load_cols<T, TE, PC>(rb.row(r0 + l + t + 1), tb, P, nb);
 #pragma unroll
       for (int c = 0; c < TE; ++c) { yb[c] = pb[c] + nb[c]; pb[c] = nb[c]; }
       b.rank1(xa, yb);
     }
     rg.release(ci, lane);
+    if (!near) rp.release(ci, lane);
   }
+  rg.view(0, 0, kNBuf);
 }
 
 // acc[k] = sum_i x_i[j] x_{i+k0+k}[j] for lane j, k < kAcfGroup: the 16 + 16 partner values of a chunk sit in registers
@@ -433,7 +455,9 @@ __global__ void __launch_bounds__(kStatWarps * 32, stats_min_blocks<T, TE>()) ch
 
   Ring<T, PC> rg;
   rg.s_iter = a.s_iter; rg.s_param = a.s_param; rg.n = n; rg.p_rt = P;
-  rg.X = X; rg.mean = mean; rg.bar = bar; rg.phase = 0;
+  uint32_t ring_phase = 0;
+  rg.X = X; rg.mean = mean; rg.bar = bar; rg.phase = &ring_phase;
+  rg.view(0, 0, kNBuf);
   const int h = lane >> 4, ta = (lane >> 2) & 3, tb = lane & 3;
   const T inv_n = T(1) / T(n);
   const bool want_second = a.out_cov || a.out_inse || a.out_ess;
