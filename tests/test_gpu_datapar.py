@@ -212,3 +212,18 @@ def test_persistent_run_kernel_matches_the_per_evaluation_launches(n):
         assert runs["persistent"][2] == runs["launches"][2] and 0 < runs["persistent"][2] <= 2 * T
         assert runs["persistent"][3] == runs["launches"][3]
         assert torch.equal(runs["persistent"][4], runs["launches"][4]) and torch.equal(runs["persistent"][5], runs["launches"][5])
+
+
+def test_two_rank_peer_store_exchange():
+    """The exchange step needs two GPUs (CUDA IPC peer mappings cannot be exercised by the gloo tests): two ranks under
+    torch.distributed.run -- peer-store chain == NCCL chain, identical on both ranks, persistent kernel == per-evaluation
+    launches bitwise, and equal to the one-shard chain up to fp32 summation order (tools/check_dp_p2p.py)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr=127.0.0.1",
+                        "--master-port=29517", str(root / "tools" / "check_dp_p2p.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -2,7 +2,9 @@
    * the peer-store exchange (exchange="p2p") and the NCCL all-reduce formulation give the same chain
    * every rank holds the same chain
    * the chain equals the one-shard run of rank 0 over the whole data set up to fp32 summation order
-   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_dp_p2p.py"""
+   * the persistent run kernel (exchange inside one cooperative launch) equals the per-evaluation launches bitwise
+   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_dp_p2p.py
+Also run by tests/test_gpu_datapar.py::test_two_rank_peer_store_exchange when two GPUs are visible."""
 import os
 import sys
 import time
@@ -40,8 +42,10 @@ def main():
     xs, ys = torch.from_numpy(x[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev)
     T, L, step = 6, 5, 2e-4
     out = {}
-    for mode in ("p2p", "nccl"):
-        s = DataShardedHMC(model, theta0, xs, ys, step=step, num_steps=L, seed=3, exchange=mode)
+    for mode in ("p2p", "p2p-launches", "nccl"):
+        s = DataShardedHMC(model, theta0, xs, ys, step=step, num_steps=L, seed=3, exchange=mode.split("-")[0],
+                           trajectory="launches" if mode.endswith("launches") else "persistent")
+        assert s.persistent == (mode == "p2p")
         samples, targets, accepted = s.run(num_epochs=T, num_burnin_epochs=0)
         torch.cuda.synchronize()
         s.check_status()
@@ -58,13 +62,15 @@ def main():
                   flush=True)
         s.close()
     ok = True
+    # the persistent kernel (one cooperative launch per run, exchange inside) and the per-evaluation launches: bitwise equal
+    same_traj = all(torch.equal(a, b) for a, b in zip(out["p2p"], out["p2p-launches"]))
     same = torch.equal(out["p2p"][0], out["nccl"][0]) and torch.equal(out["p2p"][2], out["nccl"][2])
     err_modes = (out["p2p"][0] - out["nccl"][0]).abs().max().item()
     # every rank holds the same chain
     ref = out["p2p"][0].clone()
     dist.broadcast(ref, src=0)
     same_ranks = torch.equal(ref, out["p2p"][0])
-    flags = torch.tensor([int(same_ranks)], device=dev)
+    flags = torch.tensor([int(same_ranks and same_traj)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         full = DataShardedHMC(model, theta0, torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), step=step, num_steps=L,
@@ -75,7 +81,8 @@ def main():
         torch.cuda.synchronize()
         rel = ((fs - out["p2p"][0]).abs().max() / fs.abs().max()).item()
         acc_same = torch.equal(fa, out["p2p"][2])
-        print(f"p2p == nccl bitwise: {same} (max abs diff {err_modes:.2e}); identical on all ranks: {bool(flags.item())}; "
+        print(f"persistent == per-evaluation launches bitwise: {same_traj}; p2p == nccl bitwise: {same} (max abs diff {err_modes:.2e}); "
+              f"identical on all ranks: {bool(flags.item())}; "
               f"vs one shard: rel {rel:.2e}, accepts equal {acc_same}; acceptance {out['p2p'][2].float().mean().item():.2f}", flush=True)
         ok = (err_modes < 1e-6) and bool(flags.item()) and rel < 1e-5 and acc_same
         print("CHECK", "OK" if ok else "FAILED", flush=True)
