@@ -66,8 +66,20 @@ __device__ __forceinline__ void dp_post_entries(const double* partials, int n_pa
                                                 float* theta_p, double* scratch, int* status, double* red, int cta, int tid) {
   const int e = cta * DP_POST_THREADS + tid;          // entry of [loglik, dloglik]; e <= DP_P is valid
   double tot = 0.0;
-  if (e <= DP_P)
-    for (int c = 0; c < n_parts; ++c) tot += __ldcg(&partials[(size_t)c * (DP_P + 1) + e]);
+  if (e <= DP_P) {
+    // fixed order c = 0, 1, ...; the loads of 16 rows are in flight together (one dependent load per add would make the fold
+    // a chain of n_parts L2 round trips: it was the largest fixed cost of an evaluation)
+    const double* col = partials + e;
+    int c = 0;
+    for (; c + 16 <= n_parts; c += 16) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldcg(col + (size_t)(c + i) * (DP_P + 1));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tot += v[i];
+    }
+    for (; c < n_parts; ++c) tot += __ldcg(col + (size_t)c * (DP_P + 1));
+  }
   if (xc.world > 1) {
     const int par = (int)(seq & 1ull);
     const size_t slot = (size_t)(par * DP_XMAXW + xc.rank) * DP_XSLOT + e;

@@ -179,7 +179,9 @@ EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) 
 // (then 0 < p < 1 strictly and nothing is NaN); otherwise the lane redoes the forward pass with the general code, which
 // reproduces the reference's saturation / NaN semantics.  Both paths evaluate identical arithmetic where both are valid.
 // (The FP64 pipe and the dispatch port are the bound: the selects were a fifth of the instructions of a row.)
-template <typename T, class NET, bool GRAD, bool HARD = false, class TH, class GV>
+// VALUE = false (the inner leapfrog steps of an HMC trajectory, which use the gradient only): the fp64 fast path skips the
+// logarithm of the row's term; everything that decides between the fast and the general path is unchanged.
+template <typename T, class NET, bool GRAD, bool HARD = false, bool VALUE = true, class TH, class GV>
 EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g) {
   T h0[NET::D0];
 #pragma unroll
@@ -202,7 +204,7 @@ EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g)
     if constexpr (NET::LOSS == LOSS_BINARY) {
       const T p = sigmoid_fast(a[0]);
       const bool y1 = prob_is_one<T>(y);
-      term = log_pos_normal(y1 ? p : T(1) - p);
+      if constexpr (VALUE) term = log_pos_normal(y1 ? p : T(1) - p);
       dl[0] = y - p;
       done = mx <= kAbsHi708 && abs_hi(a[0]) <= kAbsHi36;
     } else {
@@ -258,7 +260,7 @@ EB_HD void layer_fast_rows(const TH& th, const double (&in)[R][DIN], double (&ou
   }
 }
 
-template <typename T, class NET, bool GRAD, int R, class TH, class GV>
+template <typename T, class NET, bool GRAD, int R, bool VALUE = true, class TH, class GV>
 EB_HD bool accumulate_rows_fast(const TH& th, const T* const (&xr)[R], const T (&y)[R], const int (&cls)[R], T& ll, GV& g) {
   if constexpr (sizeof(T) != 8) {
     return false;
@@ -287,7 +289,8 @@ EB_HD bool accumulate_rows_fast(const TH& th, const T* const (&xr)[R], const T (
     ok = mh <= kAbsHi36;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      term[r] = log_pos_normal(prob_is_one<T>(y[r]) ? p[r] : T(1) - p[r]);
+      term[r] = T(0);
+      if constexpr (VALUE) term[r] = log_pos_normal(prob_is_one<T>(y[r]) ? p[r] : T(1) - p[r]);
       dl[r][0] = y[r] - p[r];
     }
   } else {
@@ -295,8 +298,10 @@ EB_HD bool accumulate_rows_fast(const TH& th, const T* const (&xr)[R], const T (
     for (int r = 0; r < R; ++r) term[r] = head_loss<T, NET, true>(a[r], y[r], cls[r], dl[r], (T*)nullptr);
   }
   if (!(ok && mx <= kAbsHi708)) return false;
+  if constexpr (VALUE) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) ll += term[r];
+    for (int r = 0; r < R; ++r) ll += term[r];
+  }
   if constexpr (GRAD) {
     T d1[R][NET::D1], d0[NET::D0];
     if constexpr (NET::NL == 2) {
@@ -335,7 +340,10 @@ template <typename T, class NET, class TH> EB_HD void forward_row(const TH& th, 
 
 // log_target (and gradient) of one chain.  The G lanes of a chain group split the data rows (lane `sub` takes rows
 // sub, sub+G, ...), then all-reduce; every lane returns the same lt / g.  bayesian_model.py:52-56.
-template <typename T, class NET, int G, bool GRAD, class TH, class GV>
+// VALUE = false: gradient only -- lt is left untouched, the row terms skip their logarithm on the fp64 fast path and the
+// prior contributes its gradient alone (one FMA per parameter).  HMC's inner leapfrog steps need nothing else
+// (eeyore/samplers/hmc.py:110-119 evaluates the target there as well, but only the last value reaches the accept test).
+template <typename T, class NET, int G, bool GRAD, bool VALUE = true, class TH, class GV>
 EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g, T* ll_out = nullptr,
                        T* lp_out = nullptr) {
   T ll = T(0);
@@ -352,7 +360,7 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
       T y = T(0);
       int cls = 0;
       if constexpr (NET::LOSS == LOSS_BINARY) y = d.y[i]; else cls = d.cls[i];
-      accumulate_row<T, NET, GRAD, HARD>(th, d.x + i * NET::D0, y, cls, ll, g);
+      accumulate_row<T, NET, GRAD, HARD, VALUE>(th, d.x + i * NET::D0, y, cls, ll, g);
     };
     int i = sub;
 #if EB_ROW_BATCH >= 2
@@ -368,7 +376,7 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
           yr[r] = T(0); cr[r] = 0;
           if constexpr (NET::LOSS == LOSS_BINARY) yr[r] = d.y[i + r * G]; else cr[r] = d.cls[i + r * G];
         }
-        if (!accumulate_rows_fast<T, NET, GRAD, R>(th, xr, yr, cr, ll, g)) {
+        if (!accumulate_rows_fast<T, NET, GRAD, R, VALUE>(th, xr, yr, cr, ll, g)) {
 #pragma unroll 1
           for (int r = 0; r < R; ++r) one_row(i + r * G);
         }
@@ -386,7 +394,7 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
   if (NET::LOSS != LOSS_BINARY || d.hard_labels) rows(std::true_type{}); else rows(std::false_type{});
 #if defined(__CUDA_ARCH__)
   if constexpr (G > 1) {
-    ll = group_allreduce<G>(ll);
+    if constexpr (VALUE) ll = group_allreduce<G>(ll);
     if constexpr (GRAD) {
 #pragma unroll
       for (int j = 0; j < NET::P; ++j) g[j] = group_allreduce<G>(g[j]);
@@ -396,6 +404,15 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
   // vector Normal prior: sum_j -(theta_j - loc_j)^2 / (2 scale_j^2) - log scale_j - log sqrt(2 pi); bayesian_model.py:46-50
   // (initialising the accumulators with the prior gradient instead would save an add per parameter, but keeps all of them
   // live through the peeled first row: measured as spills)
+  if constexpr (!VALUE) {
+    static_assert(GRAD, "a gradient-only evaluation needs GRAD");
+#pragma unroll
+    for (int j = 0; j < NET::P; ++j) {
+      g[j] = fma_t<T>(d.ploc[j] - th[j], d.pivar[j], g[j]);
+      if (d.has_temperature) g[j] *= d.temperature;
+    }
+    return;
+  }
   T qp[4] = {T(0), T(0), T(0), T(0)};   // four partial sums: one chain of P dependent FMAs would be pure latency
 #pragma unroll
   for (int j = 0; j < NET::P; ++j) {

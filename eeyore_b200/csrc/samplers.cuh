@@ -118,7 +118,9 @@ EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_st
 #pragma unroll
     for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);           // :110, :117
     group_sync<G>();
-    eval_target<T, NET, G, true>(d, sub, thp, ltp, gp);                                   // :113, :118
+    // the target value matters at the end of the trajectory only (:141); the inner steps evaluate the gradient alone
+    if (s == num_steps - 1) eval_target<T, NET, G, true, true>(d, sub, thp, ltp, gp);     // :118
+    else eval_target<T, NET, G, true, false>(d, sub, thp, ltp, gp);                       // :113
     const T w = (s == num_steps - 1) ? half_eps : eps;                                    // :114, :119
 #pragma unroll
     for (int j = 0; j < NET::P; ++j)
