@@ -6,8 +6,8 @@
 
 The default line is config 4 (below); its `extra` object carries, measured in the same process at the same N, every other
 BASELINE configuration: cfg4_strong (524,288 chains in total, sharded), cfg4_thin1 (every iteration saved), cfg4_diagnostics
-(1,000 saved iterations per chain + on-device multi-ESS / ACF of every chain), cfg2, cfg3, cfg1 (one chain, wall time) and
-cfg5 (the data-sharded path with the peer-store exchange).
+(1,000 saved iterations per chain + on-device multi-ESS / ACF of every chain), cfg2, cfg3, cfg4_f32 / cfg2_f32 (the fp32 chain
+kernels), cfg1 (one chain, wall time) and cfg5 (the data-sharded path with the peer-store exchange).
 
 Workload (default cfg4 = BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on):
 MLP 2-3-2-1 on XOR, HMC with 10 leapfrog steps, 524,288 independent fp64 chains PER GPU (chains are sharded across
@@ -679,6 +679,11 @@ def run_ours(args):
             if ctx.rank == 0:
                 r["roofline"] = chain_roofline(ctx, r, WORKLOADS[name])
             extra[name] = strip(r)
+        for name in ("cfg4", "cfg2"):      # the "+fp32" of SURVEY.md section 8 (the reference's iris examples run in fp32)
+            r = bench_chains(ctx, name, k, wu, e2e=False, dtype="f32")
+            if ctx.rank == 0:
+                r["roofline"] = chain_roofline(ctx, r, WORKLOADS[name])
+            extra[name + "_f32"] = strip(r)
         extra["cfg1"] = bench_cfg1(ctx)
         extra["cfg5"] = bench_datapar(ctx, k, wu, clocks=None, full=False)
     if ctx.rank == 0:

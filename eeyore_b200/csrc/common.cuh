@@ -294,6 +294,69 @@ template <int M> EB_HD void sigmoid_fast_vec(const double (&g)[M], double (&out)
   for (int i = 0; i < M; ++i) { const int ah = abs_hi(g[i]); mx = ah > mx ? ah : mx; }
 }
 
+// ---- fp32 fast paths ----------------------------------------------------------------------------------------------------
+// The fp32 chain kernels are bound by instruction issue (one warp instruction per cycle and scheduler) and by the MUFU unit,
+// not by an arithmetic pipe: libm's expf + IEEE division + logf cost ~45 instructions per sigmoid.  On the fast path (the head's
+// pre-activation within +-16, where 0 < p < 1 strictly in fp32 and nothing saturates) a sigmoid is ex2.approx + add +
+// rcp.approx (2 ulp each: 3e-7 relative, against a 1e-5 bar), a log is lg2.approx * ln 2; anything else goes through the
+// general code, which reproduces the reference's saturation / NaN semantics with libm.
+EB_HD float sigmoid_fast(float g) {
+#if defined(__CUDA_ARCH__)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(g * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+#else
+  return 1.0f / (1.0f + expf(-g));
+#endif
+}
+EB_HD float exp_nonpos_fast(float a) {
+#if defined(__CUDA_ARCH__)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * 1.4426950408889634f));
+  return e;
+#else
+  return expf(a);
+#endif
+}
+EB_HD float rcp_fast(float s) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+  return r;
+#else
+  return 1.0f / s;
+#endif
+}
+EB_HD float log_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return __logf(x);
+#else
+  return logf(x);
+#endif
+}
+EB_HD int abs_hi(float g) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(g) & 0x7fffffff;
+#else
+  uint32_t b; memcpy(&b, &g, 4); return (int)(b & 0x7fffffffu);
+#endif
+}
+constexpr int kAbsBits16f = 0x41800000;   // bit pattern of 16.0f: below, 0 < sigmoid < 1 strictly in fp32
+template <int M> EB_HD void sigmoid_fast_vec(const float (&g)[M], float (&out)[M], int& mx) {
+#pragma unroll
+  for (int i = 0; i < M; ++i) out[i] = sigmoid_fast(g[i]);
+#pragma unroll
+  for (int i = 0; i < M; ++i) { const int ah = abs_hi(g[i]); mx = ah > mx ? ah : mx; }
+}
+// bounds of the fast path per type: hidden pre-activations (fp64: the table-based exp wraps beyond 708; fp32: ex2.approx
+// saturates correctly everywhere) and the head's (0 < p < 1 strictly)
+template <typename T> struct FastBounds;
+template <> struct FastBounds<double> { static constexpr int hidden = kAbsHi708, head = kAbsHi36; };
+template <> struct FastBounds<float> { static constexpr int hidden = 0x7fffffff, head = kAbsBits16f; };
+EB_HD double log_prob_fast(double q) { return log_pos_normal(q); }
+EB_HD float log_prob_fast(float q) { return log_fast(q); }
+
 // N sigmoids evaluated stage by stage ("vertically"): the N dependency chains are written interleaved so that the
 // instruction scheduler keeps all of them in flight (a hidden layer's units are independent; each chain alone is
 // latency-bound: ~14 dependent FP64 operations plus a table lookup and a MUFU).

@@ -76,14 +76,14 @@ EB_HD void dense_fwd(const TH& th, const T (&in)[DIN], T (&out)[DOUT]) {
 
 // fp64 fast path of a sigmoid layer: no saturation / NaN handling inside; `mx` collects the largest |pre-activation|
 // high word so that the caller can fall back to the general code (mlp_static.cuh: accumulate_row).
-template <int DIN, int DOUT, int OFF, class TH>
-EB_HD void dense_fwd_sig_fast(const TH& th, const double (&in)[DIN], double (&out)[DOUT], int& mx) {
-  double pre[DOUT];
+template <typename T, int DIN, int DOUT, int OFF, class TH>
+EB_HD void dense_fwd_sig_fast(const TH& th, const T (&in)[DIN], T (&out)[DOUT], int& mx) {
+  T pre[DOUT];
 #pragma unroll
   for (int o = 0; o < DOUT; ++o) {
-    double a = th[OFF + DIN * DOUT + o];
+    T a = th[OFF + DIN * DOUT + o];
 #pragma unroll
-    for (int i = 0; i < DIN; ++i) a = fma(th[OFF + o * DIN + i], in[i], a);
+    for (int i = 0; i < DIN; ++i) a = fma_t<T>(th[OFF + o * DIN + i], in[i], a);
     pre[o] = a;
   }
 #pragma unroll
@@ -117,6 +117,16 @@ EB_HD void dense_bwd(const TH& th, const T (&in)[DIN], const T (&dout)[DOUT], GV
 
 template <typename T> EB_HD T rcp_sum_t(T s) { return T(1) / s; }
 template <> EB_HD double rcp_sum_t<double>(double s) { return rcp_ge1(s); }
+// the fp32 fast path (HARD = true marks it for the multiclass head): MUFU-based exp / reciprocal / log
+template <typename T, bool FAST> EB_HD T head_exp(T a) { return exp_nonpos_t<T>(a); }
+template <> EB_HD float head_exp<float, true>(float a) { return exp_nonpos_fast(a); }
+template <typename T, bool FAST> EB_HD T head_rcp(T s) { return rcp_sum_t<T>(s); }
+template <> EB_HD float head_rcp<float, true>(float s) { return rcp_fast(s); }
+template <typename T, bool FAST> EB_HD T head_logsum(T s);
+template <> EB_HD double head_logsum<double, true>(double s) { return log_pos_normal(s > 0.0 ? s : 1.0); }
+template <> EB_HD double head_logsum<double, false>(double s) { return log_pos_normal(s > 0.0 ? s : 1.0); }
+template <> EB_HD float head_logsum<float, true>(float s) { return log_fast(s); }
+template <> EB_HD float head_logsum<float, false>(float s) { return logf(s); }
 template <typename T> EB_HD T head_log(T q) { return log_t<T>(q); }
 // fp64: q is a probability in [0, 1]; 0 is patched by the caller, tiny values are normal numbers (>= 1e-304)
 template <> EB_HD double head_log<double>(double q) { return log_pos_normal(q > 0.0 ? q : 1.0); }
@@ -159,9 +169,9 @@ EB_HD T head_loss(T (&a)[NET::DL], T y, int cls, T (&delta)[NET::DL], T* p_out) 
     T e[K];
     T s = T(0);
 #pragma unroll
-    for (int k = 0; k < K; ++k) { e[k] = exp_nonpos_t<T>(a[k] - m); s += e[k]; }
-    const T inv = rcp_sum_t<T>(s);   // s >= 1 (the maximal logit contributes e^0)
-    const T ls = head_log<T>(s);
+    for (int k = 0; k < K; ++k) { e[k] = head_exp<T, HARD>(a[k] - m); s += e[k]; }
+    const T inv = head_rcp<T, HARD>(s);   // s >= 1 (the maximal logit contributes e^0)
+    const T ls = head_logsum<T, HARD>(s);
     T term = T(0);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -191,25 +201,25 @@ EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g)
   T dl[NET::DL];
   T term = T(0);
   bool done = false;
-  if constexpr (sizeof(T) == 8 && (HARD || NET::LOSS != LOSS_BINARY)) {
+  if constexpr (HARD || NET::LOSS != LOSS_BINARY) {
     int mx = 0;
     T a[NET::DL];
-    dense_fwd_sig_fast<NET::D0, NET::D1, NET::OFF0>(th, h0, h1, mx);
+    dense_fwd_sig_fast<T, NET::D0, NET::D1, NET::OFF0>(th, h0, h1, mx);
     if constexpr (NET::NL == 2) {
       dense_fwd<T, NET::D1, NET::D2, NET::OFF1, false>(th, h1, a);
     } else {
-      dense_fwd_sig_fast<NET::D1, NET::D2, NET::OFF1>(th, h1, h2, mx);
+      dense_fwd_sig_fast<T, NET::D1, NET::D2, NET::OFF1>(th, h1, h2, mx);
       dense_fwd<T, NET::D2, NET::DL, NET::OFF2, false>(th, h2, a);
     }
     if constexpr (NET::LOSS == LOSS_BINARY) {
       const T p = sigmoid_fast(a[0]);
       const bool y1 = prob_is_one<T>(y);
-      if constexpr (VALUE) term = log_pos_normal(y1 ? p : T(1) - p);
+      if constexpr (VALUE) term = log_prob_fast(y1 ? p : T(1) - p);
       dl[0] = y - p;
-      done = mx <= kAbsHi708 && abs_hi(a[0]) <= kAbsHi36;
+      done = mx <= FastBounds<T>::hidden && abs_hi(a[0]) <= FastBounds<T>::head;
     } else {
-      term = head_loss<T, NET, HARD>(a, y, cls, dl, (T*)nullptr);
-      done = mx <= kAbsHi708;
+      term = head_loss<T, NET, true>(a, y, cls, dl, (T*)nullptr);
+      done = mx <= FastBounds<T>::hidden;
     }
   }
   if (!done) {
@@ -221,7 +231,7 @@ EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g)
       dense_fwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, h2);
       dense_fwd<T, NET::D2, NET::DL, NET::OFF2, false>(th, h2, a);
     }
-    term = head_loss<T, NET, HARD>(a, y, cls, dl, (T*)nullptr);
+    term = head_loss<T, NET, HARD && NET::LOSS == LOSS_BINARY>(a, y, cls, dl, (T*)nullptr);
   }
   ll += term;
   if constexpr (GRAD) {
@@ -239,16 +249,16 @@ EB_HD void accumulate_row(const TH& th, const T* xr, T y, int cls, T& ll, GV& g)
 
 // R rows at once through the fp64 fast path (see accumulate_row), every stage written across the rows.  Returns false --
 // with nothing accumulated -- when a bound of the fast path is violated; the caller then takes the rows one by one.
-template <int DIN, int DOUT, int OFF, int R, class TH>
-EB_HD void layer_fast_rows(const TH& th, const double (&in)[R][DIN], double (&out)[R][DOUT], int& mx) {
-  double pre[R * DOUT], s[R * DOUT];
+template <typename T, int DIN, int DOUT, int OFF, int R, class TH>
+EB_HD void layer_fast_rows(const TH& th, const T (&in)[R][DIN], T (&out)[R][DOUT], int& mx) {
+  T pre[R * DOUT], s[R * DOUT];
 #pragma unroll
   for (int o = 0; o < DOUT; ++o) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      double a = th[OFF + DIN * DOUT + o];
+      T a = th[OFF + DIN * DOUT + o];
 #pragma unroll
-      for (int i = 0; i < DIN; ++i) a = fma(th[OFF + o * DIN + i], in[r][i], a);
+      for (int i = 0; i < DIN; ++i) a = fma_t<T>(th[OFF + o * DIN + i], in[r][i], a);
       pre[r * DOUT + o] = a;
     }
   }
@@ -262,9 +272,7 @@ EB_HD void layer_fast_rows(const TH& th, const double (&in)[R][DIN], double (&ou
 
 template <typename T, class NET, bool GRAD, int R, bool VALUE = true, class TH, class GV>
 EB_HD bool accumulate_rows_fast(const TH& th, const T* const (&xr)[R], const T (&y)[R], const int (&cls)[R], T& ll, GV& g) {
-  if constexpr (sizeof(T) != 8) {
-    return false;
-  } else {
+  {
   T h0[R][NET::D0], h1[R][NET::D1], h2[R][NET::NL == 3 ? NET::D2 : 1], a[R][NET::DL], dl[R][NET::DL], term[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -272,8 +280,8 @@ EB_HD bool accumulate_rows_fast(const TH& th, const T* const (&xr)[R], const T (
     for (int i = 0; i < NET::D0; ++i) h0[r][i] = xr[r][i];
   }
   int mx = 0;
-  layer_fast_rows<NET::D0, NET::D1, NET::OFF0, R>(th, h0, h1, mx);
-  if constexpr (NET::NL == 3) layer_fast_rows<NET::D1, NET::D2, NET::OFF1, R>(th, h1, h2, mx);
+  layer_fast_rows<T, NET::D0, NET::D1, NET::OFF0, R>(th, h0, h1, mx);
+  if constexpr (NET::NL == 3) layer_fast_rows<T, NET::D1, NET::D2, NET::OFF1, R>(th, h1, h2, mx);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if constexpr (NET::NL == 2) dense_fwd<T, NET::D1, NET::D2, NET::OFF1, false>(th, h1[r], a[r]);
@@ -286,18 +294,18 @@ EB_HD bool accumulate_rows_fast(const TH& th, const T* const (&xr)[R], const T (
 #pragma unroll
     for (int r = 0; r < R; ++r) a0[r] = a[r][0];
     sigmoid_fast_vec<R>(a0, p, mh);
-    ok = mh <= kAbsHi36;
+    ok = mh <= FastBounds<T>::head;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       term[r] = T(0);
-      if constexpr (VALUE) term[r] = log_pos_normal(prob_is_one<T>(y[r]) ? p[r] : T(1) - p[r]);
+      if constexpr (VALUE) term[r] = log_prob_fast(prob_is_one<T>(y[r]) ? p[r] : T(1) - p[r]);
       dl[r][0] = y[r] - p[r];
     }
   } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) term[r] = head_loss<T, NET, true>(a[r], y[r], cls[r], dl[r], (T*)nullptr);
   }
-  if (!(ok && mx <= kAbsHi708)) return false;
+  if (!(ok && mx <= FastBounds<T>::hidden)) return false;
   if constexpr (VALUE) {
 #pragma unroll
     for (int r = 0; r < R; ++r) ll += term[r];
@@ -364,7 +372,7 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
     };
     int i = sub;
 #if EB_ROW_BATCH >= 2
-    if constexpr (sizeof(T) == 8 && (HARD || NET::LOSS != LOSS_BINARY)) {
+    if constexpr (HARD || NET::LOSS != LOSS_BINARY) {
       constexpr int R = EB_ROW_BATCH;
       for (; i + (R - 1) * G < d.n_rows; i += R * G) {
         const T* xr[R];
