@@ -13,7 +13,9 @@
 // Work split inside the warp, per batch of 32 data rows:
 //   phase A (lane = data row): forward pass, Jacobian row J_i, log-lik term, gradient += (y_i - p_i) J_i;
 //                              J_i and w_i = p_i (1 - p_i) go to shared memory;
-//   phase B (lane = 2x4 tile of the lower triangle of G): G_tile += w_r J_r[a] J_r[b] over the 32 staged rows.
+//   phase B (lane = 4x4 block of the lower triangle of G, two slices of the staged rows when the blocks fit 16 lanes):
+//                              G_block += w_r J_r[a] J_r[b]; five 128-bit shared-memory loads per 16 FMAs (2x4 tiles fed by
+//                              seven 64-bit loads per 8 FMAs kept the shared-memory pipe at 64 % of its peak).
 // Then a warp-level in-place Cholesky, two triangular solves (lane = vector element) and the accept test.
 #pragma once
 #include "chain_kernels.cuh"
@@ -24,19 +26,16 @@ constexpr int kSmWarps = 4;  // chains (warps) per block
 
 template <class NET> struct SmGeom {
   static constexpr int P = NET::P;
-  static constexpr int RP = (P + 1) / 2;       // row pairs
-  static constexpr int CQ = (P + 3) / 4;       // column quads
-  static constexpr int PSV = 4 * CQ + 1;       // staged row: J (zero padded) then w
+  static constexpr int CQ = (P + 3) / 4;       // column / row quads
+  static constexpr int PSV = 4 * CQ + 2;       // staged row: J (zero padded), w, one pad: rows are 16-byte aligned (LDS.128)
   static constexpr int LD = P + 1;             // leading dimension of the P x P matrices in shared memory
-  static constexpr int ntiles() {
-    int n = 0;
-    for (int rp = 0; rp < RP; ++rp) n += (2 * rp + 1) / 4 + 1 < CQ ? (2 * rp + 1) / 4 + 1 : CQ;
-    return n;
-  }
+  static constexpr int NB = CQ * (CQ + 1) / 2; // 4x4 blocks of the lower triangle
+  static constexpr int SLICES = NB <= 16 ? 2 : 1;
   static_assert(P <= 32, "one lane per vector element");
+  static_assert(NB <= 32, "one 4x4 metric block per lane");
 };
 
-template <typename T, class NET> struct SmWarpMem {
+template <typename T, class NET> struct alignas(16) SmWarpMem {
   using Geo = SmGeom<NET>;
   T v[32 * Geo::PSV];
   T mat[2][NET::P * Geo::LD];   // metric / Cholesky factors: [cur], [proposal] (roles swap on accept)
@@ -83,25 +82,38 @@ template <typename T> EB_D T warp_sum(T v) {
 
 // In-place Cholesky of the lower triangle of m (P x P, leading dimension LD); dinv[j] = 1 / R_jj.
 // Returns false if a pivot is not positive / not finite (linalg/is_pos_def.py:5-9 semantics); logdet = sum log R_jj.
+// Right-looking (outer-product) form, lane = row: after column j is scaled, every lane subtracts L_ij L_cj from its own row
+// entries c = j + 1 .. i -- independent updates, no serial dot products (the left-looking form spent sum_j 2 j dependent
+// LDS + FMA pairs, 45 % of the kernel's stall samples).  Element (i, c) receives the same FMAs in the same order k = 0 .. c - 1 as
+// before, so the factor is bit-identical.
+template <typename T> EB_D T chol_log(T l) { return log_t<T>(l); }
+template <> EB_D double chol_log<double>(double l) { return log_pos_normal(l); }   // l = sqrt(d), d > 0 finite: a normal number
 template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, T& logdet) {
   const int lane = threadIdx.x & 31;
   bool ok = true;
   T ld = T(0);
+  T* my = m + (lane < P ? lane : 0) * LD;
   for (int j = 0; j < P; ++j) {
-    T d = m[j * LD + j];
-    for (int k = 0; k < j; ++k) d = fma_t<T>(-m[j * LD + k], m[j * LD + k], d);
-    if (!(d > T(0)) || !(d < T(INFINITY))) { ok = false; break; }
+    const T d = m[j * LD + j];
+    if (!(d > T(0)) || !(d < T(INFINITY))) { ok = false; break; }     // uniform: every lane reads the same element
     const T l = sqrt_t<T>(d);
     const T li = T(1) / l;
-    ld += log_t<T>(l);
+    ld += chol_log<T>(l);
+    const bool below = lane > j && lane < P;
+    const T lij = below ? my[j] * li : T(0);
+    if (below) my[j] = lij;
+    if (lane == j) { my[j] = l; dinv[j] = li; }
     __syncwarp();
-    const int i = j + 1 + lane;
-    if (i < P) {
-      T s = m[i * LD + j];
-      for (int k = 0; k < j; ++k) s = fma_t<T>(-m[i * LD + k], m[j * LD + k], s);
-      m[i * LD + j] = s * li;
+    if (below) {   // four entries per trip, loads first: the compiler cannot tell that column j and the row entries never alias
+      int c = j + 1;
+      for (; c + 3 <= lane; c += 4) {
+        const T l0 = m[c * LD + j], l1 = m[(c + 1) * LD + j], l2 = m[(c + 2) * LD + j], l3 = m[(c + 3) * LD + j];
+        const T a0 = my[c], a1 = my[c + 1], a2 = my[c + 2], a3 = my[c + 3];
+        my[c] = fma_t<T>(-lij, l0, a0); my[c + 1] = fma_t<T>(-lij, l1, a1);
+        my[c + 2] = fma_t<T>(-lij, l2, a2); my[c + 3] = fma_t<T>(-lij, l3, a3);
+      }
+      for (; c <= lane; ++c) my[c] = fma_t<T>(-lij, m[c * LD + j], my[c]);
     }
-    if (lane == 0) { m[j * LD + j] = l; dinv[j] = li; }
     __syncwarp();
   }
   __syncwarp();
@@ -112,11 +124,23 @@ template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, 
 // R y = b (forward substitution); lane i holds b_i on entry and y_i on return (i < P).
 template <typename T, int P, int LD> EB_D T warp_solve_lower(const T* R, const T* dinv, T b) {
   const int lane = threadIdx.x & 31;
+  const T* my = R + (lane < P ? lane : 0) * LD;
+  // the dependent chain is shuffle -> multiply -> FMA per step; the matrix entries and reciprocal pivots of four steps are
+  // fetched together so that no shared-memory latency sits inside it
 #pragma unroll 1
-  for (int j = 0; j < P; ++j) {
-    const T yj = __shfl_sync(0xffffffffu, b, j) * dinv[j];
-    if (lane == j) b = yj;
-    else if (lane > j && lane < P) b = fma_t<T>(-R[lane * LD + j], yj, b);
+  for (int j0 = 0; j0 < P; j0 += 4) {
+    T r[4], di[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int j = j0 + k < P ? j0 + k : P - 1; r[k] = my[j]; di[k] = dinv[j]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + k;
+      if (j < P) {
+        const T yj = __shfl_sync(0xffffffffu, b, j) * di[k];
+        if (lane == j) b = yj;
+        else if (lane > j && lane < P) b = fma_t<T>(-r[k], yj, b);
+      }
+    }
   }
   return b;
 }
@@ -125,10 +149,19 @@ template <typename T, int P, int LD> EB_D T warp_solve_lower(const T* R, const T
 template <typename T, int P, int LD> EB_D T warp_solve_upper_t(const T* R, const T* dinv, T y) {
   const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int j = P - 1; j >= 0; --j) {
-    const T xj = __shfl_sync(0xffffffffu, y, j) * dinv[j];
-    if (lane == j) y = xj;
-    else if (lane < j) y = fma_t<T>(-R[j * LD + lane], xj, y);
+  for (int j0 = P - 1; j0 >= 0; j0 -= 4) {
+    T r[4], di[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int j = j0 - k >= 0 ? j0 - k : 0; r[k] = R[j * LD + (lane < P ? lane : 0)]; di[k] = dinv[j]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 - k;
+      if (j >= 0) {
+        const T xj = __shfl_sync(0xffffffffu, y, j) * di[k];
+        if (lane == j) y = xj;
+        else if (lane < j) y = fma_t<T>(-r[k], xj, y);
+      }
+    }
   }
   return y;
 }
@@ -152,12 +185,13 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
   using Geo = SmGeom<NET>;
   constexpr int P = NET::P, PSV = Geo::PSV, LD = Geo::LD;
   const int lane = threadIdx.x & 31;
+  const int slice = (Geo::SLICES == 2 && lane >= Geo::NB) ? 1 : 0;   // tile_rp / tile_cq: this lane's block (row quad, col quad)
   T ll = T(0);
 #pragma unroll
   for (int j = 0; j < P; ++j) g[j] = T(0);
-  T acc[2][4];
+  T acc[4][4];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = T(0);
 
@@ -172,8 +206,8 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
 #pragma unroll
       for (int j = 0; j < P; ++j) { g[j] = fma_t<T>(dl[0], J[j], g[j]); vrow[j] = J[j]; }
 #pragma unroll
-      for (int j = P; j < PSV - 1; ++j) vrow[j] = T(0);
-      vrow[PSV - 1] = p * (T(1) - p);
+      for (int j = P; j < 4 * Geo::CQ; ++j) vrow[j] = T(0);
+      vrow[4 * Geo::CQ] = p * (T(1) - p);
     } else {
 #pragma unroll
       for (int j = 0; j < PSV; ++j) vrow[j] = T(0);
@@ -181,16 +215,19 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
     __syncwarp();
     const int rows = min(32, d.n_rows - base);
     if (tile_rp >= 0) {
-      for (int r = 0; r < rows; ++r) {
+#pragma unroll 2
+      for (int r = slice; r < rows; r += Geo::SLICES) {
         const T* vr = sm.v + r * PSV;
-        const T w = vr[PSV - 1];
-        const T a0 = w * vr[2 * tile_rp], a1 = w * vr[2 * tile_rp + 1];
+        const T w = vr[4 * Geo::CQ];
+        T av[4], bv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const T b = vr[4 * tile_cq + c];
-          acc[0][c] = fma_t<T>(a0, b, acc[0][c]);
-          acc[1][c] = fma_t<T>(a1, b, acc[1][c]);
-        }
+        for (int q = 0; q < 4; ++q) { av[q] = vr[4 * tile_rp + q]; bv[q] = vr[4 * tile_cq + q]; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) av[q] *= w;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[q][c] = fma_t<T>(av[q], bv[c], acc[q][c]);
       }
     }
     __syncwarp();
@@ -213,20 +250,19 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
   lt = ll + lp;
   // assemble the lower triangle of G in shared memory
   T* G = sm.mat[buf];
-  if (tile_rp >= 0) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int row = 2 * tile_rp + r, col = 4 * tile_cq + c;
-        if (row < P && col <= row) {
-          T val = acc[r][c];
-          if (row == col) val += d.pivar[row];
-          if (d.has_temperature) val *= d.temperature;
-          G[row * LD + col] = val;
-        }
+    for (int c = 0; c < 4; ++c) {
+      T val = acc[r][c];
+      if constexpr (Geo::SLICES == 2) val += __shfl_down_sync(0xffffffffu, val, Geo::NB);   // the other slice of the rows
+      const int row = 4 * tile_rp + r, col = 4 * tile_cq + c;
+      if (tile_rp >= 0 && slice == 0 && row < P && col <= row) {
+        if (row == col) val += d.pivar[row];
+        if (d.has_temperature) val *= d.temperature;
+        G[row * LD + col] = val;
       }
-  }
+    }
   __syncwarp();
   return warp_chol_inplace<T, P, LD>(G, sm.dinv[buf], logdet);
 }
@@ -235,7 +271,7 @@ template <typename T, class NET>
 __global__ void __launch_bounds__(kSmWarps * 32) smmala_kernel(const ChainArgs<T> a) {
   using Geo = SmGeom<NET>;
   constexpr int P = NET::P, LD = Geo::LD;
-  static_assert(Geo::ntiles() <= 32, "one 2x4 metric tile per lane");
+
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout<T, NET> lay(a.n_rows, kSmWarps, false);
   const DataView<T> d = stage_data<T, NET>(smem, lay, a);
@@ -245,15 +281,15 @@ __global__ void __launch_bounds__(kSmWarps * 32) smmala_kernel(const ChainArgs<T
   const bool live = chain < a.n_chains;
   if (!live) chain = a.n_chains - 1;
 
-  // lane -> 2x4 tile of the lower triangle
+  // lane -> 4x4 block (row quad, column quad <= row quad) of the lower triangle; with two slices lanes NB .. 2 NB - 1 own the
+  // same blocks for the odd staged rows
   int tile_rp = -1, tile_cq = -1;
   {
     int t = 0;
-    for (int rp = 0; rp < Geo::RP; ++rp) {
-      const int ncq = min((2 * rp + 1) / 4 + 1, Geo::CQ);
-      for (int cq = 0; cq < ncq; ++cq, ++t)
-        if (t == lane) { tile_rp = rp; tile_cq = cq; }
-    }
+    const int want = lane < Geo::NB ? lane : (Geo::SLICES == 2 && lane < 2 * Geo::NB ? lane - Geo::NB : -1);
+    for (int rq = 0; rq < Geo::CQ; ++rq)
+      for (int cq = 0; cq <= rq; ++cq, ++t)
+        if (t == want) { tile_rp = rq; tile_cq = cq; }
   }
 
   const T step = a.step, half_step = T(0.5) * step, sq_step = sqrt_t<T>(step);
