@@ -84,18 +84,18 @@ __device__ __forceinline__ void dp_post_entries(const double* partials, int n_pa
     const int par = (int)(seq & 1ull);
     const size_t slot = (size_t)(par * DP_XMAXW + xc.rank) * DP_XSLOT + e;
     for (int p = 0; p < xc.world; ++p) xc.inbox[p][slot] = tot;      // coalesced 2 KB per CTA per peer, over NVLink
+    __threadfence_system();
     __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      for (int p = 0; p < xc.world; ++p) st_release_sys(&xc.flags[p][(par * DP_XMAXW + xc.rank) * 32 + cta], seq);
-      for (int src = 0; src < xc.world; ++src) {
-        const unsigned long long* f = &xc.flags[xc.rank][(par * DP_XMAXW + src) * 32 + cta];
-        long spins = 0;
-        while (ld_acquire_sys(f) < seq) {
-          if (++spins > (1L << 28)) {   // seconds: a peer is gone; fail loudly instead of hanging the box
-            status[0] = 1;
-            __trap();
-          }
+    // thread p < world releases this CTA's flag on peer p and waits for peer p's flag here: the W system-scope stores and the
+    // W polling loops run side by side (one thread doing them in turn cost a round trip per peer)
+    if (tid < xc.world) {
+      st_release_sys(&xc.flags[tid][(par * DP_XMAXW + xc.rank) * 32 + cta], seq);
+      const unsigned long long* f = &xc.flags[xc.rank][(par * DP_XMAXW + tid) * 32 + cta];
+      long spins = 0;
+      while (ld_acquire_sys(f) < seq) {
+        if (++spins > (1L << 28)) {   // seconds: a peer is gone; fail loudly instead of hanging the box
+          status[0] = 1;
+          __trap();
         }
       }
     }

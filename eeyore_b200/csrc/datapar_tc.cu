@@ -269,13 +269,27 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
   long long last_ = clock64();
 #endif
 
-  // ---- one-time staging: weights as bf16 pieces, constants, barriers, TMEM ------------------------------------------
-  // power-of-two scales of the fp16 operands, from the parameter magnitudes (identical in every CTA and on every rank)
+  // ---- per-evaluation staging: the parameter vector is read ONCE, 21 coalesced L2 loads per thread all in flight together
+  // (element e = tid + 256 k; the loop versions of this prologue -- one pass for the maxima, one per matrix for the pieces,
+  // each a chain of dependent load latencies -- took 21,000 cycles per evaluation); then the power-of-two scales of the fp16
+  // operands from the parameter magnitudes (identical in every CTA and on every rank) and the weights as fp16 pieces.
+  constexpr int TV = (DP_P + TC_THREADS - 1) / TC_THREADS;   // 21
+  float tv[TV];
+#pragma unroll
+  for (int k = 0; k < TV; ++k) {
+    const int e = tid + TC_THREADS * k;
+    tv[k] = e < DP_P ? __ldcg(theta + e) : 0.f;
+  }
   {
     float m1 = 0.f, m2 = 0.f, m0 = 0.f;
-    for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) m1 = fmaxf(m1, fabsf(__ldcg(theta + DP_OFF_W1 + e)));
-    for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) m0 = fmaxf(m0, fabsf(__ldcg(theta + e)));
-    if (tid < DP_H) m2 = fabsf(__ldcg(theta + DP_OFF_W2 + tid));
+#pragma unroll
+    for (int k = 0; k < TV; ++k) {
+      const int e = tid + TC_THREADS * k;
+      const float av = fabsf(tv[k]);
+      if (e < DP_OFF_B0) m0 = fmaxf(m0, av);
+      else if (e >= DP_OFF_W1 && e < DP_OFF_B1) m1 = fmaxf(m1, av);
+      else if (e >= DP_OFF_W2 && e < DP_OFF_B2) m2 = fmaxf(m2, av);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
@@ -301,36 +315,47 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
   const float inv_z1 = pow2i(-e_x) * pow2i(-e_w0);              // Z1 = (X sx)(W0 sw0)^T
   const float inv_w0 = pow2i(-e_d1) * pow2i(-e_x);              // dW0 = (Delta1 sd1)^T (X sx)
   const float inv_b0 = pow2i(-e_d1);                            // db0 = (Delta1 sd1)^T 1
-  for (int e = tid; e < DP_H * DP_D0; e += TC_THREADS) {  // W0[o][j]
-    const int o = e / DP_D0, j = e % DP_D0;
-    uint16_t p[2];
-    split2h_scalar(__ldcg(theta + e) * s_w0, p[0], p[1]);
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * k + o, j, TC_WCS2)) = p[k];
-  }
   const float inv_z2 = pow2i(-e_w) * (1.0f / TC_SH);            // Z2 = (H1 sh)(W1 sw)^T
   const float inv_d1 = pow2i(-e_w) * pow2i(-e_d);               // D1 = (Delta2 sd)(W1 sw)
   const float inv_w1 = pow2i(-e_d) * (1.0f / TC_SH);            // dW1 = (Delta2 sd)^T (H1 sh)
   const float inv_b1 = pow2i(-e_d);                             // db1 = (Delta2 sd)^T 1
-  for (int e = tid; e < DP_H * DP_H; e += TC_THREADS) {   // W1[o][i]
-    const int o = e / DP_H, i = e % DP_H;
-    uint16_t p[2];
-    split2h_scalar(__ldcg(theta + DP_OFF_W1 + e) * s_w, p[0], p[1]);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1a) + cm_off(64 * k + o, i, TC_WCS2)) = p[k];
-      *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * k + i, o, TC_WCS2)) = p[k];
+  for (int k = 0; k < TV; ++k) {
+    const int e = tid + TC_THREADS * k;
+    uint16_t p[2];
+    if (e < DP_OFF_B0) {                                  // W0[o][j]                                   (B of MMA1)
+      const int o = e / DP_D0, j = e % DP_D0;
+      split2h_scalar(tv[k] * s_w0, p[0], p[1]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * c + o, j, TC_WCS2)) = p[c];
+    } else if (e < DP_OFF_W1) {
+      s.b0[e - DP_OFF_B0] = tv[k];
+    } else if (e < DP_OFF_B1) {                           // W1[o][i]                                   (B of MMA2 and of MMA3)
+      const int o = (e - DP_OFF_W1) / DP_H, i = (e - DP_OFF_W1) % DP_H;
+      split2h_scalar(tv[k] * s_w, p[0], p[1]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1a) + cm_off(64 * c + o, i, TC_WCS2)) = p[c];
+        *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * c + i, o, TC_WCS2)) = p[c];
+      }
+    } else if (e < DP_OFF_W2) {
+      s.b1[e - DP_OFF_B1] = tv[k];
+    } else if (e < DP_OFF_B2) {
+      s.w2[e - DP_OFF_W2] = tv[k];
+    } else if (e == DP_OFF_B2) {
+      s.b2 = tv[k];
     }
   }
-  if (tid < DP_H) {
-    s.b0[tid] = __ldcg(theta + DP_OFF_B0 + tid);
-    s.b1[tid] = __ldcg(theta + DP_OFF_B1 + tid);
-    s.w2[tid] = __ldcg(theta + DP_OFF_W2 + tid);
-  }
-  if (tid == 0) {
-    s.b2 = __ldcg(theta + DP_OFF_B2);
-    if (again) {
+  if (again) {   // the previous evaluation staged its row of sums over the operand buffers, the blocks of ones included
+    for (int e = tid; e < 1024; e += TC_THREADS) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        s.ctx[c].ones_h[e] = 0x3C00;
+        s.ctx[c].ones_x[e] = 0x3C00;
+      }
+    }
+    if (tid == 0) {
 #pragma unroll
       for (int b = 0; b < 12; ++b) { mbar_inval(&s.bar[0][0] + b); mbar_init(&s.bar[0][0] + b, 1); }
       mbar_fence_init();
@@ -607,22 +632,24 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
   }
   // every MMA has completed: the last fold waited for the last one issued
 
-  // ---- write this CTA's partial sums ---------------------------------------------------------------------------------
+  // ---- this CTA's row of partial sums: staged in shared memory (the operand buffers are free now), written out coalesced ------
   fence_before_sync();
   __syncthreads();
+  static_assert(sizeof(TcCtx) >= sizeof(double) * (DP_P + 1) && sizeof(TcCtx) >= sizeof(double) * 3 * TC_THREADS, "staging space");
+  double* row = reinterpret_cast<double*>(&s.ctx[0]);     // [DP_P + 1]
+  double* red = reinterpret_cast<double*>(&s.ctx[1]);     // [3][TC_THREADS]
   if (lane < 16) {
     const int o = 16 * q + lane;
 #pragma unroll
-    for (int i = 0; i < TC_FW; ++i) out[1 + DP_OFF_W1 + o * DP_H + TC_FW * hf + i] = (double)g1[i] + (double)g1e[i];
+    for (int i = 0; i < TC_FW; ++i) row[1 + DP_OFF_W1 + o * DP_H + TC_FW * hf + i] = (double)g1[i] + (double)g1e[i];
 #pragma unroll
-    for (int j = 0; j < TC_XW; ++j) out[1 + o * DP_D0 + TC_XW * hf + j] = (double)g0[j] + (double)g0e[j];
+    for (int j = 0; j < TC_XW; ++j) row[1 + o * DP_D0 + TC_XW * hf + j] = (double)g0[j] + (double)g0e[j];
     if (hf == 0) {
-      out[1 + DP_OFF_B1 + o] = (double)gb1 + (double)gb1e;
-      out[1 + DP_OFF_B0 + o] = (double)gb0 + (double)gb0e;
+      row[1 + DP_OFF_B1 + o] = (double)gb1 + (double)gb1e;
+      row[1 + DP_OFF_B0 + o] = (double)gb0 + (double)gb0e;
     }
   }
   // dW2: unit 32 hf + lane, partial over the rows of quadrant q; log-likelihood and db2: fixed-order block sums
-  double* red = reinterpret_cast<double*>(s.ctx[0].dl);   // the activation buffers are free now
   red[tid] = (double)gw2 + (double)gw2e;
   red[TC_THREADS + tid] = (double)ll + (double)lle;
   red[2 * TC_THREADS + tid] = (double)gb2 + (double)gb2e;
@@ -632,18 +659,21 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
     double t = 0.0;
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) t += red[(4 * h2 + qq) * 32 + l2];
-    out[1 + DP_OFF_W2 + tid] = t;
+    row[1 + DP_OFF_W2 + tid] = t;
   }
   if (tid == 64) {
     double t = 0.0;
     for (int i = 0; i < DP_R; ++i) t += red[TC_THREADS + i];      // hf == 0 threads are tid 0..127
-    out[0] = t;
+    row[0] = t;
   }
   if (tid == 96) {
     double t = 0.0;
     for (int i = 0; i < DP_R; ++i) t += red[2 * TC_THREADS + i];
-    out[1 + DP_OFF_B2] = t;
+    row[1 + DP_OFF_B2] = t;
   }
+  __syncthreads();
+  for (int e = tid; e <= DP_P; e += TC_THREADS) out[e] = row[e];
+  __syncthreads();   // the next evaluation of a persistent run writes the operand buffers again
   TC_STAMP(21);
 }
 
