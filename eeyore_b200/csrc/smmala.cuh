@@ -22,7 +22,12 @@
 
 namespace eb {
 
-constexpr int kSmWarps = 4;  // chains (warps) per block
+// chains (warps) per block.  The kernel is latency-bound (serial factorisation / solves per chain), so resident warps are
+// what counts: one 12-warp CTA per SM (the fp64 math tables cost 32 KB per CTA whatever its size; 13.6 KB per warp).
+#ifndef EB_SM_WARPS
+#define EB_SM_WARPS 12
+#endif
+constexpr int kSmWarps = EB_SM_WARPS;
 
 template <class NET> struct SmGeom {
   static constexpr int P = NET::P;
@@ -41,6 +46,12 @@ template <typename T, class NET> struct alignas(16) SmWarpMem {
   T mat[2][NET::P * Geo::LD];   // metric / Cholesky factors: [cur], [proposal] (roles swap on accept)
   T dinv[2][32];                // 1 / R_jj
   T vec[32];                    // scratch vector (lane-indexed)
+  T th[32];                     // the parameter vector under evaluation (read as broadcasts: no per-lane register copy)
+};
+
+template <typename T> struct SmemVec {   // read-only vector in shared memory with the [] of the register arrays
+  const T* p;
+  EB_HD T operator[](int j) const { return p[j]; }
 };
 
 // d a_L / d theta for one row (binary head, linear last pre-activation): back-propagation with seed 1.
@@ -179,16 +190,18 @@ template <typename T, int P, int LD> EB_D T warp_rt_norm2(const T* R, T d, T* sc
 }
 
 // log_target, gradient (replicated in every lane) and the metric's Cholesky factor (shared memory) at theta.
+// theta is in sm.th (lane j wrote element j); on return lane j < P holds element j of the gradient in g_l.
 template <typename T, class NET>
-EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, NET>& sm, int buf, int tile_rp,
-                      int tile_cq, T& lt, T (&g)[NET::P], T& logdet) {
+EB_D bool smmala_eval(const DataView<T>& d, SmWarpMem<T, NET>& sm, int buf, int tile_rp, int tile_cq, T& lt, T& g_l,
+                      T& logdet) {
   using Geo = SmGeom<NET>;
   constexpr int P = NET::P, PSV = Geo::PSV, LD = Geo::LD;
   const int lane = threadIdx.x & 31;
   const int slice = (Geo::SLICES == 2 && lane >= Geo::NB) ? 1 : 0;   // tile_rp / tile_cq: this lane's block (row quad, col quad)
+  const SmemVec<T> th{sm.th};
+  const int jl = lane < P ? lane : 0;
   T ll = T(0);
-#pragma unroll
-  for (int j = 0; j < P; ++j) g[j] = T(0);
+  g_l = T(0);
   T acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -200,20 +213,30 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
     T* vrow = sm.v + lane * PSV;
     if (i < d.n_rows) {
       T J[P], a;
-      jacobian_row<T, NET>(th, d.x + i * NET::D0, J, a);
+      jacobian_row<T, NET>(th, d.x + i * NET::D0, J, a);   // th: broadcast reads of sm.th
       T al[1] = {a}, dl[1], p;
       ll += head_loss<T, NET>(al, d.y[i], 0, dl, &p);
 #pragma unroll
-      for (int j = 0; j < P; ++j) { g[j] = fma_t<T>(dl[0], J[j], g[j]); vrow[j] = J[j]; }
+      for (int j = 0; j < P; ++j) vrow[j] = J[j];
 #pragma unroll
       for (int j = P; j < 4 * Geo::CQ; ++j) vrow[j] = T(0);
       vrow[4 * Geo::CQ] = p * (T(1) - p);
+      vrow[4 * Geo::CQ + 1] = dl[0];          // d loglik_i / d a_L,i: the gradient is J^T delta over the staged rows
     } else {
 #pragma unroll
       for (int j = 0; j < PSV; ++j) vrow[j] = T(0);
     }
     __syncwarp();
     const int rows = min(32, d.n_rows - base);
+    {   // gradient: lane j sums delta_r J_r[j] over the staged rows (replaces 20 per-lane accumulators + 20 warp reductions)
+      T s0 = T(0), s1 = T(0);
+#pragma unroll 4
+      for (int r = 0; r + 1 < 32; r += 2) {
+        s0 = fma_t<T>(sm.v[r * PSV + 4 * Geo::CQ + 1], sm.v[r * PSV + jl], s0);
+        s1 = fma_t<T>(sm.v[(r + 1) * PSV + 4 * Geo::CQ + 1], sm.v[(r + 1) * PSV + jl], s1);
+      }
+      g_l += s0 + s1;                          // rows beyond the data were staged as zeros
+    }
     if (tile_rp >= 0) {
 #pragma unroll 2
       for (int r = slice; r < rows; r += Geo::SLICES) {
@@ -233,20 +256,16 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
     __syncwarp();
   }
   ll = warp_sum<T>(ll);
-#pragma unroll
-  for (int j = 0; j < P; ++j) g[j] = warp_sum<T>(g[j]);
+  // prior: lane j owns parameter j; the value is summed in parameter order by every lane (as before: identical in all lanes)
   T lp = d.lp_const;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     const T dd = th[j] - d.ploc[j];
     lp = fma_t<T>(-(dd * dd), T(0.5) * d.pivar[j], lp);
-    g[j] = fma_t<T>(-dd, d.pivar[j], g[j]);
   }
-  if (d.has_temperature) {
-    ll *= d.temperature; lp *= d.temperature;
-#pragma unroll
-    for (int j = 0; j < P; ++j) g[j] *= d.temperature;
-  }
+  g_l = fma_t<T>(-(th[jl] - d.ploc[jl]), d.pivar[jl], g_l);
+  if (d.has_temperature) { ll *= d.temperature; lp *= d.temperature; g_l *= d.temperature; }
+  if (lane >= P) g_l = T(0);
   lt = ll + lp;
   // assemble the lower triangle of G in shared memory
   T* G = sm.mat[buf];
@@ -268,7 +287,7 @@ EB_D bool smmala_eval(const DataView<T>& d, const T (&th)[NET::P], SmWarpMem<T, 
 }
 
 template <typename T, class NET>
-__global__ void __launch_bounds__(kSmWarps * 32) smmala_kernel(const ChainArgs<T> a) {
+__global__ void __launch_bounds__(kSmWarps * 32, 1) smmala_kernel(const ChainArgs<T> a) {
   using Geo = SmGeom<NET>;
   constexpr int P = NET::P, LD = Geo::LD;
 
@@ -301,12 +320,10 @@ __global__ void __launch_bounds__(kSmWarps * 32) smmala_kernel(const ChainArgs<T
   int cur = 0;
   bool ok_c;
   {
-    T th0[P], g0[P];
-#pragma unroll
-    for (int j = 0; j < P; ++j) th0[j] = a.theta[chain * a.st_c + j * a.st_p];
-    ok_c = smmala_eval<T, NET>(d, th0, sm, cur, tile_rp, tile_cq, lt_c, g0, logdet_c);
-#pragma unroll
-    for (int j = 0; j < P; ++j) if (lane == j) { gc_l = g0[j]; thc_l = th0[j]; }
+    if (lane < P) thc_l = a.theta[chain * a.st_c + lane * a.st_p];
+    sm.th[lane] = thc_l;
+    __syncwarp();
+    ok_c = smmala_eval<T, NET>(d, sm, cur, tile_rp, tile_cq, lt_c, gc_l, logdet_c);
   }
   T mean_c = thc_l + half_step * warp_solve_upper_t<T, P, LD>(sm.mat[cur], sm.dinv[cur],
                                                             warp_solve_lower<T, P, LD>(sm.mat[cur], sm.dinv[cur], gc_l));
@@ -341,14 +358,10 @@ __global__ void __launch_bounds__(kSmWarps * 32) smmala_kernel(const ChainArgs<T
     const int nxt = cur ^ 1;
     T lt_p, logdet_p, gpl = T(0);
     bool ok_p;
-    {
-      T th_p[P], g_p[P];
-#pragma unroll
-      for (int j = 0; j < P; ++j) th_p[j] = __shfl_sync(0xffffffffu, propl, j);
-      ok_p = smmala_eval<T, NET>(d, th_p, sm, nxt, tile_rp, tile_cq, lt_p, g_p, logdet_p);
-#pragma unroll
-      for (int j = 0; j < P; ++j) if (lane == j) gpl = g_p[j];
-    }
+    __syncwarp();
+    sm.th[lane] = propl;
+    __syncwarp();
+    ok_p = smmala_eval<T, NET>(d, sm, nxt, tile_rp, tile_cq, lt_p, gpl, logdet_p);
     bool acc = false;
     T mean_p = T(0);
     if (ok_p && ok_c) {
