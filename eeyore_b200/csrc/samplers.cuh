@@ -114,18 +114,35 @@ EB_HD bool hmc_draw(const DataView<T>& d, int sub, T eps, T half_eps, int num_st
   }
   group_sync<G>();
   ltp = lt_cur;
-  for (int s = 0; s < num_steps; ++s) {
+  if constexpr (G == 1) {   // one lane owns the chain: the first position update reads the momentum it has just formed
 #pragma unroll
-    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);           // :110, :117
-    group_sync<G>();
+    for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);           // :110
+  }
+  for (int s = 0; s < num_steps; ++s) {
+    if constexpr (G > 1) {
+#pragma unroll
+      for (int j = 0; j < NET::P; ++j) thp[j] = fma_t<T>(eps, p[j], thp[j]);         // :110, :117
+      group_sync<G>();
+    }
     // the target value matters at the end of the trajectory only (:141); the inner steps evaluate the gradient alone
     if (s == num_steps - 1) eval_target<T, NET, G, true, true>(d, sub, thp, ltp, gp);     // :118
     else eval_target<T, NET, G, true, false>(d, sub, thp, ltp, gp);                       // :113
     const T w = (s == num_steps - 1) ? half_eps : eps;                                    // :114, :119
+    if constexpr (G == 1) {   // momentum and the next position update in one pass over the parameters (no shared-memory
+                              // round trip of the momentum between the two)
+      const bool more = s + 1 < num_steps;
 #pragma unroll
-    for (int j = 0; j < NET::P; ++j)
-      if (j % G == sub) p[j] = fma_t<T>(w, gp[j], p[j]);
-    group_sync<G>();
+      for (int j = 0; j < NET::P; ++j) {
+        const T pj = fma_t<T>(w, gp[j], p[j]);
+        p[j] = pj;
+        if (more) thp[j] = fma_t<T>(eps, pj, thp[j]);                                 // :117
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NET::P; ++j)
+        if (j % G == sub) p[j] = fma_t<T>(w, gp[j], p[j]);
+      group_sync<G>();
+    }
   }
   // momentum negation (:122) leaves the kinetic energy unchanged
   T kin1 = T(0);
