@@ -651,9 +651,22 @@ def run_ours(args):
         line = None
         if ctx.rank == 0:
             roof = chain_roofline(ctx, head, w)
-            tfile = ROOT / "profiles" / "r01_traffic_cfg4.json"
+            tfile = ROOT / "profiles" / "r02_traffic_cfg4.json"
             if wname == "cfg4" and not args.chains and not args.iters and not args.dtype and tfile.exists():
-                roof["traffic"] = json.loads(tfile.read_text())["dram_bytes_total"]   # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
+                rec = json.loads(tfile.read_text())
+                roof["traffic"] = rec["dram_bytes_total"]   # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
+                # instruction-level view: the FP64 pipe takes one warp instruction every two cycles per SM sub-partition
+                sm_mhz = (clocks.summary().get("sm_mhz") or 1965.0)
+                sms = torch.cuda.get_device_properties(ctx.dev).multi_processor_count
+                pipe_rate = sms * 2 * sm_mhz * 1e6
+                n64 = rec["fp64_pipe_warp_instructions_per_warp_evaluation"]
+                roof["fp64_pipe_view"] = {
+                    "fp64_pipe_warp_instructions_per_warp_evaluation": n64,
+                    "warp_instructions_per_warp_evaluation": rec["warp_instructions_per_warp_evaluation"],
+                    "pipe_rate_warp_instructions_per_s": pipe_rate,
+                    "frac": (head["value"] / ctx.world / 32.0) * n64 / pipe_rate,
+                    "ncu_fp64_pipe_cycles_active_pct": rec["fp64_pipe_cycles_active_pct"],
+                    "source": "instruction counts from the committed ncu capture (profiles/r02_traffic_cfg4.json); rate = SMs x 2 per cycle x SM clock sampled during the timed region"}
             line = {"metric": "log_target_grad_evals_per_sec", "value": head["value"], "unit": "evals/s", "n_gpus": ctx.world,
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
                     "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",

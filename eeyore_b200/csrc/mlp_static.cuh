@@ -373,7 +373,11 @@ EB_HD void eval_target(const DataView<T>& d, int sub, const TH& th, T& lt, GV& g
     int i = sub;
 #if EB_ROW_BATCH >= 2
     if constexpr (HARD || NET::LOSS != LOSS_BINARY) {
+#ifdef EB_ROW_BATCH_GRADONLY
+      constexpr int R = VALUE ? EB_ROW_BATCH : EB_ROW_BATCH_GRADONLY;
+#else
       constexpr int R = EB_ROW_BATCH;
+#endif
       for (; i + (R - 1) * G < d.n_rows; i += R * G) {
         const T* xr[R];
         T yr[R];
