@@ -50,6 +50,7 @@ template <> struct Uni<float> {
 
 // log of a uniform in (0, 1): a positive normal number in both precisions
 template <typename T> EB_HD T log_unit_t(T u) { return log_t<T>(u); }
+template <> EB_HD float log_unit_t<float>(float u) { return log_fast(u); }   // lg2.approx: u is a normal number in (0, 1)
 template <> EB_HD double log_unit_t<double>(double u) { return log_pos_normal(u); }
 
 // radius of the pair: -2 log u1 lies in [0, 75) for the 53-bit (24-bit) uniforms of Uni<>
