@@ -296,6 +296,30 @@ def stats_goldens():
     print("stats multi_ess", esss, "rhat", out["multi_rhat"])
 
 
+def acf_goldens():
+    """ACF lives in the un-vendored `kanga` package, so the reference cannot pin it.  These
+    goldens come from two THIRD-PARTY implementations of the sample autocorrelation function over the reference's own chain
+    fixtures (examples/stats/chain01..04.csv): scipy.signal.correlate (FFT method) and numpy.correlate (direct), both with
+    the biased 1/n normalisation rho_k = c_k / c_0 (the convention of R's acf and of statsmodels).  Neither
+    calls any code of this repository; the two must agree with each other before the file is written."""
+    from scipy import signal
+    x = np.stack([np.loadtxt(REF / "examples" / "stats" / f"chain0{i}.csv", delimiter=",") for i in range(1, 5)])   # [4,1000,3]
+    C, n, P = x.shape
+    max_lag = 40
+    a_fft = np.empty((C, max_lag + 1, P))
+    a_dir = np.empty_like(a_fft)
+    for c in range(C):
+        for j in range(P):
+            v = x[c, :, j] - x[c, :, j].mean()
+            full = signal.correlate(v, v, mode="full", method="fft")[n - 1:]
+            a_fft[c, :, j] = full[: max_lag + 1] / full[0]
+            d = np.correlate(v, v, mode="full")[n - 1:]
+            a_dir[c, :, j] = d[: max_lag + 1] / d[0]
+    assert np.max(np.abs(a_fft - a_dir)) < 1e-12
+    np.savez_compressed(OUT / "acf_goldens.npz", acf=a_dir, acf_fft=a_fft, max_lag=np.array(max_lag))
+    print("acf goldens: lag-1 of chain01", a_dir[0, 1], "max |fft - direct|", np.max(np.abs(a_fft - a_dir)))
+
+
 def datapar_goldens():
     """BASELINE config 5 architecture (16-64-64-1, fp32) on a 4,099-row synthetic binary data set (ragged on purpose:
     not a multiple of the 128-row tile nor of 4): log_target and gradient from the unmodified reference."""
@@ -428,6 +452,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "smmala":
         smmala_goldens()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "acf":
+        acf_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f32ref":
         model_goldens_f32_inputs_in_f64()
         sys.exit(0)
@@ -463,6 +490,7 @@ if __name__ == "__main__":
     run_sampler("mh_xor2321_f64_nonsym", "mh", "2321", torch.float64, 300, 0, s3, 6, symmetric=False,
                 prop_scale=0.4)
     stats_goldens()
+    acf_goldens()
     power_posterior_goldens()
     adaptive_goldens()
     model_goldens_f32_inputs_in_f64()

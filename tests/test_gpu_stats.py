@@ -33,6 +33,17 @@ def test_reference_stats_goldens():
     assert np.allclose(npy(ch.mc_se(mc_cov_mat=ch.mc_cov())), se, rtol=1e-12)
 
 
+def test_acf_against_third_party_goldens():
+    """ACF over the reference's chain fixtures against scipy.signal.correlate / numpy.correlate (acf_goldens.npz)."""
+    gd, ga = load("stats_goldens"), load("acf_goldens")
+    x, k = torch.from_numpy(gd["chains"]), int(ga["max_lag"])
+    for i in range(4):
+        assert np.max(np.abs(npy(st.acf(x[i], k)) - ga["acf"][i])) < 1e-12
+    soa = x.permute(1, 2, 0).contiguous()                   # [n, P, C]: the layout the samplers save in
+    batch = npy(st.acf_soa(soa.cuda(), k))
+    assert np.max(np.abs(batch - ga["acf"])) < 1e-12
+
+
 def test_config1_chain_multi_ess():
     gd = load("mala_xor221_f64")
     ch = ChainList(vals={"sample": list(torch.from_numpy(gd["samples"]).unbind(0))})

@@ -139,6 +139,16 @@ def test_stats_goldens():
     assert abs(oracle.cov(x[0])[0, 0] - 6.895458038624478) < 1e-12
 
 
+def test_acf_against_third_party_implementations():
+    """ACF is absent from the reference (kanga, un-vendored): the restatement is checked against scipy.signal.correlate and
+    numpy.correlate evaluated over the reference's chain fixtures (oracle/make_golden.py acf_goldens)."""
+    gd, ga = load("stats_goldens"), load("acf_goldens")
+    x, k = gd["chains"], int(ga["max_lag"])
+    for i in range(4):
+        assert np.max(np.abs(oracle.acf(x[i], k) - ga["acf"][i])) < 1e-13
+        assert np.max(np.abs(oracle.acf(x[i], k) - ga["acf_fft"][i])) < 1e-13
+
+
 def test_inse_not_enough_samples():
     x = np.array([[0.0, 1.0], [1.0, 0.0], [0.5, 0.5]])
     with pytest.raises(RuntimeError, match="Not enough samples"):
