@@ -76,7 +76,7 @@ struct TcSmem {
   alignas(16) uint16_t w0s[2 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols j      (B of MMA1)
   alignas(16) uint16_t w1a[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols i      (B of MMA2)
   alignas(16) uint16_t w1b[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + i, cols o      (B of MMA3)
-  alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H];
+  alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H], w2d[DP_H];   // w2d = w2 * (scale of Delta2)
   alignas(16) float exch[TC_CG][DP_R];
   alignas(8) unsigned long long bar[2][6];       // per context, 1..5: MMA groups
   float b2;
@@ -99,21 +99,27 @@ __device__ unsigned long long dp_tc_prof[24];
 #define TC_STAMP(i)
 #endif
 
-// 1 / (1 + 2^(-z log2 e)): two MUFU ops (ex2, rcp; both within 2 ulp) and no slow path -- exp overflow gives exactly 0
+// SC / (1 + 2^(-z log2 e)), SC = 1 or TC_SH: two MUFU ops (ex2, rcp; both within 2 ulp) and no slow path -- exp overflow gives
+// exactly 0.  The power-of-two scale of the fp16 split rides on the reciprocal's argument: rcp((1 + e) / SC) = SC rcp(1 + e)
+// bit for bit (one FFMA instead of FADD + FMUL).
+template <bool SCALED>
 __device__ __forceinline__ float tc_sigmoid(float z) {
+  constexpr float c = SCALED ? 1.0f / TC_SH : 1.0f;
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(e, c, c)));
   return r;
 }
 
 // The same value with the reciprocal on the FMA pipe (integer seed, error <= 12 %, three Newton steps -> 4e-8).  With two
 // tiles in flight the epilogues are the critical path and the MUFU pipe (two ops per sigmoid) is their busiest unit: every
 // other unit takes this route (measured: 0 % 0.539 ms, 50 % 0.525 ms, 75 % 0.534 ms per 2M rows).
+template <bool SCALED>
 __device__ __forceinline__ float tc_sigmoid_fma(float z) {
+  constexpr float c = SCALED ? 1.0f / TC_SH : 1.0f;
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
-  const float d = fminf(1.0f + e, 1.0e30f);
+  const float d = fminf(fmaf(e, c, c), 1.0e30f);
   float r = __uint_as_float(0x7EF311C7u - __float_as_uint(d));
   r = r * fmaf(-d, r, 2.0f);
   r = r * fmaf(-d, r, 2.0f);
@@ -131,6 +137,21 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {
   asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(h));
   return r;
 }
+// x0 - lo(h), x1 - hi(h) for h = pack_f16x2(x0, x1): Blackwell's mixed-precision FMA (fp16 x fp16 + fp32 -> fp32, SASS FHFMA)
+// takes the packed halves as they are -- no conversion back to fp32 -- and the difference is exact.
+__device__ __forceinline__ void resid_f16x2(uint32_t h, float x0, float x1, float& r0, float& r1) {
+  asm("{\n\t.reg .f16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, lo, m1, %3;\n\tfma.rn.f32.f16 %1, hi, m1, %4;\n\t}"
+      : "=f"(r0), "=f"(r1) : "r"(h), "f"(x0), "f"(x1));
+}
+// float(a) + float(b) per half of two fp16 pairs (one conversion + one mixed-precision add, SASS FHADD, per value)
+__device__ __forceinline__ float2 sum_f16x2(uint32_t a, uint32_t b) {
+  float2 r;
+  asm("{\n\t.reg .f16 a0, a1, b0, b1;\n\t.reg .f32 t0, t1;\n\tmov.b32 {a0, a1}, %2;\n\tmov.b32 {b0, b1}, %3;\n\t"
+      "cvt.f32.f16 t0, a0;\n\tcvt.f32.f16 t1, a1;\n\tadd.rn.f32.f16 %0, b0, t0;\n\tadd.rn.f32.f16 %1, b1, t1;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "r"(a), "r"(b));
+  return r;
+}
 // 8 consecutive fp32 values (already scaled) -> two 16-byte rows of fp16 pieces: v = p1 + p2 + O(2^-22 v) (exact residual)
 __device__ __forceinline__ void split2h(const float* v, uint4& p1, uint4& p2) {
   uint32_t a[4], b[4];
@@ -138,9 +159,10 @@ __device__ __forceinline__ void split2h(const float* v, uint4& p1, uint4& p2) {
   for (int j = 0; j < 4; ++j) {
     const float x0 = v[2 * j], x1 = v[2 * j + 1];
     const uint32_t h = pack_f16x2(x0, x1);
-    const float2 hf2 = unpack_f16x2(h);
+    float r0, r1;
+    resid_f16x2(h, x0, x1, r0, r1);
     a[j] = h;
-    b[j] = pack_f16x2(x0 - hf2.x, x1 - hf2.y);
+    b[j] = pack_f16x2(r0, r1);
   }
   p1 = make_uint4(a[0], a[1], a[2], a[3]);
   p2 = make_uint4(b[0], b[1], b[2], b[3]);
@@ -151,16 +173,13 @@ __device__ __forceinline__ void split2h_scalar(float x, uint16_t& p1, uint16_t& 
   p1 = (uint16_t)h;
   p2 = (uint16_t)pack_f16x2(r, 0.f);
 }
-// TC_FW features of one row (scaled by `scale`), starting at chunk `chunk0` -> the two fp16 piece buffers
-__device__ __forceinline__ void store_pieces32h(unsigned char* base, int chunk0, int r, const float* v, float scale) {
+// TC_FW features of one row (already scaled), starting at chunk `chunk0` -> the two fp16 piece buffers
+__device__ __forceinline__ void store_pieces32h(unsigned char* base, int chunk0, int r, const float* v) {
   unsigned char* p = base + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)chunk0 * TC_CS;
 #pragma unroll
   for (int c = 0; c < TC_FW / 8; ++c) {
-    float w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = v[8 * c + j] * scale;
     uint4 p1, p2;
-    split2h(w, p1, p2);
+    split2h(v + 8 * c, p1, p2);
     *reinterpret_cast<uint4*>(p + c * TC_CS) = p1;
     *reinterpret_cast<uint4*>(p + c * TC_CS + TC_ACT) = p2;
   }
@@ -311,12 +330,12 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
   const int e_w0 = scale_exp(w0max);
   const int e_x = scale_exp(x_absmax[0]);           // the shard's max |x|
   const int e_d1 = scale_exp(4.0f * w2max * w1max); // |Delta1| <= 64 max|Delta2| max|W1| / 4
-  const float s_w = pow2i(e_w), s_d = pow2i(e_d), s_w0 = pow2i(e_w0), s_x = pow2i(e_x), s_d1 = pow2i(e_d1);
+  const float s_w = pow2i(e_w), s_d = pow2i(e_d), s_w0 = pow2i(e_w0), s_x = pow2i(e_x);
   const float inv_z1 = pow2i(-e_x) * pow2i(-e_w0);              // Z1 = (X sx)(W0 sw0)^T
   const float inv_w0 = pow2i(-e_d1) * pow2i(-e_x);              // dW0 = (Delta1 sd1)^T (X sx)
   const float inv_b0 = pow2i(-e_d1);                            // db0 = (Delta1 sd1)^T 1
   const float inv_z2 = pow2i(-e_w) * (1.0f / TC_SH);            // Z2 = (H1 sh)(W1 sw)^T
-  const float inv_d1 = pow2i(-e_w) * pow2i(-e_d);               // D1 = (Delta2 sd)(W1 sw)
+  const float c_d1 = pow2i(-e_w - e_d + e_d1) * (1.0f / (TC_SH * TC_SH));   // Delta1 sd1 = D1' c_d1 (sh - H1')(H1'), primes = scaled
   const float inv_w1 = pow2i(-e_d) * (1.0f / TC_SH);            // dW1 = (Delta2 sd)^T (H1 sh)
   const float inv_b1 = pow2i(-e_d);                             // db1 = (Delta2 sd)^T 1
 #pragma unroll
@@ -343,6 +362,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       s.b1[e - DP_OFF_B1] = tv[k];
     } else if (e < DP_OFF_B2) {
       s.w2[e - DP_OFF_W2] = tv[k];
+      s.w2d[e - DP_OFF_W2] = tv[k] * s_d;
     } else if (e == DP_OFF_B2) {
       s.b2 = tv[k];
     }
@@ -457,8 +477,9 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j)
-          v[j] = (j & 1) ? tc_sigmoid_fma(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j])) : tc_sigmoid(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]));
-        store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), (TC_FW / 8) * hf, r, v, TC_SH);
+          v[j] = (j & 1) ? tc_sigmoid_fma<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]))
+                         : tc_sigmoid<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]));     // H1 * TC_SH
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), (TC_FW / 8) * hf, r, v);
       }
       fence_async_smem();
       fence_before_sync();
@@ -491,10 +512,15 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         float apart = 0.f;
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j) {
-          h[j] = (j & 1) ? tc_sigmoid_fma(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j])) : tc_sigmoid(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]));
+          h[j] = (j & 1) ? tc_sigmoid_fma<false>(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]))
+                         : tc_sigmoid<false>(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]));
           apart = fmaf(h[j], s.w2[TC_FW * hf + j], apart);
         }
         s.exch[hf][r] = apart;
+        // everything of Delta2 that does not depend on the head runs before the rendez-vous with the other half of the row:
+        // w2 sd H2 (1 - H2), with H2 (1 - H2) as one FMA (a single rounding of the exact value)
+#pragma unroll
+        for (int j = 0; j < TC_FW; ++j) t[j] = fmaf(-h[j], h[j], h[j]) * s.w2d[TC_FW * hf + j];
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * TC_CG) : "memory");   // the warps that share rows 32 q .. 32 q + 31
         float asum = s.exch[0][r];
 #pragma unroll
@@ -508,10 +534,11 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         d_head = d;
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j) {
-          t[j] = d * h[j];                                                   // dW2 terms
-          h[j] = d * s.w2[TC_FW * hf + j] * (1.f - h[j]) * h[j];             // Delta2
+          const float dh = d * h[j];                                         // dW2 terms
+          h[j] = d * t[j];                                                   // Delta2 * sd
+          t[j] = dh;
         }
-        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, h, s_d);
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, h);
       }
       fence_async_smem();
       fence_before_sync();
@@ -572,14 +599,13 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
           const uint32_t w1[4] = {p1.x, p1.y, p1.z, p1.w}, w2v[4] = {p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 a = unpack_f16x2(w1[k]), b = unpack_f16x2(w2v[k]);
-            const float h0 = (a.x + b.x) * (1.0f / TC_SH), h1v = (a.y + b.y) * (1.0f / TC_SH);
-            v[8 * ch + 2 * k] = (v[8 * ch + 2 * k] * inv_d1) * (1.f - h0) * h0;
-            v[8 * ch + 2 * k + 1] = (v[8 * ch + 2 * k + 1] * inv_d1) * (1.f - h1v) * h1v;
+            const float2 hs = sum_f16x2(w1[k], w2v[k]);                     // H1 * TC_SH
+            v[8 * ch + 2 * k] = (v[8 * ch + 2 * k] * c_d1) * ((TC_SH - hs.x) * hs.x);
+            v[8 * ch + 2 * k + 1] = (v[8 * ch + 2 * k + 1] * c_d1) * ((TC_SH - hs.y) * hs.y);
           }
         }
         mbar_wait(&s.bar[c][4], par);                        // MMA4 has read Delta2 (and H1)
-        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, v, s_d1);
+        store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, v);
       }
       fence_async_smem();
       fence_before_sync();
