@@ -40,6 +40,13 @@ class NativeChainSampler(SerialSampler):
         # coalesced) or "cnp" = [C, n_saved, P] (every chain contiguous: what the diagnostics kernel streams with bulk
         # copies).  Either way DeviceChains sees the [n, P, C] indexing (a strided view for "cnp").
         self.sample_layout = "npc"
+        # Where a batched run saves its states.  False: device buffers (DeviceChains, on-device diagnostics).  True: pinned
+        # host buffers -- with unified addressing cudaHostAlloc'd memory is directly addressable by the device, so the kernel's
+        # coalesced stores of the saved states ARE the device->host transfer (posted PCIe writes under the computation; no
+        # staging copy, no device memory for the samples).  The buffers are kept and re-used by later runs of the same
+        # shape; their contents are valid once the stream has been synchronised.
+        self.host_output = False
+        self._host_blocks = {}
         self.num_chains = 1
         self.current = {key: None for key in self.keys}
         if theta0 is not None:
@@ -172,16 +179,26 @@ class NativeChainSampler(SerialSampler):
         n_saved = int(nv.lib().eeyore_b200_num_saved(n_iters, n_burnin, thin))
         out = {}
         chain_major = self.sample_layout == "cnp"
-        new_block = (lambda: torch.empty(c, n_saved, pn, dtype=m.dtype, device=dev).permute(1, 2, 0)) if chain_major else \
-            (lambda: torch.empty(n_saved, pn, c, dtype=m.dtype, device=dev))
+        host = bool(self.host_output) and self._batched
+
+        def alloc(key, shape, dtype):
+            if not host:
+                return torch.empty(*shape, dtype=dtype, device=dev)
+            buf = self._host_blocks.get(key)
+            if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+                buf = self._host_blocks[key] = torch.empty(*shape, dtype=dtype).pin_memory()
+            return buf
+
+        new_block = (lambda k: alloc(k, (c, n_saved, pn), m.dtype).permute(1, 2, 0)) if chain_major else \
+            (lambda k: alloc(k, (n_saved, pn, c), m.dtype))
         if n_saved > 0:
             if "sample" in want:
-                out["sample"] = new_block()
+                out["sample"] = new_block("sample")
             if "grad_val" in want and self._uses_grad:
-                out["grad_val"] = new_block()
+                out["grad_val"] = new_block("grad_val")
             if "target_val" in want:
-                out["target_val"] = torch.empty(n_saved, c, dtype=m.dtype, device=dev)
-            out["accepted"] = torch.empty(n_saved, c, dtype=torch.uint8, device=dev)
+                out["target_val"] = alloc("target_val", (n_saved, c), m.dtype)
+            out["accepted"] = alloc("accepted", (n_saved, c), torch.uint8)
         loc, scale = m.prior_on_device()
         p = nv.RunParams()
         p.n_chains, p.n_iters, p.n_burnin, p.thin = c, n_iters, n_burnin, thin
@@ -262,8 +279,8 @@ class NativeChainSampler(SerialSampler):
         n_burnin = max(0, min(n_iters, (self.counter.num_burnin_iters or 0) - self.counter.idx))
         out = self._launch(n_iters, n_burnin, xd, yd, want=self._wanted_keys())
         self._store(out)
-        if "accepted" in out:
-            self._last_accepted = out["accepted"][-1].to(torch.int64)
+        if "accepted" in out:   # host_output: a view of the pinned buffer (valid once the stream has been synchronised)
+            self._last_accepted = out["accepted"][-1] if out["accepted"].device.type == "cpu" else out["accepted"][-1].to(torch.int64)
         self.counter.increment_idx(n_iters)
         self._publish_current()
 

@@ -174,6 +174,35 @@ def test_philox_mode_hmc_matches_oracle_and_is_shard_invariant():
     assert torch.equal(s3_.get_chain().samples_soa, got.samples_soa)
 
 
+@pytest.mark.parametrize("layout", ["npc", "cnp"])
+def test_host_output_saved_states_equal_the_device_blocks(layout):
+    """host_output: the kernel stores the saved states straight into pinned host memory (no staging copy).  Same seed => the
+    host buffers hold bit for bit what the device blocks of an ordinary run hold, across two runs re-using the buffers."""
+    arch, P, C, T, seed = "2321", 20, 333, 12, 77
+    theta0 = torch.from_numpy(np.random.default_rng(5).normal(size=(C, P)))
+    m = make_model(arch, "f64", 3 ** 0.5)
+    ds = dataset(arch, "f64")
+    runs = {}
+    for host in (False, True):
+        s = HMC(m, theta0=theta0, dataloader=loader(ds), step=0.3, num_steps=4, seed=seed, thin=3)
+        s.sample_layout = layout
+        s.host_output = host
+        blocks = []
+        for rep in range(2):
+            s.reset(theta0 + rep)
+            s.run(num_epochs=T, num_burnin_epochs=2)
+            torch.cuda.synchronize()
+            b = s._device_blocks[-1]
+            assert b["sample"].device.type == ("cpu" if host else "cuda")
+            assert not host or b["sample"].is_pinned() or b["sample"].permute(2, 0, 1).is_pinned()
+            blocks.append({k: v.cpu().clone() for k, v in b.items()})
+        runs[host] = blocks
+    for rep in range(2):
+        for k in ("sample", "target_val", "accepted"):
+            assert torch.equal(runs[True][rep][k], runs[False][rep][k]), (rep, k)
+    assert not torch.equal(runs[True][0]["sample"], runs[True][1]["sample"])
+
+
 def test_nan_proposals_are_rejected():
     """a saturated proposal gives a NaN target; comparisons with NaN are False => reject, state intact."""
     m = make_model("221", "f32", 1.0)
