@@ -49,6 +49,7 @@ constexpr uint32_t TC_CS = 2048;                 // chunk stride of [128 x C] ac
 constexpr uint32_t TC_ACT = 8 * TC_CS;           // one bf16 piece of a [128 x 64] activation: 16 KB
 constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] x tile: 4 KB
 constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-stacked weight buffers ([128 x K])
+constexpr float TC_NL2E = -1.4426950408889634f;  // -log2 e
 constexpr float TC_SH = 1024.f;                  // scale of H1 before the fp16 split (keeps the low piece normal)
 // TMEM columns (fp32)
 constexpr uint32_t TM_Z = 0;                     // per context (c * 128): Z1, then Z2, then D1 (2 groups of 64)
@@ -99,14 +100,14 @@ __device__ unsigned long long dp_tc_prof[24];
 #define TC_STAMP(i)
 #endif
 
-// SC / (1 + 2^(-z log2 e)), SC = 1 or TC_SH: two MUFU ops (ex2, rcp; both within 2 ulp) and no slow path -- exp overflow gives
+// SC / (1 + 2^zl), zl = -z log2 e (the factor rides on the bias and on the scale of the pre-activation), SC = 1 or TC_SH: two MUFU ops (ex2, rcp; both within 2 ulp) and no slow path -- exp overflow gives
 // exactly 0.  The power-of-two scale of the fp16 split rides on the reciprocal's argument: rcp((1 + e) / SC) = SC rcp(1 + e)
 // bit for bit (one FFMA instead of FADD + FMUL).
 template <bool SCALED>
-__device__ __forceinline__ float tc_sigmoid(float z) {
+__device__ __forceinline__ float tc_sigmoid(float zl) {
   constexpr float c = SCALED ? 1.0f / TC_SH : 1.0f;
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zl));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(e, c, c)));
   return r;
 }
@@ -115,10 +116,10 @@ __device__ __forceinline__ float tc_sigmoid(float z) {
 // tiles in flight the epilogues are the critical path and the MUFU pipe (two ops per sigmoid) is their busiest unit: every
 // other unit takes this route (measured: 0 % 0.539 ms, 50 % 0.525 ms, 75 % 0.534 ms per 2M rows).
 template <bool SCALED>
-__device__ __forceinline__ float tc_sigmoid_fma(float z) {
+__device__ __forceinline__ float tc_sigmoid_fma(float zl) {
   constexpr float c = SCALED ? 1.0f / TC_SH : 1.0f;
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zl));
   const float d = fminf(fmaf(e, c, c), 1.0e30f);
   float r = __uint_as_float(0x7EF311C7u - __float_as_uint(d));
   r = r * fmaf(-d, r, 2.0f);
@@ -192,6 +193,22 @@ __device__ __forceinline__ int scale_exp(float vmax) {
   return e < -40 ? -40 : (e > 40 ? 40 : e);
 }
 
+// v[j] = accumulator columns taddr + j, j < TC_FW
+__device__ __forceinline__ void load_acc(uint32_t taddr, float* v) {
+  if constexpr (TC_FW == 32) {
+    uint32_t a[32];
+    tmem_ld32(taddr, a);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]);
+  } else {
+    uint32_t a[16];
+    tmem_ld16(taddr, a);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]);
+  }
+}
 // v[j] = sum of the two accumulator groups (64 columns apart) of a two-piece product at columns col0 + j, j < 32
 __device__ __forceinline__ void load_sum2(uint32_t taddr, float* v) {
   if constexpr (TC_FW == 32) {
@@ -247,6 +264,23 @@ __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_d
     mma_bf16(d_tmem, desc_advance(a_desc[0], k * a_step), bd, id0, (k > 0) ? 1u : accumulate);
     mma_bf16(d_tmem, desc_advance(a_desc[1], k * a_step), bd, id1, 1u);
     if constexpr (NP == 3) mma_bf16(d_tmem, desc_advance(a_desc[2], k * a_step), bd, id2, 1u);
+  }
+}
+
+// A1 B1 + A1 B2 + A2 B1 accumulated into ONE group of N columns (three MMAs per k-step; B2 = B1 + 64 rows = 1024 bytes in the
+// core-matrix layout).  The tensor pipe has the slack (a quarter busy) and the epilogue is what bounds the kernel: summing
+// the piece products in TMEM instead of two accumulator groups in the epilogue saves a TMEM load and TC_FW additions per
+// thread and phase.
+template <int M, int N>
+__device__ __forceinline__ void mma_product_sum(uint32_t d_tmem, const uint64_t* a_desc, uint64_t b_desc, uint32_t a_step,
+                                                uint32_t b_step, int k_steps) {
+  constexpr uint32_t id = idesc_f16kind(M, N, 0, 0, 0, 0);
+  for (int k = 0; k < k_steps; ++k) {
+    const uint64_t b1 = desc_advance(b_desc, k * b_step), b2 = desc_advance(b1, 1024);
+    const uint64_t a1 = desc_advance(a_desc[0], k * a_step), a2 = desc_advance(a_desc[1], k * a_step);
+    mma_bf16(d_tmem, a1, b1, id, (k > 0) ? 1u : 0u);
+    mma_bf16(d_tmem, a1, b2, id, 1u);
+    mma_bf16(d_tmem, a2, b1, id, 1u);
   }
 }
 
@@ -331,10 +365,10 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
   const int e_x = scale_exp(x_absmax[0]);           // the shard's max |x|
   const int e_d1 = scale_exp(4.0f * w2max * w1max); // |Delta1| <= 64 max|Delta2| max|W1| / 4
   const float s_w = pow2i(e_w), s_d = pow2i(e_d), s_w0 = pow2i(e_w0), s_x = pow2i(e_x);
-  const float inv_z1 = pow2i(-e_x) * pow2i(-e_w0);              // Z1 = (X sx)(W0 sw0)^T
+  const float inv_z1 = pow2i(-e_x) * pow2i(-e_w0) * TC_NL2E;    // -log2 e Z1, Z1 = (X sx)(W0 sw0)^T
   const float inv_w0 = pow2i(-e_d1) * pow2i(-e_x);              // dW0 = (Delta1 sd1)^T (X sx)
   const float inv_b0 = pow2i(-e_d1);                            // db0 = (Delta1 sd1)^T 1
-  const float inv_z2 = pow2i(-e_w) * (1.0f / TC_SH);            // Z2 = (H1 sh)(W1 sw)^T
+  const float inv_z2 = pow2i(-e_w) * (1.0f / TC_SH) * TC_NL2E;  // -log2 e Z2, Z2 = (H1 sh)(W1 sw)^T
   const float c_d1 = pow2i(-e_w - e_d + e_d1) * (1.0f / (TC_SH * TC_SH));   // Delta1 sd1 = D1' c_d1 (sh - H1')(H1'), primes = scaled
   const float inv_w1 = pow2i(-e_d) * (1.0f / TC_SH);            // dW1 = (Delta2 sd)^T (H1 sh)
   const float inv_b1 = pow2i(-e_d);                             // db1 = (Delta2 sd)^T 1
@@ -349,7 +383,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       for (int c = 0; c < 2; ++c)
         *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w0s) + cm_off(64 * c + o, j, TC_WCS2)) = p[c];
     } else if (e < DP_OFF_W1) {
-      s.b0[e - DP_OFF_B0] = tv[k];
+      s.b0[e - DP_OFF_B0] = tv[k] * TC_NL2E;                 // biases pre-multiplied by -log2 e (see tc_sigmoid)
     } else if (e < DP_OFF_B1) {                           // W1[o][i]                                   (B of MMA2 and of MMA3)
       const int o = (e - DP_OFF_W1) / DP_H, i = (e - DP_OFF_W1) % DP_H;
       split2h_scalar(tv[k] * s_w, p[0], p[1]);
@@ -359,7 +393,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s.w1b) + cm_off(64 * c + i, o, TC_WCS2)) = p[c];
       }
     } else if (e < DP_OFF_W2) {
-      s.b1[e - DP_OFF_B1] = tv[k];
+      s.b1[e - DP_OFF_B1] = tv[k] * TC_NL2E;
     } else if (e < DP_OFF_B2) {
       s.w2[e - DP_OFF_W2] = tv[k];
       s.w2d[e - DP_OFF_W2] = tv[k] * s_d;
@@ -457,7 +491,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
           fence_after_sync();
           uint64_t dA[2];
           descs2(a_ctx0 + c * CTXB + OFF_XP, TC_XP, TC_CS, 128, dA);                      // K-major A (M = row, K = feature)
-          mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z + 128 * c, dA, smem_desc(a_w0, TC_WCS2, 128), 0, 0, 1);   // MMA1
+          mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w0, TC_WCS2, 128), 0, 0, 1);              // MMA1
           mma_commit(&s.bar[c][1]);
         }
         __syncwarp();
@@ -474,7 +508,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       fence_after_sync();
       {
         float v[TC_FW];
-        load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
+        load_acc(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j)
           v[j] = (j & 1) ? tc_sigmoid_fma<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]))
@@ -489,7 +523,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
           fence_after_sync();
           uint64_t dA[2];
           descs2(a_ctx0 + c * CTXB + OFF_H1, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = hidden unit)
-          mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1a, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
+          mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1a, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
           mma_commit(&s.bar[c][2]);                                                       // MMA2: Z2 = H1 W1^T
         }
         __syncwarp();
@@ -508,7 +542,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       float t[TC_FW], p_head = 0.5f, d_head = 0.f;
       {
         float h[TC_FW];
-        load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, h);
+        load_acc(tm_lane + TM_Z + 128 * c + TC_FW * hf, h);
         float apart = 0.f;
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j) {
@@ -550,7 +584,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
           uint64_t dA[2], dM[2];
           descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = unit)
           descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
-          mma_product<2, 0, 128, 0, 64, 0, 0>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1b, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
+          mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1b, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
           mma_commit(&s.bar[c][3]);                                                       // MMA3: D1 = Delta2 W1
           mma_product<2, 0, 64, 8, 64, 1, 1>(tm + TM_W1, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESH, 128, TC_CS), 256, 256, 8, keep);
           mma_commit(&s.bar[c][4]);                                                       // MMA4: Delta2^T [1 H1]
@@ -588,7 +622,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       fence_after_sync();
       {
         float v[TC_FW];
-        load_sum2(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
+        load_acc(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
         // H1 of this row from its two fp16 pieces (exact up to 2^-22): no fp32 copy is kept
         const unsigned char* hp = reinterpret_cast<const unsigned char*>(cx.h1) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u +
                                   (uint32_t)((TC_FW / 8) * hf) * TC_CS;
