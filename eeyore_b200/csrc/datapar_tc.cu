@@ -52,7 +52,7 @@ constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-
 constexpr float TC_NL2E = -1.4426950408889634f;  // -log2 e
 constexpr float TC_SH = 1024.f;                  // scale of H1 before the fp16 split (keeps the low piece normal)
 // TMEM columns (fp32)
-constexpr uint32_t TM_Z = 0;                     // per context (c * 128): Z1, then Z2, then D1 (2 groups of 64)
+constexpr uint32_t TM_Z = 0;                     // per context (c * 128): columns 0..63 Z1, then Z2, then D1; 64..127 sh^2 H1 (1 - H1)
 constexpr uint32_t TM_W1 = 256;                  // [ones(8) | dW1 (2 x 64)] on lanes 16q..16q+15, accumulated over TC_FLUSH tiles
 constexpr uint32_t TM_W0 = 392;                  // [ones(8) | dW0 (2 x 16)]     (432 of 512 columns)
 constexpr int TC_FLUSH = 2;                      // PAIRS of tiles between two folds (4 tiles)
@@ -513,7 +513,14 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         for (int j = 0; j < TC_FW; ++j)
           v[j] = (j & 1) ? tc_sigmoid_fma<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]))
                          : tc_sigmoid<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]));     // H1 * TC_SH
+        if constexpr (TC_FW == 32) {   // sh^2 H1 (1 - H1) parked in the free half of this context's Z columns until P3
+          uint32_t m[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m[j] = __float_as_uint((TC_SH - v[j]) * v[j]);
+          tmem_st32(tm_lane + TM_Z + 128 * c + 64 + TC_FW * hf, m);
+        }
         store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), (TC_FW / 8) * hf, r, v);
+        if constexpr (TC_FW == 32) tmem_st_wait();
       }
       fence_async_smem();
       fence_before_sync();
@@ -622,20 +629,29 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       fence_after_sync();
       {
         float v[TC_FW];
-        load_acc(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
-        // H1 of this row from its two fp16 pieces (exact up to 2^-22): no fp32 copy is kept
-        const unsigned char* hp = reinterpret_cast<const unsigned char*>(cx.h1) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u +
-                                  (uint32_t)((TC_FW / 8) * hf) * TC_CS;
+        if constexpr (TC_FW == 32) {   // D1 and the parked sh^2 H1 (1 - H1): two TMEM loads in flight together
+          uint32_t d1[32], m[32];
+          tmem_ld32(tm_lane + TM_Z + 128 * c + TC_FW * hf, d1);
+          tmem_ld32(tm_lane + TM_Z + 128 * c + 64 + TC_FW * hf, m);
+          tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < TC_FW / 8; ++ch) {
-          const uint4 p1 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS);
-          const uint4 p2 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS + TC_ACT);
-          const uint32_t w1[4] = {p1.x, p1.y, p1.z, p1.w}, w2v[4] = {p2.x, p2.y, p2.z, p2.w};
+          for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(d1[j]) * c_d1) * __uint_as_float(m[j]);
+        } else {
+          load_acc(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
+          // H1 of this row from its two fp16 pieces (exact up to 2^-22)
+          const unsigned char* hp = reinterpret_cast<const unsigned char*>(cx.h1) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u +
+                                    (uint32_t)((TC_FW / 8) * hf) * TC_CS;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 hs = sum_f16x2(w1[k], w2v[k]);                     // H1 * TC_SH
-            v[8 * ch + 2 * k] = (v[8 * ch + 2 * k] * c_d1) * ((TC_SH - hs.x) * hs.x);
-            v[8 * ch + 2 * k + 1] = (v[8 * ch + 2 * k + 1] * c_d1) * ((TC_SH - hs.y) * hs.y);
+          for (int ch = 0; ch < TC_FW / 8; ++ch) {
+            const uint4 p1 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS);
+            const uint4 p2 = *reinterpret_cast<const uint4*>(hp + ch * TC_CS + TC_ACT);
+            const uint32_t w1[4] = {p1.x, p1.y, p1.z, p1.w}, w2v[4] = {p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 hs = sum_f16x2(w1[k], w2v[k]);                     // H1 * TC_SH
+              v[8 * ch + 2 * k] = (v[8 * ch + 2 * k] * c_d1) * ((TC_SH - hs.x) * hs.x);
+              v[8 * ch + 2 * k + 1] = (v[8 * ch + 2 * k + 1] * c_d1) * ((TC_SH - hs.y) * hs.y);
+            }
           }
         }
         mbar_wait(&s.bar[c][4], par);                        // MMA4 has read Delta2 (and H1)
