@@ -36,13 +36,23 @@ template <class NET> struct SmGeom {
   static constexpr int LD = P + 1;             // leading dimension of the P x P matrices in shared memory
   static constexpr int NB = CQ * (CQ + 1) / 2; // 4x4 blocks of the lower triangle
   static constexpr int SLICES = NB <= 16 ? 2 : 1;
+  // fp64: the metric is accumulated by FP64 tensor-core MMAs (DMMA m8n8k4) over 8 x 8 tiles of the lower triangle.  Row P of
+  // the padded matrix carries the gradient (see smmala_eval), hence P + 1 rows.  Staged row: 8 NT columns, then w; the row
+  // stride is = 4 (mod 8) doubles so that the 4 data rows x 4 columns a half-warp loads fall into 32 distinct banks.
+  static constexpr int NT = (P + 1 + 7) / 8;
+  static constexpr int PSV_D = ((8 * NT + 1 - 4 + 7) / 8) * 8 + 4;
+  static_assert(PSV_D >= 8 * NT + 1 && PSV_D % 8 == 4, "staged row stride of the DMMA path");
   static_assert(P <= 32, "one lane per vector element");
   static_assert(NB <= 32, "one 4x4 metric block per lane");
 };
 
+template <typename T> struct SmIsF64 { static constexpr bool value = false; };
+template <> struct SmIsF64<double> { static constexpr bool value = true; };
+
 template <typename T, class NET> struct alignas(16) SmWarpMem {
   using Geo = SmGeom<NET>;
-  T v[32 * Geo::PSV];
+  static constexpr int PSV = SmIsF64<T>::value ? Geo::PSV_D : Geo::PSV;
+  T v[32 * PSV];
   T mat[2][NET::P * Geo::LD];   // metric / Cholesky factors: [cur], [proposal] (roles swap on accept)
   T dinv[2][32];                // 1 / R_jj
   T vec[32];                    // scratch vector (lane-indexed)
@@ -83,6 +93,13 @@ EB_HD void jacobian_row(const TH& th, const T* xr, T (&J)[NET::P], T& a_out) {
     dense_bwd<T, NET::D1, NET::D2, NET::OFF1, true>(th, h1, d2, J, d1);
     dense_bwd<T, NET::D0, NET::D1, NET::OFF0, false>(th, h0, d1, J, d0);
   }
+}
+
+// D (8 x 8, fp64) += A (8 x 4) B (4 x 8) on the FP64 tensor cores.  Fragments: lane l holds A[l / 4][l % 4], B[l % 4][l / 4]
+// and D[l / 4][2 (l % 4) + {0, 1}].  On B200 a DMMA.8x8x4 keeps the FP64 pipe busy for 16 cycles (512 FLOP: the DFMA rate,
+// tools/dmma_probe.cu) but costs ONE issue slot and two operand registers instead of 8 DFMAs fed by shared-memory loads.
+EB_D void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 template <typename T> EB_D T warp_sum(T v) {
@@ -195,13 +212,98 @@ template <typename T, class NET>
 EB_D bool smmala_eval(const DataView<T>& d, SmWarpMem<T, NET>& sm, int buf, int tile_rp, int tile_cq, T& lt, T& g_l,
                       T& logdet) {
   using Geo = SmGeom<NET>;
-  constexpr int P = NET::P, PSV = Geo::PSV, LD = Geo::LD;
+  constexpr int P = NET::P, PSV = SmWarpMem<T, NET>::PSV, LD = Geo::LD;
+  constexpr bool F64 = SmIsF64<T>::value;
   const int lane = threadIdx.x & 31;
-  const int slice = (Geo::SLICES == 2 && lane >= Geo::NB) ? 1 : 0;   // tile_rp / tile_cq: this lane's block (row quad, col quad)
   const SmemVec<T> th{sm.th};
   const int jl = lane < P ? lane : 0;
   T ll = T(0);
   g_l = T(0);
+  T* G = sm.mat[buf];
+
+  if constexpr (F64) {
+    // ---- fp64: metric AND gradient on the FP64 tensor cores ---------------------------------------------------------------
+    // Staged row r: [J_r (P) | delta_r | 0 .. | w_r].  With A = rows of (w J | delta) and B = (J | delta), the padded product
+    // sum_r A_r B_r^T holds the metric in its leading P x P block and, in row P, sum_r delta_r J_r = the gradient of the
+    // log-likelihood: no separate gradient pass over the staged rows.  Per four data rows a lane loads NT values + w from
+    // shared memory (bank-conflict free, see PSV_D) and issues NT (NT + 1) / 2 DMMAs.
+    constexpr int NT = Geo::NT, NTT = NT * (NT + 1) / 2;
+    const int fk = lane & 3, fn = lane >> 2;
+    double acc[NTT][2];
+#pragma unroll
+    for (int q = 0; q < NTT; ++q) acc[q][0] = acc[q][1] = 0.0;
+    for (int base = 0; base < d.n_rows; base += 32) {
+      const int i = base + lane;
+      T* vrow = sm.v + lane * PSV;
+      if (i < d.n_rows) {
+        T J[P], a;
+        jacobian_row<T, NET>(th, d.x + i * NET::D0, J, a);   // th: broadcast reads of sm.th
+        T al[1] = {a}, dl[1], p;
+        ll += head_loss<T, NET>(al, d.y[i], 0, dl, &p);
+#pragma unroll
+        for (int j = 0; j < P; ++j) vrow[j] = J[j];
+        vrow[P] = dl[0];                       // d loglik_i / d a_L,i
+#pragma unroll
+        for (int j = P + 1; j < 8 * NT; ++j) vrow[j] = T(0);
+        vrow[8 * NT] = p * (T(1) - p);
+      } else {
+#pragma unroll
+        for (int j = 0; j <= 8 * NT; ++j) vrow[j] = T(0);
+      }
+      __syncwarp();
+      const int rows = min(32, d.n_rows - base);
+#pragma unroll 2
+      for (int k0 = 0; k0 < rows; k0 += 4) {   // rows beyond the data were staged as zeros
+        const T* vr = sm.v + (k0 + fk) * PSV;
+        const T w = vr[8 * NT];
+        T av[NT], bv[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) bv[t] = vr[8 * t + fn];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) av[t] = bv[t] * ((8 * t + fn == P) ? T(1) : w);
+        int q = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+          for (int tj = 0; tj <= ti; ++tj, ++q) dmma884(acc[q][0], acc[q][1], av[ti], bv[tj]);
+      }
+      __syncwarp();
+    }
+    // row P of the padded product -> the gradient, lane j = element j
+    {
+      constexpr int TG = P / 8;
+      int q = TG * (TG + 1) / 2;
+#pragma unroll
+      for (int tj = 0; tj <= TG; ++tj, ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * tj + 2 * fk + e;
+          if (fn == P % 8 && col < P) sm.vec[col] = acc[q][e];
+        }
+      __syncwarp();
+      g_l = sm.vec[jl];
+      __syncwarp();
+    }
+    // the lower triangle of the metric
+    {
+      int q = 0;
+#pragma unroll
+      for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+        for (int tj = 0; tj <= ti; ++tj, ++q)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int row = 8 * ti + fn, col = 8 * tj + 2 * fk + e;
+            if (row < P && col <= row) {
+              T val = acc[q][e];
+              if (row == col) val += d.pivar[row];
+              if (d.has_temperature) val *= d.temperature;
+              G[row * LD + col] = val;
+            }
+          }
+    }
+  } else {
+  const int slice = (Geo::SLICES == 2 && lane >= Geo::NB) ? 1 : 0;   // tile_rp / tile_cq: this lane's block (row quad, col quad)
   T acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -255,20 +357,7 @@ EB_D bool smmala_eval(const DataView<T>& d, SmWarpMem<T, NET>& sm, int buf, int 
     }
     __syncwarp();
   }
-  ll = warp_sum<T>(ll);
-  // prior: lane j owns parameter j; the value is summed in parameter order by every lane (as before: identical in all lanes)
-  T lp = d.lp_const;
-#pragma unroll
-  for (int j = 0; j < P; ++j) {
-    const T dd = th[j] - d.ploc[j];
-    lp = fma_t<T>(-(dd * dd), T(0.5) * d.pivar[j], lp);
-  }
-  g_l = fma_t<T>(-(th[jl] - d.ploc[jl]), d.pivar[jl], g_l);
-  if (d.has_temperature) { ll *= d.temperature; lp *= d.temperature; g_l *= d.temperature; }
-  if (lane >= P) g_l = T(0);
-  lt = ll + lp;
   // assemble the lower triangle of G in shared memory
-  T* G = sm.mat[buf];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -282,6 +371,19 @@ EB_D bool smmala_eval(const DataView<T>& d, SmWarpMem<T, NET>& sm, int buf, int 
         G[row * LD + col] = val;
       }
     }
+  }
+  ll = warp_sum<T>(ll);
+  // prior: lane j owns parameter j; the value is summed in parameter order by every lane (as before: identical in all lanes)
+  T lp = d.lp_const;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const T dd = th[j] - d.ploc[j];
+    lp = fma_t<T>(-(dd * dd), T(0.5) * d.pivar[j], lp);
+  }
+  g_l = fma_t<T>(-(th[jl] - d.ploc[jl]), d.pivar[jl], g_l);
+  if (d.has_temperature) { ll *= d.temperature; lp *= d.temperature; g_l *= d.temperature; }
+  if (lane >= P) g_l = T(0);
+  lt = ll + lp;
   __syncwarp();
   return warp_chol_inplace<T, P, LD>(G, sm.dinv[buf], logdet);
 }
