@@ -416,6 +416,26 @@ EB_HD double sqrt_pos(double x) {
   return fma(fma(-g, g, x), h, g);
 }
 
+// l = sqrt(x) and li = 1 / l together, for positive x with 1e-290 < x < 1e290 (Cholesky pivots): the coupled Newton iteration of
+// sqrt_pos carries h ~ 1 / (2 sqrt x) anyway, so the reciprocal pivot costs one more FMA instead of an IEEE division whose
+// dependent chain (seed, refinements, slow-path test) is as long as the square root's.  Both within 2 ulp.
+EB_HD void sqrt_rsqrt_pos(double x, double* l, double* li) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  const double y = 1.0 / sqrt(x);
+#endif
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);                       // residual of the pair: both take their last correction from it
+  *l = fma(fma(-g, g, x), h, g);
+  *li = 2.0 * fma(h, r, h);
+}
+
 // sin(2 pi u), cos(2 pi u) for u in [0, 1): q = rint(4 u), r = 2 u - q / 2 in [-1/4, 1/4] (exact), Taylor polynomials of
 // sin(pi r) / cos(pi r) in r^2 (truncation 5e-17 / 2e-18), quadrant fix-up by integer sign flips.  Branch-free.
 EB_HD void sincos2pi_f64(double u, double* sn, double* cs) {

@@ -116,6 +116,16 @@ template <typename T> EB_D T warp_sum(T v) {
 // before, so the factor is bit-identical.
 template <typename T> EB_D T chol_log(T l) { return log_t<T>(l); }
 template <> EB_D double chol_log<double>(double l) { return log_pos_normal(l); }   // l = sqrt(d), d > 0 finite: a normal number
+// pivot l = sqrt(d) and its reciprocal; fp64: one coupled Newton chain for both inside the safe exponent range
+template <typename T> EB_D void chol_pivot(T d, T& l, T& li) { l = sqrt_t<T>(d); li = T(1) / l; }
+template <> EB_D void chol_pivot<double>(double d, double& l, double& li) {
+  if (d > 1e-290 && d < 1e290) {            // uniform over the warp: every lane holds the same pivot
+    sqrt_rsqrt_pos(d, &l, &li);
+  } else {
+    l = sqrt(d);
+    li = 1.0 / l;
+  }
+}
 template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, T& logdet) {
   const int lane = threadIdx.x & 31;
   bool ok = true;
@@ -124,8 +134,8 @@ template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, 
   for (int j = 0; j < P; ++j) {
     const T d = m[j * LD + j];
     if (!(d > T(0)) || !(d < T(INFINITY))) { ok = false; break; }     // uniform: every lane reads the same element
-    const T l = sqrt_t<T>(d);
-    const T li = T(1) / l;
+    T l, li;
+    chol_pivot<T>(d, l, li);
     ld += chol_log<T>(l);
     const bool below = lane > j && lane < P;
     const T lij = below ? my[j] * li : T(0);
