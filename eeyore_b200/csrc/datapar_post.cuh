@@ -43,16 +43,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+// barrier over the DP_POST_THREADS post / epilogue threads (named barrier 5).  In the stand-alone post kernel that is the whole
+// CTA; in the persistent run kernel the CTA also holds the MMA-issue warp group, which never takes part in these.
+__device__ __forceinline__ void post_sync() { asm volatile("bar.sync 5, %0;" ::"n"(DP_POST_THREADS) : "memory"); }
+
 __device__ __forceinline__ double block_sum_256(double v, double* red) {
   // fixed order: lanes by xor-shuffle, then the 8 warp sums in warp order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  post_sync();
   double t = 0.0;
   if (threadIdx.x == 0)
     for (int w = 0; w < DP_POST_THREADS / 32; ++w) t += red[w];
-  __syncthreads();
+  post_sync();
   return t;   // valid in thread 0
 }
 
@@ -85,7 +89,7 @@ __device__ __forceinline__ void dp_post_entries(const double* partials, int n_pa
     const size_t slot = (size_t)(par * DP_XMAXW + xc.rank) * DP_XSLOT + e;
     for (int p = 0; p < xc.world; ++p) xc.inbox[p][slot] = tot;      // coalesced 2 KB per CTA per peer, over NVLink
     __threadfence_system();
-    __syncthreads();
+    post_sync();
     // thread p < world releases this CTA's flag on peer p and waits for peer p's flag here: the W system-scope stores and the
     // W polling loops run side by side (one thread doing them in turn cost a round trip per peer)
     if (tid < xc.world) {
@@ -99,7 +103,7 @@ __device__ __forceinline__ void dp_post_entries(const double* partials, int n_pa
         }
       }
     }
-    __syncthreads();
+    post_sync();
     tot = 0.0;
     for (int src = 0; src < xc.world; ++src)
       tot += __ldcg(&xc.inbox[xc.rank][(size_t)(par * DP_XMAXW + src) * DP_XSLOT + e]);

@@ -62,7 +62,9 @@ constexpr int TC_FLUSH = 2;                      // PAIRS of tiles between two f
 constexpr int TC_CG = EB_TC_CG;                 // column groups: thread = (row, group of TC_FW of the 64 hidden units)
 constexpr int TC_FW = DP_H / TC_CG;              // hidden units per thread
 constexpr int TC_XW = DP_D0 / TC_CG;             // dW0 columns per thread
-constexpr int TC_THREADS = 128 * TC_CG;          // every warp an epilogue warp; warp 0 also issues the MMAs                      // tiles between two folds of the TMEM weight-gradient sums into FP64
+constexpr int TC_THREADS = 128 * TC_CG;          // epilogue threads (warps 0 .. 4 TC_CG - 1)
+constexpr int TC_LAUNCH = TC_THREADS + 128;      // + one warp group whose first warp only issues the MMAs (see tc_issuer_body)
+constexpr int TC_REG_EPI = 232, TC_REG_ISSUE = 40;   // setmaxnreg: 2 x 232 + 40 = 3 x 168 (the launch bound of 384 threads)
 
 struct TcCtx {                                   // operand buffers of one tile in flight
   alignas(1024) uint16_t ones_h[1024];           // 2 KB of fp16 1.0: the N-chunk in front of the H1 pieces
@@ -78,8 +80,9 @@ struct TcSmem {
   alignas(16) uint16_t w1a[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + o, cols i      (B of MMA2)
   alignas(16) uint16_t w1b[8 * TC_WCS2 / 2];     // fp16 x 2, scaled: rows 64 p + i, cols o      (B of MMA3)
   alignas(16) float b0[DP_H], b1[DP_H], w2[DP_H], w2d[DP_H];   // w2d = w2 * (scale of Delta2)
-  alignas(16) float exch[TC_CG][DP_R];
-  alignas(8) unsigned long long bar[2][6];       // per context, 1..5: MMA groups
+  alignas(16) float exch[2][TC_CG][DP_R];          // per context: the head's partial sums of the column groups
+  alignas(8) unsigned long long bar[2][6];       // per context, 1..5: MMA groups (completion, tcgen05.commit)
+  alignas(8) unsigned long long ready[2];        // per context: the epilogue warps have finished the current phase (8 arrivals)
   float b2;
   float red_max[3][TC_THREADS / 32];             // prologue: max |W1|, max |w2|, max |W0| per warp
   uint32_t tmem_base;
@@ -267,6 +270,21 @@ __device__ __forceinline__ void mma_product(uint32_t d_tmem, const uint64_t* a_d
   }
 }
 
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 5, %0;" ::"n"(TC_THREADS) : "memory"); }   // the epilogue warps
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// End of an epilogue phase of one context: this warp's operand pieces are in shared memory and visible to the async proxy,
+// its TMEM reads have completed.  One arrival per warp; nobody waits here -- the issue warp does (tc_issuer_body).
+__device__ __forceinline__ void phase_done(unsigned long long* ready, int lane) {
+  fence_async_smem();
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(ready);
+}
+
 // A1 B1 + A1 B2 + A2 B1 accumulated into ONE group of N columns (three MMAs per k-step; B2 = B1 + 64 rows = 1024 bytes in the
 // core-matrix layout).  The tensor pipe has the slack (a quarter busy) and the epilogue is what bounds the kernel: summing
 // the piece products in TMEM instead of two accumulator groups in the epilogue saves a TMEM load and TC_FW additions per
@@ -297,6 +315,8 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s) {
   if (tid == 0) {
 #pragma unroll
     for (int b = 0; b < 12; ++b) mbar_init(&s.bar[0][0] + b, 1);
+    mbar_init(&s.ready[0], TC_THREADS / 32);
+    mbar_init(&s.ready[1], TC_THREADS / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&s.tmem_base);
@@ -351,7 +371,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
     }
     if (lane == 0) { s.red_max[0][warp] = m1; s.red_max[1][warp] = m2; s.red_max[2][warp] = m0; }
   }
-  __syncthreads();
+  epi_sync();
   float w1max = 0.f, w2max = 0.f, w0max = 0.f;
 #pragma unroll
   for (int w = 0; w < TC_THREADS / 32; ++w) {
@@ -412,26 +432,16 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
     if (tid == 0) {
 #pragma unroll
       for (int b = 0; b < 12; ++b) { mbar_inval(&s.bar[0][0] + b); mbar_init(&s.bar[0][0] + b, 1); }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) { mbar_inval(&s.ready[c]); mbar_init(&s.ready[c], TC_THREADS / 32); }
       mbar_fence_init();
     }
   }
   fence_async_smem();
   fence_before_sync();
-  __syncthreads();
+  __syncthreads();           // the whole CTA: the issue warp starts from here (tc_issuer_body)
   fence_after_sync();
   const uint32_t tm_lane = tm + ((uint32_t)(32 * q) << 16);   // this warp's lane quadrant
-
-  // shared-memory bases (32-bit shared addresses) of the operand buffers; descriptors are built where the MMAs are issued
-  const uint32_t a_ctx0 = smem_u32(&s.ctx[0]);
-  constexpr uint32_t CTXB = (uint32_t)sizeof(TcCtx);
-  constexpr uint32_t OFF_H1 = (uint32_t)offsetof(TcCtx, h1), OFF_ONESH = (uint32_t)offsetof(TcCtx, ones_h);
-  constexpr uint32_t OFF_XP = (uint32_t)offsetof(TcCtx, xp), OFF_ONESX = (uint32_t)offsetof(TcCtx, ones_x);
-  constexpr uint32_t OFF_DL = (uint32_t)offsetof(TcCtx, dl);
-  const uint32_t a_w0 = smem_u32(s.w0s), a_w1a = smem_u32(s.w1a), a_w1b = smem_u32(s.w1b);
-  auto descs2 = [](uint32_t base, uint32_t piece_bytes, uint32_t lbo, uint32_t sbo, uint64_t (&d)[2]) {
-    d[0] = smem_desc(base, lbo, sbo);
-    d[1] = smem_desc(base + piece_bytes, lbo, sbo);
-  };
 
   // weight-gradient sums: lanes 0..15 of every warp own unit o = 16 q + lane (M = 64 accumulator layout)
   float g1[TC_FW], g1e[TC_FW], g0[TC_XW], g0e[TC_XW];   // (sum, error term) pairs, see acc2
@@ -483,19 +493,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         *reinterpret_cast<uint4*>(dst) = p1;
         *reinterpret_cast<uint4*>(dst + TC_XP) = p2;
       }
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (warp == 0) {
-        if (elect_one()) {
-          fence_after_sync();
-          uint64_t dA[2];
-          descs2(a_ctx0 + c * CTXB + OFF_XP, TC_XP, TC_CS, 128, dA);                      // K-major A (M = row, K = feature)
-          mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w0, TC_WCS2, 128), 0, 0, 1);              // MMA1
-          mma_commit(&s.bar[c][1]);
-        }
-        __syncwarp();
-      }
+      phase_done(&s.ready[c], lane);
     }
     prefetch_x(tile0 + 2L * gridDim.x, xa0, xb0, yn0);
     prefetch_x(tile0 + 3L * gridDim.x, xa1, xb1, yn1);
@@ -522,19 +520,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         store_pieces32h(reinterpret_cast<unsigned char*>(cx.h1), (TC_FW / 8) * hf, r, v);
         if constexpr (TC_FW == 32) tmem_st_wait();
       }
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (warp == 0) {
-        if (elect_one()) {
-          fence_after_sync();
-          uint64_t dA[2];
-          descs2(a_ctx0 + c * CTXB + OFF_H1, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = hidden unit)
-          mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1a, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
-          mma_commit(&s.bar[c][2]);                                                       // MMA2: Z2 = H1 W1^T
-        }
-        __syncwarp();
-      }
+      phase_done(&s.ready[c], lane);
     }
     TC_STAMP(3);
     // ---- P2: H2, head, log-likelihood, delta3, dW2, Delta2 -------------------------------------------------------------
@@ -557,15 +543,15 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
                          : tc_sigmoid<false>(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]));
           apart = fmaf(h[j], s.w2[TC_FW * hf + j], apart);
         }
-        s.exch[hf][r] = apart;
+        s.exch[c][hf][r] = apart;
         // everything of Delta2 that does not depend on the head runs before the rendez-vous with the other half of the row:
         // w2 sd H2 (1 - H2), with H2 (1 - H2) as one FMA (a single rounding of the exact value)
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j) t[j] = fmaf(-h[j], h[j], h[j]) * s.w2d[TC_FW * hf + j];
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * TC_CG) : "memory");   // the warps that share rows 32 q .. 32 q + 31
-        float asum = s.exch[0][r];
+        float asum = s.exch[c][0][r];
 #pragma unroll
-        for (int cg = 1; cg < TC_CG; ++cg) asum += s.exch[cg][r];
+        for (int cg = 1; cg < TC_CG; ++cg) asum += s.exch[c][cg][r];
         const float a = asum + s.b2;
         float d = 0.f;
         if (r < rows) {   // stats/loss.py:2 semantics, saturation -> NaN
@@ -581,23 +567,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         }
         store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, h);
       }
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (warp == 0) {
-        if (elect_one()) {
-          fence_after_sync();
-          const uint32_t keep = (c > 0 || pair % TC_FLUSH != 0) ? 1u : 0u;   // sums continue from the previous tile
-          uint64_t dA[2], dM[2];
-          descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = unit)
-          descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
-          mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1b, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
-          mma_commit(&s.bar[c][3]);                                                       // MMA3: D1 = Delta2 W1
-          mma_product<2, 0, 64, 8, 64, 1, 1>(tm + TM_W1, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESH, 128, TC_CS), 256, 256, 8, keep);
-          mma_commit(&s.bar[c][4]);                                                       // MMA4: Delta2^T [1 H1]
-        }
-        __syncwarp();
-      }
+      phase_done(&s.ready[c], lane);
       // while the MMAs run: the log-likelihood term and the column sums for dW2
       if (hf == 0) {   // one branch-free log per row for hard labels; soft labels take the general form
         const float qv = (yv == 1.0f) ? p_head : 1.0f - p_head;
@@ -657,20 +627,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         mbar_wait(&s.bar[c][4], par);                        // MMA4 has read Delta2 (and H1)
         store_pieces32h(reinterpret_cast<unsigned char*>(cx.dl), (TC_FW / 8) * hf, r, v);
       }
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (warp == 0) {
-        if (elect_one()) {
-          fence_after_sync();
-          const uint32_t keep = (c > 0 || pair % TC_FLUSH != 0) ? 1u : 0u;
-          uint64_t dM[2];
-          descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
-          mma_product<2, 0, 64, 8, 16, 1, 1>(tm + TM_W0, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESX, 128, TC_CS), 256, 256, 8, keep);
-          mma_commit(&s.bar[c][5]);                                                       // MMA5: Delta1^T [1 X]
-        }
-        __syncwarp();
-      }
+      phase_done(&s.ready[c], lane);
     }
     TC_STAMP(9);
     // ---- P4: every TC_FLUSH pairs fold the weight-gradient sums into the (sum, error) accumulators ---------------------------
@@ -702,7 +659,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         for (int i = 0; i < TC_XW; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
         acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
       }
-      fence_before_sync();                                   // ordered before the next pair's MMAs by its first __syncthreads
+      fence_before_sync();                                   // ordered before the next pair's MMAs by the phase_done arrivals
     }
     TC_STAMP(12);
   }
@@ -710,7 +667,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
 
   // ---- this CTA's row of partial sums: staged in shared memory (the operand buffers are free now), written out coalesced ------
   fence_before_sync();
-  __syncthreads();
+  epi_sync();
   static_assert(sizeof(TcCtx) >= sizeof(double) * (DP_P + 1) && sizeof(TcCtx) >= sizeof(double) * 3 * TC_THREADS, "staging space");
   double* row = reinterpret_cast<double*>(&s.ctx[0]);     // [DP_P + 1]
   double* red = reinterpret_cast<double*>(&s.ctx[1]);     // [3][TC_THREADS]
@@ -729,7 +686,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
   red[tid] = (double)gw2 + (double)gw2e;
   red[TC_THREADS + tid] = (double)ll + (double)lle;
   red[2 * TC_THREADS + tid] = (double)gb2 + (double)gb2e;
-  __syncthreads();
+  epi_sync();
   if (tid < DP_H) {
     const int h2 = tid / TC_FW, l2 = tid % TC_FW;        // unit tid lives in column group h2, lane l2 of its warps
     double t = 0.0;
@@ -747,20 +704,110 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
     for (int i = 0; i < DP_R; ++i) t += red[2 * TC_THREADS + i];
     row[1 + DP_OFF_B2] = t;
   }
-  __syncthreads();
+  epi_sync();
   for (int e = tid; e <= DP_P; e += TC_THREADS) out[e] = row[e];
-  __syncthreads();   // the next evaluation of a persistent run writes the operand buffers again
+  epi_sync();   // the next evaluation of a persistent run writes the operand buffers again
   TC_STAMP(21);
 }
 
+// The MMA-issue warp (first warp of the extra warp group; its three siblings only hold the group together for setmaxnreg).
+// It walks through the same phases as the epilogue warps, waits until all eight have finished a phase of a context
+// (s.ready[c]), and issues that phase's MMAs; completion goes back through tcgen05.commit -> s.bar[c][k].  Before round 2's
+// last change warp 0 issued the MMAs behind a CTA barrier: ncu showed it spending a fifth of its time in UTCHMMA issue while
+// the other seven warps waited for it at the next barrier (19 % of the kernel's warp-stall samples).
+__device__ __forceinline__ void tc_issuer_body(TcSmem& s, const uint32_t tm, const long n_rows) {
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();           // pairs with the CTA barrier at the end of the epilogue warps' prologue
+  fence_after_sync();
+  if ((threadIdx.x >> 5) != TC_THREADS / 32) return;
+  const long n_tiles = (n_rows + DP_R - 1) / DP_R;
+  const uint32_t a_ctx0 = smem_u32(&s.ctx[0]);
+  constexpr uint32_t CTXB = (uint32_t)sizeof(TcCtx);
+  constexpr uint32_t OFF_H1 = (uint32_t)offsetof(TcCtx, h1), OFF_ONESH = (uint32_t)offsetof(TcCtx, ones_h);
+  constexpr uint32_t OFF_XP = (uint32_t)offsetof(TcCtx, xp), OFF_ONESX = (uint32_t)offsetof(TcCtx, ones_x);
+  constexpr uint32_t OFF_DL = (uint32_t)offsetof(TcCtx, dl);
+  const uint32_t a_w0 = smem_u32(s.w0s), a_w1a = smem_u32(s.w1a), a_w1b = smem_u32(s.w1b);
+  auto descs2 = [](uint32_t base, uint32_t piece_bytes, uint32_t lbo, uint32_t sbo, uint64_t (&d)[2]) {
+    d[0] = smem_desc(base, lbo, sbo);
+    d[1] = smem_desc(base + piece_bytes, lbo, sbo);
+  };
+  uint32_t rp0 = 0, rp1 = 0;                 // phase parities of s.ready[0 / 1]
+  auto wait_ready = [&](int c) {
+    uint32_t& rp = c ? rp1 : rp0;
+    mbar_wait(&s.ready[c], rp);
+    rp ^= 1u;
+    fence_after_sync();
+  };
+  int pair = 0;
+  for (long tile0 = blockIdx.x; tile0 < n_tiles; tile0 += 2L * gridDim.x, ++pair) {
+    const int n_ctx = (tile0 + gridDim.x < n_tiles) ? 2 : 1;
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {        // after P0: MMA1  Z1 = X W0^T
+      wait_ready(c);
+      if (elect_one()) {
+        uint64_t dA[2];
+        descs2(a_ctx0 + c * CTXB + OFF_XP, TC_XP, TC_CS, 128, dA);                      // K-major A (M = row, K = feature)
+        mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w0, TC_WCS2, 128), 0, 0, 1);
+        mma_commit(&s.bar[c][1]);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {        // after P1: MMA2  Z2 = H1 W1^T
+      wait_ready(c);
+      if (elect_one()) {
+        uint64_t dA[2];
+        descs2(a_ctx0 + c * CTXB + OFF_H1, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = hidden unit)
+        mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1a, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
+        mma_commit(&s.bar[c][2]);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {        // after P2: MMA3  D1 = Delta2 W1,  MMA4  [db1 dW1] = Delta2^T [1 H1]
+      wait_ready(c);
+      if (elect_one()) {
+        const uint32_t keep = (c > 0 || pair % TC_FLUSH != 0) ? 1u : 0u;   // sums continue from the previous tile
+        uint64_t dA[2], dM[2];
+        descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, TC_CS, 128, dA);                     // K-major A (M = row, K = unit)
+        descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
+        mma_product_sum<128, 64>(tm + TM_Z + 128 * c, dA, smem_desc(a_w1b, TC_WCS2, 128), 2 * TC_CS, 2 * TC_WCS2, 4);
+        mma_commit(&s.bar[c][3]);
+        mma_product<2, 0, 64, 8, 64, 1, 1>(tm + TM_W1, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESH, 128, TC_CS), 256, 256, 8, keep);
+        mma_commit(&s.bar[c][4]);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < n_ctx; ++c) {        // after P3: MMA5  [db0 dW0] = Delta1^T [1 X]
+      wait_ready(c);
+      if (elect_one()) {
+        const uint32_t keep = (c > 0 || pair % TC_FLUSH != 0) ? 1u : 0u;
+        uint64_t dM[2];
+        descs2(a_ctx0 + c * CTXB + OFF_DL, TC_ACT, 128, TC_CS, dM);                     // MN-major A (M = unit, K = row)
+        mma_product<2, 0, 64, 8, 16, 1, 1>(tm + TM_W0, dM, smem_desc(a_ctx0 + c * CTXB + OFF_ONESX, 128, TC_CS), 256, 256, 8, keep);
+        mma_commit(&s.bar[c][5]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // partials: [gridDim.x][DP_P + 1] doubles
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_LAUNCH, 1)
 dp_eval_tc_kernel(const float* __restrict__ theta, const float* __restrict__ x, const float* __restrict__ y, long n_rows,
                   const float* __restrict__ x_absmax, double* __restrict__ partials) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
   const uint32_t tm = tc_setup(s);
-  tc_eval_body(s, tm, theta, x, y, n_rows, x_absmax, partials + (size_t)blockIdx.x * (DP_P + 1), false);
+  if (threadIdx.x >= TC_THREADS) {            // the issue warp group gives its registers to the epilogue warps
+    reg_dec<TC_REG_ISSUE>();
+    tc_issuer_body(s, tm, n_rows);
+  } else {
+    reg_inc<TC_REG_EPI>();
+    tc_eval_body(s, tm, theta, x, y, n_rows, x_absmax, partials + (size_t)blockIdx.x * (DP_P + 1), false);
+  }
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tmem_dealloc<512>(tm);
 }
@@ -800,9 +847,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
   return v;
 }
 
-// all CTAs of the (co-resident) grid; `epoch` counts the arrivals expected so far
+// all CTAs of the (co-resident) grid; `epoch` counts the arrivals expected so far.  Called by the epilogue / post threads only.
 __device__ __forceinline__ void grid_sync(unsigned long long* ctr, unsigned long long& epoch, int* status) {
-  __syncthreads();
+  epi_sync();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
     __threadfence();
@@ -816,10 +863,10 @@ __device__ __forceinline__ void grid_sync(unsigned long long* ctr, unsigned long
       }
     }
   }
-  __syncthreads();
+  epi_sync();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) dp_hmc_run_kernel(const DpRunArgs a) {
+__global__ void __launch_bounds__(TC_LAUNCH, 1) dp_hmc_run_kernel(const DpRunArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(tc_raw);
   __shared__ double red[DP_POST_THREADS / 32];
@@ -831,6 +878,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dp_hmc_run_kernel(const DpRunAr
   const int e = cta * DP_POST_THREADS + tid, j = e - 1; // entry of [loglik, dloglik]; parameter j
   const bool own = post && e >= 1 && e <= DP_P;
   const uint32_t tm = tc_setup(s);
+  if (tid >= TC_THREADS) {   // the issue warp group: one tc_issuer_body per evaluation, nothing else (no post work, no grid barrier)
+    reg_dec<TC_REG_ISSUE>();
+    for (long ev = 0; ev < a.n_iters * (long)a.num_steps; ++ev) tc_issuer_body(s, tm, a.n_rows);
+    __syncthreads();
+    return;
+  }
+  reg_inc<TC_REG_EPI>();
   unsigned long long epoch = 0;
   unsigned long long seq = a.xc.seq;
   double lt_cur = __ldcg(a.target_cur);
@@ -887,7 +941,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dp_hmc_run_kernel(const DpRunAr
         acc_s = ((double)u < rate) ? 1 : 0;
         bc[0] = lt_p;
       }
-      __syncthreads();
+      epi_sync();
       const int acc = acc_s;
       if (acc) lt_cur = bc[0];
       n_acc += (uint32_t)acc;
@@ -900,7 +954,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dp_hmc_run_kernel(const DpRunAr
         if (a.out_target) a.out_target[k] = lt_cur;
         if (a.out_acc) a.out_acc[k] = (uint8_t)acc;
       }
-      __syncthreads();   // acc_s / bc are rewritten in the next iteration
+      epi_sync();   // acc_s / bc are rewritten in the next iteration
     }
   }
   if (cta == 0 && tid == 0) {
@@ -976,7 +1030,7 @@ int eeyore_b200_dp_loglik_grad_x(const void* theta, const void* x, const void* y
     if (e != cudaSuccess) return fail(e, "dp_loglik_grad(attr)");
     attr_set = true;
   }
-  dp_eval_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
+  dp_eval_tc_kernel<<<grid, TC_LAUNCH, sizeof(TcSmem), st>>>((const float*)theta, (const float*)x, (const float*)y,
                                                               (long)n_rows, absmax, partials);
   if (out_sums)   // NULL: the caller folds the per-CTA rows itself (dp_post does, together with the exchange step)
     dp_reduce_tc_kernel<<<(DP_P + 1 + 255) / 256, 256, 0, st>>>(partials, grid, (double*)out_sums);
@@ -1043,7 +1097,7 @@ int eeyore_b200_dp_hmc_run(const void* x, const void* y, int64_t n_rows, const v
   void* params[] = {(void*)&a};
   // every SM gets one CTA (195 KB of shared memory each): the grid barrier needs all of them resident, which the cooperative
   // launch guarantees (it fails instead of dead-locking when the device is shared)
-  e = cudaLaunchCooperativeKernel((const void*)dp_hmc_run_kernel, dim3((unsigned)sms), dim3(TC_THREADS), params, sizeof(TcSmem), st);
+  e = cudaLaunchCooperativeKernel((const void*)dp_hmc_run_kernel, dim3((unsigned)sms), dim3(TC_LAUNCH), params, sizeof(TcSmem), st);
   if (e != cudaSuccess) return fail(e, "dp_hmc_run");
   return EEYORE_B200_OK;
 }
