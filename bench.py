@@ -293,6 +293,27 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pins this rank's threads to the CPUs NVML lists as local to its GPU (before any pinned host buffer is allocated, so the
+    pages land on that socket): with eight ranks streaming 36 GB/s each into host memory the traffic should not cross the
+    socket interconnect.  Best effort: a container may not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to GPU %d" % (len(cpus), phys)
+    except Exception as e:      # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+    return "not bound"
+
+
 class Ctx:
     """Process-wide state of one bench run: rank / device / process group and the timing helpers every record uses."""
 
@@ -307,6 +328,7 @@ class Ctx:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.args = args
@@ -490,6 +512,8 @@ def bench_chains(ctx, wname, steps, warmup, chains=None, thin=None, iters=None, 
                       "note": "public sampler API (reset + run, host_output) on %d persistent per-batch samplers / streams; chain "
                               "states arrive by pinned host->device copies, saved states leave as the kernel's own stores into "
                               "pinned host memory, final states by device->host copies" % nb}
+        if ctx.numa:
+            rec["e2e"]["host_binding"] = ctx.numa
         rec["gpu_launches_e2e"] = (4 * nb) * steps   # per batch: eval + two transposes of reset, the fused run
         del samplers
     torch.cuda.empty_cache()

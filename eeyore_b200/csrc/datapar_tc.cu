@@ -468,6 +468,43 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
     }
   };
 
+  // Fold of the weight-gradient sums (TMEM -> (sum, error) register pairs).  It runs one phase late -- after P1 of the NEXT pair of
+  // tiles, when the group's last MMA5 has long completed (waiting for it right behind P3 stalled every warp: 3 % of the samples)
+  // and before that pair's P2 hand-over, after which the issue warp may restart the sums (keep = 0).
+  bool fold_due = false;
+  int fctx = 0;
+  uint32_t fpar = 0;
+  auto do_fold = [&]() {
+      mbar_wait(&s.bar[fctx][5], fpar);                      // the last MMA of the group: everything before it is complete
+      fence_after_sync();
+      {
+        float v[TC_FW];
+        load_sum2(tm_lane + TM_W1 + 8 + TC_FW * hf, v);
+#pragma unroll
+        for (int i = 0; i < TC_FW; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
+        uint32_t o4[4];
+        tmem_ld4(tm_lane + TM_W1, o4);
+        tmem_ld_wait();
+        acc2(gb1, gb1e, __uint_as_float(o4[0]) * inv_b1);
+      }
+      {
+        uint32_t a[TC_XW], b[TC_XW], o4[4];
+        if constexpr (TC_XW == 8) {
+          tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, *reinterpret_cast<uint32_t(*)[8]>(a));
+          tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, *reinterpret_cast<uint32_t(*)[8]>(b));
+        } else {
+          tmem_ld4(tm_lane + TM_W0 + 8 + 4 * hf, *reinterpret_cast<uint32_t(*)[4]>(a));
+          tmem_ld4(tm_lane + TM_W0 + 8 + 16 + 4 * hf, *reinterpret_cast<uint32_t(*)[4]>(b));
+        }
+        tmem_ld4(tm_lane + TM_W0, o4);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < TC_XW; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
+        acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
+      }
+      fence_before_sync();                                   // ordered before the next pair's MMAs by the phase_done arrivals
+    fold_due = false;
+  };
   long tile0 = blockIdx.x;                       // context c works on tile0 + c * gridDim.x
   prefetch_x(tile0, xa0, xb0, yn0);
   prefetch_x(tile0 + gridDim.x, xa1, xb1, yn1);
@@ -523,6 +560,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       phase_done(&s.ready[c], lane);
     }
     TC_STAMP(3);
+    if (fold_due) do_fold();
     // ---- P2: H2, head, log-likelihood, delta3, dW2, Delta2 -------------------------------------------------------------
 #pragma unroll 1
     for (int c = 0; c < n_ctx; ++c) {
@@ -630,39 +668,11 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
       phase_done(&s.ready[c], lane);
     }
     TC_STAMP(9);
-    // ---- P4: every TC_FLUSH pairs fold the weight-gradient sums into the (sum, error) accumulators ---------------------------
-    if (fold) {
-      mbar_wait(&s.bar[n_ctx - 1][5], par);                  // the last MMA issued: everything before it is complete
-      fence_after_sync();
-      {
-        float v[TC_FW];
-        load_sum2(tm_lane + TM_W1 + 8 + TC_FW * hf, v);
-#pragma unroll
-        for (int i = 0; i < TC_FW; ++i) acc2(g1[i], g1e[i], v[i] * inv_w1);
-        uint32_t o4[4];
-        tmem_ld4(tm_lane + TM_W1, o4);
-        tmem_ld_wait();
-        acc2(gb1, gb1e, __uint_as_float(o4[0]) * inv_b1);
-      }
-      {
-        uint32_t a[TC_XW], b[TC_XW], o4[4];
-        if constexpr (TC_XW == 8) {
-          tmem_ld8(tm_lane + TM_W0 + 8 + 8 * hf, *reinterpret_cast<uint32_t(*)[8]>(a));
-          tmem_ld8(tm_lane + TM_W0 + 8 + 16 + 8 * hf, *reinterpret_cast<uint32_t(*)[8]>(b));
-        } else {
-          tmem_ld4(tm_lane + TM_W0 + 8 + 4 * hf, *reinterpret_cast<uint32_t(*)[4]>(a));
-          tmem_ld4(tm_lane + TM_W0 + 8 + 16 + 4 * hf, *reinterpret_cast<uint32_t(*)[4]>(b));
-        }
-        tmem_ld4(tm_lane + TM_W0, o4);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < TC_XW; ++i) acc2(g0[i], g0e[i], (__uint_as_float(b[i]) + __uint_as_float(a[i])) * inv_w0);
-        acc2(gb0, gb0e, __uint_as_float(o4[0]) * inv_b0);
-      }
-      fence_before_sync();                                   // ordered before the next pair's MMAs by the phase_done arrivals
-    }
+    // ---- P4: every TC_FLUSH pairs the weight-gradient sums are folded (do_fold, one phase late) -----------------------------------
+    if (fold) { fold_due = true; fctx = n_ctx - 1; fpar = par; }
     TC_STAMP(12);
   }
+  if (fold_due) do_fold();
   // every MMA has completed: the last fold waited for the last one issued
 
   // ---- this CTA's row of partial sums: staged in shared memory (the operand buffers are free now), written out coalesced ------

@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1) smmala_kernel(const ChainArg
     if (ok_p && ok_c) {
       mean_p = propl + half_step * warp_solve_upper_t<T, P, LD>(sm.mat[nxt], sm.dinv[nxt],
                                                               warp_solve_lower<T, P, LD>(sm.mat[nxt], sm.dinv[nxt], gpl));
-      const T q_f = qconst + logdet_c - warp_rt_norm2<T, P, LD>(sm.mat[cur], propl - mean_c, sm.vec) / (T(2) * step);
+      // forward density: theta' - mean_c = sqrt(step) R_c^-T z, so |R_c^T (theta' - mean_c)|^2 = step |z|^2 -- no product with R_c
+      const T q_f = qconst + logdet_c - T(0.5) * warp_sum<T>(lane < P ? zl * zl : T(0));
       const T q_b = qconst + logdet_p - warp_rt_norm2<T, P, LD>(sm.mat[nxt], thc_l - mean_p, sm.vec) / (T(2) * step);
       const T log_rate = lt_p - lt_c - q_f + q_b;
       acc = log_t<T>(u) < log_rate;
