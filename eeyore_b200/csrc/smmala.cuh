@@ -23,9 +23,10 @@
 namespace eb {
 
 // chains (warps) per block.  The kernel is latency-bound (serial factorisation / solves per chain), so resident warps are
-// what counts: one 12-warp CTA per SM (the fp64 math tables cost 32 KB per CTA whatever its size; 13.6 KB per warp).
+// what counts: one 16-warp CTA per SM (the fp64 math tables cost 32 KB per CTA whatever its size; 11.3 KB per warp with the two
+// factors stored as packed triangles; 128 registers per thread, no spills).
 #ifndef EB_SM_WARPS
-#define EB_SM_WARPS 12
+#define EB_SM_WARPS 16
 #endif
 constexpr int kSmWarps = EB_SM_WARPS;
 
@@ -33,7 +34,8 @@ template <class NET> struct SmGeom {
   static constexpr int P = NET::P;
   static constexpr int CQ = (P + 3) / 4;       // column / row quads
   static constexpr int PSV = 4 * CQ + 2;       // staged row: J (zero padded), w, one pad: rows are 16-byte aligned (LDS.128)
-  static constexpr int LD = P + 1;             // leading dimension of the P x P matrices in shared memory
+  static constexpr int LD = 0;                 // the P x P factors are stored as packed lower triangles (tri_at)
+  static constexpr int MATN = P * (P + 1) / 2;
   static constexpr int NB = CQ * (CQ + 1) / 2; // 4x4 blocks of the lower triangle
   static constexpr int SLICES = NB <= 16 ? 2 : 1;
   // fp64: the metric is accumulated by FP64 tensor-core MMAs (DMMA m8n8k4) over 8 x 8 tiles of the lower triangle.  Row P of
@@ -53,7 +55,7 @@ template <typename T, class NET> struct alignas(16) SmWarpMem {
   using Geo = SmGeom<NET>;
   static constexpr int PSV = SmIsF64<T>::value ? Geo::PSV_D : Geo::PSV;
   T v[32 * PSV];
-  T mat[2][NET::P * Geo::LD];   // metric / Cholesky factors: [cur], [proposal] (roles swap on accept)
+  T mat[2][Geo::MATN + (Geo::MATN & 1)];   // metric / Cholesky factors, packed lower triangles: [cur], [proposal] (roles swap on accept)
   T dinv[2][32];                // 1 / R_jj
   T vec[32];                    // scratch vector (lane-indexed)
   T th[32];                     // the parameter vector under evaluation (read as broadcasts: no per-lane register copy)
@@ -102,6 +104,11 @@ EB_D void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// Element (i, j), j <= i, of a lower-triangular P x P matrix in shared memory: LD > 0 = full rows with leading dimension LD,
+// LD == 0 = packed rows (row i starts at i (i + 1) / 2; half the memory -- SMMALA keeps two factors per warp, and the packed
+// form is what lets 16 warps share an SM).  Row starts i (i + 1) / 2 of consecutive lanes fall into distinct banks.
+template <int LD> EB_HD constexpr int tri_at(int i, int j) { return LD > 0 ? i * LD + j : i * (i + 1) / 2 + j; }
+
 template <typename T> EB_D T warp_sum(T v) {
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
@@ -130,9 +137,9 @@ template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, 
   const int lane = threadIdx.x & 31;
   bool ok = true;
   T ld = T(0);
-  T* my = m + (lane < P ? lane : 0) * LD;
+  T* my = m + tri_at<LD>(lane < P ? lane : 0, 0);
   for (int j = 0; j < P; ++j) {
-    const T d = m[j * LD + j];
+    const T d = m[tri_at<LD>(j, j)];
     if (!(d > T(0)) || !(d < T(INFINITY))) { ok = false; break; }     // uniform: every lane reads the same element
     T l, li;
     chol_pivot<T>(d, l, li);
@@ -145,12 +152,12 @@ template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, 
     if (below) {   // four entries per trip, loads first: the compiler cannot tell that column j and the row entries never alias
       int c = j + 1;
       for (; c + 3 <= lane; c += 4) {
-        const T l0 = m[c * LD + j], l1 = m[(c + 1) * LD + j], l2 = m[(c + 2) * LD + j], l3 = m[(c + 3) * LD + j];
+        const T l0 = m[tri_at<LD>(c, j)], l1 = m[tri_at<LD>(c + 1, j)], l2 = m[tri_at<LD>(c + 2, j)], l3 = m[tri_at<LD>(c + 3, j)];
         const T a0 = my[c], a1 = my[c + 1], a2 = my[c + 2], a3 = my[c + 3];
         my[c] = fma_t<T>(-lij, l0, a0); my[c + 1] = fma_t<T>(-lij, l1, a1);
         my[c + 2] = fma_t<T>(-lij, l2, a2); my[c + 3] = fma_t<T>(-lij, l3, a3);
       }
-      for (; c <= lane; ++c) my[c] = fma_t<T>(-lij, m[c * LD + j], my[c]);
+      for (; c <= lane; ++c) my[c] = fma_t<T>(-lij, m[tri_at<LD>(c, j)], my[c]);
     }
     __syncwarp();
   }
@@ -162,7 +169,7 @@ template <typename T, int P, int LD> EB_D bool warp_chol_inplace(T* m, T* dinv, 
 // R y = b (forward substitution); lane i holds b_i on entry and y_i on return (i < P).
 template <typename T, int P, int LD> EB_D T warp_solve_lower(const T* R, const T* dinv, T b) {
   const int lane = threadIdx.x & 31;
-  const T* my = R + (lane < P ? lane : 0) * LD;
+  const T* my = R + tri_at<LD>(lane < P ? lane : 0, 0);
   // the dependent chain is shuffle -> multiply -> FMA per step; the matrix entries and reciprocal pivots of four steps are
   // fetched together so that no shared-memory latency sits inside it
 #pragma unroll 1
@@ -190,7 +197,7 @@ template <typename T, int P, int LD> EB_D T warp_solve_upper_t(const T* R, const
   for (int j0 = P - 1; j0 >= 0; j0 -= 4) {
     T r[4], di[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const int j = j0 - k >= 0 ? j0 - k : 0; r[k] = R[j * LD + (lane < P ? lane : 0)]; di[k] = dinv[j]; }
+    for (int k = 0; k < 4; ++k) { const int j = j0 - k >= 0 ? j0 - k : 0; r[k] = R[tri_at<LD>(j, lane <= j ? lane : 0)]; di[k] = dinv[j]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = j0 - k;
@@ -211,7 +218,7 @@ template <typename T, int P, int LD> EB_D T warp_rt_norm2(const T* R, T d, T* sc
   __syncwarp();
   T w = T(0);
   if (lane < P)
-    for (int j = lane; j < P; ++j) w = fma_t<T>(R[j * LD + lane], scratch[j], w);
+    for (int j = lane; j < P; ++j) w = fma_t<T>(R[tri_at<LD>(j, lane)], scratch[j], w);
   __syncwarp();
   return warp_sum<T>(w * w);
 }
@@ -308,7 +315,7 @@ EB_D bool smmala_eval(const DataView<T>& d, SmWarpMem<T, NET>& sm, int buf, int 
               T val = acc[q][e];
               if (row == col) val += d.pivar[row];
               if (d.has_temperature) val *= d.temperature;
-              G[row * LD + col] = val;
+              G[tri_at<LD>(row, col)] = val;
             }
           }
     }
@@ -378,7 +385,7 @@ EB_D bool smmala_eval(const DataView<T>& d, SmWarpMem<T, NET>& sm, int buf, int 
       if (tile_rp >= 0 && slice == 0 && row < P && col <= row) {
         if (row == col) val += d.pivar[row];
         if (d.has_temperature) val *= d.temperature;
-        G[row * LD + col] = val;
+        G[tri_at<LD>(row, col)] = val;
       }
     }
   }
