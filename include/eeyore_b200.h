@@ -7,8 +7,12 @@
  * of the reference would add.
  *
  * Conventions
- *   - every pointer is DEVICE memory unless its name ends in _host; all work is enqueued on `stream`
- *     (a cudaStream_t passed as void*, NULL = legacy default stream) and is asynchronous;
+ *   - every pointer is DEVICE-ADDRESSABLE memory unless its name ends in _host; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream) and is asynchronous.  The saved-state outputs of the
+ *     run entry points (out_samples / out_grad / out_target / out_accepted) may also be PINNED HOST memory
+ *     (cudaHostAlloc; directly addressable by the device under unified addressing): the kernel's coalesced stores then
+ *     are the device->host transfer of the chain (what ChainList holds in the reference, chains/chain_list.py:12-30),
+ *     overlapped with the sampling; contents are valid once `stream` has been synchronised;
  *   - dtype: EEYORE_B200_F32 or EEYORE_B200_F64 -- theta, x, y, prior and outputs all use it
  *     (the reference's model.dtype, eeyore/models/model.py:7);
  *   - theta is the reference's flat parameter vector (eeyore/models/model.py:44-55): per layer the weight
