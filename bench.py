@@ -957,7 +957,9 @@ def main():
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="default cfg4 line only, without the sub-records of the other BASELINE configurations")
     ap.add_argument("--diag-samples", type=int, default=1000, help="saved iterations per chain of the diagnostics stage")
-    ap.add_argument("--diag-chunk", type=int, default=65536, help="chains per chunk of the diagnostics stage")
+    ap.add_argument("--diag-chunk", type=int, default=75776,
+                    help="chains per chunk of the diagnostics stage (default: two full waves of the fp64 chain kernel, 2 x 148 SMs x 2 CTAs "
+                         "x 128 chains; 65,536 chains are 1.73 waves and take as long)")
     ap.add_argument("--e2e-batches", type=int, default=4,
                     help="chain batches (streams) of the end-to-end arm: copies of one batch overlap the kernel of another")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
