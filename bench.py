@@ -471,6 +471,10 @@ def bench_chains(ctx, wname, steps, warmup, chains=None, thin=None, iters=None, 
             s = make_sampler(w, model, loader, theta_host[lo:hi], 999, thin, args.lanes)
             s.chain_offset = rank * C + lo
             s.host_output = True
+            if kind == "smmala":
+                # warp-per-chain kernel: lane = parameter.  Chain-major blocks make a chain's saved sample one contiguous 160-byte
+                # store; in the chain-minor layout every lane's 8 bytes would cross PCIe as a transaction of their own
+                s.sample_layout = "cnp"
             samplers.append(s)
         pin = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype).pin_memory()
         out_theta, out_lt, out_acc = pin(C, P), pin(C), pin(C, dtype=torch.int32)
