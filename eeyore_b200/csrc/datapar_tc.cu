@@ -60,6 +60,9 @@ constexpr int TC_FLUSH = 2;                      // PAIRS of tiles between two f
 #define EB_TC_CG 2
 #endif
 constexpr int TC_CG = EB_TC_CG;                 // column groups: thread = (row, group of TC_FW of the 64 hidden units)
+// 4 was round 1's 16-warp experiment (same speed at 128 registers); since round 2 the persistent run kernel and the register
+// split with the issue warp group assume the 8 epilogue warps of TC_CG = 2.
+static_assert(TC_CG == 2, "EB_TC_CG: only 2 column groups (256 epilogue threads) are supported");
 constexpr int TC_FW = DP_H / TC_CG;              // hidden units per thread
 constexpr int TC_XW = DP_D0 / TC_CG;             // dW0 columns per thread
 constexpr int TC_THREADS = 128 * TC_CG;          // epilogue threads (warps 0 .. 4 TC_CG - 1)
