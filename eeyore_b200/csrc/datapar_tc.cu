@@ -49,6 +49,11 @@ constexpr uint32_t TC_CS = 2048;                 // chunk stride of [128 x C] ac
 constexpr uint32_t TC_ACT = 8 * TC_CS;           // one bf16 piece of a [128 x 64] activation: 16 KB
 constexpr uint32_t TC_XP = 2 * TC_CS;            // one piece of the [128 x 16] x tile: 4 KB
 constexpr uint32_t TC_WCS2 = 128 * 16;           // chunk stride of the 2-piece-stacked weight buffers ([128 x K])
+#ifndef EB_TC_FMA_EVERY
+#define EB_TC_FMA_EVERY 2
+#endif
+// every EB_TC_FMA_EVERY-th sigmoid takes its reciprocal on the FMA pipe instead of the MUFU unit (0 = none)
+#define TC_FMA_RCP(j) (EB_TC_FMA_EVERY > 0 && ((j) % (EB_TC_FMA_EVERY > 0 ? EB_TC_FMA_EVERY : 1)) == 1)
 constexpr float TC_NL2E = -1.4426950408889634f;  // -log2 e
 constexpr float TC_SH = 1024.f;                  // scale of H1 before the fp16 split (keeps the low piece normal)
 // TMEM columns (fp32)
@@ -549,7 +554,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         load_acc(tm_lane + TM_Z + 128 * c + TC_FW * hf, v);
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j)
-          v[j] = (j & 1) ? tc_sigmoid_fma<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]))
+          v[j] = TC_FMA_RCP(j) ? tc_sigmoid_fma<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]))
                          : tc_sigmoid<true>(fmaf(v[j], inv_z1, s.b0[TC_FW * hf + j]));     // H1 * TC_SH
         if constexpr (TC_FW == 32) {   // sh^2 H1 (1 - H1) parked in the free half of this context's Z columns until P3
           uint32_t m[32];
@@ -580,7 +585,7 @@ __device__ __forceinline__ void tc_eval_body(TcSmem& s, const uint32_t tm, const
         float apart = 0.f;
 #pragma unroll
         for (int j = 0; j < TC_FW; ++j) {
-          h[j] = (j & 1) ? tc_sigmoid_fma<false>(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]))
+          h[j] = TC_FMA_RCP(j) ? tc_sigmoid_fma<false>(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]))
                          : tc_sigmoid<false>(fmaf(h[j], inv_z2, s.b1[TC_FW * hf + j]));
           apart = fmaf(h[j], s.w2[TC_FW * hf + j], apart);
         }
