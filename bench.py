@@ -486,14 +486,17 @@ def bench_chains(ctx, wname, steps, warmup, chains=None, thin=None, iters=None, 
                 with torch.cuda.stream(st):
                     s.reset(theta_host[lo:hi])
                     s.run(num_epochs=iters, num_burnin_epochs=0)
-                    out_theta[lo:hi].copy_(s.current["sample"], non_blocking=True)
-                    out_lt[lo:hi].copy_(s.current["target_val"], non_blocking=True)
-                    out_acc[lo:hi].copy_(s.acceptance_counts(), non_blocking=True)
+                    if s.host_current is None:       # samplers without the final-state host outputs (SMMALA): staged copies
+                        out_theta[lo:hi].copy_(s.current["sample"], non_blocking=True)
+                        out_lt[lo:hi].copy_(s.current["target_val"], non_blocking=True)
+                        out_acc[lo:hi].copy_(s.acceptance_counts(), non_blocking=True)
             for st in streams:
                 cur.wait_stream(st)
             cur.synchronize()
             blk = samplers[-1]._device_blocks[-1]              # pinned host tensors, complete after the synchronisation
-            return out_lt[0].item() + float(blk["sample"][-1, 0, -1]) + float(blk["target_val"][-1, -1])
+            fin = samplers[-1].host_current
+            last_lt = out_lt[-1].item() if fin is None else float(fin["target_val"][-1]) + float(fin["sample"][-1, 0])
+            return last_lt + float(blk["sample"][-1, 0, -1]) + float(blk["target_val"][-1, -1])
 
         for _ in range(max(2, warmup // 2)):
             step_e2e()
@@ -508,14 +511,17 @@ def bench_chains(ctx, wname, steps, warmup, chains=None, thin=None, iters=None, 
         h2d = theta_host.numel() * esz
         host_blocks = [t for s in samplers for t in s._device_blocks[-1].values()]
         assert all(t.device.type == "cpu" for t in host_blocks)
-        d2h = sum(t.numel() * t.element_size() for t in (out_theta, out_lt, out_acc, *host_blocks))
+        finals = [t for s in samplers if s.host_current is not None for t in s.host_current.values()]
+        if not finals:
+            finals = [out_theta, out_lt, out_acc]
+        d2h = sum(t.numel() * t.element_size() for t in (*finals, *host_blocks))
         rec["e2e"] = {"value": world * evals_step * steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / steps, "chain_batches": nb,
                       "returns": "every saved sample [n_saved, P, C], its target and accept flag, the final states / targets / "
                                  "accept counts: what the ChainList objects of the run hold",
                       "note": "public sampler API (reset + run, host_output) on %d persistent per-batch samplers / streams; chain "
-                              "states arrive by pinned host->device copies, saved states leave as the kernel's own stores into "
-                              "pinned host memory, final states by device->host copies" % nb}
+                              "states arrive by pinned host->device copies; saved states and (HMC) the final states / targets / "
+                              "accept counts leave as the kernel's own stores into pinned host memory" % nb}
         if ctx.numa:
             rec["e2e"]["host_binding"] = ctx.numa
         rec["gpu_launches_e2e"] = (4 * nb) * steps   # per batch: eval + two transposes of reset, the fused run

@@ -53,6 +53,8 @@ class RunParams(C.Structure):
         ("stream", C.c_void_p),
         ("adapt_p", C.c_double * 3), ("adapt_t0", C.c_int32), ("adapt_pad", C.c_int32), ("adapt_iter0", C.c_int64),
         ("adapt_state", C.c_void_p), ("adapt_cov0", C.c_void_p), ("adapt_status", C.c_void_p),
+        ("final_theta", C.c_void_p), ("fs_chain", C.c_int64), ("fs_param", C.c_int64),
+        ("final_target", C.c_void_p), ("final_accept_count", C.c_void_p),
     ]
 
 

@@ -45,6 +45,10 @@ template <typename T> struct ChainArgs {
   T* out_ll;   // eval kernel only
   T* out_lp;   // eval kernel only
   int use_bulk;
+  T* final_theta;      // sampler kernels: final state once more (host-visible copy), or nullptr
+  long fs_c, fs_p;
+  T* final_target;
+  uint32_t* final_acc;
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
@@ -386,9 +390,17 @@ __global__ void __launch_bounds__(sampler_block<T, NET, KIND>(), min_blocks<T, N
       }
     }
   }
+  if (live && a.final_theta) {   // each lane re-reads the elements it owns (it wrote them itself on accept)
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+      if (j % G == sub) a.final_theta[chain * a.fs_c + j * a.fs_p] = cur.th[j * cur.stride];
+  }
   if (live && sub == 0) {
     a.target[chain] = lt_cur;
-    if (a.acc_count) a.acc_count[chain] += n_acc;
+    uint32_t total = n_acc;
+    if (a.acc_count) { total += a.acc_count[chain]; a.acc_count[chain] = total; }
+    if (a.final_target) a.final_target[chain] = lt_cur;
+    if (a.final_acc) a.final_acc[chain] = total;
     if (tuned) {
       a.tuner_state[chain] = tn_barh;
       a.tuner_state[a.n_chains + chain] = tn_logbare;

@@ -35,6 +35,8 @@ template <typename T> ChainArgs<T> chain_args_from(const eeyore_b200_run_params&
   a.out_samples = (T*)p.out_samples; a.ss_i = p.ss_iter; a.ss_c = p.ss_chain; a.ss_p = p.ss_param;
   a.out_target = (T*)p.out_target; a.out_grad = (T*)p.out_grad; a.out_acc = p.out_accepted;
   a.acc_count = p.accept_count;
+  a.final_theta = (T*)p.final_theta; a.fs_c = p.fs_chain; a.fs_p = p.fs_param;
+  a.final_target = (T*)p.final_target; a.final_acc = p.final_accept_count;
   a.use_bulk = use_bulk;
   a.tuner = DaTuner{p.tuner_l, p.tuner_d, p.tuner_m, p.tuner_logeub, p.tuner_has_eub};
   a.tuner_iter0 = p.tuner_iter0; a.tuner_burnin = p.tuner_burnin; a.tuner_state = p.tuner_state;

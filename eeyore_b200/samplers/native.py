@@ -47,6 +47,10 @@ class NativeChainSampler(SerialSampler):
         # shape; their contents are valid once the stream has been synchronised.
         self.host_output = False
         self._host_blocks = {}
+        # With host_output, HMC / MALA / MH on a compiled network specialisation also leave the FINAL state of every run in
+        # pinned host memory (`host_current`: 'sample' [C, P] as a view of the chain-minor buffer the kernel stores into,
+        # 'target_val' [C], 'accept_count' [C]); None for the other samplers, whose final state is read from `current`.
+        self.host_current = None
         self.num_chains = 1
         self.current = {key: None for key in self.keys}
         if theta0 is not None:
@@ -233,6 +237,16 @@ class NativeChainSampler(SerialSampler):
         if "accepted" in out:
             p.out_accepted = out["accepted"].data_ptr()
         p.accept_count = self._acc_count.data_ptr()
+        if host and self._entry in ("eeyore_b200_hmc_run", "eeyore_b200_mala_run", "eeyore_b200_mh_run") and \
+                nv.lib().eeyore_b200_mlp_is_specialised(m.handle()) == 1:
+            fin = alloc("final_theta", (pn, c), m.dtype)             # chain-minor: a warp's 32 chains store 256 contiguous bytes
+            self.host_current = {"sample": fin.t(), "target_val": alloc("final_target", (c,), m.dtype),
+                                 "accept_count": alloc("final_accept_count", (c,), torch.int32)}
+            p.final_theta, p.fs_chain, p.fs_param = fin.data_ptr(), 1, c
+            p.final_target = self.host_current["target_val"].data_ptr()
+            p.final_accept_count = self.host_current["accept_count"].data_ptr()
+        else:
+            self.host_current = None
         p.lanes_per_chain = int(self.lanes_per_chain or 0)
         p.stream = torch.cuda.current_stream(dev).cuda_stream
         self._fill_params(p)

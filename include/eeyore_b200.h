@@ -142,6 +142,16 @@ typedef struct eeyore_b200_run_params {
   void *adapt_state;
   const void *adapt_cov0;
   int32_t *adapt_status;
+  /* Final state of the call written a second time, for the host (mh_run / mala_run / hmc_run on the compiled network
+   * specialisations; ignored elsewhere; NULL = off).  Like the saved-state outputs these may be pinned host memory: every
+   * chain's last stores are then its device->host transfer, spread over the run as the CTAs finish, instead of a copy
+   * after the kernel.  final_theta: element (c, j) at c*fs_chain + j*fs_param (chain-minor -- fs_chain = 1, fs_param = C
+   * -- keeps a warp's stores contiguous); final_target [C]; final_accept_count [C] = accept_count after this call (the
+   * number accepted in this call when accept_count is NULL). */
+  void *final_theta;
+  int64_t fs_chain, fs_param;
+  void *final_target;
+  uint32_t *final_accept_count;
 } eeyore_b200_run_params;
 
 /* number of states a run with these (n_iters, n_burnin, thin) saves */

@@ -201,6 +201,12 @@ def test_host_output_saved_states_equal_the_device_blocks(layout):
         for k in ("sample", "target_val", "accepted"):
             assert torch.equal(runs[True][rep][k], runs[False][rep][k]), (rep, k)
     assert not torch.equal(runs[True][0]["sample"], runs[True][1]["sample"])
+    # the final state of the last run, written by the kernel into pinned host memory beside the device state
+    fin = s.host_current
+    assert fin is not None and fin["sample"].device.type == "cpu"
+    assert torch.equal(fin["sample"], s.current["sample"].cpu())
+    assert torch.equal(fin["target_val"], s.current["target_val"].cpu())
+    assert torch.equal(fin["accept_count"], s.acceptance_counts().cpu().to(torch.int32))
 
 
 def test_nan_proposals_are_rejected():
