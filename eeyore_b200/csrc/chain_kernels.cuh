@@ -254,7 +254,12 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const ChainArgs<T> a, T
 // (HMC) the momentum.  Global memory (coalesced in the chain-minor layout): the chain's current sample / gradient, read
 // once per iteration and written on accept.
 template <typename T, class NET, int G, int KIND>
+#ifdef EB_MAXNREG   // experiment: an explicit register cap instead of the launch bounds.  Config 4 on B200 (1.753e10 evals/s with the
+                    // launch bounds, 236 registers): cap 224 -> 1.720e10, 192 -> 1.556e10, 168 (3 CTAs per SM, 116 B of spills) -> 1.576e10
+__global__ void __maxnreg__(EB_MAXNREG) sampler_kernel(const ChainArgs<T> a) {
+#else
 __global__ void __launch_bounds__(sampler_block<T, NET, KIND>(), min_blocks<T, NET, KIND>()) sampler_kernel(const ChainArgs<T> a) {
+#endif
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int KB = sampler_block<T, NET, KIND>();
   constexpr int CPB = KB / G;
